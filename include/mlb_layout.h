@@ -1,0 +1,315 @@
+/*
+ * mlb_layout.h — layout of the "model block": the flat FP64 array that describes one
+ * Monte Carlo case (integrator, environment, rocket stages/components, tables) to the
+ * batched trajectory kernels. Built on the host by mapleaf_b200/model.py from a .mapleaf
+ * SimDefinition; consumed by libmapleaf_b200.so (CUDA) and by the test oracle.
+ *
+ * Every entry is a double (integers / enums are stored as exactly-representable doubles).
+ * All offsets (…_OFF) are indices into the same array. This header is the single source of
+ * truth: the Python side parses the `#define NAME value` lines below.
+ *
+ * What each field restates in the reference (paths relative to MAPLEAF/):
+ *   integrator + adaptive parameters ........ Motion/Integration.py:56-103,144-195,238-329
+ *   end condition ........................... SimulationRunners/SingleSimulations.py:205-248
+ *   earth / atmosphere / wind / turbulence .. ENV/environment.py:39-103, ENV/*Modelling.py
+ *   launch rail ............................. ENV/launchRail.py:8-14
+ *   stage records ........................... Rocket/stage.py:10-41, Rocket/CompositeObject.py:23-63
+ *   component records ....................... Rocket/{noseCone,bodyTube,boatTail,Fins,Propulsion,Recovery,RocketComponents}.py constructors
+ */
+#ifndef MLB_LAYOUT_H
+#define MLB_LAYOUT_H
+
+#define MLB_MAGIC 20261019
+#define MLB_VERSION 1
+
+/* ---- header ---------------------------------------------------------------------- */
+#define H_MAGIC 0
+#define H_VERSION 1
+#define H_LEN 2
+#define H_INTEGRATOR 3
+#define H_DT0 4
+#define H_END_TYPE 5
+#define H_END_VALUE 6
+#define H_MAX_STEPS 7
+#define H_AD_TARGET 8
+#define H_AD_MINF 9
+#define H_AD_MAXF 10
+#define H_AD_MINDT 11
+#define H_AD_MAXDT 12
+#define H_AD_CTRL 13
+#define H_AD_P 14
+#define H_AD_I 15
+#define H_AD_D 16
+#define H_AD_SAFETY 17
+#define H_EVENT_DT 18
+#define H_EARTH 19
+#define H_LAT 20
+#define H_LON 21
+#define H_ELEV 22
+#define H_ATM 23
+#define H_ATM_CONST 24
+#define H_ATM_TAB_OFF 28
+#define H_ATM_TAB_N 29
+#define H_WIND 30
+#define H_WIND_V 31
+#define H_HELLMAN_ALPHA 34
+#define H_HELLMAN_LIMIT 35
+#define H_WIND_TAB_OFF 36
+#define H_WIND_TAB_N 37
+#define H_TURB 38
+#define H_TURB_INTENSITY 39
+#define H_TURB_STD 40
+#define H_GUST_START 41
+#define H_GUST_BLEND 42
+#define H_GUST_THICK 43
+#define H_GUST_MAG 44
+#define H_GUST_DIR 45
+#define H_TURB_OFF_CHUTE 48
+#define H_RAIL_LEN 49
+#define H_RAIL_POS 50
+#define H_RAIL_DIR 53
+#define H_AREF 56
+#define H_FULLY_TURB 57
+#define H_MAXDIAM 58
+#define H_INIT_STATE 59
+#define H_NSTAGES 72
+#define H_STAGE_OFF 73
+#define H_FINENESS 77
+#define H_TABLEAU_OFF 81
+#define H_TAB_NSTAGE_ROWS 82
+#define H_TAB_NRESULT_ROWS 83
+#define H_RECOVERY_OFF 84
+#define H_CTRL_OFF 85
+#define H_EARTH_ROT 86
+#define H_USSTD_OFF 87
+#define H_PINK_C0 88
+#define H_PINK_C1 89
+#define H_PINK_SEED 90
+#define H_EARTH_GM 93
+#define H_EARTH_RADIUS 94
+#define H_ROCKET_ROUGHNESS 95
+#define H_ADD_AUTO_BT 96
+#define H_PINK_HAS_SEED 97
+#define H_NOSE_POS0 98
+#define H_SIZE 128
+
+/* integrator ids (H_INTEGRATOR) */
+#define INT_EULER 0
+#define INT_RK2_MIDPOINT 1
+#define INT_RK2_HEUN 2
+#define INT_RK4 3
+#define INT_RK4_38 4
+#define INT_RK12A 10
+#define INT_RK23A 11
+#define INT_RK45A 12
+#define INT_RK78A 13
+#define TABLEAU_STRIDE 14
+
+/* end conditions (H_END_TYPE) */
+#define END_APOGEE 0
+#define END_ALT_ASCENDING 1
+#define END_ALT_DESCENDING 2
+#define END_TIME 3
+
+/* adaptive step controller (H_AD_CTRL) */
+#define CTRL_PID 0
+#define CTRL_ELEMENTARY 1
+#define CTRL_CONSTANT 2
+
+/* models */
+#define EARTH_NONE 0
+#define EARTH_FLAT 1
+#define EARTH_ROUND 2
+#define EARTH_WGS84 3
+#define ATM_CONSTANT 0
+#define ATM_USSTD 1
+#define ATM_TABULATED 2
+#define WIND_CONSTANT 0
+#define WIND_HELLMAN 1
+#define WIND_INTERPOLATED 2
+#define TURB_NONE 0
+#define TURB_PINK1D 1
+#define TURB_PINK2D 2
+#define TURB_PINK3D 3
+#define TURB_SINE_GUST 4
+
+/* event types (Rocket/simEventDetector.py:14-19) */
+#define EV_NONE 0
+#define EV_APOGEE 1
+#define EV_ASCENDING_ALT 2
+#define EV_DESCENDING_ALT 3
+#define EV_MOTOR_BURNOUT 4
+#define EV_TIME_REACHED 5
+/* event callbacks */
+#define CB_RECOVERY_DEPLOY 1
+#define CB_STAGE_SEPARATION 2
+#define MLB_MAX_EVENTS 6
+
+/* ---- stage record ------------------------------------------------------------------ */
+#define S_NCOMP 0
+#define S_POS 1
+#define S_SEP_TYPE 4
+#define S_SEP_VALUE 5
+#define S_SEP_DELAY 6
+#define S_OVR_FLAGS 7
+#define S_OVR_CG 8
+#define S_OVR_MASS 11
+#define S_OVR_MOI 12
+#define S_FIXED_MOI 15
+#define S_FIXED_CG 18
+#define S_FIXED_MASS 21
+#define S_BURN_DURATION 22
+#define S_MOTOR 23
+#define S_IGNITION0 24
+#define S_AUTO_BT_OFF 25
+#define S_COMP_OFF 26
+#define S_MAX_COMP 30
+#define S_SIZE 56
+#define OVR_CG 1
+#define OVR_MASS 2
+#define OVR_MOI 4
+
+/* ---- component records: common prefix ------------------------------------------------ */
+#define C_TYPE 0
+#define C_LEN 1
+#define C_POS 2
+#define C_MOI 5
+#define C_CG 8
+#define C_MASS 11
+#define C_P 12
+
+#define CT_NOSECONE 1
+#define CT_BODYTUBE 2
+#define CT_FINSET 3
+#define CT_MOTOR 4
+#define CT_MASS 5
+#define CT_RECOVERY 6
+#define CT_BOATTAIL 7
+#define CT_TRANSITION 8
+#define CT_TAB_AERO 9
+#define CT_TAB_INERTIA 10
+#define CT_JET_DAMPING 11
+#define CT_FIXED_FORCE 12
+#define CT_AERO_FORCE 13
+#define CT_AERO_DAMPING 14
+
+/* nose cone (Rocket/noseCone.py:58-101) */
+#define NC_BASE_AREA 12
+#define NC_LENGTH 13
+#define NC_WETTED 14
+#define NC_CP 15
+#define NC_HALF_ANGLE 18
+#define NC_SUB 19
+#define NC_TRANS 21
+#define NC_ROUGH 25
+#define NC_SIZE 26
+
+/* body tube (Rocket/bodyTube.py:13-33) */
+#define BT_LENGTH 12
+#define BT_DIAM 13
+#define BT_PLANFORM 14
+#define BT_WETTED 15
+#define BT_CP 16
+#define BT_ROUGH 19
+#define BT_SIZE 20
+
+/* boat tail / transition (Rocket/boatTail.py:12-99) */
+#define TR_TOP_AREA 12
+#define TR_BOTTOM_AREA 13
+#define TR_FRONTAL 14
+#define TR_LENGTH 15
+#define TR_WETTED 16
+#define TR_CP 17
+#define TR_CD_ADJ 20
+#define TR_GROWING 21
+#define TR_HALF_ANGLE 22
+#define TR_SUB 23
+#define TR_TRANS 25
+#define TR_ROUGH 29
+#define TR_START_D 30
+#define TR_END_D 31
+#define TR_SIZE 32
+
+/* fin set (Rocket/Fins.py:45-262, 430-462) */
+#define FS_NFINS 12
+#define FS_SPAN 13
+#define FS_ROOT 14
+#define FS_TIP 15
+#define FS_THICK 16
+#define FS_ROUGH 17
+#define FS_SWEEP 18
+#define FS_MIDSWEEP 19
+#define FS_PLANFORM 20
+#define FS_WETTED 21
+#define FS_AR 22
+#define FS_STALL 23
+#define FS_BODY_R 24
+#define FS_BODY_INTERF 25
+#define FS_NUM_INTERF 26
+#define FS_MAC_LEN 27
+#define FS_MAC_Y 28
+#define FS_XMAC_LE 29
+#define FS_LE_SHAPE 30
+#define FS_LE_THICK 31
+#define FS_TE_THICK 32
+#define FS_CP_POLY 33
+#define FS_CANT 39
+#define FS_NSLICES 40
+#define FS_ACTUATED 41
+#define FS_TIP_POS 42
+#define FS_THICK_K 43
+#define FS_SPANDIR 44
+#define FS_MAX_FINS 8
+#define FS_SLICE_R 60
+#define FS_MAX_SLICES 16
+#define FS_SLICE_A 76
+#define FS_SLICE_LE 92
+#define FS_SLICE_LEN 108
+#define FS_CDTT_STAR 124
+#define FS_SIZE 126
+
+/* tabulated motor (Rocket/Propulsion.py:8-128). Table: 10 columns of MT_NROWS each, column-major,
+   starting at C_P+MT_TABLE: time, thrust, oxWeight, fuelWeight, oxMOI xyz, fuelMOI xyz */
+#define MT_NROWS 12
+#define MT_OX_CG0 13
+#define MT_OX_CG1 14
+#define MT_FUEL_CG0 15
+#define MT_FUEL_CG1 16
+#define MT_OX_W0 17
+#define MT_FUEL_W0 18
+#define MT_TABLE 19
+
+/* recovery system (Rocket/Recovery.py:10-48): up to 4 chute stages of 5 doubles:
+   trigger event type, trigger value, chute area, Cd, delay */
+#define RC_NSTAGES 12
+#define RC_STAGE0 13
+#define RC_STAGE_STRIDE 5
+#define RC_MAX_STAGES 4
+#define RC_SIZE 33
+
+/* ---- per-lane input arrays (mlb_set_lanes arrayIds) ----------------------------------- */
+#define LANE_WIND 0          /* 3: Environment.ConstantMeanWind.velocity (ENU)        */
+#define LANE_INIT_STATE 1    /* 13: pos, vel, quat, body-frame angular velocity         */
+#define LANE_PINK_SEED 2     /* 3: integer seeds of the pink-noise generators           */
+#define LANE_NUM_ARRAYS 3
+
+/* ---- per-lane outputs -------------------------------------------------------------------- */
+#define RES_LAND_X 0
+#define RES_LAND_Y 1
+#define RES_LAND_Z 2
+#define RES_APOGEE 3
+#define RES_MAX_SPEED 4
+#define RES_FLIGHT_TIME 5
+#define RES_MAX_HVEL 6
+#define RES_SIZE 7
+/* final-state rows: pos3 vel3 quat4 angvel3 time */
+#define FIN_SIZE 14
+
+/* lane status */
+#define ST_OK 0
+#define ST_RUNNING 1
+#define ST_STEP_LIMIT 2
+#define ST_NAN 3
+#define ST_UNSUPPORTED 4
+
+#endif

@@ -1,0 +1,6 @@
+"""
+mapleaf_b200 — B200-native batched Monte Carlo 6-DOF trajectory integration behind MAPLEAF's
+`runMonteCarloSimulation` interface. See DESIGN.md / INTEGRATION.md.
+"""
+from .simdef import SimDefinition, SubDictReader, defaultConfigValues  # noqa: F401
+from .model import buildModel, L  # noqa: F401

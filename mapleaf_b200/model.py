@@ -1,0 +1,975 @@
+"""
+Model-block builder: SimDefinition -> flat FP64 array consumed by the batched trajectory kernels.
+
+This is the host half of the drop-in boundary. It restates what the reference's constructors
+precompute once per simulation so that the per-lane device code only has to
+evaluate forces and integrate:
+
+  Environment.__init__ ................ MAPLEAF/ENV/environment.py:39-103
+  USStandardAtmosphere.__init__ ....... MAPLEAF/ENV/AtmosphereModelling.py:98-145
+  integratorFactory / tableaus ........ MAPLEAF/Motion/Integration.py:31-103,144-195,238-329
+  Rocket.__init__ and helpers ......... MAPLEAF/Rocket/rocket.py:34-219,251-291,325-337,408-421,489-528
+  Stage / CompositeObject ............. MAPLEAF/Rocket/stage.py:13-70, Rocket/CompositeObject.py:23-63
+  component constructors .............. Rocket/{noseCone,bodyTube,boatTail,Fins,Propulsion,Recovery,RocketComponents}.py
+
+The layout is defined in include/mlb_layout.h (parsed here, single source of truth).
+Component classes the kernels do not implement raise NotImplementedError naming the class
+(there is no CPU fallback by design).
+"""
+import math
+import os
+import re
+from math import cos, sqrt
+from typing import Dict, List
+
+import numpy as np
+
+from . import hostmath as hm
+from .simdef import SimDefinition, SubDictReader
+
+__all__ = ["L", "buildModel", "Model"]
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+
+
+def _loadLayout() -> Dict[str, int]:
+    for cand in (os.path.join(_PKG_DIR, "..", "include", "mlb_layout.h"), os.path.join(_PKG_DIR, "include", "mlb_layout.h")):
+        if os.path.exists(cand):
+            out = {}
+            with open(cand) as f:
+                for m in re.finditer(r"^#define\s+(\w+)\s+(-?\d+)\s*(?:/\*.*)?$", f.read(), re.M):
+                    out[m.group(1)] = int(m.group(2))
+            return out
+    raise FileNotFoundError("include/mlb_layout.h not found")
+
+
+class _Layout:
+    def __init__(self, d):
+        self.__dict__.update(d)
+        self._d = d
+
+
+L = _Layout(_loadLayout())
+
+_BODY_CLASSES = {"Nosecone", "Bodytube", "BoatTail", "Transition"}
+_FIXED_MASS_CLASSES = {"Nosecone", "Bodytube", "BoatTail", "Transition", "FinSet", "Mass", "RecoverySystem"}
+_SUPPORTED_CLASSES = _FIXED_MASS_CLASSES | {"Motor"}
+
+_INTEGRATORS = {"Euler": L.INT_EULER, "RK2Midpoint": L.INT_RK2_MIDPOINT, "RK2Heun": L.INT_RK2_HEUN, "RK4": L.INT_RK4,
+                "RK4_3/8": L.INT_RK4_38, "RK12Adaptive": L.INT_RK12A, "RK23Adaptive": L.INT_RK23A,
+                "RK45Adaptive": L.INT_RK45A, "RK78Adaptive": L.INT_RK78A}
+
+
+def butcherTableau(method: str):
+    """Rows of [c_i, a_i1..] followed by the result row(s); zeros are replaced by 1e-16 exactly as the
+    reference does before use (Integration.py:51-54, App. A #1)."""
+    if method == "Euler":
+        return None, 0
+    tabs = {
+        "RK2Midpoint": ([[0.5, 0.5], [0, 1]], 1),
+        "RK2Heun": ([[1, 1], [0.5, 0.5]], 1),
+        "RK4": ([[0.5, 0.5], [0.5, 0, 0.5], [1, 0, 0, 1], [1 / 6, 1 / 3, 1 / 3, 1 / 6]], 1),
+        "RK4_3/8": ([[1 / 3, 1 / 3], [2 / 3, -1 / 3, 1.0], [1.0, 1.0, -1.0, 1.0], [1 / 8, 3 / 8, 3 / 8, 1 / 8]], 1),
+        "RK12Adaptive": ([[0.5, 0.5], [0.0, 1.0], [1.0, 0.0]], 2),
+        "RK23Adaptive": ([[0.5, 0.5], [3 / 4, 0.0, 3 / 4], [1.0, 2 / 9, 1 / 3, 4 / 9], [2 / 9, 1 / 3, 4 / 9, 0.0],
+                          [7 / 24, 1 / 4, 1 / 3, 1 / 8]], 2),
+        "RK45Adaptive": ([[1 / 5, 1 / 5], [3 / 10, 3 / 40, 9 / 40], [4 / 5, 44 / 45, -56 / 15, 32 / 9],
+                          [8 / 9, 19372 / 6561, -25360 / 2187, 64448 / 6561, -212 / 729],
+                          [1.0, 9017 / 3168, -355 / 33, 46732 / 5247, 49 / 176, -5103 / 18656],
+                          [1.0, 35 / 384, 0.0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84],
+                          [35 / 384, 0.0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84, 0.0],
+                          [5179 / 57600, 0.0, 7571 / 16695, 393 / 640, -92097 / 339200, 187 / 2100, 1 / 40]], 2),
+    }
+    if method not in tabs:
+        raise ValueError("Integration method: {} not implemented. See SimDefinitionTemplate.txt for options.".format(method))
+    rows, nResult = tabs[method]
+    rows = [[(1e-16 if x == 0 else float(x)) for x in r] for r in rows]
+    return rows, nResult
+
+
+class Inertia:
+    """MOI about CG (diagonal), CG, mass. Combination follows Motion/inertia.py:78-115 term by term."""
+
+    def __init__(self, MOI, CG, mass):
+        self.MOI, self.CG, self.mass = tuple(MOI), tuple(CG), mass
+
+    @staticmethod
+    def combine(items: List["Inertia"]) -> "Inertia":
+        totalMass = 0
+        totalCG = (0, 0, 0)
+        for it in items:
+            totalMass += it.mass
+            totalCG = hm.v_add(totalCG, hm.v_scale(it.CG, it.mass))
+        totalCG = hm.v_div(totalCG, totalMass) if totalMass > 0 else (0, 0, 0)
+        mx = my = mz = 0
+        for it in items:
+            mx += it.MOI[0]
+            my += it.MOI[1]
+            mz += it.MOI[2]
+            d = hm.v_sub(totalCG, it.CG)
+            mx += it.mass * (d[1] * d[1] + d[2] * d[2])
+            my += it.mass * (d[0] * d[0] + d[2] * d[2])
+            mz += it.mass * (d[0] * d[0] + d[1] * d[1])
+        return Inertia((mx, my, mz), totalCG, totalMass)
+
+
+def _linInterp(X, Y, x):
+    """Motion/Interpolation.py:15-41 for scalar Y."""
+    from bisect import bisect
+    i = bisect(X, x)
+    if i >= len(X):
+        return Y[len(X) - 1]
+    if i < 1:
+        return Y[0]
+    return (Y[i] - Y[i - 1]) * (x - X[i - 1]) / (X[i] - X[i - 1]) + Y[i - 1]
+
+
+# ======================================================================================
+# component builders: each returns (record: list[float], info: dict)
+# ======================================================================================
+def _fixedMassPrefix(r: SubDictReader, stagePos, ctype, size):
+    mass = r.getFloat("mass")
+    position = hm.v_add(r.getVector("position"), stagePos)
+    cg = hm.v_add(r.getVector("cg"), position)
+    try:
+        MOI = r.getVector("MOI")
+    except Exception:
+        MOI = (mass * 0.01, mass * 0.01, mass * 0.01)
+    rec = [0.0] * size
+    rec[L.C_TYPE] = ctype
+    rec[L.C_LEN] = size
+    rec[L.C_POS:L.C_POS + 3] = position
+    rec[L.C_MOI:L.C_MOI + 3] = MOI
+    rec[L.C_CG:L.C_CG + 3] = cg
+    rec[L.C_MASS] = mass
+    return rec, position, Inertia(MOI, cg, mass)
+
+
+def _subsonicPolyCoeffs(coneHalfAngle):
+    gamma = 1.4
+    dCd_dMa_M1 = 4 / (gamma + 1) * (1 - 0.5 * math.sin(coneHalfAngle))
+    Cd_M1 = math.sin(coneHalfAngle)
+    return [Cd_M1, (dCd_dMa_M1 / Cd_M1)]
+
+
+def _hoerner(coneHalfAngle, Mach):
+    return 2.1 * (math.sin(coneHalfAngle)) ** 2 + 0.5 * math.sin(coneHalfAngle) / math.sqrt(Mach ** 2 - 1)
+
+
+def cubicInterpInverseMatrix(X1, X2):
+    """inverse of the 4x4 Hermite constraint matrix (Motion/Interpolation.py:73-84, scipy.linalg.inv)."""
+    import scipy.linalg as linalg
+    A = np.array([[1, X1, X1 ** 2, X1 ** 3], [1, X2, X2 ** 2, X2 ** 3], [0, 1, 2 * X1, 3 * X1 ** 2], [0, 1, 2 * X2, 3 * X2 ** 2]])
+    return linalg.inv(A)
+
+
+def _transonicPolyCoeffs(coneHalfAngle):
+    gamma = 1.4
+    dCd_dMa_M1 = 4 / (gamma + 1) * (1 - 0.5 * math.sin(coneHalfAngle))
+    Cd_M1 = math.sin(coneHalfAngle)
+    Cd_M13 = _hoerner(coneHalfAngle, 1.3)
+    Cd_M1301 = _hoerner(coneHalfAngle, 1.301)
+    dCd_dMa_M13 = (Cd_M1301 - Cd_M13) / 0.001
+    B = np.array([[Cd_M1], [Cd_M13], [dCd_dMa_M1], [dCd_dMa_M13]])
+    return [float(x) for x in cubicInterpInverseMatrix(1.0, 1.3).dot(B)[:, 0]]
+
+
+def _barrowmanCP(length, areaTop, areaBottom, volume, top=(0, 0, 0)):
+    if areaTop == areaBottom:
+        d = length / 2
+    else:
+        d = (length * areaBottom - volume) / (areaBottom - areaTop)
+    return (top[0], top[1], top[2] - d)
+
+
+def _buildNosecone(r, stagePos, rocketRoughness):
+    rec, position, inertia = _fixedMassPrefix(r, stagePos, L.CT_NOSECONE, L.NC_SIZE)
+    aspectRatio = r.getFloat("aspectRatio")
+    baseDiameter = r.getFloat("baseDiameter")
+    shape = r.getString("shape")
+    roughness = r.tryGetFloat("surfaceRoughness", defaultValue=rocketRoughness)
+    length = baseDiameter * aspectRatio
+    baseRadius = baseDiameter / 2
+    if shape == "tangentOgive":
+        rho = (baseRadius ** 2 + length ** 2) / (2 * baseRadius)
+        volume = math.pi * (length * rho ** 2 - length ** 3 / 3 - (rho - baseRadius) * rho ** 2 * (math.asin(length / rho)))
+        numSteps = 2000
+        stepSize = length / numSteps
+        wetted = 0
+        for x in range(numSteps + 1):
+            wetted += 2 * math.pi * ((math.sqrt(rho ** 2 - (length - x * stepSize) ** 2)) + baseRadius - rho) * stepSize
+    elif shape == "cone":
+        volume = math.pi * (baseDiameter) ** 2 * length / 3
+        wetted = math.pi * baseRadius * math.sqrt(baseRadius ** 2 + length ** 2)
+    else:
+        raise TypeError("The nosecone shape {} is not recognized".format(shape))
+    baseArea = baseDiameter ** 2 * math.pi / 4
+    CP = _barrowmanCP(length, 0, baseArea, volume)
+    half = abs(math.atan((baseDiameter / 2) / length))
+    rec[L.NC_BASE_AREA] = baseArea
+    rec[L.NC_LENGTH] = length
+    rec[L.NC_WETTED] = wetted
+    rec[L.NC_CP:L.NC_CP + 3] = CP
+    rec[L.NC_HALF_ANGLE] = half
+    rec[L.NC_SUB:L.NC_SUB + 2] = _subsonicPolyCoeffs(half)
+    rec[L.NC_TRANS:L.NC_TRANS + 4] = _transonicPolyCoeffs(half)
+    rec[L.NC_ROUGH] = roughness
+
+    def getRadius(d):
+        if shape == "cone":
+            return (baseDiameter / 2) * (d / length)
+        curveRadius = ((baseDiameter / 2) ** 2 + length ** 2) / (baseDiameter)
+        y = math.sqrt(curveRadius ** 2 - (length - d) ** 2)
+        return y - (curveRadius - (baseDiameter / 2))
+    return rec, dict(position=position, inertia=inertia, length=length, maxDiameter=baseDiameter, getRadius=getRadius, body=True,
+                     canConnectBelow=True)
+
+
+def _buildBodytube(r, stagePos, rocketRoughness):
+    rec, position, inertia = _fixedMassPrefix(r, stagePos, L.CT_BODYTUBE, L.BT_SIZE)
+    length = r.getFloat("length")
+    D = r.getFloat("outerDiameter")
+    roughness = r.tryGetFloat("surfaceRoughness", defaultValue=rocketRoughness)
+    rec[L.BT_LENGTH] = length
+    rec[L.BT_DIAM] = D
+    rec[L.BT_PLANFORM] = D * length
+    rec[L.BT_WETTED] = math.pi * D * length
+    rec[L.BT_CP:L.BT_CP + 3] = hm.v_sub(position, (0, 0, length / 2))
+    rec[L.BT_ROUGH] = roughness
+    return rec, dict(position=position, inertia=inertia, length=length, maxDiameter=D, getRadius=lambda _: D / 2, body=True,
+                     canConnectBelow=True)
+
+
+def _transitionRecord(rec, startD, endD, length, position, roughness):
+    topArea = startD ** 2 * math.pi / 4
+    bottomArea = endD ** 2 * math.pi / 4
+    frontal = abs(topArea - bottomArea)
+    if length == 0:
+        wetted, volume, CP = 0.0, 0.0, position
+    else:
+        maxD, minD = max(startD, endD), min(startD, endD)
+        slope = ((maxD - minD) / length)
+        baseConeHeight = maxD / slope
+        baseHyp = math.sqrt((maxD / 2) ** 2 + baseConeHeight ** 2)
+        fullArea = math.pi * (maxD / 2) * baseHyp
+        tipConeHeight = minD / slope
+        tipHyp = math.sqrt((minD / 2) ** 2 + tipConeHeight ** 2)
+        tipArea = math.pi * (minD / 2) * tipHyp
+        wetted = fullArea - tipArea
+        volume = topArea * baseConeHeight / 3 - bottomArea * tipConeHeight / 3
+        CP = _barrowmanCP(length, topArea, bottomArea, volume, position)
+    aspectRatio = 100 if startD == endD else length / abs(startD - endD)
+    rec[L.TR_TOP_AREA] = topArea
+    rec[L.TR_BOTTOM_AREA] = bottomArea
+    rec[L.TR_FRONTAL] = frontal
+    rec[L.TR_LENGTH] = length
+    rec[L.TR_WETTED] = wetted
+    rec[L.TR_CP:L.TR_CP + 3] = CP
+    rec[L.TR_ROUGH] = roughness
+    rec[L.TR_START_D] = startD
+    rec[L.TR_END_D] = endD
+    if endD <= startD:
+        rec[L.TR_GROWING] = 0
+        rec[L.TR_CD_ADJ] = 1 if aspectRatio < 1 else ((3 - aspectRatio) / 2 if aspectRatio < 3 else 0)
+    else:
+        half = math.pi / 2 if length == 0 else math.atan(abs(startD - endD) / 2 / length)
+        rec[L.TR_GROWING] = 1
+        rec[L.TR_HALF_ANGLE] = half
+        rec[L.TR_SUB:L.TR_SUB + 2] = _subsonicPolyCoeffs(half)
+        rec[L.TR_TRANS:L.TR_TRANS + 4] = _transonicPolyCoeffs(half)
+    return rec
+
+
+def _buildTransition(r, stagePos, rocketRoughness, ctype):
+    rec, position, inertia = _fixedMassPrefix(r, stagePos, ctype, L.TR_SIZE)
+    length = r.getFloat("length")
+    startD = r.getFloat("startDiameter")
+    endD = r.getFloat("endDiameter")
+    roughness = r.tryGetFloat("surfaceRoughness", defaultValue=rocketRoughness)
+    _transitionRecord(rec, startD, endD, length, position, roughness)
+    return rec, dict(position=position, inertia=inertia, length=length, maxDiameter=max(startD, endD), body=True,
+                     getRadius=lambda d: (d / length * (endD - startD) + startD) / 2, canConnectBelow=(ctype == L.CT_TRANSITION),
+                     isBoatTail=(ctype == L.CT_BOATTAIL))
+
+
+def _autoBoatTailRecord(diameter, position, roughness):
+    rec = [0.0] * L.TR_SIZE
+    rec[L.C_TYPE] = L.CT_BOATTAIL
+    rec[L.C_LEN] = L.TR_SIZE
+    rec[L.C_POS:L.C_POS + 3] = position
+    return _transitionRecord(rec, diameter, diameter, 0, position, roughness)
+
+
+def _buildFinSet(r, stagePos, rocketRoughness):
+    rec, position, inertia = _fixedMassPrefix(r, stagePos, L.CT_FINSET, L.FS_SIZE)
+    numFins = r.getInt("numFins")
+    firstFinAngle = r.getFloat("firstFinAngle")
+    finAngle = r.getFloat("finCantAngle")
+    sweepAngle = math.radians(r.getFloat("sweepAngle"))
+    rootChord = r.getFloat("rootChord")
+    tipChord = r.getFloat("tipChord")
+    span = r.getFloat("span")
+    roughness = r.tryGetFloat("surfaceRoughness", defaultValue=rocketRoughness)
+    thickness = r.getFloat("thickness")
+    nSlices = r.getInt("numFinSpanSlicesForIntegration")
+    if numFins > L.FS_MAX_FINS or nSlices > L.FS_MAX_SLICES:
+        raise NotImplementedError("FinSet with more than {} fins or {} span slices".format(L.FS_MAX_FINS, L.FS_MAX_SLICES))
+    leShape = r.getString("LeadingEdge.shape")
+    if leShape == "Round":
+        leThick = r.tryGetFloat("LeadingEdge.radius", defaultValue=thickness / 100) * 2
+    elif leShape == "Blunt":
+        leThick = r.tryGetFloat("LeadingEdge.thickness", defaultValue=thickness)
+    else:
+        raise ValueError("ERROR: Leading edge shape: {} not implemented. Use 'Round' or 'Blunt'".format(leShape))
+    teShape = r.getString("TrailingEdge.shape")
+    if teShape == "Round":
+        teThick = r.getFloat("TrailingEdge.radius")
+    elif teShape == "Blunt":
+        teThick = r.getFloat("TrailingEdge.thickness")
+    elif teShape == "Tapered":
+        teThick = 0
+    else:
+        raise ValueError("ERROR: Trailing edge shape: {} not implemented. Use 'Round', 'Blunt', or 'Tapered'".format(teShape))
+    rec[L.FS_NFINS] = numFins
+    rec[L.FS_SPAN] = span
+    rec[L.FS_ROOT] = rootChord
+    rec[L.FS_TIP] = tipChord
+    rec[L.FS_THICK] = thickness
+    rec[L.FS_ROUGH] = roughness
+    rec[L.FS_SWEEP] = sweepAngle
+    rec[L.FS_LE_SHAPE] = 0 if leShape == "Round" else 1
+    rec[L.FS_LE_THICK] = leThick
+    rec[L.FS_TE_THICK] = teThick
+    rec[L.FS_CANT] = finAngle
+    rec[L.FS_NSLICES] = nSlices
+    info = dict(position=position, inertia=inertia, body=False, finset=dict(
+        numFins=numFins, firstFinAngle=firstFinAngle, sweepAngle=sweepAngle, rootChord=rootChord, tipChord=tipChord, span=span,
+        thickness=thickness, nSlices=nSlices))
+    return rec, info
+
+
+def _finishFinSet(rec, fs, bodyRadius):
+    """FinSet.precomputeProperties (Fins.py:93-262) once the mounting radius is known."""
+    span, rootChord, tipChord, sweepAngle = fs["span"], fs["rootChord"], fs["tipChord"], fs["sweepAngle"]
+    thickness, nSlices, numFins = fs["thickness"], fs["nSlices"], fs["numFins"]
+    LEtip = span * math.tan(sweepAngle)
+    TEtip = tipChord + LEtip - rootChord
+    if TEtip == 0:
+        teSweep = 0.0
+    elif TEtip < 0:
+        teSweep = -1 * math.atan2(abs(TEtip), span)
+    else:
+        teSweep = math.atan2(abs(TEtip), span)
+    midChordSweep = (sweepAngle + teSweep) / 2
+    dZdS_LE = math.tan(sweepAngle)
+    planform = span * (tipChord + rootChord) / 2
+    wetted = 2 * planform
+    AR = (2 * span) ** 2 / planform
+    stall = 15 * (1 + 1.1 / AR)          # degrees, compared against radians downstream (App. A #7)
+    bodyInterf = 1 + bodyRadius / (span + bodyRadius)
+    if numFins <= 4:
+        numInterf = 1.0
+    elif numFins <= 8:
+        raise AttributeError("'FinSet' object has no attribute 'finNumber'")   # reference bug, Fins.py:154
+    else:
+        numInterf = 0.75
+
+    def getChord(y):
+        return (tipChord - rootChord) * (y / span) + rootChord
+    numSpanSteps = round(span / 0.0001)
+    step = span / numSpanSteps
+    sMAC = sY = sX = 0
+    for i in range(numSpanSteps):
+        y = i * step + step / 2
+        sMAC += ((getChord(y) ** 2) * step)
+        sY += y * (getChord(y) * step)
+        sX += (dZdS_LE * y) * getChord(y) * step
+    MACLength, MACYPos, XMACLeadingEdge = sMAC / planform, sY / planform, sX / planform
+
+    stepSize = span / nSlices
+    for i in range(nSlices):
+        y = i * stepSize + stepSize * 0.5
+        rec[L.FS_SLICE_R + i] = y + bodyRadius
+        rec[L.FS_SLICE_A + i] = stepSize * getChord(y)
+        rec[L.FS_SLICE_LE + i] = y * dZdS_LE
+        rec[L.FS_SLICE_LEN + i] = getChord(y)
+
+    sigma = (AR / 2) * (thickness / rootChord) ** (1 / 3)
+    CD_TT_star = 1.15 * (thickness / rootChord) ** (5 / 3) * (1.61 + sigma - sqrt((sigma - 1.43) ** 2 + 0.578))
+
+    f_2 = (AR * (3) ** 0.5 - 0.67) / (2 * (3) ** 0.5 * AR - 1)
+    t1 = (2 * (3) ** -0.5 * AR) * (2 * AR * (3) ** 0.5 - 1)
+    t2 = ((3) ** 0.5 * AR - 0.67) * (AR * 4 * (3) ** -0.5)
+    den = (2 * AR * (3) ** 0.5 - 1) ** 2
+    f_prime_2 = (t1 - t2) / den
+    a_mat = [[0.5 ** 5, 0.5 ** 4, 0.5 ** 3, 0.5 ** 2, 0.5, 1], [5 * (0.5) ** 4, 4 * (0.5) ** 3, 3 * (0.5) ** 2, 2 * (0.5), 1, 0],
+             [2 ** 5, 2 ** 4, 2 ** 3, 2 ** 2, 2, 1], [5 * (2) ** 4, 4 * (2) ** 3, 3 * (2) ** 2, 2 * 2, 1, 0],
+             [20 * 2 ** 3, 12 * 2 ** 2, 6 * 2, 2, 0, 0], [60 * 2 ** 2, 24 * 2, 6, 0, 0, 0]]
+    poly = np.linalg.solve(a_mat, [0.25, 0, f_2, f_prime_2, 0, 0])
+
+    rec[L.FS_MIDSWEEP] = midChordSweep
+    rec[L.FS_PLANFORM] = planform
+    rec[L.FS_WETTED] = wetted
+    rec[L.FS_AR] = AR
+    rec[L.FS_STALL] = stall
+    rec[L.FS_BODY_R] = bodyRadius
+    rec[L.FS_BODY_INTERF] = bodyInterf
+    rec[L.FS_NUM_INTERF] = numInterf
+    rec[L.FS_MAC_LEN] = MACLength
+    rec[L.FS_MAC_Y] = MACYPos
+    rec[L.FS_XMAC_LE] = XMACLeadingEdge
+    rec[L.FS_CP_POLY:L.FS_CP_POLY + 6] = [float(x) for x in poly]
+    rec[L.FS_TIP_POS] = dZdS_LE * span
+    rec[L.FS_CDTT_STAR] = CD_TT_star
+    sep = 360 / numFins
+    for i in range(numFins):
+        rec[L.FS_SPANDIR + 2 * i] = math.cos(math.radians(fs["firstFinAngle"] + i * sep))
+        rec[L.FS_SPANDIR + 2 * i + 1] = math.sin(math.radians(fs["firstFinAngle"] + i * sep))
+
+
+def parseMotorFile(path, stagePosZ, impulseAdjustFactor=1.0, burnTimeAdjustFactor=1.0):
+    """Propulsion.py:51-128: returns dict with times, thrust, oxWeights, fuelWeights, MOIs, CG end points."""
+    with open(path, "r") as f:
+        text = re.sub(re.compile("#.*"), "", f.read())
+    lines = [ln for ln in text.split("\n") if ln.strip() != ""]
+    cg = [float(lines[i].split()[1]) + stagePosZ for i in range(4)]
+    times, thrust, oxFlow, fuelFlow, oxMOIs, fuelMOIs = [], [], [], [], [], []
+    from .simdef import parseVector
+    for ln in lines[4:]:
+        info = ln.split()
+        times.append(float(info[0]))
+        thrust.append(float(info[1]))
+        oxFlow.append(float(info[2]))
+        fuelFlow.append(float(info[3]))
+        a = ln.index("(")
+        b = ln.index(")", a) + 1
+        oxMOIs.append(parseVector(ln[a:b]))
+        c = ln.index("(", b)
+        d = ln.index(")", c) + 1
+        fuelMOIs.append(parseVector(ln[c:d]))
+    burnDuration0 = times[-1]      # stage.engineShutOffTime is recorded BEFORE the burn-time factor is applied
+    thrust = [t * impulseAdjustFactor / burnTimeAdjustFactor for t in thrust]
+    times = [t * burnTimeAdjustFactor for t in times]
+    initOx = 0
+    initFuel = 0
+    oxW = [0]
+    fuelW = [0]
+    for i in range(len(times) - 1, 0, -1):
+        dT = times[i] - times[i - 1]
+        initOx += dT * (oxFlow[i - 1] + oxFlow[i]) / 2
+        oxW.insert(0, initOx)
+        initFuel += dT * (fuelFlow[i - 1] + fuelFlow[i]) / 2
+        fuelW.insert(0, initFuel)
+    return dict(times=times, thrust=thrust, oxW=oxW, fuelW=fuelW, oxMOIs=oxMOIs, fuelMOIs=fuelMOIs, cg=cg,
+                initOx=initOx, initFuel=initFuel, engineShutOff=burnDuration0)
+
+
+def motorInertia(m, tSinceIgnition) -> Inertia:
+    """TabulatedMotor.getInertia (Propulsion.py:130-135,171-204)."""
+    def part(W0, W, cg0, cg1, MOIs):
+        if W0 == 0:
+            return Inertia((0, 0, 0), (0, 0, 0), 0)
+        w = _linInterp(m["times"], W, tSinceIgnition)
+        frac = 1 - (w / W0)
+        z = cg0 * (1 - frac) + cg1 * frac
+        from bisect import bisect
+        X = m["times"]
+        i = bisect(X, tSinceIgnition)
+        if i >= len(X):
+            moi = MOIs[len(X) - 1]
+        elif i < 1:
+            moi = MOIs[0]
+        else:
+            moi = hm.v_add(hm.v_div(hm.v_scale(hm.v_sub(MOIs[i], MOIs[i - 1]), (tSinceIgnition - X[i - 1])), (X[i] - X[i - 1])), MOIs[i - 1])
+        return Inertia(moi, (0, 0, z), w)
+    ox = part(m["initOx"], m["oxW"], m["cg"][0], m["cg"][1], m["oxMOIs"])
+    fuel = part(m["initFuel"], m["fuelW"], m["cg"][2], m["cg"][3], m["fuelMOIs"])
+    return Inertia.combine([fuel, ox])      # ox + fuel == ox.combineInertias([fuel]) -> list [fuel, ox]
+
+
+def _buildMotor(r, stagePos):
+    impulse = r.getFloat("impulseAdjustFactor")
+    burn = r.getFloat("burnTimeAdjustFactor")
+    path = r.getString("path")
+    if not os.path.exists(path):
+        found = r.simDefinition._findFile(path)
+        if found is None:
+            raise FileNotFoundError(path)
+        path = found
+    m = parseMotorFile(path, stagePos[2], impulse, burn)
+    n = len(m["times"])
+    size = L.C_P + L.MT_TABLE - L.C_P + 10 * n
+    rec = [0.0] * size
+    rec[L.C_TYPE] = L.CT_MOTOR
+    rec[L.C_LEN] = size
+    rec[L.MT_NROWS] = n
+    rec[L.MT_OX_CG0], rec[L.MT_OX_CG1], rec[L.MT_FUEL_CG0], rec[L.MT_FUEL_CG1] = m["cg"]
+    rec[L.MT_OX_W0] = m["initOx"]
+    rec[L.MT_FUEL_W0] = m["initFuel"]
+    t = L.MT_TABLE
+    cols = [m["times"], m["thrust"], m["oxW"], m["fuelW"]] + [[v[k] for v in m["oxMOIs"]] for k in range(3)] + \
+           [[v[k] for v in m["fuelMOIs"]] for k in range(3)]
+    for c, col in enumerate(cols):
+        rec[t + c * n:t + (c + 1) * n] = col
+    init = motorInertia(m, 0)
+    rec[L.C_POS:L.C_POS + 3] = init.CG      # motor "position" = its initial CG (Propulsion.py:47-49)
+    return rec, dict(position=init.CG, motor=m, body=False)
+
+
+_TRIGGERS = {"Apogee": L.EV_APOGEE, "Altitude": L.EV_DESCENDING_ALT, "Time": L.EV_TIME_REACHED}
+
+
+def _buildRecovery(r, stagePos):
+    rec, position, inertia = _fixedMassPrefix(r, stagePos, L.CT_RECOVERY, L.RC_SIZE)
+    n = r.getInt("numStages")
+    if n > L.RC_MAX_STAGES:
+        raise NotImplementedError("RecoverySystem with more than {} stages".format(L.RC_MAX_STAGES))
+    rec[L.RC_NSTAGES] = n
+    for i in range(1, n + 1):
+        trig = r.getString("stage{}Trigger".format(i))
+        if trig not in _TRIGGERS:
+            raise KeyError(trig)
+        try:
+            val = r.getFloat("stage{}TriggerValue".format(i))
+        except KeyError:
+            val = 0.0
+        o = L.RC_STAGE0 + (i - 1) * L.RC_STAGE_STRIDE
+        rec[o:o + 5] = [_TRIGGERS[trig], val, r.getFloat("stage{}ChuteArea".format(i)), r.getFloat("stage{}Cd".format(i)),
+                        r.getFloat("stage{}DelayTime".format(i))]
+    return rec, dict(position=position, inertia=inertia, body=False)
+
+
+def _buildMass(r, stagePos):
+    rec, position, inertia = _fixedMassPrefix(r, stagePos, L.CT_MASS, L.C_P)
+    return rec, dict(position=position, inertia=inertia, body=False)
+
+
+# ======================================================================================
+class Model:
+    """Result of buildModel: `.blob` (np.float64 array) plus host-side metadata."""
+
+    def __init__(self, blob, meta):
+        self.blob = blob
+        self.meta = meta
+
+    def header(self, name):
+        return float(self.blob[getattr(L, name)])
+
+    def stageRecord(self, i):
+        off = int(self.blob[L.H_STAGE_OFF + i])
+        return self.blob[off:off + L.S_SIZE]
+
+    def components(self, i):
+        s = self.stageRecord(i)
+        out = []
+        for c in range(int(s[L.S_NCOMP])):
+            off = int(s[L.S_COMP_OFF + c])
+            out.append(self.blob[off:off + int(self.blob[off + L.C_LEN])])
+        return out
+
+
+def usStandardAtmosphereBases():
+    """USStandardAtmosphere.__init__ (AtmosphereModelling.py:98-145): base temperature/pressure per layer."""
+    T0, p0, M, R, G = 288.15, 101325, 28.9644, 8.31432, 9.80665
+    baseHeights = [-2000, 11000, 20000, 32000, 47000, 51000, 71000, 84852]
+    dt_dh = [-6.5e-3, 0, 1.0e-3, 2.8e-3, 0, -2.8e-3, -2.0e-3, 0]
+    temps = [T0 + dt_dh[0] * baseHeights[0]]
+    Pb_over_P0 = ((T0 + dt_dh[0] * baseHeights[0]) / T0) ** (-G * M / (R * dt_dh[0] * 1000))
+    pressures = [Pb_over_P0 * p0]
+    for i in range(1, len(baseHeights)):
+        Tb, Pb, lapse = temps[-1], pressures[i - 1], dt_dh[i - 1]
+        dh = float(baseHeights[i] - baseHeights[i - 1])
+        nextTemp = Tb + lapse * dh
+        if lapse == 0.0:
+            nextP = math.exp(-G * M * dh / (R * Tb * 1000)) * Pb
+        else:
+            nextP = ((Tb + lapse * dh) / Tb) ** (-G * M / (R * lapse * 1000)) * Pb
+        temps.append(nextTemp)
+        pressures.append(nextP)
+    return [float(h) for h in baseHeights], dt_dh, temps, pressures
+
+
+def initialStateLaunchTowerFrame(rocketReader: SubDictReader):
+    """rocket.py:251-272 — position, velocity, orientation, angular velocity in the launch-tower frame."""
+    initPos = rocketReader.getVector("position")
+    initVel = rocketReader.getVector("velocity")
+    rotationAxis = rocketReader.tryGetVector("rotationAxis", defaultValue=None)
+    if rotationAxis is not None:
+        q = hm.q_from_axis_angle(rotationAxis, math.radians(rocketReader.getFloat("rotationAngle")))
+    else:
+        d = hm.v_normalize(rocketReader.getVector("initialDirection"))
+        angle = hm.v_angle((0, 0, 1), d)
+        axis = hm.v_cross((0, 0, 1), d)
+        q = hm.q_from_axis_angle(axis, angle)
+    w = rocketReader.getVector("angularVelocity")
+    return initPos, initVel, q, w
+
+
+def buildModel(simDefinition: SimDefinition, maxSteps: int = 2000000) -> Model:
+    sd = simDefinition
+    env = SubDictReader("Environment", sd)
+    rk = SubDictReader("Rocket", sd)
+    H = [0.0] * L.H_SIZE
+    tail: List[float] = []          # everything after the header; offsets are H_SIZE + index
+
+    def append(rec) -> int:
+        off = L.H_SIZE + len(tail)
+        tail.extend(float(x) for x in rec)
+        return off
+
+    H[L.H_MAGIC] = L.MLB_MAGIC
+    H[L.H_VERSION] = L.MLB_VERSION
+
+    # ---- integrator (Integration.py:56-103) ----
+    method = rk.getString("SimControl.timeDiscretization")
+    if method not in _INTEGRATORS:
+        raise ValueError("Integration method: {} not implemented. See SimDefinitionTemplate.txt for options.".format(method))
+    H[L.H_INTEGRATOR] = _INTEGRATORS[method]
+    H[L.H_DT0] = float(sd.getValue("SimControl.timeStep"))
+    rows, nResult = butcherTableau(method)
+    if rows is not None:
+        flat = []
+        for row in rows:
+            flat.extend(row + [0.0] * (L.TABLEAU_STRIDE - len(row)))
+        H[L.H_TABLEAU_OFF] = append(flat)
+        H[L.H_TAB_NSTAGE_ROWS] = len(rows) - nResult
+        H[L.H_TAB_NRESULT_ROWS] = nResult
+    if "Adapt" in method:
+        ad = SubDictReader("SimControl.TimeStepAdaptation", sd)
+        controller = ad.getString("controller")
+        H[L.H_AD_SAFETY] = 1.0
+        if controller == "PID":
+            H[L.H_AD_CTRL] = L.CTRL_PID
+            H[L.H_AD_P], H[L.H_AD_I], H[L.H_AD_D] = [float(x) for x in ad.getString("PID.coefficients").split()]
+        elif controller == "elementary":
+            H[L.H_AD_CTRL] = L.CTRL_ELEMENTARY
+            H[L.H_AD_SAFETY] = ad.getFloat("Elementary.safetyFactor")
+        elif controller == "Constant":
+            H[L.H_AD_CTRL] = L.CTRL_CONSTANT
+        else:
+            raise ValueError("Adaptive Integrator requires non-constant step size controller such as 'PID' or 'elementary'")
+        H[L.H_AD_TARGET] = ad.getFloat("targetError")
+        H[L.H_AD_MINF] = ad.getFloat("minFactor")
+        H[L.H_AD_MAXF] = ad.getFloat("maxFactor")
+        H[L.H_AD_MAXDT] = ad.getFloat("maxTimeStep")
+        H[L.H_AD_MINDT] = ad.getFloat("minTimeStep")
+    H[L.H_EVENT_DT] = rk.getFloat("SimControl.TimeStepAdaptation.eventTimingAccuracy")
+    H[L.H_MAX_STEPS] = maxSteps
+
+    # ---- earth / atmosphere / wind / turbulence (ENV/*.py factories) ----
+    earth = env.getString("EarthModel")
+    if earth == "Flat":
+        H[L.H_EARTH], H[L.H_EARTH_GM], H[L.H_EARTH_RADIUS] = L.EARTH_FLAT, 398600.5e9, 6371000
+    elif earth == "None":
+        H[L.H_EARTH] = L.EARTH_NONE
+    elif earth in ("Round", "WGS84"):
+        raise NotImplementedError("Earth model '{}' is not implemented by the B200 backend yet".format(earth))
+    else:
+        raise NotImplementedError("Earth model: {} not found. Try 'Flat', 'Round' or 'WGS84'".format(earth))
+    H[L.H_EARTH_ROT] = 0.0
+    H[L.H_ELEV] = env.tryGetFloat("LaunchSite.elevation")
+    H[L.H_LAT] = env.tryGetFloat("LaunchSite.latitude")
+    H[L.H_LON] = env.tryGetFloat("LaunchSite.longitude")
+
+    atm = env.getString("AtmosphericPropertiesModel")
+    if atm == "Constant":
+        H[L.H_ATM] = L.ATM_CONSTANT
+        H[L.H_ATM_CONST:L.H_ATM_CONST + 4] = [env.getFloat("ConstantAtmosphere.temp") + 273.15, env.getFloat("ConstantAtmosphere.pressure"),
+                                             env.getFloat("ConstantAtmosphere.density"), env.getFloat("ConstantAtmosphere.viscosity")]
+    elif atm == "USStandardAtmosphere":
+        H[L.H_ATM] = L.ATM_USSTD
+        bh, lapse, temps, pres = usStandardAtmosphereBases()
+        H[L.H_USSTD_OFF] = append(bh + lapse + temps + pres)
+    elif atm == "TabulatedAtmosphere":
+        path = env.getString("TabulatedAtmosphere.filePath")
+        table = np.loadtxt(path, skiprows=1)
+        table[:, 4] *= 1E-5
+        H[L.H_ATM] = L.ATM_TABULATED
+        H[L.H_ATM_TAB_N] = table.shape[0]
+        H[L.H_ATM_TAB_OFF] = append(table.T.reshape(-1))      # column-major: h, T, P, rho, mu
+    else:
+        raise ValueError("Atmospheric model: {} not implemented, try using 'USStandardAtmosphere'".format(atm))
+
+    wind = env.getString("MeanWindModel")
+    if wind == "Constant":
+        H[L.H_WIND] = L.WIND_CONSTANT
+        H[L.H_WIND_V:L.H_WIND_V + 3] = env.getVector("ConstantMeanWind.velocity")
+    elif wind == "Hellman":
+        if env.getString("Hellman.groundWindModel") != "Constant":
+            raise NotImplementedError("Hellman.groundWindModel other than 'Constant' (wind-rose sampling is host-side, SURVEY §8f)")
+        H[L.H_WIND] = L.WIND_HELLMAN
+        H[L.H_WIND_V:L.H_WIND_V + 3] = env.getVector("ConstantMeanWind.velocity")
+        H[L.H_HELLMAN_ALPHA] = env.getFloat("Hellman.alphaCoeff")
+        H[L.H_HELLMAN_LIMIT] = env.getFloat("Hellman.altitudeLimit")
+    elif wind == "CustomWindProfile":
+        prof = np.loadtxt(env.getString("CustomWindProfile.filePath"), skiprows=1)
+        H[L.H_WIND] = L.WIND_INTERPOLATED
+        H[L.H_WIND_TAB_N] = prof.shape[0]
+        H[L.H_WIND_TAB_OFF] = append(prof.T.reshape(-1))
+    else:
+        raise NotImplementedError("MeanWindModel '{}' is not implemented by the B200 backend (SURVEY §8f)".format(wind))
+
+    turb = env.getString("Environment.TurbulenceModel")
+    H[L.H_TURB_INTENSITY] = float("nan")
+    H[L.H_TURB_STD] = float("nan")
+    if turb == "None":
+        H[L.H_TURB] = L.TURB_NONE
+    elif "PinkNoise" in turb:
+        H[L.H_TURB] = {"PinkNoise1D": L.TURB_PINK1D, "PinkNoise2D": L.TURB_PINK2D, "PinkNoise3D": L.TURB_PINK3D}[turb]
+        ti = env.tryGetInt("PinkNoiseModel.turbulenceIntensity")
+        if ti is not None:
+            H[L.H_TURB_INTENSITY] = ti / (2.26 * 100)
+        sdv = env.tryGetInt("PinkNoiseModel.velocityStdDeviation")
+        if sdv is not None:
+            H[L.H_TURB_STD] = sdv / 2.26
+        coeffs = [1, ]
+        alpha = 5 / 3
+        for i in range(2):
+            coeffs.append((i - alpha / 2) * coeffs[i] / (i + 1))
+        H[L.H_PINK_C0], H[L.H_PINK_C1] = coeffs[1], coeffs[2]
+        hasSeed = 0
+        for i in range(3):
+            s = env.tryGetInt("PinkNoiseModel.randomSeed{}".format(i + 1))
+            if s is not None:
+                H[L.H_PINK_SEED + i] = s
+                hasSeed |= (1 << i)
+        H[L.H_PINK_HAS_SEED] = hasSeed
+    elif turb == "customSineGust":
+        H[L.H_TURB] = L.TURB_SINE_GUST
+        H[L.H_GUST_START] = env.getFloat("CustomSineGust.startAltitude")
+        H[L.H_GUST_MAG] = env.getFloat("CustomSineGust.magnitude")
+        H[L.H_GUST_BLEND] = env.getFloat("CustomSineGust.sineBlendDistance")
+        H[L.H_GUST_THICK] = env.getFloat("CustomSineGust.thickness")
+        H[L.H_GUST_DIR:L.H_GUST_DIR + 3] = hm.v_normalize(env.getVector("CustomSineGust.direction"))
+    else:
+        raise ValueError("Turbulence Model {} not found. Please choose from: None, PinkNoise1/2/3D or customSineGust")
+    H[L.H_TURB_OFF_CHUTE] = 1.0 if rk.getBool("Environment.turbulenceOffWhenUnderChute") else 0.0
+
+    # ---- initial state, launch rail (rocket.py:251-291, environment.py:57-91,105-128) ----
+    initPos, initVel, q0, w0 = initialStateLaunchTowerFrame(rk)
+    railLength = env.getFloat("LaunchSite.railLength")
+    H[L.H_RAIL_LEN] = railLength
+    initPos = hm.v_add(initPos, (0, 0, H[L.H_ELEV]))
+    if railLength > 0:
+        w0 = (0.0, 0.0, 0.0)
+        d = hm.v_normalize(env.getVector("Rocket.initialDirection"))
+        qr = hm.q_from_axis_angle(hm.v_cross((0, 0, 1), d), hm.v_angle((0, 0, 1), d))
+        railPos = hm.v_add(env.getVector("Rocket.position"), (0, 0, H[L.H_ELEV]))
+        railDir, _ = hm.q_rotate(qr, (0, 0, 1))
+        H[L.H_RAIL_POS:L.H_RAIL_POS + 3] = railPos
+        H[L.H_RAIL_DIR:L.H_RAIL_DIR + 3] = hm.v_normalize(railDir)
+
+    # ---- rocket-level constants (rocket.py:100-140,221-249) ----
+    rocketRoughness = rk.getFloat("Aero.surfaceRoughness")
+    H[L.H_ROCKET_ROUGHNESS] = rocketRoughness
+    H[L.H_FULLY_TURB] = 1.0 if rk.getBool("Aero.fullyTurbulentBL") else 0.0
+    addAutoBT = rk.getBool("Aero.addZeroLengthBoatTailsToAccountForBaseDrag")
+    H[L.H_ADD_AUTO_BT] = 1.0 if addAutoBT else 0.0
+    stageDicts = [d for d in rk.getImmediateSubDicts() if d not in ("Rocket.ControlSystem", "Rocket.HIL", "Rocket.Aero")]
+    if rk.tryGetString("ControlSystem.controlledSystem") is not None or "Rocket.ControlSystem" in rk.getImmediateSubDicts():
+        raise NotImplementedError("Rocket.ControlSystem (GNC) is not implemented by the B200 backend yet")
+    maxDiameter = 0
+    for sdict in stageDicts:
+        for cdict in sd.getImmediateSubDicts(sdict):
+            if sd.getValue(cdict + ".class") == "Bodytube":
+                maxDiameter = max(maxDiameter, float(sd.getValue(cdict + ".outerDiameter")))
+    H[L.H_MAXDIAM] = maxDiameter
+    H[L.H_AREF] = math.pi * maxDiameter ** 2 / 4
+
+    # ---- stages and components (stage.py:13-70; sort rules: stage.py:47-59, RocketComponents.py:131-143) ----
+    stages = []
+    for sdict in stageDicts:
+        sr = SubDictReader(sdict, sd)
+        stagePos = sr.getVector("position")
+        compDicts = sd.getImmediateSubDicts(sdict)
+        for c in compDicts:
+            cls = sd.getValue(c + ".class")
+            if cls not in _SUPPORTED_CLASSES:
+                raise NotImplementedError("Rocket component class '{}' ({}) is not implemented by the B200 backend".format(cls, c))
+        compDicts.sort(key=lambda c: (0 if sd.getValue(c + ".class") in _BODY_CLASSES else 1, c))
+        comps = []
+        for c in compDicts:
+            cr = SubDictReader(c, sd)
+            cls = cr.getString("class")
+            if cls == "Nosecone":
+                rec, info = _buildNosecone(cr, stagePos, rocketRoughness)
+            elif cls == "Bodytube":
+                rec, info = _buildBodytube(cr, stagePos, rocketRoughness)
+            elif cls == "BoatTail":
+                rec, info = _buildTransition(cr, stagePos, rocketRoughness, L.CT_BOATTAIL)
+            elif cls == "Transition":
+                rec, info = _buildTransition(cr, stagePos, rocketRoughness, L.CT_TRANSITION)
+            elif cls == "FinSet":
+                rec, info = _buildFinSet(cr, stagePos, rocketRoughness)
+            elif cls == "Motor":
+                rec, info = _buildMotor(cr, stagePos)
+            elif cls == "RecoverySystem":
+                rec, info = _buildRecovery(cr, stagePos)
+            else:
+                rec, info = _buildMass(cr, stagePos)
+            info["name"] = cr.getDictName()
+            info["cls"] = cls
+            info["rec"] = rec
+            comps.append(info)
+        # fixed-mass inertia pre-sum in construction order (CompositeObject.py:52-63)
+        fixed = [c["inertia"] for c in comps if c["cls"] in _FIXED_MASS_CLASSES]
+        fixedInertia = Inertia.combine(fixed) if fixed else Inertia((0, 0, 0), (0, 0, 0), 0)
+        motors = [c for c in comps if c["cls"] == "Motor"]
+        if len(motors) > 1:
+            raise NotImplementedError("more than one Motor per stage")
+        cgOvr = sr.tryGetVector("constCG", defaultValue=None)
+        if cgOvr is not None:
+            cgOvr = hm.v_add(cgOvr, stagePos)
+        stages.append(dict(name=sr.getDictName(), reader=sr, pos=stagePos, comps=comps, fixed=fixedInertia,
+                           motor=(motors[0] if motors else None), cgOvr=cgOvr, massOvr=sr.tryGetFloat("constMass", defaultValue=None),
+                           moiOvr=sr.tryGetVector("constMOI", defaultValue=None), stageNumber=sr.getInt("stageNumber"),
+                           sepType=sr.getString("separationTriggerType"), sepDelay=sr.getFloat("separationDelay"),
+                           sepValue=sr.getFloat("separationTriggerValue")))
+
+    def zKey(c):
+        return c["position"][2]
+    for st in stages:
+        st["comps"].sort(key=zKey, reverse=True)      # stable, top -> bottom
+    stages.sort(key=lambda s: s["pos"][2], reverse=True)
+    if len(stages) > 4:
+        raise NotImplementedError("more than 4 stages")
+    if len(stages) > 1:
+        raise NotImplementedError("multi-stage rockets are not implemented by the B200 backend yet")
+
+    # auto-added zero-length boat tail for base drag (rocket.py:489-519)
+    def bottomInterfaceZ(st):
+        for c in reversed(st["comps"]):
+            if c.get("body"):
+                return c["position"][2] - c["length"] if c.get("canConnectBelow", True) else None
+        return None
+    for st in stages:
+        st["autoBT"] = None
+    if maxDiameter > 0:
+        bottom = stages[-1]
+        hasBT = False
+        for c in reversed(bottom["comps"]):
+            if c.get("body"):
+                hasBT = bool(c.get("isBoatTail"))
+                break
+        if not hasBT and addAutoBT:
+            z = bottomInterfaceZ(bottom)
+            pos = (bottom["pos"][0], bottom["pos"][1], z)
+            rec = _autoBoatTailRecord(maxDiameter, pos, rocketRoughness)
+            bottom["comps"].append(dict(name="Auto-AddedZeroLengthBoatTail", cls="BoatTail", rec=rec, position=pos, body=True, length=0,
+                                        maxDiameter=maxDiameter, getRadius=lambda d: maxDiameter / 2, isBoatTail=True,
+                                        inertia=Inertia((0, 0, 0), (0, 0, 0), 0), auto=True))
+
+    # fin sets need the body radius at their mounting station (Fins.py:107-110, stage.py:126-143)
+    for st in stages:
+        for c in st["comps"]:
+            if c["cls"] == "FinSet":
+                desiredZ = st["pos"][2] - (st["pos"][2] - c["position"][2])
+                radius = None
+                for b in st["comps"]:
+                    if "length" in b:
+                        top = b["position"][2]
+                        bot = top - b["length"]
+                        if desiredZ <= top and desiredZ >= bot:
+                            radius = b["getRadius"](top - desiredZ)
+                            break
+                if radius is None:
+                    raise ValueError("Length {} from the top of stage '{}' does not fall between the top and bottom of any of its components".format(
+                        st["pos"][2] - c["position"][2], st["name"]))
+                _finishFinSet(c["rec"], c["finset"], radius)
+
+    # fineness ratio (rocket.py:521-528)
+    def stageLength(st):
+        bodies = [c for c in st["comps"] if c.get("body")]
+        if not bodies:
+            return None
+        return bodies[0]["position"][2] - (bodies[-1]["position"][2] - bodies[-1]["length"])
+    for nRemaining in range(1, len(stages) + 1):
+        sub = stages[:nRemaining]
+        length = 0
+        for st in sub:
+            ln = stageLength(st)
+            if ln is not None:
+                length += ln
+        md = max(max([c.get("maxDiameter", 0) for c in st["comps"]] + [0]) for st in sub)
+        H[L.H_FINENESS + nRemaining - 1] = (length / md) if md != 0 else float("nan")
+
+    # ---- serialise stages ----
+    H[L.H_NSTAGES] = len(stages)
+    H[L.H_RECOVERY_OFF] = 0
+    for si, st in enumerate(stages):
+        S = [0.0] * L.S_SIZE
+        if len(st["comps"]) > L.S_MAX_COMP:
+            raise NotImplementedError("more than {} components per stage".format(L.S_MAX_COMP))
+        S[L.S_NCOMP] = len(st["comps"])
+        S[L.S_POS:L.S_POS + 3] = st["pos"]
+        sepTypes = {"None": L.EV_NONE, "apogee": L.EV_APOGEE, "ascendingThroughAltitude": L.EV_ASCENDING_ALT,
+                    "descendingThroughAltitude": L.EV_DESCENDING_ALT, "motorBurnout": L.EV_MOTOR_BURNOUT, "timeReached": L.EV_TIME_REACHED}
+        S[L.S_SEP_TYPE] = sepTypes[st["sepType"]]
+        S[L.S_SEP_VALUE] = st["sepValue"]
+        S[L.S_SEP_DELAY] = st["sepDelay"]
+        flags = 0
+        if st["cgOvr"] is not None:
+            flags |= L.OVR_CG
+            S[L.S_OVR_CG:L.S_OVR_CG + 3] = st["cgOvr"]
+        if st["massOvr"] is not None:
+            flags |= L.OVR_MASS
+            S[L.S_OVR_MASS] = st["massOvr"]
+        if st["moiOvr"] is not None:
+            flags |= L.OVR_MOI
+            S[L.S_OVR_MOI:L.S_OVR_MOI + 3] = st["moiOvr"]
+        S[L.S_OVR_FLAGS] = flags
+        S[L.S_FIXED_MOI:L.S_FIXED_MOI + 3] = st["fixed"].MOI
+        S[L.S_FIXED_CG:L.S_FIXED_CG + 3] = st["fixed"].CG
+        S[L.S_FIXED_MASS] = st["fixed"].mass
+        S[L.S_MOTOR] = -1
+        S[L.S_BURN_DURATION] = -1
+        S[L.S_IGNITION0] = 0.0 if si == len(stages) - 1 else 1000000000
+        for ci, c in enumerate(st["comps"]):
+            off = append(c["rec"])
+            S[L.S_COMP_OFF + ci] = off
+            if c["cls"] == "Motor":
+                S[L.S_MOTOR] = ci
+                S[L.S_BURN_DURATION] = c["motor"]["engineShutOff"]
+            if c["cls"] == "RecoverySystem":
+                H[L.H_RECOVERY_OFF] = off
+        H[L.H_STAGE_OFF + si] = append(S)
+
+    # ---- initial inertia -> CG shift of the integrated position (rocket.py:416-421) ----
+    def stageInertia(st, t):
+        items = [st["fixed"]]
+        if st["motor"] is not None:
+            items.append(motorInertia(st["motor"]["motor"], max(0, t - (0.0 if st is stages[-1] else 1000000000))))
+        comb = Inertia.combine(items)
+        if st["cgOvr"] is not None:
+            comb.CG = st["cgOvr"]
+        if st["moiOvr"] is not None:
+            comb.MOI = st["moiOvr"]
+        if st["massOvr"] is not None:
+            comb.mass = st["massOvr"]
+        return comb
+    zero = Inertia((0, 0, 0), (0, 0, 0), 0)
+    items = [zero] + [stageInertia(st, 0) for st in stages]
+    rocketInertia0 = Inertia.combine(items)
+    cgGlobal, q0n = hm.q_rotate(q0, rocketInertia0.CG)
+    posCG = hm.v_add(initPos, cgGlobal)
+    H[L.H_NOSE_POS0:L.H_NOSE_POS0 + 3] = initPos
+    H[L.H_INIT_STATE:L.H_INIT_STATE + 13] = list(posCG) + list(initVel) + list(q0n) + list(w0)
+
+    # ---- end condition (SingleSimulations.py:205-248) ----
+    endCondition = sd.getValue("SimControl.EndCondition")
+    endValue = float(sd.getValue("SimControl.EndConditionValue"))
+    H[L.H_END_VALUE] = endValue
+    if endCondition == "Apogee":
+        H[L.H_END_TYPE] = L.END_APOGEE
+    elif endCondition == "Altitude" and posCG[2] < endValue:
+        H[L.H_END_TYPE] = L.END_ALT_ASCENDING
+    elif endCondition == "Altitude":
+        H[L.H_END_TYPE] = L.END_ALT_DESCENDING
+    else:
+        H[L.H_END_TYPE] = L.END_TIME
+
+    blob = np.array(H + tail, dtype=np.float64)
+    blob[L.H_LEN] = blob.size
+    meta = dict(stages=[dict(name=st["name"], components=[(c["name"], c["cls"]) for c in st["comps"]]) for st in stages],
+                initialInertia=rocketInertia0, method=method)
+    return Model(blob, meta)
