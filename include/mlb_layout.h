@@ -11,7 +11,7 @@
  * What each field restates in the reference (paths relative to MAPLEAF/):
  *   integrator + adaptive parameters ........ Motion/Integration.py:56-103,144-195,238-329
  *   end condition ........................... SimulationRunners/SingleSimulations.py:205-248
- *   earth / atmosphere / wind / turbulence .. ENV/environment.py:39-103, ENV/*Modelling.py
+ *   earth / atmosphere / wind / turbulence .. ENV/environment.py:39-103, ENV/{Earth,Atmosphere,MeanWind,Turbulence}Modelling.py
  *   launch rail ............................. ENV/launchRail.py:8-14
  *   stage records ........................... Rocket/stage.py:10-41, Rocket/CompositeObject.py:23-63
  *   component records ....................... Rocket/{noseCone,bodyTube,boatTail,Fins,Propulsion,Recovery,RocketComponents}.py constructors
@@ -91,6 +91,8 @@
 #define H_ADD_AUTO_BT 96
 #define H_PINK_HAS_SEED 97
 #define H_NOSE_POS0 98
+#define H_FIN_CUBIC_OFF 101
+#define H_START_TIME 102
 #define H_SIZE 128
 
 /* integrator ids (H_INTEGRATOR) */

@@ -655,6 +655,8 @@ def buildModel(simDefinition: SimDefinition, maxSteps: int = 2000000) -> Model:
         H[L.H_AD_MINDT] = ad.getFloat("minTimeStep")
     H[L.H_EVENT_DT] = rk.getFloat("SimControl.TimeStepAdaptation.eventTimingAccuracy")
     H[L.H_MAX_STEPS] = maxSteps
+    # inverse Hermite matrix of the transonic fin-force blend between Mach 0.8 and 1.4 (Fins.py:508-528)
+    H[L.H_FIN_CUBIC_OFF] = append(cubicInterpInverseMatrix(0.8, 1.4).reshape(-1))
 
     # ---- earth / atmosphere / wind / turbulence (ENV/*.py factories) ----
     earth = env.getString("EarthModel")

@@ -1,0 +1,82 @@
+"""ctypes wrapper around the CPU oracle (oracle/mapleaf_oracle.c). TEST INFRASTRUCTURE ONLY."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_DIR, "_build", "libmapleaf_oracle.so")
+TRACE_W = 16
+
+
+def build(force=False):
+    src = os.path.join(_DIR, "mapleaf_oracle.c")
+    hdr = os.path.join(_DIR, "..", "include", "mlb_layout.h")
+    if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["make", "-s", "-C", _DIR])
+    return _LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(build())
+        _lib.oracle_run.restype = ctypes.c_int
+        _lib.oracle_force_eval.restype = ctypes.c_int
+    return _lib
+
+
+def _p(a, t=ctypes.c_double):
+    return a.ctypes.data_as(ctypes.POINTER(t)) if a is not None else None
+
+
+def run(blob, nLanes, laneArrays=None, traceLane=-1, traceMaxRows=0, dtReplay=None):
+    """laneArrays: dict {arrayId: ndarray [ncomp, nLanes]}. Returns dict of results."""
+    blob = np.ascontiguousarray(blob, dtype=np.float64)
+    laneArrays = laneArrays or {}
+    ids = np.array(list(laneArrays.keys()), dtype=np.int32)
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in laneArrays.values()]
+    for a in arrs:
+        assert a.shape[-1] == nLanes
+    ptrs = (ctypes.POINTER(ctypes.c_double) * max(1, len(arrs)))(*[_p(a) for a in arrs])
+    results = np.zeros((nLanes, 7))
+    finals = np.zeros((nLanes, 14))
+    status = np.zeros(nLanes, dtype=np.int32)
+    counters = np.zeros((nLanes, 3), dtype=np.int64)
+    trace = np.zeros((max(1, traceMaxRows), TRACE_W))
+    rows = ctypes.c_int64(0)
+    replay = np.ascontiguousarray(dtReplay, dtype=np.float64) if dtReplay is not None else None
+    rc = lib().oracle_run(_p(blob), ctypes.c_int64(nLanes), ptrs, _p(ids, ctypes.c_int), ctypes.c_int(len(arrs)),
+                          _p(results), _p(finals), _p(status, ctypes.c_int32), _p(counters, ctypes.c_int64),
+                          _p(trace) if traceMaxRows > 0 else None, ctypes.c_int64(traceLane), ctypes.c_int64(traceMaxRows),
+                          ctypes.byref(rows), _p(replay), ctypes.c_int64(0 if replay is None else replay.size))
+    if rc != 0:
+        raise ValueError("oracle_run failed: bad model block")
+    return dict(results=results, finals=finals, status=status, counters=counters, trace=trace[:rows.value])
+
+
+def forceEval(blob, state13, time=0.0, wind=None):
+    blob = np.ascontiguousarray(blob, dtype=np.float64)
+    s = np.ascontiguousarray(state13, dtype=np.float64)
+    w = np.ascontiguousarray(wind, dtype=np.float64) if wind is not None else None
+    out = np.zeros(19 + 9 * 30)
+    lib().oracle_force_eval(_p(blob), _p(s), ctypes.c_double(time), _p(w), _p(out))
+    return out
+
+
+def gaussStream(seed, n, mu=0.0, sigma=1.0):
+    out = np.zeros(n)
+    lib().oracle_gauss_stream(ctypes.c_uint64(seed), ctypes.c_double(mu), ctypes.c_double(sigma), ctypes.c_int(n), _p(out))
+    return out
+
+
+def pinkNoise(seed, times):
+    """times < 0 means 'next raw sample' (getValue() with no time)."""
+    t = np.ascontiguousarray(times, dtype=np.float64)
+    out = np.zeros(t.size)
+    lib().oracle_pink_noise(ctypes.c_uint64(seed), _p(t), ctypes.c_int(t.size), _p(out))
+    return out
