@@ -195,6 +195,8 @@
 #define CT_AERO_FORCE 13
 #define CT_AERO_DAMPING 14
 
+/* *_CRIT_RE / *_ROUGH_CF: roughness-critical Reynolds number and fully-rough skin-friction coefficient of the
+   component (AeroFunctions.py:95-104), constant per component, precomputed on the host for the device path */
 /* nose cone (Rocket/noseCone.py:58-101) */
 #define NC_BASE_AREA 12
 #define NC_LENGTH 13
@@ -204,7 +206,9 @@
 #define NC_SUB 19
 #define NC_TRANS 21
 #define NC_ROUGH 25
-#define NC_SIZE 26
+#define NC_CRIT_RE 26
+#define NC_ROUGH_CF 27
+#define NC_SIZE 28
 
 /* body tube (Rocket/bodyTube.py:13-33) */
 #define BT_LENGTH 12
@@ -213,7 +217,9 @@
 #define BT_WETTED 15
 #define BT_CP 16
 #define BT_ROUGH 19
-#define BT_SIZE 20
+#define BT_CRIT_RE 20
+#define BT_ROUGH_CF 21
+#define BT_SIZE 22
 
 /* boat tail / transition (Rocket/boatTail.py:12-99) */
 #define TR_TOP_AREA 12
@@ -230,7 +236,9 @@
 #define TR_ROUGH 29
 #define TR_START_D 30
 #define TR_END_D 31
-#define TR_SIZE 32
+#define TR_CRIT_RE 32
+#define TR_ROUGH_CF 33
+#define TR_SIZE 34
 
 /* fin set (Rocket/Fins.py:45-262, 430-462) */
 #define FS_NFINS 12
@@ -268,7 +276,9 @@
 #define FS_SLICE_LE 92
 #define FS_SLICE_LEN 108
 #define FS_CDTT_STAR 124
-#define FS_SIZE 126
+#define FS_CRIT_RE 125
+#define FS_ROUGH_CF 126
+#define FS_SIZE 128
 
 /* tabulated motor (Rocket/Propulsion.py:8-128). Table: 10 columns of MT_NROWS each, column-major,
    starting at C_P+MT_TABLE: time, thrust, oxWeight, fuelWeight, oxMOI xyz, fuelMOI xyz */

