@@ -93,6 +93,7 @@
 #define H_NOSE_POS0 98
 #define H_FIN_CUBIC_OFF 101
 #define H_START_TIME 102
+#define H_INERTIA_CONST 103   /* 1: no stage's mass / CG / MOI can change in flight (full overrides or no motor) */
 #define H_SIZE 128
 
 /* integrator ids (H_INTEGRATOR) */

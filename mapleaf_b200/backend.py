@@ -1,0 +1,274 @@
+"""
+ctypes binding of libmapleaf_b200.so (C ABI: include/mapleaf_b200.h).
+
+The library is built in-tree by `__graft_entry__.build()` (nvcc, sm_100a) into mapleaf_b200/lib/.
+There is no CPU fallback: if the library is missing, or no CUDA device is usable, every call
+raises (RuntimeError / ValueError, the reference's convention for bad input, e.g.
+MAPLEAF/SimulationRunners/SingleSimulations.py:24, MAPLEAF/Motion/Integration.py:183).
+"""
+import ctypes
+import hashlib
+import os
+import subprocess
+from typing import Dict, Optional
+
+import numpy as np
+
+from .model import L
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "lib", "libmapleaf_b200.so")
+CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
+INCLUDE_DIR = os.path.join(_PKG_DIR, "..", "include")
+TRACE_W = 16
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC"]
+
+
+class Counters(ctypes.Structure):
+    _fields_ = [("lanes", ctypes.c_int64), ("steps", ctypes.c_int64), ("derivative_evals", ctypes.c_int64), ("rejected_steps", ctypes.c_int64),
+                ("steps_3dof", ctypes.c_int64), ("derivative_evals_3dof", ctypes.c_int64), ("derivative_evals_transonic", ctypes.c_int64),
+                ("lanes_ok", ctypes.c_int64), ("lanes_step_limit", ctypes.c_int64), ("lanes_nan", ctypes.c_int64),
+                ("kernel_launches", ctypes.c_int64), ("last_run_ms", ctypes.c_double), ("dominant_kernel_ms", ctypes.c_double)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+def _sources():
+    out = [os.path.join(CSRC_DIR, f) for f in sorted(os.listdir(CSRC_DIR)) if f.endswith((".cu", ".cuh"))]
+    out += [os.path.join(INCLUDE_DIR, "mlb_layout.h"), os.path.join(INCLUDE_DIR, "mapleaf_b200.h")]
+    return out
+
+
+def buildLibrary(force: bool = False, verbose: bool = False, extraFlags=()) -> str:
+    """Compiles csrc/mlb_api.cu for sm_100a into mapleaf_b200/lib/libmapleaf_b200.so (nvcc cross-compiles without a GPU)."""
+    newest = max(os.path.getmtime(p) for p in _sources())
+    if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= newest:
+        return LIB_PATH
+    os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
+    cmd = ["nvcc"] + NVCC_FLAGS + list(extraFlags) + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, os.path.join(CSRC_DIR, "mlb_api.cu")]
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """Loads the CUDA library. Raises RuntimeError when it has not been built: there is no other compute path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("libmapleaf_b200.so not found at {}: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(nvcc, sm_100a). mapleaf_b200 has no CPU fallback.".format(LIB_PATH))
+    l = ctypes.CDLL(LIB_PATH)
+    vp, i64, dp, ip = ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)
+    l.mlb_last_error.restype = ctypes.c_char_p
+    l.mlb_version.restype = ctypes.c_char_p
+    l.mlb_create.argtypes = [vp, ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(vp)]
+    l.mlb_destroy.argtypes = [vp]
+    l.mlb_destroy.restype = None
+    l.mlb_set_lanes.argtypes = [vp, i64, ctypes.POINTER(dp), ip, ctypes.c_int]
+    l.mlb_set_lanes_device.argtypes = [vp, i64, ctypes.POINTER(vp), ip, ctypes.c_int]
+    l.mlb_run.argtypes = [vp, vp]
+    l.mlb_sync.argtypes = [vp]
+    l.mlb_results.argtypes = [vp, dp, ctypes.POINTER(ctypes.c_int32)]
+    l.mlb_finals.argtypes = [vp, dp]
+    l.mlb_counters.argtypes = [vp, ctypes.POINTER(Counters)]
+    l.mlb_lane_counters.argtypes = [vp, ctypes.POINTER(ctypes.c_int64)]
+    l.mlb_device_results.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp)]
+    l.mlb_set_result_buffers.argtypes = [vp, vp, vp]
+    l.mlb_moments.argtypes = [vp, dp]
+    l.mlb_set_trace.argtypes = [vp, i64, i64]
+    l.mlb_get_trace.argtypes = [vp, dp, ctypes.POINTER(ctypes.c_int64)]
+    l.mlb_set_dt_replay.argtypes = [vp, dp, i64]
+    l.mlb_force_eval.argtypes = [vp, i64, dp, dp, dp, dp]
+    l.mlb_host_gauss_stream.argtypes = [ctypes.POINTER(ctypes.c_uint32), ctypes.c_int, i64, dp, dp, ctypes.c_int, i64, dp]
+    l.mlb_host_randrange_stream.argtypes = [ctypes.POINTER(ctypes.c_uint32), ctypes.c_int, i64, ctypes.c_uint32, i64, dp]
+    l.mlb_fp64_peak.argtypes = [ctypes.c_int, dp]
+    _lib = l
+    return l
+
+
+EXPORTED_SYMBOLS = ["mlb_create", "mlb_destroy", "mlb_last_error", "mlb_version", "mlb_set_lanes", "mlb_set_lanes_device", "mlb_run", "mlb_sync",
+                    "mlb_results", "mlb_finals", "mlb_counters", "mlb_lane_counters", "mlb_device_results", "mlb_set_result_buffers", "mlb_moments", "mlb_set_trace",
+                    "mlb_get_trace", "mlb_set_dt_replay", "mlb_force_eval", "mlb_host_gauss_stream", "mlb_host_randrange_stream", "mlb_fp64_peak"]
+
+
+def _dp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double)) if a is not None else None
+
+
+def _check(rc, what):
+    if rc != 0:
+        msg = lib().mlb_last_error().decode()
+        if rc == 2:
+            raise RuntimeError("{}: {}".format(what, msg))
+        raise ValueError("{}: {}".format(what, msg))
+
+
+_LANE_COMPONENTS = {L.LANE_WIND: 3, L.LANE_INIT_STATE: 13, L.LANE_PINK_SEED: 3}
+
+
+class TrajectoryBatch:
+    """One Monte Carlo case on one GPU: a model block plus per-lane sampled inputs."""
+
+    def __init__(self, blob, device: int = 0):
+        self._h = ctypes.c_void_p()
+        self.blob = np.ascontiguousarray(blob, dtype=np.float64)
+        self.nLanes = 0
+        self._keep = []
+        _check(lib().mlb_create(self.blob.ctypes.data_as(ctypes.c_void_p), self.blob.nbytes, device, ctypes.byref(self._h)), "mlb_create")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().mlb_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def setLanes(self, nLanes: int, laneArrays: Optional[Dict[int, np.ndarray]] = None):
+        """laneArrays: {LANE_* id: float64 array [components, nLanes]} in host memory."""
+        laneArrays = laneArrays or {}
+        ids = np.array(list(laneArrays.keys()), dtype=np.int32)
+        arrs = []
+        for k, a in laneArrays.items():
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            if a.shape != (_LANE_COMPONENTS[k], nLanes):
+                raise ValueError("lane array {} must have shape ({}, {}), got {}".format(k, _LANE_COMPONENTS[k], nLanes, a.shape))
+            arrs.append(a)
+        ptrs = (ctypes.POINTER(ctypes.c_double) * max(1, len(arrs)))(*[_dp(a) for a in arrs])
+        _check(lib().mlb_set_lanes(self._h, nLanes, ptrs, ids.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), len(arrs)), "mlb_set_lanes")
+        self.nLanes = nLanes
+
+    def setLanesDevice(self, nLanes: int, devicePointers: Dict[int, int], keepAlive=None):
+        """devicePointers: {LANE_* id: device address of a float64 [components, nLanes] array on this GPU}."""
+        ids = np.array(list(devicePointers.keys()), dtype=np.int32)
+        ptrs = (ctypes.c_void_p * max(1, len(devicePointers)))(*[ctypes.c_void_p(p) for p in devicePointers.values()])
+        _check(lib().mlb_set_lanes_device(self._h, nLanes, ptrs, ids.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), len(devicePointers)), "mlb_set_lanes_device")
+        self.nLanes = nLanes
+        self._keep = [keepAlive]
+
+    def run(self, stream: int = 0, sync: bool = False):
+        _check(lib().mlb_run(self._h, ctypes.c_void_p(stream)), "mlb_run")
+        if sync:
+            self.sync()
+
+    def sync(self):
+        _check(lib().mlb_sync(self._h), "mlb_sync")
+
+    def results(self):
+        res = np.empty((self.nLanes, L.RES_SIZE))
+        st = np.empty(self.nLanes, dtype=np.int32)
+        _check(lib().mlb_results(self._h, _dp(res), st.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))), "mlb_results")
+        return res, st
+
+    def finals(self):
+        out = np.empty((self.nLanes, L.FIN_SIZE))
+        _check(lib().mlb_finals(self._h, _dp(out)), "mlb_finals")
+        return out
+
+    def counters(self) -> dict:
+        c = Counters()
+        _check(lib().mlb_counters(self._h, ctypes.byref(c)), "mlb_counters")
+        return c.asdict()
+
+    def laneCounters(self):
+        out = np.empty((self.nLanes, 3), dtype=np.int64)
+        _check(lib().mlb_lane_counters(self._h, out.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))), "mlb_lane_counters")
+        return out
+
+    def deviceResults(self):
+        r, s = ctypes.c_void_p(), ctypes.c_void_p()
+        _check(lib().mlb_device_results(self._h, ctypes.byref(r), ctypes.byref(s)), "mlb_device_results")
+        return r.value, s.value
+
+    def setResultBuffers(self, resultsPtr: int, statusPtr: int, keepAlive=None):
+        """Device addresses of caller-owned [nLanes, 7] float64 and [nLanes] int32 buffers the next runs write into."""
+        _check(lib().mlb_set_result_buffers(self._h, ctypes.c_void_p(resultsPtr), ctypes.c_void_p(statusPtr)), "mlb_set_result_buffers")
+        self._keepOut = keepAlive
+
+    def moments(self):
+        """count, mean[7], M2[7] of the result columns over lanes that ended normally (computed on the device)."""
+        out = np.empty(15)
+        _check(lib().mlb_moments(self._h, _dp(out)), "mlb_moments")
+        return out[0], out[1::2].copy(), out[2::2].copy()
+
+    def setTrace(self, lane: int, maxRows: int):
+        _check(lib().mlb_set_trace(self._h, lane, maxRows), "mlb_set_trace")
+        self._traceMax = maxRows
+
+    def trace(self):
+        rows = np.empty((max(1, getattr(self, "_traceMax", 0)), TRACE_W))
+        n = ctypes.c_int64(0)
+        _check(lib().mlb_get_trace(self._h, _dp(rows), ctypes.byref(n)), "mlb_get_trace")
+        return rows[:n.value]
+
+    def setDtReplay(self, dts):
+        a = np.ascontiguousarray(dts, dtype=np.float64) if dts is not None else None
+        _check(lib().mlb_set_dt_replay(self._h, _dp(a), 0 if a is None else a.size), "mlb_set_dt_replay")
+
+    def forceEval(self, states, times=None, winds=None):
+        s = np.ascontiguousarray(states, dtype=np.float64).reshape(-1, 13)
+        n = s.shape[0]
+        t = np.zeros(n) if times is None else np.ascontiguousarray(times, dtype=np.float64)
+        w = None if winds is None else np.ascontiguousarray(winds, dtype=np.float64).reshape(n, 3)
+        out = np.empty((n, 18))
+        _check(lib().mlb_force_eval(self._h, n, _dp(s), _dp(t), _dp(w), _dp(out)), "mlb_force_eval")
+        return out
+
+
+def seedKey(seed) -> np.ndarray:
+    """The 32-bit key words CPython's random.seed() feeds to init_by_array: |int| in little-endian 32-bit chunks; a str
+    seed becomes int.from_bytes(s.encode() + sha512(s.encode()).digest(), 'big') (Lib/random.py, version 2)."""
+    if isinstance(seed, str):
+        b = seed.encode()
+        n = int.from_bytes(b + hashlib.sha512(b).digest(), "big")
+    else:
+        n = abs(int(seed))
+    words = []
+    while True:
+        words.append(n & 0xFFFFFFFF)
+        n >>= 32
+        if n == 0:
+            break
+    return np.array(words, dtype=np.uint32)
+
+
+def hostGaussStream(seed, mu, sigma, nSamples: int, skipDraws: int = 0) -> np.ndarray:
+    """nSamples rows of gauss(mu[j], sigma[j]) drawn from random.Random(seed) in CPython's order (C++ sampler)."""
+    mu = np.ascontiguousarray(np.atleast_1d(mu), dtype=np.float64)
+    sigma = np.ascontiguousarray(np.atleast_1d(sigma), dtype=np.float64)
+    key = seedKey(seed)
+    out = np.empty((nSamples, mu.size))
+    _check(lib().mlb_host_gauss_stream(key.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), key.size, skipDraws, _dp(mu), _dp(sigma), mu.size,
+                                      nSamples * mu.size, _dp(out)), "mlb_host_gauss_stream")
+    return out
+
+
+def hostRandrangeStream(seed, n: int, nDraws: int, skipDraws: int = 0) -> np.ndarray:
+    """nDraws values of random.Random(seed).randrange(n) in CPython's order (C++ sampler), as float64."""
+    key = seedKey(seed)
+    out = np.empty(nDraws)
+    _check(lib().mlb_host_randrange_stream(key.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), key.size, skipDraws, n, nDraws, _dp(out)),
+           "mlb_host_randrange_stream")
+    return out
+
+
+def fp64Peak(device: int = 0) -> float:
+    """Measured FP64 FMA throughput of the device in TFLOP/s."""
+    out = ctypes.c_double(0)
+    _check(lib().mlb_fp64_peak(device, ctypes.byref(out)), "mlb_fp64_peak")
+    return out.value

@@ -1,0 +1,502 @@
+/*
+ * mlb_api.cu — trajectory kernels and the C ABI of libmapleaf_b200.so (include/mapleaf_b200.h).
+ *
+ * Kernels (sm_100a, FP64, one lane = one sampled rocket = one thread):
+ *   integrateLanes ... lane prologue (sampled inputs -> initial state, pink-noise generators, per-lane fin constants),
+ *                      then the whole flight: events, RK stages with the full force model fused in, end condition,
+ *                      running reductions; writes 7 result doubles + final state + status + counters per lane.
+ *                      The model block is staged in shared memory once per CTA; RK stage derivatives live in shared
+ *                      memory columns (mlb_integrate.cuh).
+ *   forceEvalKernel .. one Rocket._getAppliedForce per thread (wind-tunnel known-answer path).
+ *   momentsKernel .... per-column count / mean / M2 of the result block (Chan's pairwise combination), the
+ *                      per-GPU half of the dispersion statistics.
+ */
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/mapleaf_b200.h"
+#include "mlb_integrate.cuh"
+
+using namespace mlb;
+
+#define MLB_BLOCK 128
+#define TRACE_W 16
+#define MLB_NCOUNTERS 6
+
+struct RunArgs {
+    const double* blob; int blobLen; int blobPad; int nSlots;
+    LaneInputs in;
+    double* results; double* finals; int* status; long long* counters;
+    uint32_t* mt;
+    double* trace; long long traceLane, traceMaxRows; long long* traceRows;
+    const double* dtReplay; long long nReplay;
+};
+
+__device__ __forceinline__ void traceRow(const RunArgs& a, const Lane& L, long long& rows, double dt, double err) {
+    if (rows >= a.traceMaxRows) return;
+    double* T = a.trace + rows * TRACE_W;
+    T[0] = L.time; T[1] = L.s.pos.x; T[2] = L.s.pos.y; T[3] = L.s.pos.z; T[4] = L.s.vel.x; T[5] = L.s.vel.y; T[6] = L.s.vel.z;
+    T[7] = L.s.q.w; T[8] = L.s.q.x; T[9] = L.s.q.y; T[10] = L.s.q.z; T[11] = L.s.w.x; T[12] = L.s.w.y; T[13] = L.s.w.z;
+    T[14] = dt; T[15] = err; rows++;
+}
+
+__global__ void __launch_bounds__(MLB_BLOCK) integrateLanes(const RunArgs a) {
+    extern __shared__ double smem[];
+    double* B = smem;
+    for (int i = threadIdx.x; i < a.blobLen; i += blockDim.x) B[i] = a.blob[i];
+    __syncthreads();
+    const long long lane = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (lane >= a.in.nLanes) return;
+    KStore ks; ks.base = smem + a.blobPad + threadIdx.x; ks.stride = blockDim.x; ks.fsalSlot = a.nSlots - 1;
+
+    Lane L;
+    laneInit(B, L, a.in, lane, a.mt);
+    double dt = B[H_DT0];
+    double apogee = -10000000, maxSpeed = 0, maxH = 0;
+    V3 prevPos = L.s.pos, lastPos = L.s.pos;
+    const long long maxSteps = (long long)B[H_MAX_STEPS];
+    int st = ST_OK;
+    const bool tracing = (a.trace != nullptr && lane == a.traceLane);
+    long long rows = 0;
+
+    /* RocketFlight reductions (rocketFlight.py:27-50), kept as running values */
+    if (L.s.pos.z > apogee) apogee = L.s.pos.z;
+    maxSpeed = fmax(maxSpeed, len(L.s.vel));
+    maxH = fmax(maxH, sqrt(L.s.vel.x * L.s.vel.x + L.s.vel.y * L.s.vel.y));
+    if (tracing) traceRow(a, L, rows, 0.0, 0.0);
+
+    bool end, haveFinal; double finalDt;
+    endDetector(B, L, dt, end, haveFinal, finalDt);
+    while (!end) {                                                                          /* SingleSimulations.py:102-139 */
+        if (haveFinal) dt = finalDt;
+        if (a.dtReplay && L.nSteps < a.nReplay) dt = a.dtReplay[L.nSteps];
+        StepResult r = rocketTimeStep(B, L, ks, dt);
+        dt = r.dt * r.factor;
+        prevPos = lastPos; lastPos = L.s.pos;
+        if (L.s.pos.z > apogee) apogee = L.s.pos.z;
+        double sp = len(L.s.vel); if (sp > maxSpeed) maxSpeed = sp;
+        double hv = sqrt(L.s.vel.x * L.s.vel.x + L.s.vel.y * L.s.vel.y); if (hv > maxH) maxH = hv;
+        if (tracing) traceRow(a, L, rows, r.dt, r.err);
+        if (!(L.s.pos.z == L.s.pos.z) || !(L.s.vel.x == L.s.vel.x)) { st = ST_NAN; break; }
+        if (L.nSteps >= maxSteps) { st = ST_STEP_LIMIT; break; }
+        endDetector(B, L, dt, end, haveFinal, finalDt);
+    }
+
+    /* RocketFlight.getLandingLocation (rocketFlight.py:52-76): linear extrapolation of the last two positions to z = 0 */
+    double* R = a.results + lane * RES_SIZE;
+    double dz = lastPos.z - prevPos.z;
+    if (L.nSteps >= 1 && lastPos.z > dz * 2) {
+        double dxdz = (lastPos.x - prevPos.x) / dz, dydz = (lastPos.y - prevPos.y) / dz;
+        double dzLand = -lastPos.z;
+        R[RES_LAND_X] = lastPos.x + dxdz * dzLand; R[RES_LAND_Y] = lastPos.y + dydz * dzLand; R[RES_LAND_Z] = 0.0;
+    } else { R[RES_LAND_X] = lastPos.x; R[RES_LAND_Y] = lastPos.y; R[RES_LAND_Z] = lastPos.z; }
+    R[RES_APOGEE] = apogee; R[RES_MAX_SPEED] = maxSpeed; R[RES_FLIGHT_TIME] = L.time; R[RES_MAX_HVEL] = maxH;
+    double* F = a.finals + lane * FIN_SIZE;
+    F[0] = L.s.pos.x; F[1] = L.s.pos.y; F[2] = L.s.pos.z; F[3] = L.s.vel.x; F[4] = L.s.vel.y; F[5] = L.s.vel.z;
+    F[6] = L.s.q.w; F[7] = L.s.q.x; F[8] = L.s.q.y; F[9] = L.s.q.z; F[10] = L.s.w.x; F[11] = L.s.w.y; F[12] = L.s.w.z; F[13] = L.time;
+    a.status[lane] = st;
+    long long* cn = a.counters + lane * MLB_NCOUNTERS;
+    cn[0] = L.nSteps; cn[1] = L.nEvals; cn[2] = L.nRejects; cn[3] = L.nSteps3; cn[4] = L.nEvals3; cn[5] = L.nEvalsTransonic;
+    if (tracing) *a.traceRows = rows;
+}
+
+__global__ void __launch_bounds__(MLB_BLOCK) forceEvalKernel(const double* blob, int blobLen, long long n, const double* states, const double* times,
+                                                             const double* winds, double* out) {
+    extern __shared__ double smem[];
+    double* B = smem;
+    for (int i = threadIdx.x; i < blobLen; i += blockDim.x) B[i] = blob[i];
+    __syncthreads();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Lane L;
+    LaneInputs in; in.wind = nullptr; in.initState = nullptr; in.pinkSeed = nullptr; in.nLanes = 1;
+    laneInit(B, L, in, 0, nullptr);
+    if (winds) { L.wind = v3(winds[3 * i], winds[3 * i + 1], winds[3 * i + 2]); laneFinConstants(B, L); }
+    const double* s13 = states + 13 * i;
+    State s; s.pos = v3(s13[0], s13[1], s13[2]); s.vel = v3(s13[3], s13[4], s13[5]);
+    s.q = q4(s13[6], s13[7], s13[8], s13[9]); s.w = v3(s13[10], s13[11], s13[12]);
+    ForceProbe p; Inertia inertia; double massSum;
+    p.Mach = 0; p.density = 0; p.wind = v3(0, 0, 0);
+    ForceMoment f = appliedForce(B, L, times[i], s, false, inertia, massSum, &p);
+    double* o = out + 18 * i;
+    o[0] = f.force.x; o[1] = f.force.y; o[2] = f.force.z; o[3] = f.moment.x; o[4] = f.moment.y; o[5] = f.moment.z;
+    o[6] = p.aero.force.x; o[7] = p.aero.force.y; o[8] = p.aero.force.z; o[9] = p.Mach; o[10] = p.density;
+    o[11] = p.wind.x; o[12] = p.wind.y; o[13] = p.wind.z;
+    o[14] = inertia.CG.x; o[15] = inertia.CG.y; o[16] = inertia.CG.z; o[17] = inertia.mass;
+}
+
+/* Per-column (count, mean, M2) over lanes with status OK. One CTA per 7 columns x chunk; partials are combined by
+   one thread per column with Chan's update, written to out[15]. Two passes of a tiny kernel: the result block is
+   56 B/lane, this is bandwidth-trivial next to the integration. */
+__global__ void momentsPartial(const double* results, const int* status, long long nLanes, double* partials /* [grid][15] */) {
+    __shared__ double sh[MLB_BLOCK * 3];
+    for (int col = 0; col < RES_SIZE; col++) {
+        double n = 0, mean = 0, M2 = 0;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nLanes; i += (long long)gridDim.x * blockDim.x) {
+            if (status[i] != ST_OK) continue;
+            double x = results[i * RES_SIZE + col];
+            n += 1; double d = x - mean; mean += d / n; M2 += d * (x - mean);
+        }
+        sh[threadIdx.x * 3] = n; sh[threadIdx.x * 3 + 1] = mean; sh[threadIdx.x * 3 + 2] = M2;
+        __syncthreads();
+        for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+            if (threadIdx.x < s) {
+                double na = sh[threadIdx.x * 3], ma = sh[threadIdx.x * 3 + 1], Sa = sh[threadIdx.x * 3 + 2];
+                double nb = sh[(threadIdx.x + s) * 3], mb = sh[(threadIdx.x + s) * 3 + 1], Sb = sh[(threadIdx.x + s) * 3 + 2];
+                double nt = na + nb;
+                if (nt > 0) { double d = mb - ma; sh[threadIdx.x * 3] = nt; sh[threadIdx.x * 3 + 1] = ma + d * (nb / nt); sh[threadIdx.x * 3 + 2] = Sa + Sb + d * d * (na * nb / nt); }
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) { double* P = partials + (size_t)blockIdx.x * 15; if (col == 0) P[0] = sh[0]; P[1 + 2 * col] = sh[1]; P[2 + 2 * col] = sh[2]; }
+        __syncthreads();
+    }
+}
+__global__ void momentsFinal(const double* partials, int nPartials, double* out15) {
+    int col = threadIdx.x;
+    if (col >= RES_SIZE) return;
+    double n = 0, mean = 0, M2 = 0;
+    for (int p = 0; p < nPartials; p++) {
+        const double* P = partials + (size_t)p * 15;
+        double nb = P[0], mb = P[1 + 2 * col], Sb = P[2 + 2 * col];
+        double nt = n + nb;
+        if (nt > 0) { double d = mb - mean; mean = mean + d * (nb / nt); M2 = M2 + Sb + d * d * (n * nb / nt); n = nt; }
+    }
+    if (col == 0) out15[0] = n;
+    out15[1 + 2 * col] = mean; out15[2 + 2 * col] = M2;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Host side
+ * ------------------------------------------------------------------------------------------- */
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(MLB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+
+struct mlb_handle {
+    int device = 0;
+    std::vector<double> blob;
+    double* d_blob = nullptr;
+    long long nLanes = 0;
+    double* d_lane[LANE_NUM_ARRAYS] = { nullptr, nullptr, nullptr };
+    bool ownLane[LANE_NUM_ARRAYS] = { false, false, false };
+    bool ownResults = true;
+    double* d_results = nullptr; double* d_finals = nullptr; int* d_status = nullptr; long long* d_counters = nullptr;
+    uint32_t* d_mt = nullptr;
+    double* d_trace = nullptr; long long traceLane = -1, traceMaxRows = 0; long long* d_traceRows = nullptr;
+    double* d_replay = nullptr; long long nReplay = 0;
+    double* d_partials = nullptr; double* d_moments = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t stream = nullptr;
+    bool ran = false;
+    long long launches = 0;
+    int nSlots = 0; size_t smemBytes = 0;
+};
+
+static int laneArrayComponents(int id) { return id == LANE_WIND ? 3 : (id == LANE_INIT_STATE ? 13 : (id == LANE_PINK_SEED ? 3 : -1)); }
+
+static void freeLanes(mlb_handle* h) {
+    for (int i = 0; i < LANE_NUM_ARRAYS; i++) { if (h->ownLane[i] && h->d_lane[i]) cudaFree(h->d_lane[i]); h->d_lane[i] = nullptr; h->ownLane[i] = false; }
+    if (h->ownResults) { cudaFree(h->d_results); cudaFree(h->d_status); }
+    h->ownResults = true;
+    cudaFree(h->d_finals); cudaFree(h->d_counters); cudaFree(h->d_mt);
+    h->d_results = h->d_finals = nullptr; h->d_status = nullptr; h->d_counters = nullptr; h->d_mt = nullptr;
+    h->nLanes = 0; h->ran = false;
+}
+
+extern "C" const char* mlb_last_error(void) { return g_err.c_str(); }
+extern "C" const char* mlb_version(void) { return "mapleaf_b200 0.1 (sm_100a)"; }
+
+extern "C" int mlb_create(const void* model_blob, size_t n, int device, mlb_handle** out) {
+    if (!model_blob || !out || n < H_SIZE * sizeof(double) || n % sizeof(double)) return fail(MLB_ERR_ARG, "mlb_create: model block missing or too short");
+    const double* b = (const double*)model_blob;
+    size_t len = n / sizeof(double);
+    if ((int)b[H_MAGIC] != MLB_MAGIC || (int)b[H_VERSION] != MLB_VERSION) return fail(MLB_ERR_ARG, "mlb_create: not a model block (magic / version mismatch)");
+    if ((size_t)b[H_LEN] != len) return fail(MLB_ERR_ARG, "mlb_create: model block length field does not match the buffer");
+    int nStages = (int)b[H_NSTAGES];
+    if (nStages < 1 || nStages > MLB_MAX_STAGES) return fail(MLB_ERR_UNSUPPORTED, "mlb_create: stage count out of range");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) return fail(MLB_ERR_CUDA, std::string("mlb_create: no CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU path");
+    if (device < 0 || device >= count) return fail(MLB_ERR_ARG, "mlb_create: device index out of range");
+    CU(cudaSetDevice(device));
+    mlb_handle* h = new mlb_handle();
+    h->device = device;
+    h->blob.assign(b, b + len);
+    int method = (int)b[H_INTEGRATOR];
+    int nRows = (int)b[H_TAB_NSTAGE_ROWS];
+    h->nSlots = (method == INT_EULER) ? 1 : nRows + 1 + (method >= INT_RK12A ? 1 : 0);
+    size_t blobPad = (len + 1) & ~(size_t)1;
+    h->smemBytes = (blobPad + (size_t)h->nSlots * 12 * MLB_BLOCK) * sizeof(double);
+    if (h->smemBytes > 227 * 1024) { delete h; return fail(MLB_ERR_UNSUPPORTED, "mlb_create: model block + stage storage exceed shared memory"); }
+    CU(cudaMalloc(&h->d_blob, len * sizeof(double)));
+    CU(cudaMemcpy(h->d_blob, b, len * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaFuncSetAttribute(integrateLanes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
+    CU(cudaFuncSetAttribute(forceEvalKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(blobPad * sizeof(double))));
+    CU(cudaEventCreate(&h->ev0)); CU(cudaEventCreate(&h->ev1));
+    CU(cudaMalloc(&h->d_traceRows, sizeof(long long)));
+    CU(cudaMemset(h->d_traceRows, 0, sizeof(long long)));
+    CU(cudaMalloc(&h->d_partials, 148 * 15 * sizeof(double)));
+    CU(cudaMalloc(&h->d_moments, 15 * sizeof(double)));
+    *out = h;
+    return MLB_OK;
+}
+
+extern "C" void mlb_destroy(mlb_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    freeLanes(h);
+    cudaFree(h->d_blob); cudaFree(h->d_trace); cudaFree(h->d_traceRows); cudaFree(h->d_replay); cudaFree(h->d_partials); cudaFree(h->d_moments);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    delete h;
+}
+
+static int setLanes(mlb_handle* h, int64_t nLanes, const double* const* arrays, const int* ids, int nArrays, bool onDevice) {
+    if (!h) return fail(MLB_ERR_ARG, "null handle");
+    if (nLanes <= 0) return fail(MLB_ERR_ARG, "mlb_set_lanes: nLanes must be positive");
+    if (nArrays < 0 || (nArrays > 0 && (!arrays || !ids))) return fail(MLB_ERR_ARG, "mlb_set_lanes: array list missing");
+    CU(cudaSetDevice(h->device));
+    freeLanes(h);
+    h->nLanes = nLanes;
+    for (int k = 0; k < nArrays; k++) {
+        int comps = laneArrayComponents(ids[k]);
+        if (comps < 0) return fail(MLB_ERR_ARG, "mlb_set_lanes: unknown array id");
+        if (!arrays[k]) return fail(MLB_ERR_ARG, "mlb_set_lanes: null array");
+        if (onDevice) { h->d_lane[ids[k]] = (double*)arrays[k]; h->ownLane[ids[k]] = false; }
+        else {
+            size_t bytes = (size_t)comps * nLanes * sizeof(double);
+            CU(cudaMalloc(&h->d_lane[ids[k]], bytes));
+            h->ownLane[ids[k]] = true;
+            CU(cudaMemcpy(h->d_lane[ids[k]], arrays[k], bytes, cudaMemcpyHostToDevice));
+        }
+    }
+    CU(cudaMalloc(&h->d_results, (size_t)nLanes * RES_SIZE * sizeof(double)));
+    CU(cudaMalloc(&h->d_finals, (size_t)nLanes * FIN_SIZE * sizeof(double)));
+    CU(cudaMalloc(&h->d_status, (size_t)nLanes * sizeof(int)));
+    CU(cudaMalloc(&h->d_counters, (size_t)nLanes * MLB_NCOUNTERS * sizeof(long long)));
+    int turb = (int)h->blob[H_TURB];
+    if (turb >= TURB_PINK1D && turb <= TURB_PINK3D) CU(cudaMalloc(&h->d_mt, (size_t)nLanes * 3 * 624 * sizeof(uint32_t)));
+    return MLB_OK;
+}
+extern "C" int mlb_set_lanes(mlb_handle* h, int64_t nLanes, const double* const* arrays, const int* ids, int nArrays) { return setLanes(h, nLanes, arrays, ids, nArrays, false); }
+extern "C" int mlb_set_lanes_device(mlb_handle* h, int64_t nLanes, const double* const* arrays, const int* ids, int nArrays) { return setLanes(h, nLanes, arrays, ids, nArrays, true); }
+
+extern "C" int mlb_run(mlb_handle* h, void* stream) {
+    if (!h) return fail(MLB_ERR_ARG, "null handle");
+    if (h->nLanes <= 0) return fail(MLB_ERR_STATE, "mlb_run: call mlb_set_lanes first");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    h->stream = s;
+    RunArgs a;
+    a.blob = h->d_blob; a.blobLen = (int)h->blob.size(); a.blobPad = (int)((h->blob.size() + 1) & ~(size_t)1); a.nSlots = h->nSlots;
+    a.in.wind = h->d_lane[LANE_WIND]; a.in.initState = h->d_lane[LANE_INIT_STATE]; a.in.pinkSeed = h->d_lane[LANE_PINK_SEED]; a.in.nLanes = h->nLanes;
+    a.results = h->d_results; a.finals = h->d_finals; a.status = h->d_status; a.counters = h->d_counters; a.mt = h->d_mt;
+    a.trace = (h->traceLane >= 0 && h->traceLane < h->nLanes) ? h->d_trace : nullptr;
+    a.traceLane = h->traceLane; a.traceMaxRows = h->traceMaxRows; a.traceRows = h->d_traceRows;
+    a.dtReplay = h->d_replay; a.nReplay = h->nReplay;
+    unsigned grid = (unsigned)((h->nLanes + MLB_BLOCK - 1) / MLB_BLOCK);
+    CU(cudaEventRecord(h->ev0, s));
+    integrateLanes<<<grid, MLB_BLOCK, h->smemBytes, s>>>(a);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(h->ev1, s));
+    h->launches = 1;
+    h->ran = true;
+    return MLB_OK;
+}
+
+extern "C" int mlb_sync(mlb_handle* h) {
+    if (!h) return fail(MLB_ERR_ARG, "null handle");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    return MLB_OK;
+}
+
+static int needRun(mlb_handle* h, const char* who) {
+    if (!h) return fail(MLB_ERR_ARG, "null handle");
+    if (!h->ran) return fail(MLB_ERR_STATE, std::string(who) + ": no completed mlb_run");
+    return mlb_sync(h);
+}
+
+extern "C" int mlb_results(mlb_handle* h, double* results, int32_t* status) {
+    int rc = needRun(h, "mlb_results"); if (rc) return rc;
+    if (results) CU(cudaMemcpy(results, h->d_results, (size_t)h->nLanes * RES_SIZE * sizeof(double), cudaMemcpyDeviceToHost));
+    if (status) CU(cudaMemcpy(status, h->d_status, (size_t)h->nLanes * sizeof(int), cudaMemcpyDeviceToHost));
+    return MLB_OK;
+}
+extern "C" int mlb_finals(mlb_handle* h, double* finals) {
+    int rc = needRun(h, "mlb_finals"); if (rc) return rc;
+    if (!finals) return fail(MLB_ERR_ARG, "mlb_finals: null buffer");
+    CU(cudaMemcpy(finals, h->d_finals, (size_t)h->nLanes * FIN_SIZE * sizeof(double), cudaMemcpyDeviceToHost));
+    return MLB_OK;
+}
+extern "C" int mlb_lane_counters(mlb_handle* h, int64_t* out) {
+    int rc = needRun(h, "mlb_lane_counters"); if (rc) return rc;
+    if (!out) return fail(MLB_ERR_ARG, "mlb_lane_counters: null buffer");
+    std::vector<long long> c((size_t)h->nLanes * MLB_NCOUNTERS);
+    CU(cudaMemcpy(c.data(), h->d_counters, c.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    for (long long i = 0; i < h->nLanes; i++) for (int k = 0; k < 3; k++) out[3 * i + k] = c[MLB_NCOUNTERS * i + k];
+    return MLB_OK;
+}
+extern "C" int mlb_counters(mlb_handle* h, mlb_counters_t* out) {
+    int rc = needRun(h, "mlb_counters"); if (rc) return rc;
+    if (!out) return fail(MLB_ERR_ARG, "mlb_counters: null buffer");
+    std::vector<long long> c((size_t)h->nLanes * MLB_NCOUNTERS); std::vector<int> st((size_t)h->nLanes);
+    CU(cudaMemcpy(c.data(), h->d_counters, c.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(st.data(), h->d_status, st.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    memset(out, 0, sizeof(*out));
+    out->lanes = h->nLanes;
+    for (long long i = 0; i < h->nLanes; i++) {
+        const long long* ci = c.data() + MLB_NCOUNTERS * i;
+        out->steps += ci[0]; out->derivative_evals += ci[1]; out->rejected_steps += ci[2];
+        out->steps_3dof += ci[3]; out->derivative_evals_3dof += ci[4]; out->derivative_evals_transonic += ci[5];
+        if (st[i] == ST_OK) out->lanes_ok++; else if (st[i] == ST_STEP_LIMIT) out->lanes_step_limit++; else if (st[i] == ST_NAN) out->lanes_nan++;
+    }
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    out->last_run_ms = ms; out->dominant_kernel_ms = ms; out->kernel_launches = h->launches;
+    return MLB_OK;
+}
+extern "C" int mlb_device_results(mlb_handle* h, void** results, void** status) {
+    if (!h || h->nLanes <= 0) return fail(MLB_ERR_STATE, "mlb_device_results: no lanes");
+    if (results) *results = h->d_results;
+    if (status) *status = h->d_status;
+    return MLB_OK;
+}
+extern "C" int mlb_set_result_buffers(mlb_handle* h, void* results, void* status) {
+    if (!h || h->nLanes <= 0) return fail(MLB_ERR_STATE, "mlb_set_result_buffers: call mlb_set_lanes first");
+    if (!results || !status) return fail(MLB_ERR_ARG, "mlb_set_result_buffers: null buffer");
+    CU(cudaSetDevice(h->device));
+    if (h->ownResults) { cudaFree(h->d_results); cudaFree(h->d_status); }
+    h->d_results = (double*)results; h->d_status = (int*)status; h->ownResults = false; h->ran = false;
+    return MLB_OK;
+}
+extern "C" int mlb_moments(mlb_handle* h, double* out15) {
+    int rc = needRun(h, "mlb_moments"); if (rc) return rc;
+    if (!out15) return fail(MLB_ERR_ARG, "mlb_moments: null buffer");
+    int grid = 148;
+    momentsPartial<<<grid, MLB_BLOCK, 0, h->stream>>>(h->d_results, h->d_status, h->nLanes, h->d_partials);
+    momentsFinal<<<1, 32, 0, h->stream>>>(h->d_partials, grid, h->d_moments);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpy(out15, h->d_moments, 15 * sizeof(double), cudaMemcpyDeviceToHost));
+    return MLB_OK;
+}
+
+extern "C" int mlb_set_trace(mlb_handle* h, int64_t lane, int64_t maxRows) {
+    if (!h) return fail(MLB_ERR_ARG, "null handle");
+    CU(cudaSetDevice(h->device));
+    cudaFree(h->d_trace); h->d_trace = nullptr;
+    h->traceLane = -1; h->traceMaxRows = 0;
+    if (lane >= 0 && maxRows > 0) {
+        CU(cudaMalloc(&h->d_trace, (size_t)maxRows * TRACE_W * sizeof(double)));
+        h->traceLane = lane; h->traceMaxRows = maxRows;
+    }
+    CU(cudaMemset(h->d_traceRows, 0, sizeof(long long)));
+    return MLB_OK;
+}
+extern "C" int mlb_get_trace(mlb_handle* h, double* rows, int64_t* nRows) {
+    int rc = needRun(h, "mlb_get_trace"); if (rc) return rc;
+    long long n = 0;
+    CU(cudaMemcpy(&n, h->d_traceRows, sizeof(long long), cudaMemcpyDeviceToHost));
+    if (nRows) *nRows = n;
+    if (rows && n > 0 && h->d_trace) CU(cudaMemcpy(rows, h->d_trace, (size_t)n * TRACE_W * sizeof(double), cudaMemcpyDeviceToHost));
+    return MLB_OK;
+}
+extern "C" int mlb_set_dt_replay(mlb_handle* h, const double* dts, int64_t n) {
+    if (!h) return fail(MLB_ERR_ARG, "null handle");
+    CU(cudaSetDevice(h->device));
+    cudaFree(h->d_replay); h->d_replay = nullptr; h->nReplay = 0;
+    if (dts && n > 0) {
+        CU(cudaMalloc(&h->d_replay, (size_t)n * sizeof(double)));
+        CU(cudaMemcpy(h->d_replay, dts, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+        h->nReplay = n;
+    }
+    return MLB_OK;
+}
+
+extern "C" int mlb_force_eval(mlb_handle* h, int64_t n, const double* states, const double* times, const double* winds, double* out) {
+    if (!h || n <= 0 || !states || !times || !out) return fail(MLB_ERR_ARG, "mlb_force_eval: bad arguments");
+    CU(cudaSetDevice(h->device));
+    double *d_s = nullptr, *d_t = nullptr, *d_w = nullptr, *d_o = nullptr;
+    CU(cudaMalloc(&d_s, (size_t)n * 13 * sizeof(double))); CU(cudaMalloc(&d_t, (size_t)n * sizeof(double))); CU(cudaMalloc(&d_o, (size_t)n * 18 * sizeof(double)));
+    CU(cudaMemcpy(d_s, states, (size_t)n * 13 * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_t, times, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+    if (winds) { CU(cudaMalloc(&d_w, (size_t)n * 3 * sizeof(double))); CU(cudaMemcpy(d_w, winds, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice)); }
+    size_t blobPad = (h->blob.size() + 1) & ~(size_t)1;
+    forceEvalKernel<<<(unsigned)((n + MLB_BLOCK - 1) / MLB_BLOCK), MLB_BLOCK, blobPad * sizeof(double)>>>(h->d_blob, (int)h->blob.size(), n, d_s, d_t, d_w, d_o);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(out, d_o, (size_t)n * 18 * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(d_s); cudaFree(d_t); cudaFree(d_w); cudaFree(d_o);
+    if (e != cudaSuccess) return fail(MLB_ERR_CUDA, std::string("mlb_force_eval: ") + cudaGetErrorString(e));
+    return MLB_OK;
+}
+
+extern "C" int mlb_host_gauss_stream(const uint32_t* key, int keyLen, int64_t skip, const double* mu, const double* sigma, int nPer, int64_t nDraws, double* out) {
+    if (!key || keyLen <= 0 || !mu || !sigma || nPer <= 0 || nDraws < 0 || !out) return fail(MLB_ERR_ARG, "mlb_host_gauss_stream: bad arguments");
+    std::vector<uint32_t> mt(624);
+    PyRandom r; r.mt = mt.data();
+    mtInitByArray(r.mt, key, keyLen);
+    r.idx = 624; r.hasNext = 0; r.next = 0;
+    for (int64_t i = 0; i < skip; i++) pyRandomGauss(r, 0, 1);
+    for (int64_t i = 0; i < nDraws; i++) out[i] = pyRandomGauss(r, mu[i % nPer], sigma[i % nPer]);
+    return MLB_OK;
+}
+
+extern "C" int mlb_host_randrange_stream(const uint32_t* key, int keyLen, int64_t skip, uint32_t n, int64_t nDraws, double* out) {
+    /* random.randrange(n) for 0 < n < 2^32: CPython's _randbelow_with_getrandbits (Lib/random.py): k = n.bit_length();
+       r = getrandbits(k) until r < n; getrandbits(k <= 32) = genrand_uint32() >> (32 - k) */
+    if (!key || keyLen <= 0 || n == 0 || nDraws < 0 || !out) return fail(MLB_ERR_ARG, "mlb_host_randrange_stream: bad arguments");
+    std::vector<uint32_t> mt(624);
+    PyRandom r; r.mt = mt.data();
+    mtInitByArray(r.mt, key, keyLen);
+    r.idx = 624; r.hasNext = 0; r.next = 0;
+    int k = 0; for (uint32_t v = n; v; v >>= 1) k++;
+    for (int64_t i = 0; i < skip + nDraws; i++) {
+        uint32_t v = mtGenrand(r) >> (32 - k);
+        while (v >= n) v = mtGenrand(r) >> (32 - k);
+        if (i >= skip) out[i - skip] = (double)v;
+    }
+    return MLB_OK;
+}
+
+/* FP64 pipe ceiling of this GPU, measured: 16 independent DFMA chains per thread, every SM full. The roofline
+   denominator of the trajectory kernels (MEASURED_PEAKS.json carries HBM and bf16 tensor figures only). */
+__global__ void __launch_bounds__(256) fp64PeakKernel(double* out, int iters, double a, double b) {
+    double x[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) x[k] = threadIdx.x * 1e-3 + k;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) x[k] = fma(x[k], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) s += x[k];
+    if (s == 12345.678) out[0] = s;
+}
+extern "C" int mlb_fp64_peak(int device, double* tflops) {
+    if (!tflops) return fail(MLB_ERR_ARG, "mlb_fp64_peak: null output");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, device));
+    double* d_out = nullptr; CU(cudaMalloc(&d_out, sizeof(double)));
+    cudaEvent_t e0, e1; CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    const int blocks = prop.multiProcessorCount * 8, iters = 20000;
+    double best = 0;
+    for (int rep = 0; rep < 5; rep++) {
+        CU(cudaEventRecord(e0, 0));
+        fp64PeakKernel<<<blocks, 256>>>(d_out, iters, 0.999999, 1e-7);
+        CU(cudaEventRecord(e1, 0));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0; CU(cudaEventElapsedTime(&ms, e0, e1));
+        double tf = 2.0 * 16 * iters * 256.0 * blocks / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
+    *tflops = best;
+    return MLB_OK;
+}

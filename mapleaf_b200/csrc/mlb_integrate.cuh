@@ -1,0 +1,332 @@
+/*
+ * mlb_integrate.cuh — per-lane time integration: Butcher-tableau Runge-Kutta steps in the reference's
+ * object algebra (fixed-step and adaptive with per-lane PID step control), flight events, the
+ * Simulation.run loop with its end conditions, and the running RocketFlight reductions.
+ *
+ * Reference behaviour restated here (paths relative to MAPLEAF/):
+ *   Motion/Integration.py:189-236 (classical), :331-449 (adaptive, retry loop, PID / elementary controllers)
+ *   GNC/PID.py:27-51 (step-size PID, integral clamped to +-1)
+ *   Rocket/simEventDetector.py:64-162, Rocket/Recovery.py:65-97, Rocket/rocket.py:658-726
+ *   ENV/launchRail.py:58-81, ENV/environment.py:195-207
+ *   SimulationRunners/SingleSimulations.py:89-139,205-248, IO/rocketFlight.py:27-76
+ *
+ * The two integrator families take different algebraic routes on purpose: the
+ * classical one sums stage derivatives weighted by 1/(1/(a dt)) and converts the sum to a rotation once; the
+ * adaptive one converts every stage derivative to a rotation, composes them and rescales the composed angle.
+ *
+ * Stage derivatives k_i live in shared memory, one column per thread ([slot][component][thread], 8-byte
+ * words of consecutive threads are consecutive: no bank conflicts), so the tableau loops can index them
+ * dynamically without forcing 84+ doubles per lane into local memory.
+ */
+#pragma once
+#include "mlb_model.cuh"
+
+namespace mlb {
+
+struct KStore {
+    double* base; int stride; int fsalSlot;      /* fsalSlot: where the adaptive integrator keeps its first-same-as-last derivative */
+    MLB_DEV void put(int slot, const Deriv& d, bool dof3) const {
+        double* p = base + (size_t)slot * 12 * stride;
+        p[0] = d.vel.x; p[stride] = d.vel.y; p[2 * stride] = d.vel.z;
+        p[3 * stride] = d.acc.x; p[4 * stride] = d.acc.y; p[5 * stride] = d.acc.z;
+        if (dof3) return;
+        p[6 * stride] = d.angvel.x; p[7 * stride] = d.angvel.y; p[8 * stride] = d.angvel.z;
+        p[9 * stride] = d.angacc.x; p[10 * stride] = d.angacc.y; p[11 * stride] = d.angacc.z;
+    }
+    MLB_DEV Deriv get(int slot, bool dof3) const {
+        const double* p = base + (size_t)slot * 12 * stride;
+        Deriv d;
+        d.vel = v3(p[0], p[stride], p[2 * stride]);
+        d.acc = v3(p[3 * stride], p[4 * stride], p[5 * stride]);
+        if (dof3) { d.angvel = v3(0, 0, 0); d.angacc = v3(0, 0, 0); return d; }
+        d.angvel = v3(p[6 * stride], p[7 * stride], p[8 * stride]);
+        d.angacc = v3(p[9 * stride], p[10 * stride], p[11 * stride]);
+        return d;
+    }
+};
+
+MLB_DEV Deriv derivScaled(const Deriv& d, double s, bool dof3) {                            /* RigidBodyStates.py:190-202 (already 1/invScalar) */
+    Deriv r;
+    r.vel = d.vel * s; r.acc = d.acc * s;
+    if (dof3) { r.angvel = v3(0, 0, 0); r.angacc = v3(0, 0, 0); return r; }
+    r.angvel = d.angvel * s; r.angacc = d.angacc * s;
+    return r;
+}
+MLB_DEV Deriv derivAdd(const Deriv& a, const Deriv& b, bool dof3) {                         /* :164-171 */
+    Deriv r;
+    r.vel = a.vel + b.vel; r.acc = a.acc + b.acc;
+    if (dof3) { r.angvel = v3(0, 0, 0); r.angacc = v3(0, 0, 0); return r; }
+    r.angvel = a.angvel + b.angvel; r.angacc = a.angacc + b.angacc;
+    return r;
+}
+
+struct StepResult { State newValue; double dt, factor, err; };
+
+MLB_DEV double stepPID(const double* B, Lane& L, double currentError, double dt) {          /* GNC/PID.py:27-51, maxIntegral = 1 */
+    double derivative = (currentError - L.pidLastError) / dt;
+    L.pidIntegral = L.pidIntegral + (currentError + L.pidLastError) * dt / 2;
+    if (fabs(L.pidIntegral) > 1) L.pidIntegral = L.pidIntegral * 1 / fabs(L.pidIntegral);
+    L.pidLastError = currentError;
+    return B[H_AD_P] * currentError + B[H_AD_I] * L.pidIntegral + B[H_AD_D] * derivative;
+}
+
+MLB_DEV bool pyIsClose(double a, double b) {                                                /* math.isclose: rel_tol 1e-9 */
+    if (a == b) return true;
+    double diff = fabs(b - a);
+    return (diff <= fabs(1e-9 * b)) || (diff <= fabs(1e-9 * a));
+}
+
+/* One Runge-Kutta step of either family. The stage loop has ONE call site of the (large) state-derivative code, shared
+   by the first stage, the classical and the adaptive stage composition and the adaptive retry loop, so the force model is
+   instantiated once in the kernel. */
+MLB_DEV StepResult integrateStep(const double* B, Lane& L, const KStore& ks, State& y, double t, double dt) {
+    const int method = (int)B[H_INTEGRATOR];
+    const bool adaptive = method >= INT_RK12A;
+    const double* tab = B + (int)B[H_TABLEAU_OFF];
+    const int nRows = (method == INT_EULER) ? 0 : (int)B[H_TAB_NSTAGE_ROWS];
+    const double target = B[H_AD_TARGET], minDt = B[H_AD_MINDT];
+    StepResult r; r.factor = 1.0; r.err = 0.0;
+    double err = 10000000;
+    if (adaptive) dt *= 3;                                                                  /* Integration.py:335: first attempt = requested dt */
+    for (;;) {
+        const bool dof3 = L.dof3;
+        if (adaptive) {
+            if (err != 10000000) L.nRejects++;
+            dt = fmax(minDt, dt / 3);
+        }
+        for (int i = -1; i < nRows; i++) {
+            State evalY; double evalTime;
+            if (i < 0) {
+                if (adaptive && L.haveCache) { ks.put(0, ks.get(ks.fsalSlot, dof3), dof3); continue; }
+                evalY = y; evalTime = t;
+            } else {
+                const double* row = tab + i * TABLEAU_STRIDE;
+                evalTime = t + dt * row[0];
+                if (!adaptive) {                                                            /* :216-231 */
+                    Deriv evalK = derivScaled(ks.get(0, dof3), 1 / (1 / (row[1] * dt)), dof3);
+                    for (int a = 2; a < i + 2; a++) evalK = derivAdd(evalK, derivScaled(ks.get(a - 1, dof3), 1 / (1 / (row[a] * dt)), dof3), dof3);
+                    evalY = stateAdd(y, derivTimes(evalK, 1.0, dof3), dof3);
+                } else {                                                                    /* :420-432 */
+                    State evalK = derivTimes(ks.get(0, dof3), row[1], dof3);
+                    for (int a = 2; a < i + 2; a++) evalK = stateAdd(evalK, derivTimes(ks.get(a - 1, dof3), row[a], dof3), dof3);
+                    evalY = stateAdd(y, stateScale(evalK, dt, dof3), dof3);
+                }
+            }
+            ks.put(i + 1, stateDerivative(B, L, evalTime, evalY, dof3), dof3);
+        }
+        if (method == INT_EULER) {                                                          /* :192-195 */
+            r.newValue = stateAdd(y, derivTimes(ks.get(0, dof3), dt, dof3), dof3);
+            r.dt = dt;
+            return r;
+        }
+        const double* fr = tab + nRows * TABLEAU_STRIDE;
+        Deriv k0 = ks.get(0, dof3);
+        Deriv fd = derivScaled(k0, 1 / (1 / fr[0]), dof3);
+        if (!adaptive) {                                                                    /* :233-236 */
+            for (int i = 1; i < nRows + 1; i++) fd = derivAdd(fd, derivScaled(ks.get(i, dof3), 1 / (1 / fr[i]), dof3), dof3);
+            r.newValue = stateAdd(y, derivTimes(fd, dt, dof3), dof3);
+            r.dt = dt;
+            return r;
+        }
+        const double* cr = tab + (nRows + 1) * TABLEAU_STRIDE;                              /* :434-447 */
+        Deriv cd = derivScaled(k0, 1 / (1 / cr[0]), dof3);
+        for (int i = 1; i < nRows + 1; i++) {
+            Deriv ki = ks.get(i, dof3);
+            fd = derivAdd(fd, derivScaled(ki, 1 / (1 / fr[i]), dof3), dof3);
+            cd = derivAdd(cd, derivScaled(ki, 1 / (1 / cr[i]), dof3), dof3);
+        }
+        r.newValue = stateAdd(y, derivTimes(fd, dt, dof3), dof3);
+        State coarsePred = stateAdd(y, derivTimes(cd, dt, dof3), dof3);
+        State neg = stateNeg(coarsePred, dof3);
+        State errEst = stateAdd(neg, r.newValue, dof3);
+        err = stateAbs(errEst, dof3);
+        if (!(err > 20 * target) || pyIsClose(dt, minDt)) break;                            /* :338-347 */
+    }
+    /* accepted adaptive step: FSAL cache, step-size controller (:349-389) */
+    if (method == INT_RK45A || method == INT_RK23A) {
+        ks.put(ks.fsalSlot, ks.get(nRows, L.dof3), L.dof3);
+        L.haveCache = true;
+    }
+    const double maxDt = B[H_AD_MAXDT];
+    double desired;
+    const int ctrl = (int)B[H_AD_CTRL];
+    if (ctrl == CTRL_PID) desired = 1 + stepPID(B, L, fmin(1.0, (err - target) / target), dt);
+    else if (ctrl == CTRL_ELEMENTARY) desired = sqrt(target / (2 * err));
+    else desired = 1;
+    double minFactor = fmax(minDt / dt, B[H_AD_MINF]);
+    double maxFactor = fmin(maxDt / dt, B[H_AD_MAXF]);
+    r.factor = B[H_AD_SAFETY] * fmin(fmax(desired, minFactor), maxFactor);
+    r.dt = dt; r.err = err;
+    return r;
+}
+
+MLB_DEV bool isAdaptive(const double* B) { return (int)B[H_INTEGRATOR] >= INT_RK12A; }
+
+/* ---------------------------------------------------------------------------------------------
+ * Flight events
+ * ------------------------------------------------------------------------------------------- */
+MLB_DEV void subscribeEvent(Lane& L, int type, double value, double delay, int cb) {
+    if (L.nEvents >= MLB_MAX_EVENTS) return;
+    Event& e = L.events[L.nEvents++];
+    e.type = type; e.value = value; e.delay = delay; e.callback = cb;
+}
+MLB_DEV void deployNextRecoveryStage(const double* B, Lane& L) {                            /* Recovery.py:65-97 */
+    const double* C = B + (int)B[H_RECOVERY_OFF];
+    L.recoveryStage += 1;
+    if (L.recoveryStage == 1) {
+        /* Rocket._switchTo3DoF (rocket.py:700-726): new 3-DoF body with a fresh integrator (no FSAL cache, fresh PID) */
+        L.underChute = true;
+        L.dof3 = true; L.s.q = qIdentity(); L.s.w = v3(0, 0, 0);
+        L.haveCache = false; L.pidLastError = 0; L.pidIntegral = 0;
+    }
+    if (L.recoveryStage < (int)C[RC_NSTAGES]) {
+        const double* st = C + RC_STAGE0 + L.recoveryStage * RC_STAGE_STRIDE;
+        subscribeEvent(L, (int)st[0], st[1], st[4], CB_RECOVERY_DEPLOY);
+    }
+}
+MLB_DEV void triggerEvents(const double* B, Lane& L, double& estTimeToNext, bool& deterministic) {   /* simEventDetector.py:64-118 */
+    double est = 1e10; bool det = false;
+    const double alt = earthAltitude(B, L.s.pos);
+    const double vz = L.s.vel.z;
+    const int n0 = L.nEvents;
+    unsigned removeMask = 0;
+    for (int i = 0; i < n0; i++) {
+        Event ev = L.events[i];
+        bool occurred = false, timeDet = false; double timeTo = 1e10;
+        switch (ev.type) {
+            case EV_APOGEE:
+                occurred = (vz <= 0 && L.time > 1.0);
+                if (L.haveLast && (L.time - L.lastTime) != 0) {
+                    double accel = (vz - L.lastVz) / (L.time - L.lastTime);
+                    if (accel < 0 && vz > 0) timeTo = -vz / accel;
+                }
+                break;
+            case EV_ASCENDING_ALT:
+                occurred = (alt >= ev.value && vz > 0);
+                if (vz > 0) timeTo = (ev.value - alt) / vz;
+                break;
+            case EV_DESCENDING_ALT:
+                occurred = (alt <= ev.value && vz < 0);
+                if (vz < 0) timeTo = (ev.value - alt) / vz;
+                break;
+            case EV_MOTOR_BURNOUT:
+                occurred = (L.time >= L.engineShutOff[L.nStages - 1]);
+                timeTo = L.engineShutOff[L.nStages - 1] - L.time; timeDet = true;
+                break;
+            case EV_TIME_REACHED:
+                occurred = (L.time >= ev.value);
+                timeTo = ev.value - L.time; timeDet = true;
+                break;
+        }
+        if (timeTo < est && !occurred) { est = timeTo; det = timeDet; }
+        if (occurred) {
+            if (ev.delay == 0) { if (ev.callback == CB_RECOVERY_DEPLOY) deployNextRecoveryStage(B, L); }
+            else subscribeEvent(L, EV_TIME_REACHED, L.time + ev.delay, 0, ev.callback);
+            removeMask |= 1u << i;
+        }
+    }
+    if (removeMask) {
+        int w = 0;
+        for (int i = 0; i < L.nEvents; i++) if (!((removeMask >> i) & 1u)) { if (w != i) L.events[w] = L.events[i]; w++; }
+        L.nEvents = w;
+    }
+    L.haveLast = true; L.lastVz = vz; L.lastTime = L.time;
+    estTimeToNext = est; deterministic = det;
+}
+
+MLB_DEV void railMotionConstraint(const double* B, Lane& L) {                                /* launchRail.py:58-81, environment.py:195-207 */
+    if (!L.onRail) return;
+    Q4 rot = qAxisAngle(v3(0, 0, 1), B[H_EARTH_ROT] * L.time);
+    V3 currPosition = qRotate(rot, ld3(B + H_RAIL_POS));
+    V3 currDirection = qRotate(rot, ld3(B + H_RAIL_DIR));
+    double distanceTravelled = dot(L.s.pos - currPosition, currDirection);
+    if (distanceTravelled < B[H_RAIL_LEN]) {
+        if (distanceTravelled <= 0) {
+            L.s.pos = currPosition;
+            if (dot(L.s.vel, currDirection) < 0) L.s.vel = cross(v3(0, 0, B[H_EARTH_ROT]), currPosition);
+        }
+    } else L.onRail = false;
+}
+
+MLB_DEV StepResult rocketTimeStep(const double* B, Lane& L, const KStore& ks, double dt) {   /* rocket.py:658-698 */
+    railMotionConstraint(B, L);
+    double est; bool det;
+    triggerEvents(B, L, est, det);
+    const bool adaptive = isAdaptive(B);
+    if (adaptive && est < dt) {
+        if (det) dt = est + 1e-5;
+        else dt = fmax(est / 1.5, B[H_EVENT_DT]);
+    }
+    StepResult r = integrateStep(B, L, ks, L.s, L.time, dt);
+    if (L.dof3) L.nSteps3++;
+    L.time += r.dt;
+    L.s = r.newValue;
+    L.nSteps++;
+    return r;
+}
+
+MLB_DEV void endDetector(const double* B, const Lane& L, double dt, bool& end, bool& haveFinalDt, double& finalDt) {   /* SingleSimulations.py:205-248 */
+    const double v = B[H_END_VALUE];
+    haveFinalDt = false; end = false;
+    switch ((int)B[H_END_TYPE]) {
+        case END_APOGEE: end = (L.s.vel.z <= 0 && L.time > 1.0); break;
+        case END_ALT_ASCENDING: end = (L.s.pos.z >= v); break;
+        case END_ALT_DESCENDING: end = (earthAltitude(B, L.s.pos) <= v); break;
+        default:
+            if (L.time < v && L.time + dt >= v) { haveFinalDt = true; finalDt = v + 1e-14 - L.time; }
+            else if (L.time >= v) end = true;
+    }
+}
+
+/* Per-lane inputs, SoA over lanes ([component][lane], lane fastest) */
+struct LaneInputs { const double* wind; const double* initState; const double* pinkSeed; long long nLanes; };
+
+/* fin-set constants that depend on the lane's sampled environment at t = 0 */
+MLB_DEV void laneFinConstants(const double* B, Lane& L) {
+    int fi = 0;
+    for (int k = 0; k < MLB_MAX_FINSETS; k++) L.finThickK[k] = 0;
+    for (int si = 0; si < L.nStages; si++) {
+        const double* S = B + (int)B[H_STAGE_OFF + si];
+        for (int ci = 0; ci < (int)S[S_NCOMP]; ci++) {
+            const double* C = B + (int)S[S_COMP_OFF + ci];
+            if ((int)C[C_TYPE] == CT_FINSET && fi < MLB_MAX_FINSETS) L.finThickK[fi++] = finThicknessK(B, L, C);
+        }
+    }
+}
+
+MLB_DEV void laneInit(const double* B, Lane& L, const LaneInputs& in, long long lane, uint32_t* mtBase) {
+    L.wind = ld3(B + H_WIND_V);
+    if (in.wind) L.wind = v3(in.wind[lane], in.wind[in.nLanes + lane], in.wind[2 * in.nLanes + lane]);
+    double st[13];
+    for (int i = 0; i < 13; i++) st[i] = in.initState ? in.initState[i * in.nLanes + lane] : B[H_INIT_STATE + i];
+    L.s.pos = v3(st[0], st[1], st[2]); L.s.vel = v3(st[3], st[4], st[5]);
+    L.s.q = q4(st[6], st[7], st[8], st[9]); L.s.w = v3(st[10], st[11], st[12]);
+    L.time = B[H_START_TIME];
+    L.dof3 = false; L.underChute = false; L.haveLast = false; L.haveCache = false;
+    L.lastVz = 0; L.lastTime = 0; L.pidLastError = 0; L.pidIntegral = 0;
+    L.nSteps = 0; L.nEvals = 0; L.nRejects = 0; L.nEvents = 0; L.nSteps3 = 0; L.nEvals3 = 0; L.nEvalsTransonic = 0;
+    L.turb = (int)B[H_TURB];
+    for (int g = 0; g < 3; g++) { L.png[g].rng.mt = nullptr; L.png[g].rng.idx = 624; L.png[g].rng.hasNext = 0; L.png[g].rng.next = 0; L.png[g].last0 = 0; L.png[g].last1 = 0; L.png[g].nextSlot = 0; L.png[g].lastValTime = 0; }
+    if (L.turb >= TURB_PINK1D && L.turb <= TURB_PINK3D) {
+        const int ng = (L.turb == TURB_PINK1D) ? 1 : (L.turb == TURB_PINK2D ? 2 : 3);
+        for (int g = 0; g < ng; g++) {
+            double seed = in.pinkSeed ? in.pinkSeed[g * in.nLanes + lane] : B[H_PINK_SEED + g];
+            L.png[g].rng.mt = mtBase + ((size_t)lane * 3 + g) * 624;
+            pinkInit(L.png[g], (uint64_t)seed, B[H_PINK_C0], B[H_PINK_C1]);
+        }
+    }
+    L.nStages = (int)B[H_NSTAGES];
+    L.onRail = B[H_RAIL_LEN] > 0;
+    for (int si = 0; si < MLB_MAX_STAGES; si++) { L.ignitionTime[si] = 0; L.engineShutOff[si] = -1; }
+    for (int si = 0; si < L.nStages; si++) {
+        const double* S = B + (int)B[H_STAGE_OFF + si];
+        L.ignitionTime[si] = S[S_IGNITION0];
+        L.engineShutOff[si] = S[S_BURN_DURATION];
+    }
+    /* RecoverySystem.__init__ -> _deployNextStage(): chute stage 0, subscribes the first trigger */
+    L.recoveryStage = -1;
+    if (B[H_RECOVERY_OFF] != 0) deployNextRecoveryStage(B, L);
+    laneFinConstants(B, L);
+}
+
+}  // namespace mlb

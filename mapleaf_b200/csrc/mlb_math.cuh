@@ -1,0 +1,147 @@
+/*
+ * mlb_math.cuh — FP64 value types of the batched trajectory kernels (device side).
+ *
+ * 3-vector, quaternion and rigid-body-state algebra with the operation order of the reference's
+ * native value types, so that fixed-step trajectories agree with the reference to ~1e-13:
+ *   MAPLEAF/Motion/CythonVector.pyx:13-139, CythonQuaternion.pyx:13-226, CythonAngularVelocity.pyx:78-86
+ *   MAPLEAF/Motion/RigidBodyStates.py:12-88 (3-DoF), :110-211 (6-DoF state / derivative algebra)
+ * Quirks that are observable in results are kept: in-place normalize that
+ * skips the divide when the norm is exactly 1, rotationAxis() dividing by sqrt(norm - q0^2),
+ * rotationAngle() = 2 atan2(sqrt(1 - q0^2), q0).
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#define MLB_DEV __device__ __forceinline__
+#define MLB_PI 3.141592653589793
+
+namespace mlb {
+
+struct V3 { double x, y, z; };
+struct Q4 { double w, x, y, z; };
+
+MLB_DEV V3 v3(double x, double y, double z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+MLB_DEV V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+MLB_DEV V3 operator-(V3 a) { return v3(-a.x, -a.y, -a.z); }
+MLB_DEV V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }          /* a + (-b): identical in IEEE */
+MLB_DEV V3 operator*(V3 a, double s) { return v3(a.x * s, a.y * s, a.z * s); }
+MLB_DEV V3 vdiv(V3 a, double s) { return a * (1 / s); }                                    /* CythonVector.pyx:105 */
+MLB_DEV double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+MLB_DEV double len(V3 a) { return sqrt(a.x * a.x + a.y * a.y + a.z * a.z); }
+MLB_DEV V3 normalize(V3 a) {                                                               /* :118 — zero stays zero */
+    double l = len(a);
+    if (l > 0) return v3(a.x / l, a.y / l, a.z / l);
+    return v3(0, 0, 0);
+}
+MLB_DEV V3 cross(V3 a, V3 b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+MLB_DEV double angleBetween(V3 a, V3 b) {                                                  /* :132 */
+    double interior = dot(a, b) / (len(a) * len(b));
+    if (fabs(interior - 1) < 0.00000001) return 0.0;                                       /* acos(1) */
+    return acos(interior);
+}
+
+MLB_DEV Q4 q4(double w, double x, double y, double z) { Q4 r; r.w = w; r.x = x; r.y = y; r.z = z; return r; }
+MLB_DEV Q4 qIdentity() { return q4(1, 0, 0, 0); }
+MLB_DEV Q4 qAxisAngle(V3 axis, double angle) {                                             /* CythonQuaternion.pyx:50 */
+    V3 ax = normalize(axis);
+    double s, c;
+    sincos(angle / 2, &s, &c);
+    return q4(c, s * ax.x, s * ax.y, s * ax.z);
+}
+MLB_DEV Q4 operator*(Q4 a, Q4 b) {                                                         /* :102 */
+    return q4(a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z,
+              a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y,
+              a.w * b.y - a.x * b.z + a.y * b.w + a.z * b.x,
+              a.w * b.z + a.x * b.y - a.y * b.x + a.z * b.w);
+}
+MLB_DEV double qNorm(Q4 q) { return sqrt(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z); }
+MLB_DEV void qNormalize(Q4& q) {                                                           /* :144 */
+    double n = qNorm(q);
+    if (n == 1.0) return;
+    q.w = q.w / n; q.x = q.x / n; q.y = q.y / n; q.z = q.z / n;
+}
+MLB_DEV Q4 qConj(Q4 q) { return q4(q.w, -q.x, -q.y, -q.z); }
+/* q (0,v) q* for a unit q, written out: the (0,v) factor makes a quarter of the products of two full
+   quaternion multiplications vanish, and the scalar part of the result is never used. Term order follows
+   the two Hamilton products of CythonQuaternion.pyx:164-169 with the zero terms dropped. */
+MLB_DEV V3 qRotateUnit(Q4 q, V3 v) {
+    double tw = -q.x * v.x - q.y * v.y - q.z * v.z;
+    double tx = q.w * v.x + q.y * v.z - q.z * v.y;
+    double ty = q.w * v.y - q.x * v.z + q.z * v.x;
+    double tz = q.w * v.z + q.x * v.y - q.y * v.x;
+    return v3(-tw * q.x + tx * q.w - ty * q.z + tz * q.y,
+              -tw * q.y + tx * q.z + ty * q.w - tz * q.x,
+              -tw * q.z - tx * q.y + ty * q.x + tz * q.w);
+}
+MLB_DEV V3 qRotate(Q4& q, V3 v) { qNormalize(q); return qRotateUnit(q, v); }               /* normalizes the receiver */
+MLB_DEV V3 qConjRotate(Q4 q, V3 v) { Q4 c = qConj(q); return qRotate(c, v); }
+MLB_DEV double qRotationAngle(Q4& q) {                                                     /* :205 */
+    qNormalize(q);
+    return 2 * atan2(sqrt(1 - q.w * q.w), q.w);
+}
+MLB_DEV V3 qRotationAxis(Q4& q) {                                                          /* :197 */
+    if (fabs(qRotationAngle(q)) > 0) {
+        double n = sqrt(qNorm(q) - q.w * q.w);
+        return v3(q.x / n, q.y / n, q.z / n);
+    }
+    return v3(1, 0, 0);
+}
+MLB_DEV Q4 qScaleRotation(Q4& q, double s) {                                               /* :128 */
+    double a = qRotationAngle(q);
+    if (a == 0) return q;
+    return qAxisAngle(qRotationAxis(q), s * a);
+}
+MLB_DEV Q4 angVelToQuat(V3 w) { return qAxisAngle(normalize(w), len(w)); }                 /* CythonAngularVelocity.pyx:78 */
+
+/* Rigid-body state and its time derivative. Under a parachute the body is 3-DoF (rocket.py:700-726): only
+   pos / vel are integrated; the caller passes `dof3` and orientation / angular velocity stay identity / zero. */
+struct State { V3 pos, vel; Q4 q; V3 w; };
+struct Deriv { V3 vel, acc, angvel, angacc; };
+
+MLB_DEV State stateAdd(State& self, const State& o, bool dof3) {                          /* RigidBodyStates.py:110-117 / :24-29 */
+    State r;
+    r.pos = self.pos + o.pos;
+    r.vel = self.vel + o.vel;
+    if (dof3) { r.q = qIdentity(); r.w = v3(0, 0, 0); return r; }
+    r.w = self.w + o.w;
+    qNormalize(self.q);
+    r.q = o.q * self.q;
+    qNormalize(r.q);
+    return r;
+}
+MLB_DEV State stateScale(State& self, double s, bool dof3) {                               /* :119-131 / :31-37 */
+    State r;
+    r.pos = self.pos * s;
+    r.vel = self.vel * s;
+    if (dof3) { r.q = qIdentity(); r.w = v3(0, 0, 0); return r; }
+    r.w = self.w * s;
+    r.q = qScaleRotation(self.q, s);
+    return r;
+}
+MLB_DEV State stateNeg(const State& self, bool dof3) {                                     /* :154-155 / :49-50 */
+    State r;
+    r.pos = self.pos * -1.0; r.vel = self.vel * -1.0;
+    if (dof3) { r.q = qIdentity(); r.w = v3(0, 0, 0); return r; }
+    r.q = qConj(self.q); r.w = self.w * -1.0;
+    return r;
+}
+MLB_DEV double stateAbs(State& self, bool dof3) {                                          /* :133-139 / :40-44 */
+    double positionMag = len(self.pos) + len(self.vel);
+    if (dof3) return positionMag;
+    double orientationMag = fabs(qRotationAngle(self.q)) + len(self.w);
+    return orientationMag * 100 + positionMag;
+}
+MLB_DEV State derivTimes(const Deriv& d, double dt, bool dof3) {                           /* :173-188: derivative * dt -> state increment */
+    State r;
+    r.pos = d.vel * dt;
+    r.vel = d.acc * dt;
+    if (dof3) { r.q = qIdentity(); r.w = v3(0, 0, 0); return r; }
+    r.q = angVelToQuat(d.angvel * dt);
+    qNormalize(r.q);
+    r.w = d.angacc * dt;
+    return r;
+}
+
+}  // namespace mlb

