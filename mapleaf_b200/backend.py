@@ -17,7 +17,7 @@ import numpy as np
 from .model import L
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "lib", "libmapleaf_b200.so")
+LIB_PATH = os.environ.get("MLB_LIB") or os.path.join(_PKG_DIR, "lib", "libmapleaf_b200.so")     # MLB_LIB: tuning variants
 CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
 INCLUDE_DIR = os.path.join(_PKG_DIR, "..", "include")
 TRACE_W = 16

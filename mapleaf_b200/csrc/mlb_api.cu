@@ -23,7 +23,12 @@
 
 using namespace mlb;
 
-#define MLB_BLOCK 128
+#define MLB_BLOCK 128               /* threads per CTA of the small helper kernels */
+#define MLB_K_SLOTS_MAX 14          /* RK78: 13 stages + first-same-as-last */
+/* The integrate kernel is built for three CTA shapes. Larger CTAs make larger convoys (see mlb_integrate.cuh) and are
+   faster as long as every SM gets a CTA; registers per lane shrink accordingly (255 / 128 / 64). */
+#define MLB_NUM_SHAPES 3
+static const int kShapeBlock[MLB_NUM_SHAPES] = { 128, 512, 1024 };
 #define TRACE_W 16
 #define MLB_NCOUNTERS 6
 
@@ -44,23 +49,27 @@ __device__ __forceinline__ void traceRow(const RunArgs& a, const Lane& L, long l
     T[14] = dt; T[15] = err; rows++;
 }
 
-__global__ void __launch_bounds__(MLB_BLOCK) integrateLanes(const RunArgs a) {
+template <int BLOCK, int MIN_BLOCKS>
+__global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) integrateLanes(const RunArgs a) {
     extern __shared__ double smem[];
     double* B = smem;
     for (int i = threadIdx.x; i < a.blobLen; i += blockDim.x) B[i] = a.blob[i];
     __syncthreads();
     const long long lane = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (lane >= a.in.nLanes) return;
-    KStore ks; ks.base = smem + a.blobPad + threadIdx.x; ks.stride = blockDim.x; ks.fsalSlot = a.nSlots - 1;
+    const bool inRange = lane < a.in.nLanes;          /* out-of-range threads stay: they take part in the CTA's barriers */
+    /* RK stage derivatives: per-thread local memory (L1-resident, hardware-interleaved across the warp), indexed
+       dynamically by the tableau loops */
+    double kLocal[MLB_K_SLOTS_MAX * 12];
+    KStore ks; ks.base = kLocal; ks.stride = 1;
 
     Lane L;
-    laneInit(B, L, a.in, lane, a.mt);
+    laneInit(B, L, a.in, inRange ? lane : 0, inRange ? a.mt : nullptr, inRange);
     double dt = B[H_DT0];
     double apogee = -10000000, maxSpeed = 0, maxH = 0;
     V3 prevPos = L.s.pos, lastPos = L.s.pos;
     const long long maxSteps = (long long)B[H_MAX_STEPS];
     int st = ST_OK;
-    const bool tracing = (a.trace != nullptr && lane == a.traceLane);
+    const bool tracing = (a.trace != nullptr && inRange && lane == a.traceLane);
     long long rows = 0;
 
     /* RocketFlight reductions (rocketFlight.py:27-50), kept as running values */
@@ -69,22 +78,28 @@ __global__ void __launch_bounds__(MLB_BLOCK) integrateLanes(const RunArgs a) {
     maxH = fmax(maxH, sqrt(L.s.vel.x * L.s.vel.x + L.s.vel.y * L.s.vel.y));
     if (tracing) traceRow(a, L, rows, 0.0, 0.0);
 
-    bool end, haveFinal; double finalDt;
-    endDetector(B, L, dt, end, haveFinal, finalDt);
-    while (!end) {                                                                          /* SingleSimulations.py:102-139 */
-        if (haveFinal) dt = finalDt;
-        if (a.dtReplay && L.nSteps < a.nReplay) dt = a.dtReplay[L.nSteps];
-        StepResult r = rocketTimeStep(B, L, ks, dt);
-        dt = r.dt * r.factor;
-        prevPos = lastPos; lastPos = L.s.pos;
-        if (L.s.pos.z > apogee) apogee = L.s.pos.z;
-        double sp = len(L.s.vel); if (sp > maxSpeed) maxSpeed = sp;
-        double hv = sqrt(L.s.vel.x * L.s.vel.x + L.s.vel.y * L.s.vel.y); if (hv > maxH) maxH = hv;
-        if (tracing) traceRow(a, L, rows, r.dt, r.err);
-        if (!(L.s.pos.z == L.s.pos.z) || !(L.s.vel.x == L.s.vel.x)) { st = ST_NAN; break; }
-        if (L.nSteps >= maxSteps) { st = ST_STEP_LIMIT; break; }
-        endDetector(B, L, dt, end, haveFinal, finalDt);
+    bool end = true, haveFinal = false; double finalDt = 0;
+    if (inRange) endDetector(B, L, dt, end, haveFinal, finalDt);
+    while (MLB_ANY(!end)) {                                                                 /* SingleSimulations.py:102-139 */
+        const bool run = !end;
+        if (run) {
+            if (haveFinal) dt = finalDt;
+            if (a.dtReplay && L.nSteps < a.nReplay) dt = a.dtReplay[L.nSteps];
+        }
+        StepResult r = rocketTimeStep(B, L, ks, dt, run);
+        if (run) {
+            dt = r.dt * r.factor;
+            prevPos = lastPos; lastPos = L.s.pos;
+            if (L.s.pos.z > apogee) apogee = L.s.pos.z;
+            double sp = len(L.s.vel); if (sp > maxSpeed) maxSpeed = sp;
+            double hv = sqrt(L.s.vel.x * L.s.vel.x + L.s.vel.y * L.s.vel.y); if (hv > maxH) maxH = hv;
+            if (tracing) traceRow(a, L, rows, r.dt, r.err);
+            if (!(L.s.pos.z == L.s.pos.z) || !(L.s.vel.x == L.s.vel.x)) { st = ST_NAN; end = true; }
+            else if (L.nSteps >= maxSteps) { st = ST_STEP_LIMIT; end = true; }
+            else endDetector(B, L, dt, end, haveFinal, finalDt);
+        }
     }
+    if (!inRange) return;
 
     /* RocketFlight.getLandingLocation (rocketFlight.py:52-76): linear extrapolation of the last two positions to z = 0 */
     double* R = a.results + lane * RES_SIZE;
@@ -105,7 +120,7 @@ __global__ void __launch_bounds__(MLB_BLOCK) integrateLanes(const RunArgs a) {
 }
 
 __global__ void __launch_bounds__(MLB_BLOCK) forceEvalKernel(const double* blob, int blobLen, long long n, const double* states, const double* times,
-                                                             const double* winds, double* out) {
+                                                             const double* winds, uint32_t* mt, double* out) {
     extern __shared__ double smem[];
     double* B = smem;
     for (int i = threadIdx.x; i < blobLen; i += blockDim.x) B[i] = blob[i];
@@ -114,7 +129,7 @@ __global__ void __launch_bounds__(MLB_BLOCK) forceEvalKernel(const double* blob,
     if (i >= n) return;
     Lane L;
     LaneInputs in; in.wind = nullptr; in.initState = nullptr; in.pinkSeed = nullptr; in.nLanes = 1;
-    laneInit(B, L, in, 0, nullptr);
+    laneInit(B, L, in, 0, mt ? mt + (size_t)i * 3 * 624 : nullptr, mt != nullptr);      /* each state gets its own generator block */
     if (winds) { L.wind = v3(winds[3 * i], winds[3 * i + 1], winds[3 * i + 2]); laneFinConstants(B, L); }
     const double* s13 = states + 13 * i;
     State s; s.pos = v3(s13[0], s13[1], s13[2]); s.vel = v3(s13[3], s13[4], s13[5]);
@@ -195,6 +210,7 @@ struct mlb_handle {
     bool ran = false;
     long long launches = 0;
     int nSlots = 0; size_t smemBytes = 0;
+    int nSM = 148; int forceBlock = 0; int lastBlock = 0;
 };
 
 static int laneArrayComponents(int id) { return id == LANE_WIND ? 3 : (id == LANE_INIT_STATE ? 13 : (id == LANE_PINK_SEED ? 3 : -1)); }
@@ -229,13 +245,17 @@ extern "C" int mlb_create(const void* model_blob, size_t n, int device, mlb_hand
     h->blob.assign(b, b + len);
     int method = (int)b[H_INTEGRATOR];
     int nRows = (int)b[H_TAB_NSTAGE_ROWS];
-    h->nSlots = (method == INT_EULER) ? 1 : nRows + 1 + (method >= INT_RK12A ? 1 : 0);
+    h->nSlots = (method == INT_EULER) ? 1 : nRows + 1;
     size_t blobPad = (len + 1) & ~(size_t)1;
-    h->smemBytes = (blobPad + (size_t)h->nSlots * 12 * MLB_BLOCK) * sizeof(double);
+    h->smemBytes = blobPad * sizeof(double);
     if (h->smemBytes > 227 * 1024) { delete h; return fail(MLB_ERR_UNSUPPORTED, "mlb_create: model block + stage storage exceed shared memory"); }
     CU(cudaMalloc(&h->d_blob, len * sizeof(double)));
     CU(cudaMemcpy(h->d_blob, b, len * sizeof(double), cudaMemcpyHostToDevice));
-    CU(cudaFuncSetAttribute(integrateLanes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
+    CU(cudaFuncSetAttribute(integrateLanes<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
+    CU(cudaFuncSetAttribute(integrateLanes<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
+    CU(cudaFuncSetAttribute(integrateLanes<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
+    { cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, device)); h->nSM = prop.multiProcessorCount; }
+    { const char* e = getenv("MLB_BLOCK_SIZE"); h->forceBlock = e ? atoi(e) : 0; }
     CU(cudaFuncSetAttribute(forceEvalKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(blobPad * sizeof(double))));
     CU(cudaEventCreate(&h->ev0)); CU(cudaEventCreate(&h->ev1));
     CU(cudaMalloc(&h->d_traceRows, sizeof(long long)));
@@ -299,9 +319,16 @@ extern "C" int mlb_run(mlb_handle* h, void* stream) {
     a.trace = (h->traceLane >= 0 && h->traceLane < h->nLanes) ? h->d_trace : nullptr;
     a.traceLane = h->traceLane; a.traceMaxRows = h->traceMaxRows; a.traceRows = h->d_traceRows;
     a.dtReplay = h->d_replay; a.nReplay = h->nReplay;
-    unsigned grid = (unsigned)((h->nLanes + MLB_BLOCK - 1) / MLB_BLOCK);
+    /* largest CTA shape that still gives every SM a CTA (MLB_BLOCK_SIZE overrides, for tuning) */
+    int block = 128;
+    for (int k = 0; k < MLB_NUM_SHAPES; k++) if (h->nLanes >= (long long)h->nSM * kShapeBlock[k]) block = kShapeBlock[k];
+    if (h->forceBlock == 128 || h->forceBlock == 512 || h->forceBlock == 1024) block = h->forceBlock;
+    h->lastBlock = block;
+    unsigned grid = (unsigned)((h->nLanes + block - 1) / block);
     CU(cudaEventRecord(h->ev0, s));
-    integrateLanes<<<grid, MLB_BLOCK, h->smemBytes, s>>>(a);
+    if (block == 1024) integrateLanes<1024, 1><<<grid, 1024, h->smemBytes, s>>>(a);
+    else if (block == 512) integrateLanes<512, 1><<<grid, 512, h->smemBytes, s>>>(a);
+    else integrateLanes<128, 2><<<grid, 128, h->smemBytes, s>>>(a);
     CU(cudaGetLastError());
     CU(cudaEventRecord(h->ev1, s));
     h->launches = 1;
@@ -422,16 +449,18 @@ extern "C" int mlb_set_dt_replay(mlb_handle* h, const double* dts, int64_t n) {
 extern "C" int mlb_force_eval(mlb_handle* h, int64_t n, const double* states, const double* times, const double* winds, double* out) {
     if (!h || n <= 0 || !states || !times || !out) return fail(MLB_ERR_ARG, "mlb_force_eval: bad arguments");
     CU(cudaSetDevice(h->device));
-    double *d_s = nullptr, *d_t = nullptr, *d_w = nullptr, *d_o = nullptr;
+    double *d_s = nullptr, *d_t = nullptr, *d_w = nullptr, *d_o = nullptr; uint32_t* d_mt = nullptr;
+    int turb = (int)h->blob[H_TURB];
+    if (turb >= TURB_PINK1D && turb <= TURB_PINK3D) CU(cudaMalloc(&d_mt, (size_t)n * 3 * 624 * sizeof(uint32_t)));
     CU(cudaMalloc(&d_s, (size_t)n * 13 * sizeof(double))); CU(cudaMalloc(&d_t, (size_t)n * sizeof(double))); CU(cudaMalloc(&d_o, (size_t)n * 18 * sizeof(double)));
     CU(cudaMemcpy(d_s, states, (size_t)n * 13 * sizeof(double), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(d_t, times, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
     if (winds) { CU(cudaMalloc(&d_w, (size_t)n * 3 * sizeof(double))); CU(cudaMemcpy(d_w, winds, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice)); }
     size_t blobPad = (h->blob.size() + 1) & ~(size_t)1;
-    forceEvalKernel<<<(unsigned)((n + MLB_BLOCK - 1) / MLB_BLOCK), MLB_BLOCK, blobPad * sizeof(double)>>>(h->d_blob, (int)h->blob.size(), n, d_s, d_t, d_w, d_o);
+    forceEvalKernel<<<(unsigned)((n + MLB_BLOCK - 1) / MLB_BLOCK), MLB_BLOCK, blobPad * sizeof(double)>>>(h->d_blob, (int)h->blob.size(), n, d_s, d_t, d_w, d_mt, d_o);
     cudaError_t e = cudaDeviceSynchronize();
     if (e == cudaSuccess) e = cudaMemcpy(out, d_o, (size_t)n * 18 * sizeof(double), cudaMemcpyDeviceToHost);
-    cudaFree(d_s); cudaFree(d_t); cudaFree(d_w); cudaFree(d_o);
+    cudaFree(d_s); cudaFree(d_t); cudaFree(d_w); cudaFree(d_o); cudaFree(d_mt);
     if (e != cudaSuccess) return fail(MLB_ERR_CUDA, std::string("mlb_force_eval: ") + cudaGetErrorString(e));
     return MLB_OK;
 }

@@ -24,7 +24,7 @@
 namespace mlb {
 
 struct KStore {
-    double* base; int stride; int fsalSlot;      /* fsalSlot: where the adaptive integrator keeps its first-same-as-last derivative */
+    double* base; int stride;
     MLB_DEV void put(int slot, const Deriv& d, bool dof3) const {
         double* p = base + (size_t)slot * 12 * stride;
         p[0] = d.vel.x; p[stride] = d.vel.y; p[2 * stride] = d.vel.z;
@@ -76,75 +76,100 @@ MLB_DEV bool pyIsClose(double a, double b) {                                    
     return (diff <= fabs(1e-9 * b)) || (diff <= fabs(1e-9 * a));
 }
 
+/* Convoy execution. The force model is ~10^4 SASS instructions per evaluation, several times the SM's instruction
+   cache, and warps that drift apart each stream it from L2 on their own (measured: 74 % of warp cycles stalled on
+   instruction fetch, ICC hit rate 46 %). With MLB_LOCKSTEP the CTA's warps re-group at a barrier before every
+   derivative evaluation, so one warp's fetch serves the others. All control flow around the barriers is CTA-uniform:
+   lanes that have nothing to do in a stage / attempt / step stay in the loops with `active` false. */
+#ifndef MLB_LOCKSTEP
+#define MLB_LOCKSTEP 1
+#endif
+#if MLB_LOCKSTEP
+#define MLB_CONVOY_SYNC() __syncthreads()
+#define MLB_ANY(pred) __syncthreads_or(pred)
+#else
+#define MLB_CONVOY_SYNC()
+#define MLB_ANY(pred) (pred)
+#endif
+
 /* One Runge-Kutta step of either family. The stage loop has ONE call site of the (large) state-derivative code, shared
    by the first stage, the classical and the adaptive stage composition and the adaptive retry loop, so the force model is
-   instantiated once in the kernel. */
-MLB_DEV StepResult integrateStep(const double* B, Lane& L, const KStore& ks, State& y, double t, double dt) {
+   instantiated once in the kernel. `active` false: the lane only keeps the CTA's barriers company. */
+MLB_DEV StepResult integrateStep(const double* B, Lane& L, const KStore& ks, State& y, double t, double dt, bool active) {
     const int method = (int)B[H_INTEGRATOR];
     const bool adaptive = method >= INT_RK12A;
     const double* tab = B + (int)B[H_TABLEAU_OFF];
     const int nRows = (method == INT_EULER) ? 0 : (int)B[H_TAB_NSTAGE_ROWS];
     const double target = B[H_AD_TARGET], minDt = B[H_AD_MINDT];
-    StepResult r; r.factor = 1.0; r.err = 0.0;
+    StepResult r; r.factor = 1.0; r.err = 0.0; r.dt = dt;
     double err = 10000000;
     if (adaptive) dt *= 3;                                                                  /* Integration.py:335: first attempt = requested dt */
+    bool attempting = active;
     for (;;) {
         const bool dof3 = L.dof3;
-        if (adaptive) {
+        if (attempting && adaptive) {
             if (err != 10000000) L.nRejects++;
             dt = fmax(minDt, dt / 3);
         }
         for (int i = -1; i < nRows; i++) {
-            State evalY; double evalTime;
-            if (i < 0) {
-                if (adaptive && L.haveCache) { ks.put(0, ks.get(ks.fsalSlot, dof3), dof3); continue; }
-                evalY = y; evalTime = t;
-            } else {
-                const double* row = tab + i * TABLEAU_STRIDE;
-                evalTime = t + dt * row[0];
-                if (!adaptive) {                                                            /* :216-231 */
-                    Deriv evalK = derivScaled(ks.get(0, dof3), 1 / (1 / (row[1] * dt)), dof3);
-                    for (int a = 2; a < i + 2; a++) evalK = derivAdd(evalK, derivScaled(ks.get(a - 1, dof3), 1 / (1 / (row[a] * dt)), dof3), dof3);
-                    evalY = stateAdd(y, derivTimes(evalK, 1.0, dof3), dof3);
-                } else {                                                                    /* :420-432 */
-                    State evalK = derivTimes(ks.get(0, dof3), row[1], dof3);
-                    for (int a = 2; a < i + 2; a++) evalK = stateAdd(evalK, derivTimes(ks.get(a - 1, dof3), row[a], dof3), dof3);
-                    evalY = stateAdd(y, stateScale(evalK, dt, dof3), dof3);
+            /* slot 0 may already hold the last stage of the previous accepted step (first-same-as-last) */
+            const bool evalNow = attempting && !(i < 0 && adaptive && L.haveCache);
+            State evalY; double evalTime = t;
+            if (evalNow) {
+                if (i < 0) evalY = y;
+                else {
+                    const double* row = tab + i * TABLEAU_STRIDE;
+                    evalTime = t + dt * row[0];
+                    if (!adaptive) {                                                        /* :216-231 */
+                        Deriv evalK = derivScaled(ks.get(0, dof3), 1 / (1 / (row[1] * dt)), dof3);
+                        for (int a = 2; a < i + 2; a++) evalK = derivAdd(evalK, derivScaled(ks.get(a - 1, dof3), 1 / (1 / (row[a] * dt)), dof3), dof3);
+                        evalY = stateAdd(y, derivTimes(evalK, 1.0, dof3), dof3);
+                    } else {                                                                /* :420-432 */
+                        State evalK = derivTimes(ks.get(0, dof3), row[1], dof3);
+                        for (int a = 2; a < i + 2; a++) evalK = stateAdd(evalK, derivTimes(ks.get(a - 1, dof3), row[a], dof3), dof3);
+                        evalY = stateAdd(y, stateScale(evalK, dt, dof3), dof3);
+                    }
                 }
             }
-            ks.put(i + 1, stateDerivative(B, L, evalTime, evalY, dof3), dof3);
+            MLB_CONVOY_SYNC();
+            if (evalNow) ks.put(i + 1, stateDerivative(B, L, evalTime, evalY, dof3), dof3);
         }
-        if (method == INT_EULER) {                                                          /* :192-195 */
-            r.newValue = stateAdd(y, derivTimes(ks.get(0, dof3), dt, dof3), dof3);
-            r.dt = dt;
-            return r;
+        if (attempting) {
+            if (method == INT_EULER) {                                                      /* :192-195 */
+                r.newValue = stateAdd(y, derivTimes(ks.get(0, dof3), dt, dof3), dof3);
+                attempting = false;
+            } else {
+                const double* fr = tab + nRows * TABLEAU_STRIDE;
+                Deriv k0 = ks.get(0, dof3);
+                Deriv fd = derivScaled(k0, 1 / (1 / fr[0]), dof3);
+                if (!adaptive) {                                                            /* :233-236 */
+                    for (int i = 1; i < nRows + 1; i++) fd = derivAdd(fd, derivScaled(ks.get(i, dof3), 1 / (1 / fr[i]), dof3), dof3);
+                    r.newValue = stateAdd(y, derivTimes(fd, dt, dof3), dof3);
+                    attempting = false;
+                } else {
+                    const double* cr = tab + (nRows + 1) * TABLEAU_STRIDE;                  /* :434-447 */
+                    Deriv cd = derivScaled(k0, 1 / (1 / cr[0]), dof3);
+                    for (int i = 1; i < nRows + 1; i++) {
+                        Deriv ki = ks.get(i, dof3);
+                        fd = derivAdd(fd, derivScaled(ki, 1 / (1 / fr[i]), dof3), dof3);
+                        cd = derivAdd(cd, derivScaled(ki, 1 / (1 / cr[i]), dof3), dof3);
+                    }
+                    r.newValue = stateAdd(y, derivTimes(fd, dt, dof3), dof3);
+                    State coarsePred = stateAdd(y, derivTimes(cd, dt, dof3), dof3);
+                    State neg = stateNeg(coarsePred, dof3);
+                    State errEst = stateAdd(neg, r.newValue, dof3);
+                    err = stateAbs(errEst, dof3);
+                    if (!(err > 20 * target) || pyIsClose(dt, minDt)) attempting = false;   /* :338-347 */
+                }
+            }
         }
-        const double* fr = tab + nRows * TABLEAU_STRIDE;
-        Deriv k0 = ks.get(0, dof3);
-        Deriv fd = derivScaled(k0, 1 / (1 / fr[0]), dof3);
-        if (!adaptive) {                                                                    /* :233-236 */
-            for (int i = 1; i < nRows + 1; i++) fd = derivAdd(fd, derivScaled(ks.get(i, dof3), 1 / (1 / fr[i]), dof3), dof3);
-            r.newValue = stateAdd(y, derivTimes(fd, dt, dof3), dof3);
-            r.dt = dt;
-            return r;
-        }
-        const double* cr = tab + (nRows + 1) * TABLEAU_STRIDE;                              /* :434-447 */
-        Deriv cd = derivScaled(k0, 1 / (1 / cr[0]), dof3);
-        for (int i = 1; i < nRows + 1; i++) {
-            Deriv ki = ks.get(i, dof3);
-            fd = derivAdd(fd, derivScaled(ki, 1 / (1 / fr[i]), dof3), dof3);
-            cd = derivAdd(cd, derivScaled(ki, 1 / (1 / cr[i]), dof3), dof3);
-        }
-        r.newValue = stateAdd(y, derivTimes(fd, dt, dof3), dof3);
-        State coarsePred = stateAdd(y, derivTimes(cd, dt, dof3), dof3);
-        State neg = stateNeg(coarsePred, dof3);
-        State errEst = stateAdd(neg, r.newValue, dof3);
-        err = stateAbs(errEst, dof3);
-        if (!(err > 20 * target) || pyIsClose(dt, minDt)) break;                            /* :338-347 */
+        if (!MLB_ANY(attempting)) break;
     }
+    r.dt = dt;
+    if (!active || !adaptive) return r;
     /* accepted adaptive step: FSAL cache, step-size controller (:349-389) */
     if (method == INT_RK45A || method == INT_RK23A) {
-        ks.put(ks.fsalSlot, ks.get(nRows, L.dof3), L.dof3);
+        ks.put(0, ks.get(nRows, L.dof3), L.dof3);            /* becomes k_0 of the next step (attempts never overwrite slot 0) */
         L.haveCache = true;
     }
     const double maxDt = B[H_AD_MAXDT];
@@ -156,7 +181,7 @@ MLB_DEV StepResult integrateStep(const double* B, Lane& L, const KStore& ks, Sta
     double minFactor = fmax(minDt / dt, B[H_AD_MINF]);
     double maxFactor = fmin(maxDt / dt, B[H_AD_MAXF]);
     r.factor = B[H_AD_SAFETY] * fmin(fmax(desired, minFactor), maxFactor);
-    r.dt = dt; r.err = err;
+    r.err = err;
     return r;
 }
 
@@ -248,20 +273,23 @@ MLB_DEV void railMotionConstraint(const double* B, Lane& L) {                   
     } else L.onRail = false;
 }
 
-MLB_DEV StepResult rocketTimeStep(const double* B, Lane& L, const KStore& ks, double dt) {   /* rocket.py:658-698 */
-    railMotionConstraint(B, L);
-    double est; bool det;
-    triggerEvents(B, L, est, det);
-    const bool adaptive = isAdaptive(B);
-    if (adaptive && est < dt) {
-        if (det) dt = est + 1e-5;
-        else dt = fmax(est / 1.5, B[H_EVENT_DT]);
+MLB_DEV StepResult rocketTimeStep(const double* B, Lane& L, const KStore& ks, double dt, bool active) {   /* rocket.py:658-698 */
+    if (active) {
+        railMotionConstraint(B, L);
+        double est; bool det;
+        triggerEvents(B, L, est, det);
+        if (isAdaptive(B) && est < dt) {
+            if (det) dt = est + 1e-5;
+            else dt = fmax(est / 1.5, B[H_EVENT_DT]);
+        }
     }
-    StepResult r = integrateStep(B, L, ks, L.s, L.time, dt);
-    if (L.dof3) L.nSteps3++;
-    L.time += r.dt;
-    L.s = r.newValue;
-    L.nSteps++;
+    StepResult r = integrateStep(B, L, ks, L.s, L.time, dt, active);
+    if (active) {
+        if (L.dof3) L.nSteps3++;
+        L.time += r.dt;
+        L.s = r.newValue;
+        L.nSteps++;
+    }
     return r;
 }
 
@@ -294,7 +322,7 @@ MLB_DEV void laneFinConstants(const double* B, Lane& L) {
     }
 }
 
-MLB_DEV void laneInit(const double* B, Lane& L, const LaneInputs& in, long long lane, uint32_t* mtBase) {
+MLB_DEV void laneInit(const double* B, Lane& L, const LaneInputs& in, long long lane, uint32_t* mtBase, bool live) {
     L.wind = ld3(B + H_WIND_V);
     if (in.wind) L.wind = v3(in.wind[lane], in.wind[in.nLanes + lane], in.wind[2 * in.nLanes + lane]);
     double st[13];
@@ -307,7 +335,7 @@ MLB_DEV void laneInit(const double* B, Lane& L, const LaneInputs& in, long long 
     L.nSteps = 0; L.nEvals = 0; L.nRejects = 0; L.nEvents = 0; L.nSteps3 = 0; L.nEvals3 = 0; L.nEvalsTransonic = 0;
     L.turb = (int)B[H_TURB];
     for (int g = 0; g < 3; g++) { L.png[g].rng.mt = nullptr; L.png[g].rng.idx = 624; L.png[g].rng.hasNext = 0; L.png[g].rng.next = 0; L.png[g].last0 = 0; L.png[g].last1 = 0; L.png[g].nextSlot = 0; L.png[g].lastValTime = 0; }
-    if (L.turb >= TURB_PINK1D && L.turb <= TURB_PINK3D) {
+    if (live && L.turb >= TURB_PINK1D && L.turb <= TURB_PINK3D) {
         const int ng = (L.turb == TURB_PINK1D) ? 1 : (L.turb == TURB_PINK2D ? 2 : 3);
         for (int g = 0; g < ng; g++) {
             double seed = in.pinkSeed ? in.pinkSeed[g * in.nLanes + lane] : B[H_PINK_SEED + g];

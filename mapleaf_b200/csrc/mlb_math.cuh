@@ -17,7 +17,28 @@
 #define MLB_DEV __device__ __forceinline__
 #define MLB_PI 3.141592653589793
 
+#ifndef MLB_MATH_NOINLINE
+#define MLB_MATH_NOINLINE 0
+#endif
+#if MLB_MATH_NOINLINE
+#define MLB_MATHFN static __device__ __noinline__      /* one copy of each libm routine: smaller instruction footprint */
+#else
+#define MLB_MATHFN static __device__ __forceinline__
+#endif
+
 namespace mlb {
+
+MLB_MATHFN double m_sin(double x) { return sin(x); }
+MLB_MATHFN double m_cos(double x) { return cos(x); }
+MLB_MATHFN void m_sincos(double x, double* s, double* c) { sincos(x, s, c); }
+MLB_MATHFN double m_tan(double x) { return tan(x); }
+MLB_MATHFN double m_asin(double x) { return asin(x); }
+MLB_MATHFN double m_acos(double x) { return acos(x); }
+MLB_MATHFN double m_atan2(double y, double x) { return atan2(y, x); }
+MLB_MATHFN double m_exp(double x) { return exp(x); }
+MLB_MATHFN double m_log(double x) { return log(x); }
+MLB_MATHFN double m_pow(double x, double y) { return pow(x, y); }
+MLB_MATHFN double m_cbrt(double x) { return cbrt(x); }
 
 struct V3 { double x, y, z; };
 struct Q4 { double w, x, y, z; };
@@ -39,7 +60,7 @@ MLB_DEV V3 cross(V3 a, V3 b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x 
 MLB_DEV double angleBetween(V3 a, V3 b) {                                                  /* :132 */
     double interior = dot(a, b) / (len(a) * len(b));
     if (fabs(interior - 1) < 0.00000001) return 0.0;                                       /* acos(1) */
-    return acos(interior);
+    return m_acos(interior);
 }
 
 MLB_DEV Q4 q4(double w, double x, double y, double z) { Q4 r; r.w = w; r.x = x; r.y = y; r.z = z; return r; }
@@ -47,7 +68,7 @@ MLB_DEV Q4 qIdentity() { return q4(1, 0, 0, 0); }
 MLB_DEV Q4 qAxisAngle(V3 axis, double angle) {                                             /* CythonQuaternion.pyx:50 */
     V3 ax = normalize(axis);
     double s, c;
-    sincos(angle / 2, &s, &c);
+    m_sincos(angle / 2, &s, &c);
     return q4(c, s * ax.x, s * ax.y, s * ax.z);
 }
 MLB_DEV Q4 operator*(Q4 a, Q4 b) {                                                         /* :102 */
@@ -79,7 +100,7 @@ MLB_DEV V3 qRotate(Q4& q, V3 v) { qNormalize(q); return qRotateUnit(q, v); }    
 MLB_DEV V3 qConjRotate(Q4 q, V3 v) { Q4 c = qConj(q); return qRotate(c, v); }
 MLB_DEV double qRotationAngle(Q4& q) {                                                     /* :205 */
     qNormalize(q);
-    return 2 * atan2(sqrt(1 - q.w * q.w), q.w);
+    return 2 * m_atan2(sqrt(1 - q.w * q.w), q.w);
 }
 MLB_DEV V3 qRotationAxis(Q4& q) {                                                          /* :197 */
     if (fabs(qRotationAngle(q)) > 0) {

@@ -110,8 +110,8 @@ MLB_DEV void atmosphere(const double* B, double asl, Air& e) {
     double temp = Tb + lapse * altitudeAboveBase;
     double Pb = U[24 + baseIndex];
     double pressure;
-    if (lapse == 0) pressure = exp(-G * M * altitudeAboveBase / (R * Tb * 1000)) * Pb;
-    else pressure = pow((Tb + lapse * altitudeAboveBase) / Tb, -G * M / (R * lapse * 1000)) * Pb;
+    if (lapse == 0) pressure = m_exp(-G * M * altitudeAboveBase / (R * Tb * 1000)) * Pb;
+    else pressure = m_pow((Tb + lapse * altitudeAboveBase) / Tb, -G * M / (R * lapse * 1000)) * Pb;
     double rho = M * pressure / (R * temp * 1000);
     double viscosity = 1.457e-6 * (temp * sqrt(temp)) / (temp + 110.4);                    /* temp**1.5 */
     if (H >= 86000) rho = 0.0;
@@ -123,7 +123,7 @@ MLB_DEV V3 meanWindAt(const double* B, const Lane& L, double agl) {
     if (model == WIND_CONSTANT) return L.wind;
     if (model == WIND_HELLMAN) {
         double h = fmax(fmin(B[H_HELLMAN_LIMIT], agl), 10.0);
-        return L.wind * pow(h / 10, B[H_HELLMAN_ALPHA]);
+        return L.wind * m_pow(h / 10, B[H_HELLMAN_ALPHA]);
     }
     int n = (int)B[H_WIND_TAB_N]; const double* T = B + (int)B[H_WIND_TAB_OFF];
     int i = bisectRight(T, n, agl);
@@ -138,9 +138,9 @@ MLB_DEV V3 turbulenceAt(const double* B, Lane& L, double altitude, V3 meanWind, 
         double b1 = start + blend, b2 = start + blend + B[H_GUST_THICK], b3 = start + blend + B[H_GUST_THICK] + blend;
         if (altitude > start) {
             double gustVel;
-            if (altitude < b1) gustVel = mag / 2 * (1 - cos(MLB_PI * (altitude - start) / blend));
+            if (altitude < b1) gustVel = mag / 2 * (1 - m_cos(MLB_PI * (altitude - start) / blend));
             else if (altitude < b2) gustVel = mag;
-            else if (altitude < b3) { double gustThickness = b3 - start; gustVel = mag / 2 * (1 - cos(MLB_PI * (altitude - start - gustThickness) / blend)); }
+            else if (altitude < b3) { double gustThickness = b3 - start; gustVel = mag / 2 * (1 - m_cos(MLB_PI * (altitude - start - gustThickness) / blend)); }
             else return v3(0, 0, 0);
             return ld3(B + H_GUST_DIR) * gustVel;
         }
@@ -270,7 +270,7 @@ MLB_DEV void aeroSetup(const double* B, const Lane& L, Aero& a, const State& s, 
 
 MLB_DEV double sfSub(double Mach, bool smooth) { return smooth ? 1 - 0.10 * (Mach * Mach) : 1 - 0.12 * (Mach * Mach); }   /* AeroFunctions.py:38-51 */
 MLB_DEV double sfSup(double Mach, bool smooth) {                                             /* :53-69 */
-    double smoothTurbFactor = 1 / pow(1 + 0.15 * (Mach * Mach), 0.58);
+    double smoothTurbFactor = 1 / m_pow(1 + 0.15 * (Mach * Mach), 0.58);
     if (smooth) return smoothTurbFactor;
     double roughTurbFactor = 1 / (1 + 0.18 * (Mach * Mach));
     return fmax(smoothTurbFactor, roughTurbFactor);
@@ -283,11 +283,11 @@ MLB_DEV double skinFrictionCoefficient(double unitRe, double length, double Mach
     if (Re > criticalRe) cf = roughCf;
     else if (fullyTurb) {
         if (Re < 1e4) cf = 0.0148;
-        else { double t = 1.5 * log(Re) - 5.6; cf = 1 / (t * t); }
+        else { double t = 1.5 * m_log(Re) - 5.6; cf = 1 / (t * t); }
     } else {
         if (Re < 1e4) cf = 0.01328;
         else if (Re < 5e5) cf = 1.328 / sqrt(Re);
-        else { double t = 1.5 * log(Re) - 5.6; cf = 1 / (t * t) - 1700 / Re; }
+        else { double t = 1.5 * m_log(Re) - 5.6; cf = 1 / (t * t) - 1700 / Re; }
     }
     double corr;
     if (Mach < 0.9) corr = sfSub(Mach, smooth);
@@ -311,7 +311,7 @@ MLB_DEV double cylinderSkinFriction(const Aero& a, double length, double roughne
 }
 MLB_DEV double baseDragCoefficient(double Mach) { return (Mach < 1) ? 0.12 + 0.13 * Mach * Mach : 0.25 / Mach; }   /* :171-175 */
 MLB_DEV double cylinderCrossFlowCd(double Mach) {                                           /* :177-189 */
-    if (Mach < 0.9) return pow(1 - Mach * Mach, -0.417) - 1;
+    if (Mach < 0.9) return m_pow(1 - Mach * Mach, -0.417) - 1;
     if (Mach <= 1) return 1 - 1.5 * (Mach - 0.9);
     double m2 = Mach * Mach, m4 = m2 * m2, m6 = m4 * m2;
     return 1.214 - 0.502 / m2 + 0.1095 / m4 + .0231 / m6;
@@ -331,11 +331,11 @@ MLB_DEV ForceMoment forceFromCdCN(const Aero& a, double Cd, double CN, V3 CP, V3
     V3 totalForce = ((v3(0, 0, -CA) + a.normalDir * CN) * a.Aref) * a.q;
     return fm(totalForce, CP, moment);
 }
-MLB_DEV double barrowmanCN(double AOA, double Aref, double top, double bottom) { return 2 * sin(AOA) * (bottom - top) / Aref; }   /* :284-289 */
+MLB_DEV double barrowmanCN(double AOA, double Aref, double top, double bottom) { return 2 * m_sin(AOA) * (bottom - top) / Aref; }   /* :284-289 */
 MLB_DEV double conePressureCd(const double* sub, const double* trans, double halfAngle, double Mach) {   /* noseCone.py:199-212 */
-    if (Mach < 1) return sub[0] * pow(Mach, sub[1]);
+    if (Mach < 1) return sub[0] * m_pow(Mach, sub[1]);
     if (Mach > 1 && Mach < 1.3) return trans[0] + trans[1] * Mach + trans[2] * (Mach * Mach) + trans[3] * (Mach * Mach * Mach);
-    double sh = sin(halfAngle);
+    double sh = m_sin(halfAngle);
     return 2.1 * (sh * sh) + 0.5 * sh / sqrt(Mach * Mach - 1);
 }
 
@@ -350,7 +350,7 @@ MLB_DEV ForceMoment noseConeForce(const Aero& a, const double* C) {             
     return forceFromCdCN(a, pressure + skin, CN, ld3(C + NC_CP), roll);
 }
 MLB_DEV ForceMoment bodyTubeForce(const Aero& a, const double* C, V3 CG) {                  /* bodyTube.py:35-97 */
-    double sa = sin(a.totalAOA);
+    double sa = m_sin(a.totalAOA);
     double CN = 1.1 * (sa * sa);
     CN *= C[BT_PLANFORM] / a.Aref;
     V3 roll;
@@ -393,7 +393,7 @@ MLB_DEV ForceMoment transitionForce(const Lane& L, const Aero& a, const double* 
 MLB_DEV double finCnAlphaSubsonic(const double* C, double Mach) {                           /* Fins.py:26-34 */
     double beta = betaOf(Mach);
     double AR = 2 * (C[FS_SPAN] * C[FS_SPAN]) / C[FS_PLANFORM];
-    double t = beta * AR / cos(C[FS_MIDSWEEP]);
+    double t = beta * AR / m_cos(C[FS_MIDSWEEP]);
     return (2 * MLB_PI * AR) / (2 + sqrt(4 + t * t));
 }
 struct Busemann { double K1, K2, K3, negZPerRadius; };
@@ -406,7 +406,7 @@ MLB_DEV Busemann busemann(double Mach) {                                        
     k.K1 = 2 / beta;
     k.K2 = ((gamma + 1) * M4 - 4 * b2) / (4 * b4);
     k.K3 = ((gamma + 1) * M8 + (2 * (gamma * gamma) - 7 * gamma - 5) * M6 + 10 * (gamma + 1) * M4 - 12 * M2 + 8) / (6 * b7);
-    k.negZPerRadius = 1 / tan(asin(1 / Mach));
+    k.negZPerRadius = 1 / m_tan(m_asin(1 / Mach));
     return k;
 }
 /* Interpolation.py:86-107 with the precomputed inverse constraint matrix; the 4x4 by 4x1 product is summed
@@ -464,11 +464,11 @@ MLB_DEV ForceMoment finSetForce(const double* B, const Aero& a, const double* C,
     double skinDrag = cf * (C[FS_WETTED] / Aref);
     skinDrag *= (1 + 2 * C[FS_THICK] / C[FS_MAC_LEN]);
     double leCd = (C[FS_LE_SHAPE] == 0) ? cylinderCrossFlowCd(Mach) : bluntBodyCd(Mach);
-    double cs = cos(C[FS_SWEEP]);
+    double cs = m_cos(C[FS_SWEEP]);
     leCd *= C[FS_LE_THICK] * C[FS_SPAN] * (cs * cs) / Aref;
     double teCd = baseDragCoefficient(Mach) * C[FS_SPAN] * C[FS_TE_THICK] / Aref;
     double tc = C[FS_THICK] / C[FS_ROOT];
-    double cm = cos(C[FS_MIDSWEEP]);
+    double cm = m_cos(C[FS_MIDSWEEP]);
     double thicknessDrag;
     if (Mach <= 1) {
         double tc2 = tc * tc, d = thickK - (Mach * Mach) * (cm * cm);
@@ -507,7 +507,7 @@ MLB_DEV ForceMoment finSetForce(const double* B, const Aero& a, const double* C,
             if (finVelMag >= 0.1) {
                 double body = dot(finNormal, finVelocity) * (1 / finVelMag);
                 if (fabs(body - 1) < 1e-14) body = 1.0;
-                al = asin(body);
+                al = m_asin(body);
             }
             if (fabs(al) > stall) al *= fabs(stall / al);
             aoa[i] = al;
@@ -560,10 +560,10 @@ MLB_DEV double finThicknessK(const double* B, Lane& L, const double* C) {
     Air e = airProperties(B, L, ld3(B + H_NOSE_POS0), 0, false);
     double unitRe = len(localFrameAirVel(m1, e.wind)) * e.density / e.viscosity;
     double CD_f_star = skinFrictionCoefficient(unitRe, C[FS_MAC_LEN], 1.0, C[FS_ROUGH], C[FS_CRIT_RE], C[FS_ROUGH_CF], B[H_FULLY_TURB] != 0);
-    double cm = cos(C[FS_MIDSWEEP]);
+    double cm = m_cos(C[FS_MIDSWEEP]);
     double tc = C[FS_THICK] / C[FS_ROOT];
     double t = (C[FS_CDTT_STAR] / CD_f_star - 4 * cm * tc) / (120 * (cm * cm) * ((tc * tc) * (tc * tc)));
-    return cm * cm + cbrt(t * t);
+    return cm * cm + m_cbrt(t * t);
 }
 
 /* ---------------------------------------------------------------------------------------------
