@@ -110,7 +110,7 @@ def algorithmicFlops(c):
 def runB200(args):
     import torch
     import torch.distributed as dist
-    from mapleaf_b200 import L, SimDefinition, backend, buildModel
+    from mapleaf_b200 import L, SimDefinition, backend, buildModel, distributed
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -145,7 +145,6 @@ def runB200(args):
     batch.setLanesDevice(n, {L.LANE_WIND: dWind.data_ptr(), L.LANE_PINK_SEED: dSeeds.data_ptr()}, keepAlive=(dWind, dSeeds))
     batch.setResultBuffers(mine.data_ptr(), mineStatus.data_ptr(), keepAlive=(gathered, gatheredStatus))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
-    momentsAll = torch.empty((world, 15), dtype=torch.float64, device=dev)
 
     def onePass():
         flush.zero_()
@@ -155,10 +154,9 @@ def runB200(args):
             # the only exchange of the path: landing locations / apogees / ... of every sample, and the moments
             dist.all_gather_into_tensor(gathered.view(-1), mine.reshape(-1))
             dist.all_gather_into_tensor(gatheredStatus.view(-1), mineStatus)
-            cnt, mean, M2 = batch.moments()
+            cnt, mean, M2 = batch.moments()               # per-GPU count / mean / M2 (device kernels), combined over ranks
             launches += 2
-            momentsAll[rank] = torch.from_numpy(np.concatenate([[cnt], np.c_[mean, M2].reshape(-1)])).to(dev)
-            dist.all_gather_into_tensor(momentsAll.view(-1), momentsAll[rank].clone())
+            distributed.gatherMoments(cnt, mean, M2, device=dev)
         return launches
 
     for _ in range(args.warmup):

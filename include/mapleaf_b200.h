@@ -81,7 +81,8 @@ int mlb_results(mlb_handle* h, double* results, int32_t* status);
 /* finals: nLanes x 14 row-major: position, velocity, orientation quaternion, body angular velocity, time */
 int mlb_finals(mlb_handle* h, double* finals);
 int mlb_counters(mlb_handle* h, mlb_counters_t* out);
-/* per lane: steps, derivative evaluations, rejected attempts (nLanes x 3) */
+/* per lane (nLanes x 6): steps, derivative evaluations, rejected attempts, 3-DoF steps, 3-DoF evaluations,
+   transonic 6-DoF evaluations */
 int mlb_lane_counters(mlb_handle* h, int64_t* out);
 /* Device addresses of the result block (nLanes x 7 doubles) and status (nLanes int32): the send buffers of the
    multi-GPU gather. Valid until the next mlb_set_lanes* or mlb_destroy. */

@@ -186,7 +186,7 @@ class TrajectoryBatch:
         return c.asdict()
 
     def laneCounters(self):
-        out = np.empty((self.nLanes, 3), dtype=np.int64)
+        out = np.empty((self.nLanes, 6), dtype=np.int64)
         _check(lib().mlb_lane_counters(self._h, out.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))), "mlb_lane_counters")
         return out
 

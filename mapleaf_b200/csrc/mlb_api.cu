@@ -364,9 +364,7 @@ extern "C" int mlb_finals(mlb_handle* h, double* finals) {
 extern "C" int mlb_lane_counters(mlb_handle* h, int64_t* out) {
     int rc = needRun(h, "mlb_lane_counters"); if (rc) return rc;
     if (!out) return fail(MLB_ERR_ARG, "mlb_lane_counters: null buffer");
-    std::vector<long long> c((size_t)h->nLanes * MLB_NCOUNTERS);
-    CU(cudaMemcpy(c.data(), h->d_counters, c.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-    for (long long i = 0; i < h->nLanes; i++) for (int k = 0; k < 3; k++) out[3 * i + k] = c[MLB_NCOUNTERS * i + k];
+    CU(cudaMemcpy(out, h->d_counters, (size_t)h->nLanes * MLB_NCOUNTERS * sizeof(long long), cudaMemcpyDeviceToHost));
     return MLB_OK;
 }
 extern "C" int mlb_counters(mlb_handle* h, mlb_counters_t* out) {

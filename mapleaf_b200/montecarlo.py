@@ -1,0 +1,283 @@
+"""
+Monte Carlo runner with the reference's entry point, running every sampled rocket as one lane of the
+B200 trajectory kernels.
+
+Mirrors MAPLEAF/SimulationRunners/MonteCarlo.py:
+    runMonteCarloSimulation(simDefinitionFilePath, simDefinition, silent, nCores)      :10-20
+    _prepSim ....................................................................... :22-46
+    _runSimulations_B200  (replaces _runSimulations_SingleThreaded :48-76 / _Parallel :78-146, same fill contract)
+    _showResults ................................................................... :148-174
+and the text half of IO/Plotting.plotAndSummarize{Vector,Scalar}Result (:671-752) and IO/Logging.MonteCarloLogger (:61-89).
+
+Sampling is the reference's: one `random.Random` owned by the SimDefinition, re-drawn once per run in dictionary order
+(IO/simDefinition.py:471-532), pink-noise seeds from the global `random` module, two (1D: one, 3D: three) per run
+(ENV/TurbulenceModelling.py:191-195). The Monte Carlo log has the same lines in the same order.
+What differs: all runs are sampled first and then flown together, so sampled keys must be ones the kernels take per
+lane (wind, initial state); any other `_stdDev` key raises NotImplementedError naming it. There is no CPU fallback.
+"""
+import os
+import random
+from statistics import mean, stdev
+from typing import List, Optional
+
+import numpy as np
+
+from . import hostmath as hm
+from .model import L, buildModel, initialStateLaunchTowerFrame
+from .simdef import SimDefinition, SubDictReader, parseVector
+
+__all__ = ["runMonteCarloSimulation", "MonteCarloLogger", "Vector", "MonteCarloResults", "laneInitialState"]
+
+# sampled keys the kernels accept per lane (everything else would change the model block itself)
+_WIND_KEY = "Environment.ConstantMeanWind.velocity"
+_INIT_STATE_KEYS = {"Rocket.position", "Rocket.velocity", "Rocket.initialDirection", "Rocket.angularVelocity", "Rocket.rotationAngle"}
+_EXACT_STATISTICS_LIMIT = 100000      # statistics.mean/stdev (exact rational arithmetic, as the reference) up to here
+
+
+class Vector:
+    """Minimal stand-in for MAPLEAF.Motion.Vector in result lists: X/Y/Z, iteration, str and format like the reference
+    (Motion/CythonVector.pyx:65-72)."""
+    __slots__ = ("X", "Y", "Z")
+
+    def __init__(self, X, Y, Z):
+        self.X, self.Y, self.Z = float(X), float(Y), float(Z)
+
+    def __iter__(self):
+        return iter((self.X, self.Y, self.Z))
+
+    def __getitem__(self, i):
+        return (self.X, self.Y, self.Z)[i]
+
+    def __format__(self, fmt_spec=""):
+        return "{} {} {}".format(*(format(c, fmt_spec) for c in (self.X, self.Y, self.Z)))
+
+    def __str__(self):
+        return "({} {} {})".format(self.X, self.Y, self.Z)
+
+    def __eq__(self, other):
+        return tuple(self) == tuple(other)
+
+
+class MonteCarloLogger:
+    """IO/Logging.py:61-89: lines go to the console and to the log that is written next to the definition file."""
+
+    def __init__(self, monteCarloLog=None, echo=True):
+        self.monteCarloLog = [] if monteCarloLog is None else monteCarloLog
+        self.echo = echo
+        from datetime import datetime
+        from platform import platform
+        self.monteCarloLog += ["# mapleaf_b200 (B200 batched trajectory kernels behind MAPLEAF's Monte Carlo interface)",
+                               "# Date: {}".format(datetime.now()), "# Platform: {}".format(platform()), ""]
+
+    def log(self, string):
+        self.monteCarloLog.append(string)
+        if self.echo:
+            print(string)
+
+    def writeToFile(self, fileBaseName="monteCarloLog", filePath=None):
+        if filePath is None:
+            n = 0
+            while filePath is None or os.path.exists(filePath):
+                n += 1
+                filePath = fileBaseName + str(n) + ".txt"
+        with open(filePath, "w+") as f:
+            for line in self.monteCarloLog:
+                f.write(line if (len(line) > 0 and line[-1] == "\n") else line + "\n")
+        return filePath
+
+
+class MonteCarloResults:
+    """What a run returns in addition to the reference's side effects (the reference returns None)."""
+
+    def __init__(self, results, status, counters, logPath, outputLists):
+        self.results, self.status, self.counters, self.logPath = results, status, counters, logPath
+        self.landingLocations, self.apogees, self.maxSpeeds, self.flightTimes, self.maxHorizontalVels, self.flights = outputLists
+
+
+def laneInitialState(simDefinition: SimDefinition, model) -> List[float]:
+    """Initial inertial-frame state of the CG for the current (sampled) Rocket.* values: rocket.py:251-291,416-421."""
+    rk = SubDictReader("Rocket", simDefinition)
+    initPos, initVel, q0, w0 = initialStateLaunchTowerFrame(rk)
+    initPos = hm.v_add(initPos, (0, 0, model.header("H_ELEV")))
+    if model.header("H_RAIL_LEN") > 0:
+        w0 = (0.0, 0.0, 0.0)
+    cgGlobal, q0n = hm.q_rotate(q0, model.meta["initialInertia"].CG)
+    return list(hm.v_add(initPos, cgGlobal)) + list(initVel) + list(q0n) + list(w0)
+
+
+def loadSimDefinition(simDefinitionFilePath=None, simDefinition=None, silent=False) -> SimDefinition:
+    """SingleSimulations.py:15-26"""
+    if simDefinition is None and simDefinitionFilePath is not None:
+        return SimDefinition(simDefinitionFilePath, silent=silent)
+    if simDefinition is not None:
+        return simDefinition
+    raise ValueError("No definition file path or SimDefinition object provided to the Monte Carlo runner")
+
+
+def _prepSim(simDefinition, echo=True):
+    simDefinition.setValue("SimControl.plot", "None")
+    simDefinition.setValue("SimControl.RocketPlot", "Off")
+    nRuns = int(simDefinition.getValue("MonteCarlo.numberRuns"))
+    mCLogger = MonteCarloLogger(echo=echo)
+    mCLogger.log("")
+    mCLogger.log("Running Monte Carlo Simulation: {} runs".format(nRuns))
+    simDefinition.monteCarloLogger = mCLogger
+    outputLists = [[], [], [], [], [], []]
+    return nRuns, mCLogger, outputLists
+
+
+def _checkSampledKeys(simDefinition):
+    keys = simDefinition.probabilisticKeys()
+    bad = [k for k in keys if k != _WIND_KEY and k not in _INIT_STATE_KEYS]
+    if bad:
+        raise NotImplementedError("Monte Carlo sampling of {} is not implemented by the B200 backend: per-lane inputs are {} and {}".format(
+            ", ".join(bad), _WIND_KEY, ", ".join(sorted(_INIT_STATE_KEYS))))
+    if any(k in _INIT_STATE_KEYS for k in keys) and float(simDefinition.getValue("Environment.LaunchSite.railLength")) > 0 \
+            and "Rocket.initialDirection" in keys:
+        raise NotImplementedError("Sampling Rocket.initialDirection with a launch rail (the rail direction is part of the model block)")
+    return keys
+
+
+def sampleRuns(simDefinition, nRuns, mCLogger, model):
+    """Draws every run's inputs in the reference's order (MonteCarlo.py:64-72) and returns the per-lane arrays."""
+    keys = _checkSampledKeys(simDefinition)
+    sampleWind = _WIND_KEY in keys
+    sampleState = any(k in _INIT_STATE_KEYS for k in keys)
+    turb = int(model.header("H_TURB"))
+    nGen = {L.TURB_PINK1D: 1, L.TURB_PINK2D: 2, L.TURB_PINK3D: 3}.get(turb, 0)
+    hasSeed = int(model.header("H_PINK_HAS_SEED"))
+    wind = np.empty((3, nRuns)) if sampleWind else None
+    state = np.empty((13, nRuns)) if sampleState else None
+    seeds = np.zeros((3, nRuns)) if nGen else None
+    for i in range(nRuns):
+        mCLogger.log("\nMonte Carlo Run #{}".format(i + 1))
+        simDefinition.resampleProbabilisticValues()
+        if sampleWind:
+            wind[:, i] = parseVector(simDefinition.getValue(_WIND_KEY))
+        if sampleState:
+            state[:, i] = laneInitialState(simDefinition, model)
+        for g in range(nGen):
+            # PinkNoiseGenerator.__init__ draws from the *global* random module when no seed key is given
+            seeds[g, i] = model.blob[L.H_PINK_SEED + g] if (hasSeed >> g) & 1 else random.randrange(1000000)
+    arrays = {}
+    if sampleWind:
+        arrays[L.LANE_WIND] = wind
+    if sampleState:
+        arrays[L.LANE_INIT_STATE] = state
+    if nGen:
+        arrays[L.LANE_PINK_SEED] = seeds
+    return arrays
+
+
+def _runSimulations_B200(simDefinition, nRuns, outputLists, mCLogger, silent=False, nGPUs=1, device=0):
+    """Same fill contract as _runSimulations_SingleThreaded: outputLists filled in sample order."""
+    from . import backend
+    landingLocations, apogees, maxSpeeds, flightTimes, maxHorizontalVels, flights = outputLists
+    resultsToOutput = simDefinition.getValue("MonteCarlo.output")
+    if "flightPaths" in resultsToOutput:
+        mCLogger.log("NOTE: MonteCarlo.output flightPaths is not produced by the B200 backend (per-step trajectories stay on the device)")
+    model = buildModel(simDefinition)
+    arrays = sampleRuns(simDefinition, nRuns, mCLogger, model)
+
+    # contiguous sample ranges per GPU: gathered results are already in sample order
+    nGPUs = max(1, min(int(nGPUs), nRuns))
+    bounds = [nRuns * g // nGPUs for g in range(nGPUs + 1)]
+    batches = []
+    for g in range(nGPUs):
+        lo, hi = bounds[g], bounds[g + 1]
+        b = backend.TrajectoryBatch(model.blob, device=device + g)
+        b.setLanes(hi - lo, {k: np.ascontiguousarray(a[:, lo:hi]) for k, a in arrays.items()})
+        b.run()                                   # asynchronous: all GPUs integrate concurrently
+        batches.append(b)
+    results = np.empty((nRuns, L.RES_SIZE))
+    status = np.empty(nRuns, dtype=np.int32)
+    counters = []
+    for g, b in enumerate(batches):
+        r, s = b.results()
+        results[bounds[g]:bounds[g + 1]], status[bounds[g]:bounds[g + 1]] = r, s
+        counters.append(b.counters())
+        b.close()
+
+    failed = np.nonzero(status != L.ST_OK)[0]
+    if failed.size:
+        names = {L.ST_STEP_LIMIT: "step limit", L.ST_NAN: "NaN state", L.ST_UNSUPPORTED: "unsupported"}
+        mCLogger.log("WARNING: {} of {} runs did not end normally: {}".format(
+            failed.size, nRuns, ", ".join("#{} ({})".format(i + 1, names.get(int(status[i]), status[i])) for i in failed[:20])))
+    for i in range(nRuns):
+        landingLocations.append(Vector(results[i, L.RES_LAND_X], results[i, L.RES_LAND_Y], results[i, L.RES_LAND_Z]))
+    apogees.extend(results[:, L.RES_APOGEE].tolist())
+    maxSpeeds.extend(results[:, L.RES_MAX_SPEED].tolist())
+    flightTimes.extend(results[:, L.RES_FLIGHT_TIME].tolist())
+    maxHorizontalVels.extend(results[:, L.RES_MAX_HVEL].tolist())
+    return results, status, counters
+
+
+def _mean(x):
+    return mean(x) if len(x) <= _EXACT_STATISTICS_LIMIT else float(np.mean(np.asarray(x, dtype=np.float64)))
+
+
+def _stdev(x):
+    if len(x) < 2:
+        return float("nan")
+    return stdev(x) if len(x) <= _EXACT_STATISTICS_LIMIT else float(np.std(np.asarray(x, dtype=np.float64), ddof=1))
+
+
+def summarizeVectorResult(vectorList, name="Landing location", monteCarloLogger=None):
+    """Text of Plotting.plotAndSummarizeVectorResult (IO/Plotting.py:671-699)."""
+    out = ["{}s:   X       Y        Z".format(name)]
+    x, y, z = [], [], []
+    for i, loc in enumerate(vectorList):
+        out.append("Simulation #{}:   {:>7.1f}".format(i + 1, loc))
+        x.append(loc.X), y.append(loc.Y), z.append(loc.Z)
+    out.append("")
+    out.append("Mean {}: ({:>8.1f} {:>8.1f} {:>8.1f})".format(name, _mean(x), _mean(y), _mean(z)))
+    out.append("Standard deviation:    ({:>8.1f} {:>8.1f} {:>8.1f})".format(_stdev(x), _stdev(y), _stdev(z)))
+    out.append("")
+    for line in out:
+        monteCarloLogger.log(line) if monteCarloLogger is not None else print(line)
+
+
+def summarizeScalarResult(scalarList, name="Apogee", monteCarloLogger=None):
+    """Text of Plotting.plotAndSummarizeScalarResult (IO/Plotting.py:723-741)."""
+    out = ["{}s:".format(name)]
+    for i, v in enumerate(scalarList):
+        out.append("Simulation #{}: {}".format(i + 1, v))
+    out.append("")
+    out.append("Mean {}:        {:>8.1f}".format(name, _mean(scalarList)))
+    out.append("Standard Deviation: {:>8.1f}".format(_stdev(scalarList)))
+    out.append("")
+    for line in out:
+        monteCarloLogger.log(line) if monteCarloLogger is not None else print(line)
+
+
+def _showResults(simDefinition, outputLists, mCLogger):
+    landingLocations, apogees, maxSpeeds, flightTimes, maxHorizontalVels, flights = outputLists
+    resultsToOutput = simDefinition.getValue("MonteCarlo.output")
+    mCLogger.log("")
+    mCLogger.log("Monte Carlo results:")
+    if "landingLocations" in resultsToOutput:
+        summarizeVectorResult(landingLocations, name="Landing location", monteCarloLogger=mCLogger)
+    if "apogees" in resultsToOutput:
+        summarizeScalarResult(apogees, name="Apogee", monteCarloLogger=mCLogger)
+    if "maxSpeeds" in resultsToOutput:
+        summarizeScalarResult(maxSpeeds, name="Max speed", monteCarloLogger=mCLogger)
+    if "flightTimes" in resultsToOutput:
+        summarizeScalarResult(flightTimes, name="Flight time", monteCarloLogger=mCLogger)
+    if "maxHorizontalVels" in resultsToOutput:
+        summarizeScalarResult(maxHorizontalVels, name="Max horizontal speed", monteCarloLogger=mCLogger)
+    logPath = None
+    if resultsToOutput != "None" and len(resultsToOutput) > 0 and simDefinition.fileName:
+        dotIndex = simDefinition.fileName.rfind(".")
+        logPath = mCLogger.writeToFile(fileBaseName=simDefinition.fileName[0:dotIndex] + "_monteCarloLog_run")
+        print("Wrote Monte Carlo Log to: {}".format(logPath))
+    return logPath
+
+
+def runMonteCarloSimulation(simDefinitionFilePath=None, simDefinition=None, silent=False, nCores=1, nGPUs: Optional[int] = None, device: int = 0):
+    """Drop-in for MAPLEAF.SimulationRunners.runMonteCarloSimulation. `nCores` (the reference's ray fan-out) is accepted
+    and ignored; `nGPUs` spreads contiguous sample ranges over that many GPUs of this box. Returns MonteCarloResults."""
+    simDefinition = loadSimDefinition(simDefinitionFilePath, simDefinition, silent)
+    nRuns, mCLogger, outputLists = _prepSim(simDefinition, echo=not silent)
+    results, status, counters = _runSimulations_B200(simDefinition, nRuns, outputLists, mCLogger, silent, nGPUs=nGPUs or 1, device=device)
+    logPath = _showResults(simDefinition, outputLists, mCLogger)
+    return MonteCarloResults(results, status, counters, logPath, outputLists)

@@ -260,3 +260,24 @@ def test_moments_match_numpy(backend):
     assert cnt == n
     assert np.allclose(mean, res.mean(axis=0), rtol=1e-12, atol=1e-9)
     assert np.allclose(M2 / (n - 1), res.var(axis=0, ddof=1), rtol=1e-9, atol=1e-9)
+
+
+def test_runner_end_to_end_matches_reference_run(backend, golden, tmp_path):
+    """runMonteCarloSimulation on the GPU: the reference's CLI anchor (seed "2394781", 3 runs to the ground)."""
+    from mapleaf_b200 import runMonteCarloSimulation
+    g = golden("rk4_ground.json")
+    sd = SimDefinition(os.path.join(DATA, g["definition"]), silent=True, disableDistributionSampling=True)
+    sd.setValue("MonteCarlo.randomSeed", g["randomSeed"])
+    sd.setValue("MonteCarlo.numberRuns", "3")
+    sd.setValue("MonteCarlo.output", "landingLocations apogees maxSpeeds flightTimes maxHorizontalVels")
+    for k, v in g["overrides"].items():
+        sd.setValue(k, v)
+    sd = SimDefinition(dictionary=dict(sd.dict), silent=True)
+    sd.fileName = str(tmp_path / "MonteCarlo.mapleaf")
+    out = runMonteCarloSimulation(simDefinition=sd, silent=True)
+    assert (out.status == L.ST_OK).all()
+    for i, r in enumerate(g["runs"]):
+        assert relErr(out.results[i], r["results"]) < FIXED_TOL
+        assert abs(out.apogees[i] - r["results"][3]) < 1e-6 and abs(out.flightTimes[i] - r["results"][5]) < 1e-6
+    log = open(out.logPath).read()
+    assert "Monte Carlo Run #3" in log and "Mean Landing location" in log and "Mean Max horizontal speed" in log

@@ -1,0 +1,192 @@
+"""
+CPU tests of the host side: the Monte Carlo runner's sampling order and log format, the C-ABI library's exported symbols,
+the bit-exact host samplers and the multi-GPU gather logic (gloo, world size 2). No CUDA device is used; where a run needs
+trajectories, the test substitutes the CPU oracle for the device (tests are the only place allowed to do that).
+"""
+import ctypes
+import os
+import random
+import re
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import DATA, REPO
+from mapleaf_b200 import L, SimDefinition, buildModel, montecarlo
+from mapleaf_b200 import backend, distributed
+
+
+class OracleBatch:
+    """Stands in for backend.TrajectoryBatch in host-logic tests: same methods, trajectories from the CPU oracle."""
+
+    def __init__(self, blob, device=0):
+        self.blob, self.device = np.asarray(blob, dtype=np.float64), device
+
+    def setLanes(self, n, arrays=None):
+        self.n, self.arrays = n, arrays or {}
+
+    def run(self, stream=0, sync=False):
+        from oracle import oracle
+        self.out = oracle.run(self.blob, self.n, self.arrays)
+
+    def results(self):
+        return self.out["results"], self.out["status"]
+
+    def counters(self):
+        c = self.out["counters"]
+        return dict(lanes=self.n, steps=int(c[:, 0].sum()), derivative_evals=int(c[:, 1].sum()), rejected_steps=int(c[:, 2].sum()))
+
+    def close(self):
+        pass
+
+
+def montecarloDefinition(tmp_path, nRuns=3, **overrides):
+    sd = SimDefinition(os.path.join(DATA, "MonteCarlo.mapleaf"), silent=True, disableDistributionSampling=True)
+    sd.setValue("MonteCarlo.randomSeed", "2394781")
+    sd.setValue("MonteCarlo.numberRuns", str(nRuns))
+    for k, v in overrides.items():
+        sd.setValue(k, v)
+    sd = SimDefinition(dictionary=dict(sd.dict), silent=True)           # seeds the rng with the *string* seed, consumes draw set 1
+    sd.fileName = str(tmp_path / "MonteCarlo.mapleaf")
+    return sd
+
+
+def test_library_exports_every_declared_symbol():
+    path = backend.buildLibrary()
+    lib = ctypes.CDLL(path)
+    hdr = open(os.path.join(REPO, "include", "mapleaf_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(mlb_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert sorted(backend.EXPORTED_SYMBOLS) == sorted(n for n in declared)
+    lib.mlb_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.mlb_version()
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(backend, "_lib", None)
+    monkeypatch.setattr(backend, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        backend.lib()
+
+
+def test_no_device_is_an_error_not_a_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    m = buildModel(SimDefinition(os.path.join(DATA, "MonteCarlo.mapleaf"), silent=True, disableDistributionSampling=True))
+    with pytest.raises(RuntimeError, match="no CPU path|no CUDA"):
+        backend.TrajectoryBatch(m.blob)
+
+
+def test_host_samplers_are_cpython_exact():
+    r = random.Random("2394781")
+    ref = [r.gauss(m, s) for _ in range(50) for m, s in ((2, 5), (0, 5), (0, 0.5))]
+    got = backend.hostGaussStream("2394781", [2, 0, 0], [5, 5, 0.5], 50)
+    assert list(got.reshape(-1)) == ref
+    assert list(backend.hostGaussStream("2394781", [2, 0, 0], [5, 5, 0.5], 10, skipDraws=120).reshape(-1)) == ref[120:150]
+    r = random.Random(987654321012)
+    ref = [float(r.randrange(1000000)) for _ in range(200)]
+    assert list(backend.hostRandrangeStream(987654321012, 1000000, 150, skipDraws=50)) == ref[50:]
+    assert list(backend.seedKey(2 ** 40 + 5)) == [5, 256]
+
+
+def test_runner_sampling_order_and_log(monkeypatch, tmp_path, golden, capsys):
+    """Run #i of the runner uses draw set i+1 of random.Random("2394781") (set 0 is consumed at construction) and the
+    log has the reference's lines in the reference's order (MonteCarlo.py:67, simDefinition.py:508-532, Plotting.py:671-741)."""
+    g = golden("rk4_apogee.json")
+    monkeypatch.setattr(backend, "TrajectoryBatch", OracleBatch)
+    sd = montecarloDefinition(tmp_path, nRuns=3, **{"MonteCarlo.output": "landingLocations apogees"})
+    out = montecarlo.runMonteCarloSimulation(simDefinition=sd, silent=True)
+    for i in range(3):
+        ref = g["runs"][i]
+        assert np.allclose(out.results[i, 3:7], ref["results"][3:7], rtol=1e-12)
+        assert out.apogees[i] == out.results[i, L.RES_APOGEE]
+        assert tuple(out.landingLocations[i]) == tuple(out.results[i, 0:3])
+    log = open(out.logPath).read().splitlines()
+    body = [l for l in log if not l.startswith("#")]
+    assert "Running Monte Carlo Simulation: 3 runs" in body
+    i1 = body.index("Monte Carlo Run #1")
+    assert body[i1 + 1] == "Sampling vector parameter: Environment.ConstantMeanWind.velocity, value: ({:1.3f} {:1.3f} {:1.3f})".format(*g["runs"][0]["wind"])
+    assert body.index("Monte Carlo Run #2") > i1 and "Monte Carlo results:" in body
+    assert "Landing locations:   X       Y        Z" in body
+    assert any(l.startswith("Mean Landing location: (") for l in body) and any(l.startswith("Standard deviation:    (") for l in body)
+    assert "Simulation #1: {}".format(out.apogees[0]) in body
+    from statistics import mean, stdev
+    assert "Mean Apogee:        {:>8.1f}".format(mean(out.apogees)) in body
+    assert "Standard Deviation: {:>8.1f}".format(stdev(out.apogees)) in body
+    assert out.logPath.endswith("MonteCarlo_monteCarloLog_run1.txt")
+
+
+def test_runner_pink_noise_seeds_follow_the_global_stream(monkeypatch, tmp_path, golden):
+    g = golden("rk45_pink.json")
+    sd = SimDefinition(os.path.join(DATA, "MonteCarloAdaptive.mapleaf"), silent=True, disableDistributionSampling=True)
+    sd.setValue("MonteCarlo.randomSeed", g["randomSeed"])
+    sd = SimDefinition(dictionary=dict(sd.dict), silent=True)
+    model = buildModel(sd)
+    random.seed(g["globalSeed"])
+    arrays = montecarlo.sampleRuns(sd, len(g["runs"]), montecarlo.MonteCarloLogger(echo=False), model)
+    for i, r in enumerate(g["runs"]):
+        assert list(arrays[L.LANE_WIND][:, i]) == r["wind"]
+        assert list(arrays[L.LANE_PINK_SEED][:2, i]) == [float(s) for s in r["pinkSeeds"]]
+
+
+def test_runner_rejects_sampled_keys_it_cannot_vary_per_lane(tmp_path):
+    sd = montecarloDefinition(tmp_path, nRuns=2, **{"Rocket.Sustainer.Motor.impulseAdjustFactor": "1.0",
+                                                     "Rocket.Sustainer.Motor.impulseAdjustFactor_stdDev": "0.02"})
+    with pytest.raises(NotImplementedError, match="impulseAdjustFactor"):
+        montecarlo._checkSampledKeys(sd)
+
+
+def test_sampled_initial_state_matches_model_builder(tmp_path):
+    sd = montecarloDefinition(tmp_path, nRuns=2)
+    sd.setValue("Rocket.initialDirection", "(0 0.1 1)")
+    m = buildModel(sd)
+    assert montecarlo.laneInitialState(sd, m) == list(m.blob[L.H_INIT_STATE:L.H_INIT_STATE + 13])
+
+
+def test_moments_combination_matches_numpy():
+    rng = np.random.default_rng(3)
+    x = rng.normal(size=(1000, 7)) * np.arange(1, 8) + 100
+    parts = [distributed.momentsOf(x[a:b]) for a, b in ((0, 10), (10, 500), (500, 1000))]
+    n, mean, std = distributed.combineMoments(parts)
+    assert n == 1000 and np.allclose(mean, x.mean(axis=0), rtol=1e-13) and np.allclose(std, x.std(axis=0, ddof=1), rtol=1e-12)
+    assert [distributed.shardRange(10, r, 4) for r in range(4)] == [(0, 2), (2, 5), (5, 7), (7, 10)]
+
+
+def _gatherWorker(rank, world, port, tmp):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, REPO)
+    from mapleaf_b200 import L, SimDefinition, buildModel, distributed
+    from oracle import oracle
+    m = buildModel(SimDefinition(os.path.join(REPO, "mapleaf_b200", "data", "Simulations", "MonteCarlo.mapleaf"), silent=True, disableDistributionSampling=True))
+    nTotal = 8
+    w = np.random.default_rng(11).normal(size=(3, nTotal)) * 5            # every rank derives the same full sample stream ...
+    lo, hi = distributed.shardRange(nTotal, rank, world)                  # ... and flies its own contiguous range
+    o = oracle.run(m.blob, hi - lo, {L.LANE_WIND: np.ascontiguousarray(w[:, lo:hi])})
+    res, st = distributed.gatherResults(torch.from_numpy(o["results"]), torch.from_numpy(o["status"]))
+    n, mean, std = distributed.gatherMoments(*distributed.momentsOf(o["results"], o["status"]))
+    np.save(os.path.join(tmp, "res{}.npy".format(rank)), res.numpy())
+    np.save(os.path.join(tmp, "mom{}.npy".format(rank)), np.concatenate([[n], mean, std]))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gather_restores_sample_order(tmp_path):
+    """world_size 2 over gloo: contiguous shards, one all-gather of results + status, combined moments on every rank."""
+    import torch.multiprocessing as mp
+    from oracle import oracle
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_gatherWorker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    m = buildModel(SimDefinition(os.path.join(DATA, "MonteCarlo.mapleaf"), silent=True, disableDistributionSampling=True))
+    w = np.random.default_rng(11).normal(size=(3, 8)) * 5
+    full = oracle.run(m.blob, 8, {L.LANE_WIND: w})["results"]
+    for rank in range(2):
+        assert np.array_equal(np.load(tmp_path / "res{}.npy".format(rank)), full)
+        mom = np.load(tmp_path / "mom{}.npy".format(rank))
+        assert mom[0] == 8 and np.allclose(mom[1:8], full.mean(axis=0), rtol=1e-12) and np.allclose(mom[8:], full.std(axis=0, ddof=1), rtol=1e-10)
