@@ -279,7 +279,12 @@
 #define FS_CDTT_STAR 124
 #define FS_CRIT_RE 125
 #define FS_ROUGH_CF 126
-#define FS_SIZE 128
+/* per fin, constant while the fin is not actuated (Fins.py:474-482,532-551): deflected normal, axial (drag) direction,
+   spanwise CP distance |span * (MACY + bodyRadius)| */
+#define FS_FIN_NORMAL 128
+#define FS_AXIAL_DIR 152
+#define FS_SPANWISE_CP 176
+#define FS_SIZE 184
 
 /* tabulated motor (Rocket/Propulsion.py:8-128). Table: 10 columns of MT_NROWS each, column-major,
    starting at C_P+MT_TABLE: time, thrust, oxWeight, fuelWeight, oxMOI xyz, fuelMOI xyz */

@@ -244,8 +244,13 @@ MLB_DEV Inertia rocketInertia(const double* B, const Lane& L, double time, doubl
 /* ---------------------------------------------------------------------------------------------
  * Aerodynamic helper quantities (Motion/AeroParameters.py) and coefficient models (Rocket/AeroFunctions.py)
  * ------------------------------------------------------------------------------------------- */
+MLB_DEV double dragToAxialFactor(double AOA);
+MLB_DEV double baseDragCoefficient(double Mach);
+MLB_DEV double skinFrictionCompressibility(double Mach, bool smooth);
+
 struct Aero {
     double Mach, totalAOA, q, airSpeed, unitRe, density, finenessRatio, Aref, time;
+    double sinAOA, axialFactor, baseDrag, sfCorrRough;      /* functions of Mach / total AOA only, shared by every component */
     V3 lfav, normalDir, w;
     bool fullyTurb;
 };
@@ -266,6 +271,10 @@ MLB_DEV void aeroSetup(const double* B, const Lane& L, Aero& a, const State& s, 
     a.finenessRatio = B[H_FINENESS + L.nStages - 1];
     a.fullyTurb = B[H_FULLY_TURB] != 0;
     a.Aref = B[H_AREF];
+    a.sinAOA = m_sin(a.totalAOA);
+    a.axialFactor = dragToAxialFactor(a.totalAOA);
+    a.baseDrag = baseDragCoefficient(a.Mach);
+    a.sfCorrRough = skinFrictionCompressibility(a.Mach, false);
 }
 
 MLB_DEV double sfSub(double Mach, bool smooth) { return smooth ? 1 - 0.10 * (Mach * Mach) : 1 - 0.12 * (Mach * Mach); }   /* AeroFunctions.py:38-51 */
@@ -275,8 +284,14 @@ MLB_DEV double sfSup(double Mach, bool smooth) {                                
     double roughTurbFactor = 1 / (1 + 0.18 * (Mach * Mach));
     return fmax(smoothTurbFactor, roughTurbFactor);
 }
-/* getSkinFrictionCoefficient (:71-136). criticalRe / roughCf are the component's roughness constants from the model block. */
-MLB_DEV double skinFrictionCoefficient(double unitRe, double length, double Mach, double roughness, double criticalRe, double roughCf, bool fullyTurb) {
+MLB_DEV double skinFrictionCompressibility(double Mach, bool smooth) {                     /* :117-134 */
+    if (Mach < 0.9) return sfSub(Mach, smooth);
+    if (Mach < 1.1) { double sub = sfSub(Mach, smooth), sup = sfSup(Mach, smooth); return sub + ((sup - sub) * (Mach - 0.9) / 0.2); }
+    return sfSup(Mach, smooth);
+}
+/* getSkinFrictionCoefficient (:71-136). criticalRe / roughCf are the component's roughness constants from the model block;
+   corrRough is the compressibility correction of a rough surface at this Mach number (computed once per evaluation). */
+MLB_DEV double skinFrictionCoefficient(double unitRe, double length, double Mach, double roughness, double criticalRe, double roughCf, bool fullyTurb, double corrRough) {
     double Re = unitRe * length;
     bool smooth = (roughness == 0);
     double cf;
@@ -289,15 +304,11 @@ MLB_DEV double skinFrictionCoefficient(double unitRe, double length, double Mach
         else if (Re < 5e5) cf = 1.328 / sqrt(Re);
         else { double t = 1.5 * m_log(Re) - 5.6; cf = 1 / (t * t) - 1700 / Re; }
     }
-    double corr;
-    if (Mach < 0.9) corr = sfSub(Mach, smooth);
-    else if (Mach < 1.1) { double sub = sfSub(Mach, smooth), sup = sfSup(Mach, smooth); corr = sub + ((sup - sub) * (Mach - 0.9) / 0.2); }
-    else corr = sfSup(Mach, smooth);
-    return cf * corr;
+    return cf * (smooth ? skinFrictionCompressibility(Mach, true) : corrRough);
 }
 /* getCylindricalSkinFrictionDragCoefficientAndRollDampingMoment (:138-168) */
 MLB_DEV double cylinderSkinFriction(const Aero& a, double length, double roughness, double criticalRe, double roughCf, double wettedArea, V3& rollDamping) {
-    double cd = skinFrictionCoefficient(a.unitRe, length, a.Mach, roughness, criticalRe, roughCf, a.fullyTurb);
+    double cd = skinFrictionCoefficient(a.unitRe, length, a.Mach, roughness, criticalRe, roughCf, a.fullyTurb, a.sfCorrRough);
     cd *= (1 + (0.5 / a.finenessRatio));
     cd *= (wettedArea / a.Aref);
     double avgRadius = (wettedArea / length) / (2 * MLB_PI);
@@ -327,11 +338,11 @@ MLB_DEV double dragToAxialFactor(double AOA) {                                  
     return 0.000006684 * (AOA * AOA * AOA) - 0.0010727204 * (AOA * AOA) + 0.030677323 * AOA + 1.055660807;
 }
 MLB_DEV ForceMoment forceFromCdCN(const Aero& a, double Cd, double CN, V3 CP, V3 moment) {   /* :218-236 */
-    double CA = dragToAxialFactor(a.totalAOA) * Cd;
+    double CA = a.axialFactor * Cd;
     V3 totalForce = ((v3(0, 0, -CA) + a.normalDir * CN) * a.Aref) * a.q;
     return fm(totalForce, CP, moment);
 }
-MLB_DEV double barrowmanCN(double AOA, double Aref, double top, double bottom) { return 2 * m_sin(AOA) * (bottom - top) / Aref; }   /* :284-289 */
+MLB_DEV double barrowmanCN(double sinAOA, double Aref, double top, double bottom) { return 2 * sinAOA * (bottom - top) / Aref; }   /* :284-289 */
 MLB_DEV double conePressureCd(const double* sub, const double* trans, double halfAngle, double Mach) {   /* noseCone.py:199-212 */
     if (Mach < 1) return sub[0] * m_pow(Mach, sub[1]);
     if (Mach > 1 && Mach < 1.3) return trans[0] + trans[1] * Mach + trans[2] * (Mach * Mach) + trans[3] * (Mach * Mach * Mach);
@@ -343,15 +354,14 @@ MLB_DEV double conePressureCd(const double* sub, const double* trans, double hal
  * Components
  * ------------------------------------------------------------------------------------------- */
 MLB_DEV ForceMoment noseConeForce(const Aero& a, const double* C) {                         /* noseCone.py:173-197 */
-    double CN = barrowmanCN(a.totalAOA, a.Aref, 0, C[NC_BASE_AREA]);
+    double CN = barrowmanCN(a.sinAOA, a.Aref, 0, C[NC_BASE_AREA]);
     V3 roll;
     double skin = cylinderSkinFriction(a, C[NC_LENGTH], C[NC_ROUGH], C[NC_CRIT_RE], C[NC_ROUGH_CF], C[NC_WETTED], roll);
     double pressure = conePressureCd(C + NC_SUB, C + NC_TRANS, C[NC_HALF_ANGLE], a.Mach) * C[NC_BASE_AREA] / a.Aref;
     return forceFromCdCN(a, pressure + skin, CN, ld3(C + NC_CP), roll);
 }
 MLB_DEV ForceMoment bodyTubeForce(const Aero& a, const double* C, V3 CG) {                  /* bodyTube.py:35-97 */
-    double sa = m_sin(a.totalAOA);
-    double CN = 1.1 * (sa * sa);
+    double CN = 1.1 * (a.sinAOA * a.sinAOA);
     CN *= C[BT_PLANFORM] / a.Aref;
     V3 roll;
     double skin = cylinderSkinFriction(a, C[BT_LENGTH], C[BT_ROUGH], C[BT_CRIT_RE], C[BT_ROUGH_CF], C[BT_WETTED], roll);
@@ -372,16 +382,16 @@ MLB_DEV ForceMoment bodyTubeForce(const Aero& a, const double* C, V3 CG) {      
     return forceFromCdCN(a, skin, CN, ld3(C + BT_CP), total);
 }
 MLB_DEV ForceMoment transitionForce(const Lane& L, const Aero& a, const double* C, int stageIdx, bool isBoatTail) {   /* boatTail.py:127-217 */
-    double CN = barrowmanCN(a.totalAOA, a.Aref, C[TR_TOP_AREA], C[TR_BOTTOM_AREA]);
+    double CN = barrowmanCN(a.sinAOA, a.Aref, C[TR_TOP_AREA], C[TR_BOTTOM_AREA]);
     double cdp;
     if (isBoatTail) {
-        double base = baseDragCoefficient(a.Mach);
+        double base = a.baseDrag;
         cdp = base * C[TR_CD_ADJ];
         cdp *= C[TR_FRONTAL] / a.Aref;
         bool noEngine = (L.engineShutOff[stageIdx] < 0);
         if (noEngine || a.time > L.engineShutOff[stageIdx]) cdp += base * C[TR_BOTTOM_AREA] / a.Aref;
     } else {
-        if (C[TR_GROWING] == 0) cdp = baseDragCoefficient(a.Mach) * C[TR_CD_ADJ];
+        if (C[TR_GROWING] == 0) cdp = a.baseDrag * C[TR_CD_ADJ];
         else cdp = conePressureCd(C + TR_SUB, C + TR_TRANS, C[TR_HALF_ANGLE], a.Mach);
         cdp *= C[TR_FRONTAL] / a.Aref;
     }
@@ -460,13 +470,13 @@ MLB_DEV void finStripSupersonic(const double* C, const double* aoa, int n, doubl
 MLB_DEV ForceMoment finSetForce(const double* B, const Aero& a, const double* C, V3 CG, double thickK) {   /* Fins.py:263-358,463-551 */
     const double Mach = a.Mach, Aref = a.Aref, q = a.q;
     /* drag build-up common to all fins of the set (Fins.py:289-358) */
-    double cf = skinFrictionCoefficient(a.unitRe, C[FS_MAC_LEN], Mach, C[FS_ROUGH], C[FS_CRIT_RE], C[FS_ROUGH_CF], a.fullyTurb);
+    double cf = skinFrictionCoefficient(a.unitRe, C[FS_MAC_LEN], Mach, C[FS_ROUGH], C[FS_CRIT_RE], C[FS_ROUGH_CF], a.fullyTurb, a.sfCorrRough);
     double skinDrag = cf * (C[FS_WETTED] / Aref);
     skinDrag *= (1 + 2 * C[FS_THICK] / C[FS_MAC_LEN]);
     double leCd = (C[FS_LE_SHAPE] == 0) ? cylinderCrossFlowCd(Mach) : bluntBodyCd(Mach);
     double cs = m_cos(C[FS_SWEEP]);
     leCd *= C[FS_LE_THICK] * C[FS_SPAN] * (cs * cs) / Aref;
-    double teCd = baseDragCoefficient(Mach) * C[FS_SPAN] * C[FS_TE_THICK] / Aref;
+    double teCd = a.baseDrag * C[FS_SPAN] * C[FS_TE_THICK] / Aref;
     double tc = C[FS_THICK] / C[FS_ROOT];
     double cm = m_cos(C[FS_MIDSWEEP]);
     double thicknessDrag;
@@ -494,10 +504,11 @@ MLB_DEV ForceMoment finSetForce(const double* B, const Aero& a, const double* C,
 #pragma unroll 1
     for (int fi = 0; fi < nFins; fi++) {
         V3 span = v3(C[FS_SPANDIR + 2 * fi], C[FS_SPANDIR + 2 * fi + 1], 0);
-        Q4 rot = qAxisAngle(span, C[FS_CANT] * (MLB_PI / 180.0));
-        V3 finNormal = qRotate(rot, v3(span.y, -span.x, 0));
+        /* deflected fin normal (Fins.py:479-480), drag direction and spanwise CP distance: constants of an un-actuated fin,
+           computed by the host with the reference's arithmetic */
+        V3 finNormal = ld3(C + FS_FIN_NORMAL + 3 * fi);
         V3 ust = cross(v3(0, 0, a.w.z), span) * -1.0;
-        double spanwiseCP = len(span * (C[FS_MAC_Y] + C[FS_BODY_R]));
+        double spanwiseCP = C[FS_SPANWISE_CP + fi];
         /* slice angles of attack (CythonFinFunctions.pyx:10-28): one asin per slice, reused by every strip sum below */
         double aoa[FS_MAX_SLICES];
         for (int i = 0; i < nS; i++) {
@@ -527,7 +538,7 @@ MLB_DEV ForceMoment finSetForce(const double* B, const Aero& a, const double* C,
         V3 normalForce = finNormal * (nf * q);
         mom *= q;
         double axialMag = dragToAxialFactor(aoa[mid]) * totalDrag * Aref * q;
-        V3 axialForce = cross(span, finNormal) * axialMag;
+        V3 axialForce = ld3(C + FS_AXIAL_DIR + 3 * fi) * axialMag;
         V3 globalCP = span * (C[FS_MAC_Y] + C[FS_BODY_R]) + (position - v3(0, 0, CPXPos));
         total = fmAdd(total, fm(normalForce + axialForce, globalCP, v3(0, 0, mom)));
     }
@@ -559,7 +570,8 @@ MLB_DEV double finThicknessK(const double* B, Lane& L, const double* C) {
     m1.vel = v3(0, 0, 340.3); m1.pos = v3(0, 0, 0); m1.w = v3(0, 0, 0);
     Air e = airProperties(B, L, ld3(B + H_NOSE_POS0), 0, false);
     double unitRe = len(localFrameAirVel(m1, e.wind)) * e.density / e.viscosity;
-    double CD_f_star = skinFrictionCoefficient(unitRe, C[FS_MAC_LEN], 1.0, C[FS_ROUGH], C[FS_CRIT_RE], C[FS_ROUGH_CF], B[H_FULLY_TURB] != 0);
+    double CD_f_star = skinFrictionCoefficient(unitRe, C[FS_MAC_LEN], 1.0, C[FS_ROUGH], C[FS_CRIT_RE], C[FS_ROUGH_CF], B[H_FULLY_TURB] != 0,
+                                               skinFrictionCompressibility(1.0, false));
     double cm = m_cos(C[FS_MIDSWEEP]);
     double tc = C[FS_THICK] / C[FS_ROOT];
     double t = (C[FS_CDTT_STAR] / CD_f_star - 4 * cm * tc) / (120 * (cm * cm) * ((tc * tc) * (tc * tc)));

@@ -438,6 +438,13 @@ def _finishFinSet(rec, fs, bodyRadius):
     for i in range(numFins):
         rec[L.FS_SPANDIR + 2 * i] = math.cos(math.radians(fs["firstFinAngle"] + i * sep))
         rec[L.FS_SPANDIR + 2 * i + 1] = math.sin(math.radians(fs["firstFinAngle"] + i * sep))
+        # constant per fin while it is not actuated: deflected normal (Fins.py:479-480), drag direction (:536), |CP span offset| (:489)
+        spanDir = (rec[L.FS_SPANDIR + 2 * i], rec[L.FS_SPANDIR + 2 * i + 1], 0.0)
+        rot = hm.q_from_axis_angle(spanDir, rec[L.FS_CANT] * (math.pi / 180.0))
+        normal, _ = hm.q_rotate(rot, (spanDir[1], -spanDir[0], 0.0))
+        rec[L.FS_FIN_NORMAL + 3 * i:L.FS_FIN_NORMAL + 3 * i + 3] = normal
+        rec[L.FS_AXIAL_DIR + 3 * i:L.FS_AXIAL_DIR + 3 * i + 3] = hm.v_cross(spanDir, normal)
+        rec[L.FS_SPANWISE_CP + i] = hm.v_len(hm.v_scale(spanDir, MACYPos + bodyRadius))
 
 
 def parseMotorFile(path, stagePosZ, impulseAdjustFactor=1.0, burnTimeAdjustFactor=1.0):
