@@ -29,6 +29,11 @@ using namespace mlb;
    faster as long as every SM gets a CTA; registers per lane shrink accordingly (255 / 128 / 64). */
 #define MLB_NUM_SHAPES 3
 static const int kShapeBlock[MLB_NUM_SHAPES] = { 128, 512, 1024 };
+#ifdef MLB_TUNE_SHAPES
+#define MLB_EXTRA_SHAPES(X) X(256) X(384) X(640) X(768) X(896)
+#else
+#define MLB_EXTRA_SHAPES(X)
+#endif
 #define TRACE_W 16
 #define MLB_NCOUNTERS 6
 
@@ -323,9 +328,13 @@ extern "C" int mlb_run(mlb_handle* h, void* stream) {
     int block = 128;
     for (int k = 0; k < MLB_NUM_SHAPES; k++) if (h->nLanes >= (long long)h->nSM * kShapeBlock[k]) block = kShapeBlock[k];
     if (h->forceBlock == 128 || h->forceBlock == 512 || h->forceBlock == 1024) block = h->forceBlock;
+#define MLB_ALLOW(N) if (h->forceBlock == N) block = N;
+    MLB_EXTRA_SHAPES(MLB_ALLOW)
     h->lastBlock = block;
     unsigned grid = (unsigned)((h->nLanes + block - 1) / block);
     CU(cudaEventRecord(h->ev0, s));
+#define MLB_LAUNCH(N) if (block == N) { cudaFuncSetAttribute(integrateLanes<N, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes); integrateLanes<N, 1><<<grid, N, h->smemBytes, s>>>(a); } else
+    MLB_EXTRA_SHAPES(MLB_LAUNCH)
     if (block == 1024) integrateLanes<1024, 1><<<grid, 1024, h->smemBytes, s>>>(a);
     else if (block == 512) integrateLanes<512, 1><<<grid, 512, h->smemBytes, s>>>(a);
     else integrateLanes<128, 2><<<grid, 128, h->smemBytes, s>>>(a);

@@ -370,12 +370,25 @@ MLB_DEV ForceMoment bodyTubeForce(const Aero& a, const double* C, V3 CG) {      
     double dA = dL * C[BT_DIAM];
     V3 position = ld3(C + C_POS);
     V3 total = v3(0, 0, 0);
+    const V3 offset = position - CG;           /* only the z component differs between strips */
+    if (offset.x == 0 && offset.y == 0) {
+        /* axisymmetric layout (tube axis through the CG): psi = (0, 0, z), so w x psi = (w.y z, -w.x z, 0) and the strip
+           moment -psi x (v|v|) = (z sy, -z sx, 0): the same products as the general form with its exact-zero terms dropped */
+#pragma unroll 5
+        for (int i = 0; i < nSegments; i++) {                                               /* longitudinal damping strips */
+            double z = (position.z + (-dL * i - dL / 2)) - CG.z;
+            double vx = a.w.y * z, vy = -(a.w.x * z);
+            double sx = vx * fabs(vx), sy = vy * fabs(vy);
+            total.x += z * sy; total.y += -(z * sx);
+        }
+    } else {
 #pragma unroll 1
-    for (int i = 0; i < nSegments; i++) {                                                   /* longitudinal damping strips */
-        V3 psi = (position + v3(0, 0, -dL * i - dL / 2)) - CG;
-        V3 segVel = cross(a.w, psi);
-        V3 sqVel = v3(segVel.x * fabs(segVel.x), segVel.y * fabs(segVel.y), segVel.z * fabs(segVel.z));
-        total = total + (-cross(psi, sqVel));
+        for (int i = 0; i < nSegments; i++) {
+            V3 psi = (position + v3(0, 0, -dL * i - dL / 2)) - CG;
+            V3 segVel = cross(a.w, psi);
+            V3 sqVel = v3(segVel.x * fabs(segVel.x), segVel.y * fabs(segVel.y), segVel.z * fabs(segVel.z));
+            total = total + (-cross(psi, sqVel));
+        }
     }
     total = total * ((1.1 / 2) * a.density * dA);
     total = total + roll;
@@ -511,7 +524,15 @@ MLB_DEV ForceMoment finSetForce(const double* B, const Aero& a, const double* C,
         double spanwiseCP = C[FS_SPANWISE_CP + fi];
         /* slice angles of attack (CythonFinFunctions.pyx:10-28): one asin per slice, reused by every strip sum below */
         double aoa[FS_MAX_SLICES];
-        for (int i = 0; i < nS; i++) {
+        /* A rocket that is not rolling has |w.z| at rounding-noise level: the spin term ust * r then vanishes when added to
+           the air velocity (checked exactly, for the outermost slice, component by component: round-to-nearest is monotonic,
+           so it vanishes for every inner slice too). All slices then see bit-identical velocities: one asin serves them all. */
+        const double rOuter = C[FS_SLICE_R + nS - 1];
+        const V3 vOuter = airVelRelativeToFin + ust * rOuter;
+        const bool uniform = (vOuter.x == airVelRelativeToFin.x) && (vOuter.y == airVelRelativeToFin.y) && (vOuter.z == airVelRelativeToFin.z)
+                             && (C[FS_SLICE_R] <= rOuter);
+        const int nAsin = uniform ? 1 : nS;
+        for (int i = 0; i < nAsin; i++) {
             V3 finVelocity = airVelRelativeToFin + ust * C[FS_SLICE_R + i];
             double finVelMag = len(finVelocity);
             double al = 0.0;
@@ -523,6 +544,7 @@ MLB_DEV ForceMoment finSetForce(const double* B, const Aero& a, const double* C,
             if (fabs(al) > stall) al *= fabs(stall / al);
             aoa[i] = al;
         }
+        if (uniform) for (int i = 1; i < nS; i++) aoa[i] = aoa[0];
         double nf, mom;
         if (regime == 0) finStripSubsonic(C, aoa, nS, spanwiseCP, cnA, nf, mom);
         else if (regime == 2) finStripSupersonic(C, aoa, nS, spanwiseCP, kM, nf, mom);

@@ -625,7 +625,7 @@ def initialStateLaunchTowerFrame(rocketReader: SubDictReader):
     return initPos, initVel, q, w
 
 
-def buildModel(simDefinition: SimDefinition, maxSteps: int = 2000000) -> Model:
+def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000) -> Model:
     sd = simDefinition
     env = SubDictReader("Environment", sd)
     rk = SubDictReader("Rocket", sd)
@@ -674,6 +674,8 @@ def buildModel(simDefinition: SimDefinition, maxSteps: int = 2000000) -> Model:
         H[L.H_AD_MAXDT] = ad.getFloat("maxTimeStep")
         H[L.H_AD_MINDT] = ad.getFloat("minTimeStep")
     H[L.H_EVENT_DT] = rk.getFloat("SimControl.TimeStepAdaptation.eventTimingAccuracy")
+    # the reference has no step limit (a rocket held aloft by an updraft runs forever); a lane that reaches this many
+    # steps ends with status ST_STEP_LIMIT. Longest flight of the example cases: 56 k steps (RK4, dt 0.01, to ground).
     H[L.H_MAX_STEPS] = maxSteps
     # inverse Hermite matrix of the transonic fin-force blend between Mach 0.8 and 1.4 (Fins.py:508-528)
     H[L.H_FIN_CUBIC_OFF] = append(cubicInterpInverseMatrix(0.8, 1.4).reshape(-1))
