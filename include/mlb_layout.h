@@ -167,7 +167,18 @@
 #define S_AUTO_BT_OFF 25
 #define S_COMP_OFF 26
 #define S_MAX_COMP 30
-#define S_SIZE 56
+/* components with time-varying inertia (Motor, TabulatedInertia), as indices into S_COMP_OFF, in the order the reference
+   combines them: construction order, not the top-to-bottom order of the force sum (CompositeObject.py:41-50,102-121) */
+#define S_NVAR 56
+#define S_VAR_IDX 57
+#define S_MAX_VAR 4
+/* the same two lists in top-to-bottom component order: the reference rebuilds them that way when a stage is dropped
+   (Rocket._dropStage -> recomputeFixedMassInertia, rocket.py:476-479, CompositeObject.py:65-77) */
+#define S_FIXED2_MOI 61
+#define S_FIXED2_CG 64
+#define S_FIXED2_MASS 67
+#define S_VAR2_IDX 68
+#define S_SIZE 72
 #define OVR_CG 1
 #define OVR_MASS 2
 #define OVR_MOI 4
@@ -304,6 +315,47 @@
 #define RC_STAGE_STRIDE 5
 #define RC_MAX_STAGES 4
 #define RC_SIZE 33
+
+/* force-only and table-driven components (Rocket/RocketComponents.py:183-413). Their `position` is NOT offset by the
+   stage position (the reference reads it straight from the dictionary, :219, :270). */
+/* FixedForce (:183-204): constant force at C_POS plus a constant moment */
+#define FF_FORCE 12
+#define FF_MOMENT 15
+#define FF_SIZE 18
+/* AeroForce (:206-231): constant Cd, Cl, CMx, CMy, CMz */
+#define AF_AREF 12
+#define AF_LREF 13
+#define AF_COEFFS 14
+#define AF_SIZE 19
+/* AeroDamping (:233-261): damping-coefficient vectors for the x, y, z moment coefficients (position is the origin) */
+#define AD_AREF 12
+#define AD_LREF 13
+#define AD_XCOEFFS 14
+#define AD_YCOEFFS 17
+#define AD_ZCOEFFS 20
+#define AD_SIZE 23
+/* TabulatedAeroForce (:263-345), one key column: keys[TA_NROWS], then TA_NVALS value columns of TA_NROWS each
+   (column-major) starting at TA_TABLE; TA_COEFF_IDX[k] = position of value column k in (CD, CL, CMx, CMy, CMz) */
+#define TA_AREF 12
+#define TA_LREF 13
+#define TA_KEY 14
+#define TA_NROWS 15
+#define TA_NVALS 16
+#define TA_COEFF_IDX 17
+#define TA_TABLE 22
+#define AKEY_MACH 0
+#define AKEY_ALTITUDE 1
+#define AKEY_UNITRE 2
+#define AKEY_TOTALAOA 3
+#define AKEY_ROLLANGLE 4
+#define AKEY_AOA 5
+#define AKEY_AOSS 6
+/* TabulatedInertia (:347-376): times[TI_NROWS], then mass, CGx, CGy, CGz, MOIx, MOIy, MOIz columns (column-major) */
+#define TI_NROWS 12
+#define TI_TABLE 13
+/* FractionalJetDamping (:378-413) */
+#define JD_FRACTION 12
+#define JD_SIZE 13
 
 /* ---- per-lane input arrays (mlb_set_lanes arrayIds) ----------------------------------- */
 #define LANE_WIND 0          /* 3: Environment.ConstantMeanWind.velocity (ENU)        */

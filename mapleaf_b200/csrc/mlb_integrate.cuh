@@ -209,6 +209,14 @@ MLB_DEV void deployNextRecoveryStage(const double* B, Lane& L) {                
         subscribeEvent(L, (int)st[0], st[1], st[4], CB_RECOVERY_DEPLOY);
     }
 }
+MLB_DEV void stageSeparation(const double* B, Lane& L) {                                    /* Rocket._stageSeparation, rocket.py:461-479 */
+    if (L.nStages <= 1) return;
+    L.nStages -= 1;                /* the bottom stage leaves; boat-tail ownership and fineness ratio follow the stage count */
+    L.resorted = true;
+    const double* S0 = B + (int)B[H_STAGE_OFF];
+    L.ignitionTime[0] = L.time;    /* stages[0].motor.updateIgnitionTime(currentTime) — the TOP stage's motor, as in the reference */
+    L.engineShutOff[0] = L.time + S0[S_BURN_DURATION];
+}
 MLB_DEV void triggerEvents(const double* B, Lane& L, double& estTimeToNext, bool& deterministic) {   /* simEventDetector.py:64-118 */
     double est = 1e10; bool det = false;
     const double alt = earthAltitude(B, L.s.pos);
@@ -245,7 +253,7 @@ MLB_DEV void triggerEvents(const double* B, Lane& L, double& estTimeToNext, bool
         }
         if (timeTo < est && !occurred) { est = timeTo; det = timeDet; }
         if (occurred) {
-            if (ev.delay == 0) { if (ev.callback == CB_RECOVERY_DEPLOY) deployNextRecoveryStage(B, L); }
+            if (ev.delay == 0) { if (ev.callback == CB_RECOVERY_DEPLOY) deployNextRecoveryStage(B, L); else if (ev.callback == CB_STAGE_SEPARATION) stageSeparation(B, L); }
             else subscribeEvent(L, EV_TIME_REACHED, L.time + ev.delay, 0, ev.callback);
             removeMask |= 1u << i;
         }
@@ -330,7 +338,7 @@ MLB_DEV void laneInit(const double* B, Lane& L, const LaneInputs& in, long long 
     L.s.pos = v3(st[0], st[1], st[2]); L.s.vel = v3(st[3], st[4], st[5]);
     L.s.q = q4(st[6], st[7], st[8], st[9]); L.s.w = v3(st[10], st[11], st[12]);
     L.time = B[H_START_TIME];
-    L.dof3 = false; L.underChute = false; L.haveLast = false; L.haveCache = false;
+    L.dof3 = false; L.underChute = false; L.haveLast = false; L.haveCache = false; L.resorted = false;
     L.lastVz = 0; L.lastTime = 0; L.pidLastError = 0; L.pidIntegral = 0;
     L.nSteps = 0; L.nEvals = 0; L.nRejects = 0; L.nEvents = 0; L.nSteps3 = 0; L.nEvals3 = 0; L.nEvalsTransonic = 0;
     L.turb = (int)B[H_TURB];
@@ -354,6 +362,11 @@ MLB_DEV void laneInit(const double* B, Lane& L, const LaneInputs& in, long long 
     /* RecoverySystem.__init__ -> _deployNextStage(): chute stage 0, subscribes the first trigger */
     L.recoveryStage = -1;
     if (B[H_RECOVERY_OFF] != 0) deployNextRecoveryStage(B, L);
+    /* Rocket._initializeStagingTriggers (rocket.py:339-361): one separation event per stage that has a trigger */
+    for (int si = 0; si < L.nStages; si++) {
+        const double* S = B + (int)B[H_STAGE_OFF + si];
+        if ((int)S[S_SEP_TYPE] != EV_NONE) subscribeEvent(L, (int)S[S_SEP_TYPE], S[S_SEP_VALUE], S[S_SEP_DELAY], CB_STAGE_SEPARATION);
+    }
     laneFinConstants(B, L);
 }
 

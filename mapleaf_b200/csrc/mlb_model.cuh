@@ -39,6 +39,7 @@ struct Lane {
     State s; double time;
     V3 wind;                                    /* sampled Environment.ConstantMeanWind.velocity */
     bool dof3, underChute, onRail, haveLast, haveCache;
+    bool resorted;                              /* a stage has been dropped: inertia lists are in top-to-bottom order (rocket.py:476-479) */
     int recoveryStage, nStages, nEvents, turb;
     double lastVz, lastTime;                    /* event detector memory (simEventDetector.py:120-132) */
     double pidLastError, pidIntegral;           /* step-size PID (GNC/PID.py:27-51) */
@@ -214,6 +215,16 @@ MLB_DEV Inertia motorInertia(const double* C, double t) {                       
     }
     return combineInertias(part, 2);
 }
+/* TabulatedInertia.getInertia (RocketComponents.py:369-372): time-tabulated mass, CG, MOI */
+MLB_DEV Inertia tabulatedInertia(const double* C, double time) {
+    int n = (int)C[TI_NROWS]; const double* T = C + TI_TABLE;
+    int i = bisectRight(T, n, time);
+    double v[7];
+#pragma unroll
+    for (int k = 0; k < 7; k++) v[k] = linInterpAt(T, T + (k + 1) * n, n, i, time);
+    Inertia r; r.MOI = v3(v[4], v[5], v[6]); r.CG = v3(v[1], v[2], v[3]); r.mass = v[0];
+    return r;
+}
 MLB_DEV Inertia stageInertia(const double* B, const Lane& L, int si, double time) {         /* CompositeObject.py:102-121 */
     const double* S = B + (int)B[H_STAGE_OFF + si];
     int flags = (int)S[S_OVR_FLAGS];
@@ -222,10 +233,15 @@ MLB_DEV Inertia stageInertia(const double* B, const Lane& L, int si, double time
         r.CG = ld3(S + S_OVR_CG); r.MOI = ld3(S + S_OVR_MOI); r.mass = S[S_OVR_MASS];
         return r;
     }
-    Inertia list[2]; int n = 1;
-    list[0].MOI = ld3(S + S_FIXED_MOI); list[0].CG = ld3(S + S_FIXED_CG); list[0].mass = S[S_FIXED_MASS];
-    int mi = (int)S[S_MOTOR];
-    if (mi >= 0) list[n++] = motorInertia(B + (int)S[S_COMP_OFF + mi], fmax(0.0, time - L.ignitionTime[si]));
+    Inertia list[1 + S_MAX_VAR]; int n = 1;
+    list[0].MOI = ld3(S + (L.resorted ? S_FIXED2_MOI : S_FIXED_MOI)); list[0].CG = ld3(S + (L.resorted ? S_FIXED2_CG : S_FIXED_CG));
+    list[0].mass = L.resorted ? S[S_FIXED2_MASS] : S[S_FIXED_MASS];
+    const int nVar = (int)S[S_NVAR];
+    for (int k = 0; k < nVar; k++) {                       /* variable-mass components, in the order the reference combines them */
+        const double* C = B + (int)S[S_COMP_OFF + (int)S[(L.resorted ? S_VAR2_IDX : S_VAR_IDX) + k]];
+        if ((int)C[C_TYPE] == CT_MOTOR) list[n++] = motorInertia(C, fmax(0.0, time - L.ignitionTime[si]));
+        else list[n++] = tabulatedInertia(C, time);
+    }
     r = combineInertias(list, n);
     if (flags & OVR_CG) r.CG = ld3(S + S_OVR_CG);
     if (flags & OVR_MOI) r.MOI = ld3(S + S_OVR_MOI);
@@ -249,7 +265,8 @@ MLB_DEV double baseDragCoefficient(double Mach);
 MLB_DEV double skinFrictionCompressibility(double Mach, bool smooth);
 
 struct Aero {
-    double Mach, totalAOA, q, airSpeed, unitRe, density, finenessRatio, Aref, time;
+    double Mach, totalAOA, q, airSpeed, unitRe, density, viscosity, asl, finenessRatio, Aref, time;
+    bool qValid;        /* dynamic pressure is computed and cached at its FIRST use in an evaluation (AeroParameters.py:141-150) */
     double sinAOA, axialFactor, baseDrag, sfCorrRough;      /* functions of Mach / total AOA only, shared by every component */
     V3 lfav, normalDir, w;
     bool fullyTurb;
@@ -259,14 +276,14 @@ MLB_DEV V3 localFrameAirVel(const State& s, V3 wind) { return qConjRotate(s.q, s
 MLB_DEV double betaOf(double Mach) { return (Mach <= 0.9) ? sqrt(1 - Mach * Mach) : sqrt(Mach * Mach - 1); }   /* :152-163 */
 
 MLB_DEV void aeroSetup(const double* B, const Lane& L, Aero& a, const State& s, const Air& e, double time) {
-    a.time = time; a.w = s.w; a.density = e.density;
+    a.time = time; a.w = s.w; a.density = e.density; a.viscosity = e.viscosity; a.asl = earthAltitude(B, s.pos);
     a.Mach = len(s.vel - e.wind) / sqrt(1.4 * 287 * e.temp);                                /* :15-20 */
     a.lfav = localFrameAirVel(s, e.wind);
     a.airSpeed = len(a.lfav);
     a.totalAOA = (a.airSpeed == 0) ? 0.0 : angleBetween(a.lfav, v3(0, 0, -1));             /* :29-39 */
     if (a.lfav.x == 0.0 && a.lfav.y == 0.0) a.normalDir = v3(1, 0, 0);                      /* :131-139 */
     else a.normalDir = normalize(v3(a.lfav.x, a.lfav.y, 0));
-    a.q = a.airSpeed * a.airSpeed * e.density / 2;                                          /* :141-150 */
+    a.qValid = false; a.q = 0;
     a.unitRe = a.airSpeed * e.density / e.viscosity;                                        /* :22-27 */
     a.finenessRatio = B[H_FINENESS + L.nStages - 1];
     a.fullyTurb = B[H_FULLY_TURB] != 0;
@@ -277,6 +294,35 @@ MLB_DEV void aeroSetup(const double* B, const Lane& L, Aero& a, const State& s, 
     a.sfCorrRough = skinFrictionCompressibility(a.Mach, false);
 }
 
+MLB_DEV double dynamicPressure(Aero& a) {
+    if (!a.qValid) { a.q = a.airSpeed * a.airSpeed * a.density / 2; a.qValid = true; }
+    return a.q;
+}
+/* getAOA / getAOSS (AeroParameters.py:41-77) zero a component of the CACHED local air-velocity vector: every later use in
+   the same evaluation (air speed, Reynolds number, drag direction, a not-yet-cached dynamic pressure) sees the mutated
+   vector. Mach, total AOA and the normal-force direction were cached before (rocket.py:563-566). */
+MLB_DEV void airVelMutated(Aero& a) { a.airSpeed = len(a.lfav); a.unitRe = a.airSpeed * a.density / a.viscosity; }
+MLB_DEV double aeroAOA(Aero& a) {
+    if (a.airSpeed == 0) return 0;
+    a.lfav.y = 0; airVelMutated(a);
+    double ang = angleBetween(a.lfav, v3(0, 0, -1));
+    return (a.lfav.x > 0) ? ang : -ang;
+}
+MLB_DEV double aeroAOSS(Aero& a) {
+    if (a.airSpeed == 0) return 0;
+    a.lfav.x = 0; airVelMutated(a);
+    double ang = angleBetween(a.lfav, v3(0, 0, -1));
+    return (a.lfav.y < 0) ? ang : -ang;
+}
+MLB_DEV double aeroRollAngle(const Aero& a) {                                               /* :79-96 */
+    V3 y = a.normalDir * -1.0;
+    if (len(y) < 0.01) return 0;
+    double rollAngle = m_atan2(-y.y, y.x) * (180.0 / MLB_PI);
+    rollAngle = (-1) * rollAngle;
+    double r = fmod(rollAngle, 360.0);                                                      /* Python float % */
+    if (r != 0 && r < 0) r += 360.0;
+    return r;
+}
 MLB_DEV double sfSub(double Mach, bool smooth) { return smooth ? 1 - 0.10 * (Mach * Mach) : 1 - 0.12 * (Mach * Mach); }   /* AeroFunctions.py:38-51 */
 MLB_DEV double sfSup(double Mach, bool smooth) {                                             /* :53-69 */
     double smoothTurbFactor = 1 / m_pow(1 + 0.15 * (Mach * Mach), 0.58);
@@ -337,9 +383,9 @@ MLB_DEV double dragToAxialFactor(double AOA) {                                  
     if (AOA <= 17) return -0.000122124 * (AOA * AOA * AOA) + 0.003114164 * (AOA * AOA) + 1;
     return 0.000006684 * (AOA * AOA * AOA) - 0.0010727204 * (AOA * AOA) + 0.030677323 * AOA + 1.055660807;
 }
-MLB_DEV ForceMoment forceFromCdCN(const Aero& a, double Cd, double CN, V3 CP, V3 moment) {   /* :218-236 */
+MLB_DEV ForceMoment forceFromCdCN(Aero& a, double Cd, double CN, V3 CP, V3 moment) {   /* :218-236 */
     double CA = a.axialFactor * Cd;
-    V3 totalForce = ((v3(0, 0, -CA) + a.normalDir * CN) * a.Aref) * a.q;
+    V3 totalForce = ((v3(0, 0, -CA) + a.normalDir * CN) * a.Aref) * dynamicPressure(a);
     return fm(totalForce, CP, moment);
 }
 MLB_DEV double barrowmanCN(double sinAOA, double Aref, double top, double bottom) { return 2 * sinAOA * (bottom - top) / Aref; }   /* :284-289 */
@@ -353,14 +399,14 @@ MLB_DEV double conePressureCd(const double* sub, const double* trans, double hal
 /* ---------------------------------------------------------------------------------------------
  * Components
  * ------------------------------------------------------------------------------------------- */
-MLB_DEV ForceMoment noseConeForce(const Aero& a, const double* C) {                         /* noseCone.py:173-197 */
+MLB_DEV ForceMoment noseConeForce(Aero& a, const double* C) {                         /* noseCone.py:173-197 */
     double CN = barrowmanCN(a.sinAOA, a.Aref, 0, C[NC_BASE_AREA]);
     V3 roll;
     double skin = cylinderSkinFriction(a, C[NC_LENGTH], C[NC_ROUGH], C[NC_CRIT_RE], C[NC_ROUGH_CF], C[NC_WETTED], roll);
     double pressure = conePressureCd(C + NC_SUB, C + NC_TRANS, C[NC_HALF_ANGLE], a.Mach) * C[NC_BASE_AREA] / a.Aref;
     return forceFromCdCN(a, pressure + skin, CN, ld3(C + NC_CP), roll);
 }
-MLB_DEV ForceMoment bodyTubeForce(const Aero& a, const double* C, V3 CG) {                  /* bodyTube.py:35-97 */
+MLB_DEV ForceMoment bodyTubeForce(Aero& a, const double* C, V3 CG) {                  /* bodyTube.py:35-97 */
     double CN = 1.1 * (a.sinAOA * a.sinAOA);
     CN *= C[BT_PLANFORM] / a.Aref;
     V3 roll;
@@ -394,7 +440,7 @@ MLB_DEV ForceMoment bodyTubeForce(const Aero& a, const double* C, V3 CG) {      
     total = total + roll;
     return forceFromCdCN(a, skin, CN, ld3(C + BT_CP), total);
 }
-MLB_DEV ForceMoment transitionForce(const Lane& L, const Aero& a, const double* C, int stageIdx, bool isBoatTail) {   /* boatTail.py:127-217 */
+MLB_DEV ForceMoment transitionForce(const Lane& L, Aero& a, const double* C, int stageIdx, bool isBoatTail) {   /* boatTail.py:127-217 */
     double CN = barrowmanCN(a.sinAOA, a.Aref, C[TR_TOP_AREA], C[TR_BOTTOM_AREA]);
     double cdp;
     if (isBoatTail) {
@@ -480,8 +526,8 @@ MLB_DEV void finStripSupersonic(const double* C, const double* aoa, int n, doubl
     force = f; moment = m;
 }
 
-MLB_DEV ForceMoment finSetForce(const double* B, const Aero& a, const double* C, V3 CG, double thickK) {   /* Fins.py:263-358,463-551 */
-    const double Mach = a.Mach, Aref = a.Aref, q = a.q;
+MLB_DEV ForceMoment finSetForce(const double* B, Aero& a, const double* C, V3 CG, double thickK) {   /* Fins.py:263-358,463-551 */
+    const double Mach = a.Mach, Aref = a.Aref, q = dynamicPressure(a);
     /* drag build-up common to all fins of the set (Fins.py:289-358) */
     double cf = skinFrictionCoefficient(a.unitRe, C[FS_MAC_LEN], Mach, C[FS_ROUGH], C[FS_CRIT_RE], C[FS_ROUGH_CF], a.fullyTurb, a.sfCorrRough);
     double skinDrag = cf * (C[FS_WETTED] / Aref);
@@ -569,6 +615,62 @@ MLB_DEV ForceMoment finSetForce(const double* B, const Aero& a, const double* C,
     return total;
 }
 
+/* AeroFunctions.forceFromCoefficients (:238-269): drag along the air velocity, lift perpendicular to it in the plane of the
+   normal-force direction, moments from coefficients */
+MLB_DEV ForceMoment forceFromCoefficients(Aero& a, const double* coeffs, V3 cp, double refArea, double refLength) {
+    double q = dynamicPressure(a);
+    if (q == 0.0) return fmZero();
+    double nonDimConstant = q * refArea;
+    V3 V = a.lfav;
+    V3 dragForce = normalize(V) * coeffs[0];
+    V3 nd = a.normalDir;
+    Q4 rotator = qAxisAngle(cross(V, nd), MLB_PI / 2 - angleBetween(V, nd));
+    V3 liftForce = qRotate(rotator, nd) * coeffs[1];
+    V3 totalForce = (dragForce + liftForce) * nonDimConstant;
+    V3 moments = (v3(coeffs[2], coeffs[3], coeffs[4]) * nonDimConstant) * refLength;
+    return fm(totalForce, cp, moments);
+}
+MLB_DEV ForceMoment aeroDampingForce(Aero& a, const double* C) {                            /* RocketComponents.py:248-261 */
+    double redimConst = C[AD_LREF] / (2 * fmax(a.airSpeed, 0.0000001));
+    double coeffs[5];
+    coeffs[0] = 0; coeffs[1] = 0;
+    coeffs[2] = dot(ld3(C + AD_XCOEFFS), a.w) * redimConst;
+    coeffs[3] = dot(ld3(C + AD_YCOEFFS), a.w) * redimConst;
+    coeffs[4] = dot(ld3(C + AD_ZCOEFFS), a.w) * redimConst;
+    return forceFromCoefficients(a, coeffs, v3(0, 0, 0), C[AD_AREF], C[AD_LREF]);
+}
+MLB_DEV ForceMoment tabulatedAeroForce(Aero& a, const double* C) {                          /* RocketComponents.py:322-345, one key column */
+    double key;
+    switch ((int)C[TA_KEY]) {
+        case AKEY_MACH: key = a.Mach; break;
+        case AKEY_ALTITUDE: key = a.asl; break;
+        case AKEY_UNITRE: key = a.unitRe * 1; break;
+        case AKEY_TOTALAOA: key = a.totalAOA; break;
+        case AKEY_ROLLANGLE: key = aeroRollAngle(a); break;
+        case AKEY_AOA: key = aeroAOA(a); break;
+        default: key = aeroAOSS(a); break;
+    }
+    const int n = (int)C[TA_NROWS], nv = (int)C[TA_NVALS]; const double* T = C + TA_TABLE;
+    const int i = bisectRight(T, n, key);
+    double coeffs[5] = { 0.0, 0.0, 0.0, 0.0, 0.0 };
+    for (int c = 0; c < nv; c++) {
+        double v = linInterpAt(T, T + (c + 1) * n, n, i, key);
+        int k = (int)C[TA_COEFF_IDX + c];
+        if (k == 0) coeffs[0] = v; else if (k == 1) coeffs[1] = v; else if (k == 2) coeffs[2] = v; else if (k == 3) coeffs[3] = v; else coeffs[4] = v;
+    }
+    return forceFromCoefficients(a, coeffs, ld3(C + C_POS), C[TA_AREF], C[TA_LREF]);
+}
+MLB_DEV Inertia rocketInertia(const double* B, const Lane& L, double time, double* massSum);
+MLB_DEV ForceMoment jetDampingForce(const double* B, const Lane& L, const Aero& a, const double* C, int si, const Inertia& current) {   /* :392-410 */
+    if (a.time > L.ignitionTime[si] && a.time < L.engineShutOff[si]) {
+        double m; const double dt = 0.001;
+        Inertia next = rocketInertia(B, L, a.time + dt, &m);
+        double dampingFactor = ((current.MOI.x - next.MOI.x) / dt) * C[JD_FRACTION];
+        return fm(v3(0, 0, 0), v3(0, 0, 0), v3(-a.w.x * dampingFactor, -a.w.y * dampingFactor, 0));
+    }
+    return fmZero();
+}
+
 MLB_DEV double motorThrust(const Lane& L, const double* C, int si, double time) {           /* Propulsion.py:138-151 */
     double t = fmax(0.0, time - L.ignitionTime[si]);
     int n = (int)C[MT_NROWS]; const double* T = C + MT_TABLE;
@@ -646,10 +748,17 @@ MLB_DEV ForceMoment appliedForce(const double* B, Lane& L, double time, State& s
                     case CT_TRANSITION: f = transitionForce(L, a, C, si, false); break;
                     case CT_FINSET: f = finSetForce(B, a, C, inertia.CG, L.finThickK[finIdx & (MLB_MAX_FINSETS - 1)]); finIdx++; break;
                     case CT_MOTOR: f = fm(v3(0, 0, motorThrust(L, C, si, time)), v3(0, 0, 0), v3(0, 0, 0)); break;
+                    case CT_FIXED_FORCE: f = fm(ld3(C + FF_FORCE), ld3(C + C_POS), ld3(C + FF_MOMENT)); break;
+                    case CT_AERO_FORCE: f = forceFromCoefficients(a, C + AF_COEFFS, ld3(C + C_POS), C[AF_AREF], C[AF_LREF]); break;
+                    case CT_AERO_DAMPING: f = aeroDampingForce(a, C); break;
+                    case CT_TAB_AERO: f = tabulatedAeroForce(a, C); break;
+                    case CT_JET_DAMPING: f = jetDampingForce(B, L, a, C, si, inertia); break;
                     default: f = fmZero(); break;                                          /* FixedMass / RecoverySystem: zero force */
                 }
                 stageTotal = fmAdd(stageTotal, f);
             }
+            /* the automatic zero-length boat tail belongs to whichever stage is currently the bottom one (rocket.py:489-519) */
+            if (si == L.nStages - 1 && S[S_AUTO_BT_OFF] != 0) stageTotal = fmAdd(stageTotal, transitionForce(L, a, B + (int)S[S_AUTO_BT_OFF], si, true));
             rocketTotal = fmAdd(rocketTotal, stageTotal);
         }
         comp = rocketTotal;

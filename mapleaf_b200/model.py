@@ -53,7 +53,8 @@ L = _Layout(_loadLayout())
 
 _BODY_CLASSES = {"Nosecone", "Bodytube", "BoatTail", "Transition"}
 _FIXED_MASS_CLASSES = {"Nosecone", "Bodytube", "BoatTail", "Transition", "FinSet", "Mass", "RecoverySystem"}
-_SUPPORTED_CLASSES = _FIXED_MASS_CLASSES | {"Motor"}
+_FORCE_ONLY_CLASSES = {"Force", "AeroForce", "AeroDamping", "TabulatedAeroForce", "FractionalJetDamping"}
+_SUPPORTED_CLASSES = _FIXED_MASS_CLASSES | {"Motor", "TabulatedInertia"} | _FORCE_ONLY_CLASSES
 
 _INTEGRATORS = {"Euler": L.INT_EULER, "RK2Midpoint": L.INT_RK2_MIDPOINT, "RK2Heun": L.INT_RK2_HEUN, "RK4": L.INT_RK4,
                 "RK4_3/8": L.INT_RK4_38, "RK12Adaptive": L.INT_RK12A, "RK23Adaptive": L.INT_RK23A,
@@ -564,6 +565,137 @@ def _buildMass(r, stagePos):
     return rec, dict(position=position, inertia=inertia, body=False)
 
 
+_ZERO_INERTIA = None
+
+
+def _zeroInertiaRecord(ctype, size, position=(0.0, 0.0, 0.0)):
+    rec = [0.0] * size
+    rec[L.C_TYPE] = ctype
+    rec[L.C_LEN] = size
+    rec[L.C_POS:L.C_POS + 3] = position
+    return rec
+
+
+def _resolvePath(r, key):
+    path = r.getString(key)
+    if not os.path.exists(path):
+        found = r.simDefinition._findFile(path)
+        if found is None:
+            raise FileNotFoundError(path)
+        path = found
+    return path
+
+
+def _buildFixedForce(r, stagePos):
+    """RocketComponents.py:183-204"""
+    rec = _zeroInertiaRecord(L.CT_FIXED_FORCE, L.FF_SIZE, r.getVector("position"))
+    rec[L.FF_FORCE:L.FF_FORCE + 3] = r.getVector("force")
+    rec[L.FF_MOMENT:L.FF_MOMENT + 3] = r.getVector("moment")
+    # FixedForce has no `position` attribute: the Z sort falls back to its (zero) inertia's CG (RocketComponents.py:137-141)
+    return rec, dict(position=(0.0, 0.0, 0.0), body=False)
+
+
+def _buildAeroForce(r, stagePos):
+    """RocketComponents.py:206-231"""
+    position = r.getVector("position")
+    rec = _zeroInertiaRecord(L.CT_AERO_FORCE, L.AF_SIZE, position)
+    rec[L.AF_AREF] = r.getFloat("Aref")
+    rec[L.AF_LREF] = r.getFloat("Lref")
+    rec[L.AF_COEFFS:L.AF_COEFFS + 5] = [r.getFloat("Cd"), r.getFloat("Cl"), *r.getVector("momentCoeffs")]
+    return rec, dict(position=position, body=False)
+
+
+def _buildAeroDamping(r, stagePos):
+    """RocketComponents.py:233-261 (class-level position = origin)"""
+    rec = _zeroInertiaRecord(L.CT_AERO_DAMPING, L.AD_SIZE)
+    rec[L.AD_AREF] = r.getFloat("Aref")
+    rec[L.AD_LREF] = r.getFloat("Lref")
+    rec[L.AD_XCOEFFS:L.AD_XCOEFFS + 3] = r.getVector("xDampingCoeffs")
+    rec[L.AD_YCOEFFS:L.AD_YCOEFFS + 3] = r.getVector("yDampingCoeffs")
+    rec[L.AD_ZCOEFFS:L.AD_ZCOEFFS + 3] = r.getVector("zDampingCoeffs")
+    return rec, dict(position=(0.0, 0.0, 0.0), body=False)
+
+
+_AERO_KEYS = {"Mach": L.AKEY_MACH, "Altitude": L.AKEY_ALTITUDE, "UnitReynolds": L.AKEY_UNITRE, "TotalAOA": L.AKEY_TOTALAOA,
+              "RollAngle": L.AKEY_ROLLANGLE, "AOA": L.AKEY_AOA, "AOSS": L.AKEY_AOSS}
+_AERO_COEFFS = ["CD", "CL", "CMx", "CMy", "CMz"]
+
+
+def _buildTabulatedAeroForce(r, stagePos):
+    """RocketComponents.py:263-345; tables with one key column (the reference's 1-D linInterp path)."""
+    position = r.getVector("position")
+    path = _resolvePath(r, "filePath")
+    with open(path) as f:
+        columnNames = f.readline().strip().split(",")
+    keys = []
+    i = 0
+    while i < len(columnNames) and columnNames[i] in _AERO_KEYS:
+        keys.append(_AERO_KEYS[columnNames[i]])
+        i += 1
+    coeffIdx = []
+    for name in columnNames[i:]:
+        if name not in _AERO_COEFFS:
+            raise ValueError("ERROR: One of the following columns: {} did not match any of the expected columns names: Keys: {}, values: {}. \
+                    Or was in the wrong order. All key columns must come BEFORE value columns.".format(columnNames, list(_AERO_KEYS), _AERO_COEFFS))
+        coeffIdx.append(_AERO_COEFFS.index(name))
+    if len(keys) != 1:
+        raise NotImplementedError("TabulatedAeroForce tables with {} key columns (scattered N-D interpolation) are not implemented by the B200 backend".format(len(keys)))
+    data = np.loadtxt(path, delimiter=",", skiprows=1)
+    if data.ndim == 1:
+        data = data.reshape(1, -1)
+    n, nVals = data.shape[0], data.shape[1] - 1
+    size = L.TA_TABLE + n * (1 + nVals)
+    rec = _zeroInertiaRecord(L.CT_TAB_AERO, size, position)
+    rec[L.TA_AREF] = r.getFloat("Aref")
+    rec[L.TA_LREF] = r.getFloat("Lref")
+    rec[L.TA_KEY] = keys[0]
+    rec[L.TA_NROWS] = n
+    rec[L.TA_NVALS] = nVals
+    rec[L.TA_COEFF_IDX:L.TA_COEFF_IDX + 5] = coeffIdx + [-1] * (5 - len(coeffIdx))
+    rec[L.TA_TABLE:L.TA_TABLE + n] = [float(x) for x in data[:, 0]]
+    for c in range(nVals):
+        rec[L.TA_TABLE + n * (1 + c):L.TA_TABLE + n * (2 + c)] = [float(x) for x in data[:, 1 + c]]
+    return rec, dict(position=position, body=False)
+
+
+def _buildTabulatedInertia(r, stagePos):
+    """RocketComponents.py:347-376. No `position` attribute: sorts by its CG at t = 0."""
+    path = _resolvePath(r, "filePath")
+    data = np.loadtxt(path, skiprows=1, delimiter=",")
+    if data.shape[1] != 8:
+        raise ValueError("Wrong number of columns in inertia table: {}. Expecting 8 columns: \
+                Time, Mass, CGx, CGy, CGz, MOIx, MOIy, MOIz")
+    n = data.shape[0]
+    rec = _zeroInertiaRecord(L.CT_TAB_INERTIA, L.TI_TABLE + 8 * n)
+    rec[L.TI_NROWS] = n
+    rec[L.TI_TABLE:L.TI_TABLE + 8 * n] = [float(x) for x in data.T.reshape(-1)]
+    table = dict(times=[float(x) for x in data[:, 0]], rows=[[float(x) for x in row[1:]] for row in data])
+    cg0 = tabulatedInertia(table, 0).CG
+    rec[L.C_POS:L.C_POS + 3] = cg0
+    return rec, dict(position=cg0, body=False, tabInertia=table)
+
+
+def tabulatedInertia(table, time) -> Inertia:
+    """TabulatedInertia.getInertia: linInterp of the 7 value columns as one numpy row (Interpolation.py:15-41)."""
+    from bisect import bisect
+    X, Y = table["times"], table["rows"]
+    i = bisect(X, time)
+    if i >= len(X):
+        row = Y[len(X) - 1]
+    elif i < 1:
+        row = Y[0]
+    else:
+        row = [(Y[i][k] - Y[i - 1][k]) * (time - X[i - 1]) / (X[i] - X[i - 1]) + Y[i - 1][k] for k in range(7)]
+    return Inertia(row[4:7], row[1:4], row[0])
+
+
+def _buildJetDamping(r, stagePos):
+    """RocketComponents.py:378-413"""
+    rec = _zeroInertiaRecord(L.CT_JET_DAMPING, L.JD_SIZE)
+    rec[L.JD_FRACTION] = r.getFloat("fraction")
+    return rec, dict(position=(0.0, 0.0, 0.0), body=False)
+
+
 # ======================================================================================
 class Model:
     """Result of buildModel: `.blob` (np.float64 array) plus host-side metadata."""
@@ -584,6 +716,9 @@ class Model:
         out = []
         for c in range(int(s[L.S_NCOMP])):
             off = int(s[L.S_COMP_OFF + c])
+            out.append(self.blob[off:off + int(self.blob[off + L.C_LEN])])
+        off = int(s[L.S_AUTO_BT_OFF])
+        if off and i == int(self.blob[L.H_NSTAGES]) - 1:      # the bottom stage's automatic zero-length boat tail
             out.append(self.blob[off:off + int(self.blob[off + L.C_LEN])])
         return out
 
@@ -829,11 +964,24 @@ def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000) -> Model:
                 rec, info = _buildMotor(cr, stagePos)
             elif cls == "RecoverySystem":
                 rec, info = _buildRecovery(cr, stagePos)
+            elif cls == "Force":
+                rec, info = _buildFixedForce(cr, stagePos)
+            elif cls == "AeroForce":
+                rec, info = _buildAeroForce(cr, stagePos)
+            elif cls == "AeroDamping":
+                rec, info = _buildAeroDamping(cr, stagePos)
+            elif cls == "TabulatedAeroForce":
+                rec, info = _buildTabulatedAeroForce(cr, stagePos)
+            elif cls == "TabulatedInertia":
+                rec, info = _buildTabulatedInertia(cr, stagePos)
+            elif cls == "FractionalJetDamping":
+                rec, info = _buildJetDamping(cr, stagePos)
             else:
                 rec, info = _buildMass(cr, stagePos)
             info["name"] = cr.getDictName()
             info["cls"] = cls
             info["rec"] = rec
+            info["order"] = len(comps)          # construction order (body components first, then by dictionary path)
             comps.append(info)
         # fixed-mass inertia pre-sum in construction order (CompositeObject.py:52-63)
         fixed = [c["inertia"] for c in comps if c["cls"] in _FIXED_MASS_CLASSES]
@@ -841,11 +989,16 @@ def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000) -> Model:
         motors = [c for c in comps if c["cls"] == "Motor"]
         if len(motors) > 1:
             raise NotImplementedError("more than one Motor per stage")
+        variable = [c for c in comps if c["cls"] in ("Motor", "TabulatedInertia")]      # construction order
+        if len(variable) > L.S_MAX_VAR:
+            raise NotImplementedError("more than {} variable-inertia components per stage".format(L.S_MAX_VAR))
+        if any(c["cls"] == "FractionalJetDamping" for c in comps) and not motors:
+            raise AttributeError("'NoneType' object has no attribute 'ignitionTime'")      # the reference's failure mode (RocketComponents.py:395)
         cgOvr = sr.tryGetVector("constCG", defaultValue=None)
         if cgOvr is not None:
             cgOvr = hm.v_add(cgOvr, stagePos)
         stages.append(dict(name=sr.getDictName(), reader=sr, pos=stagePos, comps=comps, fixed=fixedInertia,
-                           motor=(motors[0] if motors else None), cgOvr=cgOvr, massOvr=sr.tryGetFloat("constMass", defaultValue=None),
+                           motor=(motors[0] if motors else None), variable=variable, cgOvr=cgOvr, massOvr=sr.tryGetFloat("constMass", defaultValue=None),
                            moiOvr=sr.tryGetVector("constMOI", defaultValue=None), stageNumber=sr.getInt("stageNumber"),
                            sepType=sr.getString("separationTriggerType"), sepDelay=sr.getFloat("separationDelay"),
                            sepValue=sr.getFloat("separationTriggerValue")))
@@ -857,8 +1010,11 @@ def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000) -> Model:
     stages.sort(key=lambda s: s["pos"][2], reverse=True)
     if len(stages) > 4:
         raise NotImplementedError("more than 4 stages")
-    if len(stages) > 1:
-        raise NotImplementedError("multi-stage rockets are not implemented by the B200 backend yet")
+    if sum(1 for st in stages for c in st["comps"] if c["cls"] == "RecoverySystem") > 1:
+        raise NotImplementedError("more than one RecoverySystem in a rocket (the reference keeps only the last one created as Rocket.recoverySystem)")
+    for st in stages[:-1]:
+        if st["motor"] is None:
+            raise AttributeError("'NoneType' object has no attribute 'updateIgnitionTime'")      # the reference's failure mode (rocket.py:356)
 
     # auto-added zero-length boat tail for base drag (rocket.py:489-519)
     def bottomInterfaceZ(st):
@@ -866,22 +1022,21 @@ def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000) -> Model:
             if c.get("body"):
                 return c["position"][2] - c["length"] if c.get("canConnectBelow", True) else None
         return None
+    # Every stage that can become the bottom stage gets its record; the kernels evaluate it (after the stage's own components,
+    # where the reference appends it) only while the stage IS the bottom one: at launch for the last stage, after each
+    # separation for the new last stage (Rocket._stageSeparation -> _ensureBaseDragIsAccountedFor, rocket.py:461-474).
     for st in stages:
         st["autoBT"] = None
-    if maxDiameter > 0:
-        bottom = stages[-1]
-        hasBT = False
-        for c in reversed(bottom["comps"]):
-            if c.get("body"):
-                hasBT = bool(c.get("isBoatTail"))
-                break
-        if not hasBT and addAutoBT:
-            z = bottomInterfaceZ(bottom)
-            pos = (bottom["pos"][0], bottom["pos"][1], z)
-            rec = _autoBoatTailRecord(maxDiameter, pos, rocketRoughness)
-            bottom["comps"].append(dict(name="Auto-AddedZeroLengthBoatTail", cls="BoatTail", rec=rec, position=pos, body=True, length=0,
-                                        maxDiameter=maxDiameter, getRadius=lambda d: maxDiameter / 2, isBoatTail=True,
-                                        inertia=Inertia((0, 0, 0), (0, 0, 0), 0), auto=True))
+        if maxDiameter > 0 and addAutoBT:
+            hasBT, sawBody = False, False
+            for c in reversed(st["comps"]):
+                if c.get("body"):
+                    hasBT, sawBody = bool(c.get("isBoatTail")), True
+                    break
+            if sawBody and not hasBT:
+                z = bottomInterfaceZ(st)
+                pos = (st["pos"][0], st["pos"][1], z)
+                st["autoBT"] = _autoBoatTailRecord(maxDiameter, pos, rocketRoughness)
 
     # fin sets need the body radius at their mounting station (Fins.py:107-110, stage.py:126-143)
     for st in stages:
@@ -915,6 +1070,8 @@ def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000) -> Model:
             if ln is not None:
                 length += ln
         md = max(max([c.get("maxDiameter", 0) for c in st["comps"]] + [0]) for st in sub)
+        if sub[-1]["autoBT"] is not None:
+            md = max(md, maxDiameter)
         H[L.H_FINENESS + nRemaining - 1] = (length / md) if md != 0 else float("nan")
 
     # ---- serialise stages ----
@@ -922,7 +1079,7 @@ def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000) -> Model:
     H[L.H_RECOVERY_OFF] = 0
     # mass / CG / MOI cannot change in flight when every stage is motor-less or fully overridden (stage.py:33-41):
     # the CG-migration term of the state derivative (RigidBodies.py:91-97) is then exactly zero
-    H[L.H_INERTIA_CONST] = 1.0 if all(st["motor"] is None or (st["cgOvr"] is not None and st["massOvr"] is not None and st["moiOvr"] is not None)
+    H[L.H_INERTIA_CONST] = 1.0 if all(not st["variable"] or (st["cgOvr"] is not None and st["massOvr"] is not None and st["moiOvr"] is not None)
                                       for st in stages) else 0.0
     for si, st in enumerate(stages):
         S = [0.0] * L.S_SIZE
@@ -960,13 +1117,28 @@ def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000) -> Model:
                 S[L.S_BURN_DURATION] = c["motor"]["engineShutOff"]
             if c["cls"] == "RecoverySystem":
                 H[L.H_RECOVERY_OFF] = off
+        S[L.S_NVAR] = len(st["variable"])
+        for k, c in enumerate(st["variable"]):
+            S[L.S_VAR_IDX + k] = st["comps"].index(c)
+        for k, c in enumerate(sorted(st["variable"], key=lambda c: st["comps"].index(c))):
+            S[L.S_VAR2_IDX + k] = st["comps"].index(c)
+        fixedSorted = [c["inertia"] for c in st["comps"] if c["cls"] in _FIXED_MASS_CLASSES]
+        fixed2 = Inertia.combine(fixedSorted) if fixedSorted else Inertia((0, 0, 0), (0, 0, 0), 0)
+        S[L.S_FIXED2_MOI:L.S_FIXED2_MOI + 3] = fixed2.MOI
+        S[L.S_FIXED2_CG:L.S_FIXED2_CG + 3] = fixed2.CG
+        S[L.S_FIXED2_MASS] = fixed2.mass
+        if st["autoBT"] is not None:
+            S[L.S_AUTO_BT_OFF] = append(st["autoBT"])
         H[L.H_STAGE_OFF + si] = append(S)
 
     # ---- initial inertia -> CG shift of the integrated position (rocket.py:416-421) ----
     def stageInertia(st, t):
         items = [st["fixed"]]
-        if st["motor"] is not None:
-            items.append(motorInertia(st["motor"]["motor"], max(0, t - (0.0 if st is stages[-1] else 1000000000))))
+        for c in st["variable"]:
+            if c["cls"] == "Motor":
+                items.append(motorInertia(c["motor"], max(0, t - (0.0 if st is stages[-1] else 1000000000))))
+            else:
+                items.append(tabulatedInertia(c["tabInertia"], t))
         comb = Inertia.combine(items)
         if st["cgOvr"] is not None:
             comb.CG = st["cgOvr"]
@@ -998,6 +1170,8 @@ def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000) -> Model:
 
     blob = np.array(H + tail, dtype=np.float64)
     blob[L.H_LEN] = blob.size
-    meta = dict(stages=[dict(name=st["name"], components=[(c["name"], c["cls"]) for c in st["comps"]]) for st in stages],
+    meta = dict(stages=[dict(name=st["name"], components=[(c["name"], c["cls"]) for c in st["comps"]] +
+                             ([("Auto-AddedZeroLengthBoatTail", "BoatTail")] if (st is stages[-1] and st["autoBT"] is not None) else []))
+                        for st in stages],
                 initialInertia=rocketInertia0, method=method)
     return Model(blob, meta)

@@ -17,6 +17,10 @@ What is recorded, and which reference code produced it:
   rk45_pink.json .......... RK45Adaptive + PID, Hellman wind, PinkNoise2D (derived config 2), 4 runs
   windtunnel.json ......... WindTunnelSimulation.runSweep force evaluations (SingleSimulations.py:444-475)
                             + the reference's recorded regression values (BatchSims/regressionTests.mapleaf:1-27)
+  tabulated_rk4/rk45.json . TabulatedComponents.mapleaf: TabulatedInertia, TabulatedAeroForce (TotalAOA / AOA / AOSS / Mach keys),
+                            FractionalJetDamping, AeroDamping, AeroForce, FixedForce (Rocket/RocketComponents.py:183-413)
+  twostage_*.json ......... TwoStage.mapleaf: motor-burnout separation with delay, upper-stage ignition, automatic boat tail and
+                            fineness update (Rocket/rocket.py:339-361,461-528), RK4 to apogee and RK45Adaptive to the ground
   rng.json ................ random.Random / PinkNoiseGenerator known answers (test_SimDefinition.py:118-151,
                             test_TurbulenceModelling.py:37-60)
 """
@@ -192,6 +196,17 @@ def rng():
                 pinkBigSeed=987654321012, pinkRaw=raw, strSeedDraws=[random.Random("2394781").gauss(2, 5) for _ in range(1)])
 
 
+def singleFlight(defFile, overrides, traceEvery=25, keepDts=False):
+    """One un-sampled flight of a definition through the reference's Simulation.run()."""
+    sd = SimDefinition(defFile, silent=True, disableDistributionSampling=True)
+    for k, v in {**QUIET, **overrides}.items():
+        sd.setValue(k, v)
+    f = runOne(sd)
+    rec = flightRecord(f, traceEvery, keepDts)
+    print("  steps", rec["steps"], "final", rec["final"][:4], flush=True)
+    return dict(definition=os.path.basename(defFile), overrides=overrides, runs=[rec])
+
+
 def dump(name, obj):
     with open(os.path.join(HERE, name), "w") as f:
         json.dump(obj, f)
@@ -199,7 +214,7 @@ def dump(name, obj):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["model", "rng", "windtunnel", "rk4_apogee", "rk4_ground", "rk45_pink", "rk45_gust"]
+    which = sys.argv[1:] or ["model", "rng", "windtunnel", "rk4_apogee", "rk4_ground", "rk45_pink", "rk45_gust", "tabulated", "twostage"]
     mc = os.path.join(MY_DATA, "MonteCarlo.mapleaf")
     if "model" in which:
         dump("model_montecarlo.json", modelFields())
@@ -211,6 +226,14 @@ if __name__ == "__main__":
         dump("rk4_apogee.json", monteCarlo(mc, {}, "2394781", 8, traceEvery=200))
     if "rk4_ground" in which:
         dump("rk4_ground.json", monteCarlo(mc, {"SimControl.EndCondition": "Altitude", "SimControl.EndConditionValue": "0"}, "2394781", 3))
+    if "tabulated" in which:
+        tab = os.path.join(MY_DATA, "TabulatedComponents.mapleaf")
+        dump("tabulated_rk4.json", singleFlight(tab, {}))
+        dump("tabulated_rk45.json", singleFlight(tab, {"SimControl.timeDiscretization": "RK45Adaptive", "SimControl.EndConditionValue": "6"}, traceEvery=10))
+    if "twostage" in which:
+        two = os.path.join(MY_DATA, "TwoStage.mapleaf")
+        dump("twostage_rk4.json", singleFlight(two, {}, traceEvery=50))
+        dump("twostage_rk45_ground.json", singleFlight(two, {"SimControl.timeDiscretization": "RK45Adaptive", "SimControl.EndCondition": "Altitude"}, traceEvery=40, keepDts=True))
     adaptive = os.path.join(MY_DATA, "MonteCarloAdaptive.mapleaf")
     if "rk45_pink" in which:
         dump("rk45_pink.json", monteCarlo(adaptive, {}, "2394781", 4, globalSeed=2394781, keepDts=True))

@@ -281,3 +281,49 @@ def test_runner_end_to_end_matches_reference_run(backend, golden, tmp_path):
         assert abs(out.apogees[i] - r["results"][3]) < 1e-6 and abs(out.flightTimes[i] - r["results"][5]) < 1e-6
     log = open(out.logPath).read()
     assert "Monte Carlo Run #3" in log and "Mean Landing location" in log and "Mean Max horizontal speed" in log
+
+
+def test_tabulated_components_fixed_step_vs_reference(backend, golden):
+    """SURVEY §8 row a19 on the GPU: tabulated inertia / aero tables, jet damping, aero damping, constant-coefficient and fixed forces."""
+    g = golden("tabulated_rk4.json")
+    m = buildFrom(g["definition"], g["overrides"])
+    r = g["runs"][0]
+    o = gpuRun(backend, m, 1, {}, traceLane=0, traceRows=2000)
+    assert o["status"][0] == L.ST_OK and o["counters"][0, 0] == r["steps"]
+    assert stateErr(o["finals"][0], r["final"]) < FIXED_TOL
+    for idx, row in zip(r["traceIdx"], r["trace"]):
+        assert stateErr(np.concatenate([o["trace"][idx, 1:14], [0]]), row) < FIXED_TOL
+
+
+def test_tabulated_components_adaptive_vs_reference(backend, golden):
+    g = golden("tabulated_rk45.json")
+    m = buildFrom(g["definition"], g["overrides"])
+    r = g["runs"][0]
+    o = gpuRun(backend, m, 1, {})
+    assert o["status"][0] == L.ST_OK
+    assert abs(int(o["counters"][0, 0]) - r["steps"]) <= 10
+    # 6 s of flight ending on the clock: compare the final state at the 1e-5 level (adaptive step sequences decorrelate)
+    assert abs(o["finals"][0, 13] - r["final"][0]) < 1e-9
+    assert relErr(o["finals"][0, 0:3], r["final"][1:4]) < 1e-5 and relErr(o["finals"][0, 3:6], r["final"][4:7]) < 1e-5
+
+
+def test_two_stage_fixed_step_vs_reference(backend, golden):
+    g = golden("twostage_rk4.json")
+    m = buildFrom(g["definition"], g["overrides"])
+    r = g["runs"][0]
+    o = gpuRun(backend, m, 1, {}, traceLane=0, traceRows=4000)
+    assert o["status"][0] == L.ST_OK and o["counters"][0, 0] == r["steps"]
+    assert stateErr(o["finals"][0], r["final"]) < FIXED_TOL
+    for idx, row in zip(r["traceIdx"], r["trace"]):
+        assert stateErr(np.concatenate([o["trace"][idx, 1:14], [0]]), row) < FIXED_TOL
+    assert relErr(o["results"][0, 3:7], r["results"][3:7]) < FIXED_TOL
+
+
+def test_two_stage_adaptive_lockstep_vs_reference(backend, golden):
+    g = golden("twostage_rk45_ground.json")
+    m = buildFrom(g["definition"], g["overrides"])
+    r = g["runs"][0]
+    o = gpuRun(backend, m, 1, {}, traceLane=0, traceRows=4000, dtReplay=r["dts"])
+    assert o["counters"][0, 0] == r["steps"]
+    assert np.abs(o["trace"][:, 0] - np.array(r["times"])).max() < 1e-9
+    assert relErr(o["results"][0], r["results"]) < 1e-5

@@ -133,3 +133,55 @@ def test_step_limit_status():
     m.blob[L.H_MAX_STEPS] = 100
     o = oracle.run(m.blob, 1)
     assert o["status"][0] == L.ST_STEP_LIMIT and o["counters"][0, 0] == 100
+
+
+@pytest.mark.parametrize("name", ["tabulated_rk4.json", "tabulated_rk45.json"])
+def test_tabulated_and_force_only_components(golden, name):
+    """TabulatedInertia, TabulatedAeroForce (TotalAOA / AOA / AOSS / Mach keys, including the cached-vector mutation of
+    getAOA / getAOSS), FractionalJetDamping, AeroDamping, AeroForce, Force: one tumbling flight, fixed-step and adaptive."""
+    g = golden(name)
+    m = buildFrom(g["definition"], g["overrides"])
+    r = g["runs"][0]
+    o = oracle.run(m.blob, 1, {}, traceLane=0, traceMaxRows=2000)
+    assert o["status"][0] == L.ST_OK and o["counters"][0, 0] == r["steps"]
+    assert o["finals"][0, 13] == r["final"][0]
+    assert stateErr(o["finals"][0], r["final"]) < 1e-12
+    for idx, row in zip(r["traceIdx"], r["trace"]):
+        assert o["trace"][idx, 0] == row[0]
+        assert stateErr(np.concatenate([o["trace"][idx, 1:14], [0]]), row) < 1e-12
+
+
+def test_variable_inertia_components_keep_construction_order():
+    m = buildFrom("TabulatedComponents.mapleaf")
+    S = m.stageRecord(0)
+    names = [n for n, _ in m.meta["stages"][0]["components"]]
+    assert int(S[L.S_NVAR]) == 2
+    # construction order is by dictionary path (Inertia < Motor); the force sum runs top to bottom (Motor first)
+    assert [names[int(S[L.S_VAR_IDX + k])] for k in range(2)] == ["Inertia", "Motor"]
+    assert names[0] == "Motor" and names[-1] == "YawMoment"
+
+
+def test_two_stage_separation_fixed_step(golden):
+    """Booster separation 0.5 s after burnout, sustainer ignition at separation, boat-tail hand-over, fineness update, motors and
+    fixed masses without inertia overrides (Rocket/rocket.py:339-361,461-528): agreement 1e-12 (observed 1e-13, not bit-identical)."""
+    g = golden("twostage_rk4.json")
+    m = buildFrom(g["definition"], g["overrides"])
+    r = g["runs"][0]
+    o = oracle.run(m.blob, 1, {}, traceLane=0, traceMaxRows=4000)
+    assert o["status"][0] == L.ST_OK and o["counters"][0, 0] == r["steps"]
+    assert stateErr(o["finals"][0], r["final"]) < 1e-12
+    for idx, row in zip(r["traceIdx"], r["trace"]):
+        assert o["trace"][idx, 0] == row[0]
+        assert stateErr(np.concatenate([o["trace"][idx, 1:14], [0]]), row) < 1e-12
+
+
+def test_two_stage_adaptive_lockstep(golden):
+    """RK45Adaptive through separation, ignition, apogee, chute and ground impact: replaying the reference's accepted step
+    sizes, every step time is identical (same event clamps, no extra rejections) and the results agree to 1e-6."""
+    g = golden("twostage_rk45_ground.json")
+    m = buildFrom(g["definition"], g["overrides"])
+    r = g["runs"][0]
+    o = oracle.run(m.blob, 1, {}, traceLane=0, traceMaxRows=4000, dtReplay=r["dts"])
+    assert o["counters"][0, 0] == r["steps"]
+    assert np.abs(o["trace"][:, 0] - np.array(r["times"])).max() < 1e-9
+    assert relErr(o["results"][0], r["results"]) < 1e-6
