@@ -94,6 +94,10 @@
 #define H_FIN_CUBIC_OFF 101
 #define H_START_TIME 102
 #define H_INERTIA_CONST 103   /* 1: no stage's mass / CG / MOI can change in flight (full overrides or no motor) */
+/* WGS84 ellipsoid (EarthModelling.py:229-240): semi-major axis, first eccentricity squared; H_EARTH_RADIUS is the sphere radius of
+   the Round model and H_EARTH_GM the gravitational parameter of the selected model */
+#define H_WGS_A 104
+#define H_WGS_E2 105
 #define H_SIZE 128
 
 /* integrator ids (H_INTEGRATOR) */

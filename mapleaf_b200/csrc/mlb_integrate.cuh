@@ -219,8 +219,14 @@ MLB_DEV void stageSeparation(const double* B, Lane& L) {                        
 }
 MLB_DEV void triggerEvents(const double* B, Lane& L, double& estTimeToNext, bool& deterministic) {   /* simEventDetector.py:64-118 */
     double est = 1e10; bool det = false;
-    const double alt = earthAltitude(B, L.s.pos);
-    const double vz = L.s.vel.z;
+    /* Environment.convertStateToENUFrame (environment.py:130-144): altitude ASL and the vertical velocity in the local ENU frame */
+    double alt = L.s.pos.z, vz = L.s.vel.z;
+    if (earthIsRound(B)) {
+        Geodetic geo = cartesianToGeodetic(B, L.s.pos);
+        alt = geo.height;
+        Q4 enuToGlobal = qConj(enuRotationOf(geo));
+        vz = qRotate(enuToGlobal, L.s.vel).z;
+    }
     const int n0 = L.nEvents;
     unsigned removeMask = 0;
     for (int i = 0; i < n0; i++) {

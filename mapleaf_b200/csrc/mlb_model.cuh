@@ -31,7 +31,7 @@ namespace mlb {
 
 struct ForceMoment { V3 force, location, moment; };      /* Motion/forceMomentSystem.py */
 struct Inertia { V3 MOI, CG; double mass; };             /* Motion/inertia.py */
-struct Air { double temp, density, viscosity; V3 wind, meanWind; };
+struct Air { double temp, density, viscosity, asl; V3 wind, meanWind; };
 struct Event { int type; int callback; double value; double delay; };
 
 /* Everything one lane carries between time steps. */
@@ -84,7 +84,46 @@ MLB_DEV V3 linInterpV(const double* X, const double* Yx, const double* Yy, const
 /* ---------------------------------------------------------------------------------------------
  * Environment
  * ------------------------------------------------------------------------------------------- */
-MLB_DEV double earthAltitude(const double* B, V3 p) { return p.z; }                         /* No/FlatEarth.getAltitude */
+/* Earth models (ENV/EarthModelling.py): None / Flat use the launch-tower frame as the inertial frame; Round and WGS84 integrate in
+   an earth-centred inertial frame and need the geodetic latitude / longitude / height of a position: closed form for the
+   sphere (:147-160), Newton-Raphson on the latitude parameter for the ellipsoid (:305-341). Angles in radians here. */
+struct Geodetic { double lat, lon, height; };
+MLB_DEV bool earthIsRound(const double* B) { int m = (int)B[H_EARTH]; return m == EARTH_ROUND || m == EARTH_WGS84; }
+MLB_DEV Geodetic cartesianToGeodetic(const double* B, V3 pos) {
+    Geodetic g;
+    const double x = pos.x, y = pos.y, z = pos.z;
+    const double p = sqrt(x * x + y * y);
+    g.lon = m_atan2(y, x);
+    if ((int)B[H_EARTH] == EARTH_ROUND) {
+        g.lat = m_atan2(z, p);
+        g.height = sqrt(x * x + y * y + z * z) - B[H_EARTH_RADIUS];
+        return g;
+    }
+    const double e2 = B[H_WGS_E2], a = B[H_WGS_A];
+    double Kold = 1 / (1 - e2), Knew; const double Korig = Kold;
+    for (int it = 0; it < 50; it++) {
+        double t = p * p + (1 - e2) * z * z * (Kold * Kold);
+        double ci = (t * sqrt(t)) / (a * e2);
+        Knew = 1 + (p * p + (1 - e2) * z * z * (Kold * Kold * Kold)) / (ci - p * p);
+        if (fabs(Knew - Kold) < 1e-10) break;
+        Kold = Knew;
+    }
+    const double k = Knew;
+    g.lat = m_atan2(k * z, p);
+    g.height = (1 / e2) * (1 / k - 1 / Korig) * sqrt(p * p + z * z * k * k);
+    return g;
+}
+MLB_DEV Q4 enuRotationOf(const Geodetic& g) {                                               /* getInertialToENUFrameRotation :170-190 */
+    /* the reference converts to degrees and back: radians(degrees(lon) + 90), radians(90 - degrees(lat)) */
+    double lonDeg = g.lon * (180.0 / MLB_PI), latDeg = g.lat * (180.0 / MLB_PI);
+    Q4 rot1 = qAxisAngle(v3(0, 0, 1), (lonDeg + 90) * (MLB_PI / 180.0));
+    Q4 rot2 = qAxisAngle(v3(1, 0, 0), (90 - latDeg) * (MLB_PI / 180.0));
+    return rot1 * rot2;
+}
+MLB_DEV double earthAltitude(const double* B, V3 p) {
+    if (!earthIsRound(B)) return p.z;                                                       /* No/FlatEarth.getAltitude */
+    return cartesianToGeodetic(B, p).height;
+}
 
 MLB_DEV void atmosphere(const double* B, double asl, Air& e) {
     int model = (int)B[H_ATM];
@@ -159,7 +198,11 @@ MLB_DEV V3 turbulenceAt(const double* B, Lane& L, double altitude, V3 meanWind, 
 
 MLB_DEV Air airProperties(const double* B, Lane& L, V3 position, double time, bool skipTurbulence) {   /* environment.py:146-181 */
     Air e;
-    double asl = earthAltitude(B, position);
+    const bool round = earthIsRound(B);
+    Geodetic geo;
+    if (round) geo = cartesianToGeodetic(B, position);      /* one geodetic solve serves altitude and the ENU rotation */
+    double asl = round ? geo.height : position.z;
+    e.asl = asl;
     double agl = asl - B[H_ELEV];
     V3 meanWind = meanWindAt(B, L, agl);
     /* under a parachute with turbulenceOffWhenUnderChute the reference still evaluates the turbulence model and
@@ -167,15 +210,33 @@ MLB_DEV Air airProperties(const double* B, Lane& L, V3 position, double time, bo
     V3 turbWind = skipTurbulence ? v3(0, 0, 0) : turbulenceAt(B, L, agl, meanWind, time);
     double earthRotationSpeed = B[H_EARTH_ROT] * sqrt(position.x * position.x + position.y * position.y);
     meanWind = meanWind + v3(earthRotationSpeed, 0, 0);
-    e.wind = meanWind + turbWind; e.meanWind = meanWind;                                   /* flat earth: ENU == inertial */
+    if (round) {                                            /* wind is modelled in the local ENU frame: rotate into the inertial frame */
+        Q4 enu = enuRotationOf(geo);
+        meanWind = qRotate(enu, meanWind);
+        turbWind = qRotate(enu, turbWind);
+    }
+    e.wind = meanWind + turbWind; e.meanWind = meanWind;
     atmosphere(B, asl, e);
     return e;
 }
 
-MLB_DEV V3 gravityForceGlobal(const double* B, double mass, V3 pos) {                       /* EarthModelling.py:93-105 */
-    if ((int)B[H_EARTH] == EARTH_NONE) return v3(0, 0, 0);
-    double r = pos.z + 6371000;
-    return v3(0, 0, -1) * (mass * B[H_EARTH_GM] / (r * r));
+MLB_DEV V3 gravityForceGlobal(const double* B, double mass, V3 pos) {                       /* EarthModelling.py:93-105,162-168,348-369 */
+    const int model = (int)B[H_EARTH];
+    if (model == EARTH_NONE) return v3(0, 0, 0);
+    if (model == EARTH_FLAT) {
+        double r = pos.z + 6371000;
+        return v3(0, 0, -1) * (mass * B[H_EARTH_GM] / (r * r));
+    }
+    const double r = len(pos);
+    if (model == EARTH_ROUND) return (-normalize(pos)) * (mass * B[H_EARTH_GM] / (r * r));
+    const double J2 = 0.00108262982, re = B[H_WGS_A];                                       /* WGS84: J2 gravity (NESC-RP-12-00770 eq. 29-31) */
+    const double r2 = r * r;
+    double frac = (3 * J2 * re * re) / (2 * (r2 * r2));
+    double multiplier = -B[H_EARTH_GM] * mass / (r2 * r);
+    double zz = pos.z * pos.z;
+    return v3(pos.x * multiplier * (1 - frac * (5 * zz - r2)),
+              pos.y * multiplier * (1 - frac * (5 * zz - r2)),
+              pos.z * multiplier * (1 - frac * (5 * zz - 3 * r2)));
 }
 
 /* ---------------------------------------------------------------------------------------------
@@ -276,7 +337,7 @@ MLB_DEV V3 localFrameAirVel(const State& s, V3 wind) { return qConjRotate(s.q, s
 MLB_DEV double betaOf(double Mach) { return (Mach <= 0.9) ? sqrt(1 - Mach * Mach) : sqrt(Mach * Mach - 1); }   /* :152-163 */
 
 MLB_DEV void aeroSetup(const double* B, const Lane& L, Aero& a, const State& s, const Air& e, double time) {
-    a.time = time; a.w = s.w; a.density = e.density; a.viscosity = e.viscosity; a.asl = earthAltitude(B, s.pos);
+    a.time = time; a.w = s.w; a.density = e.density; a.viscosity = e.viscosity; a.asl = e.asl;
     a.Mach = len(s.vel - e.wind) / sqrt(1.4 * 287 * e.temp);                                /* :15-20 */
     a.lfav = localFrameAirVel(s, e.wind);
     a.airSpeed = len(a.lfav);

@@ -760,6 +760,18 @@ def initialStateLaunchTowerFrame(rocketReader: SubDictReader):
     return initPos, initVel, q, w
 
 
+def initialStateGlobalFrame(rocketReader: SubDictReader, earth: str, elevation: float, latitude: float, longitude: float, onRail: bool):
+    """Environment.convertInitialStateToGlobalFrame (environment.py:105-128): launch-tower frame -> inertial frame of the earth model."""
+    initPos, initVel, q0, w0 = initialStateLaunchTowerFrame(rocketReader)
+    initPos = hm.v_add(initPos, (0, 0, elevation))
+    if onRail:
+        w0 = (0.0, 0.0, 0.0)
+    if earth in ("Round", "WGS84"):
+        # SphericalEarth.convertIntoGlobalFrame (EarthModelling.py:197-227)
+        initPos, initVel, q0, w0 = hm.convertIntoGlobalFrame(earth, initPos, initVel, q0, w0, latitude, longitude)
+    return initPos, initVel, q0, w0
+
+
 def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000) -> Model:
     sd = simDefinition
     env = SubDictReader("Environment", sd)
@@ -821,11 +833,14 @@ def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000) -> Model:
         H[L.H_EARTH], H[L.H_EARTH_GM], H[L.H_EARTH_RADIUS] = L.EARTH_FLAT, 398600.5e9, 6371000
     elif earth == "None":
         H[L.H_EARTH] = L.EARTH_NONE
-    elif earth in ("Round", "WGS84"):
-        raise NotImplementedError("Earth model '{}' is not implemented by the B200 backend yet".format(earth))
+    elif earth == "Round":
+        H[L.H_EARTH], H[L.H_EARTH_GM], H[L.H_EARTH_RADIUS] = L.EARTH_ROUND, hm.SPHERE_GM, hm.SPHERE_RADIUS
+    elif earth == "WGS84":
+        H[L.H_EARTH], H[L.H_EARTH_GM], H[L.H_EARTH_RADIUS] = L.EARTH_WGS84, hm.SPHERE_GM, hm.SPHERE_RADIUS
+        H[L.H_WGS_A], H[L.H_WGS_E2] = hm.WGS_A, hm.WGS_E2
     else:
         raise NotImplementedError("Earth model: {} not found. Try 'Flat', 'Round' or 'WGS84'".format(earth))
-    H[L.H_EARTH_ROT] = 0.0
+    H[L.H_EARTH_ROT] = hm.EARTH_ROTATION_RATE if earth in ("Round", "WGS84") else 0.0
     H[L.H_ELEV] = env.tryGetFloat("LaunchSite.elevation")
     H[L.H_LAT] = env.tryGetFloat("LaunchSite.latitude")
     H[L.H_LON] = env.tryGetFloat("LaunchSite.longitude")
@@ -905,15 +920,15 @@ def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000) -> Model:
     H[L.H_TURB_OFF_CHUTE] = 1.0 if rk.getBool("Environment.turbulenceOffWhenUnderChute") else 0.0
 
     # ---- initial state, launch rail (rocket.py:251-291, environment.py:57-91,105-128) ----
-    initPos, initVel, q0, w0 = initialStateLaunchTowerFrame(rk)
     railLength = env.getFloat("LaunchSite.railLength")
     H[L.H_RAIL_LEN] = railLength
-    initPos = hm.v_add(initPos, (0, 0, H[L.H_ELEV]))
+    initPos, initVel, q0, w0 = initialStateGlobalFrame(rk, earth, H[L.H_ELEV], H[L.H_LAT], H[L.H_LON], railLength > 0)
     if railLength > 0:
-        w0 = (0.0, 0.0, 0.0)
         d = hm.v_normalize(env.getVector("Rocket.initialDirection"))
         qr = hm.q_from_axis_angle(hm.v_cross((0, 0, 1), d), hm.v_angle((0, 0, 1), d))
         railPos = hm.v_add(env.getVector("Rocket.position"), (0, 0, H[L.H_ELEV]))
+        if earth in ("Round", "WGS84"):
+            railPos, _, qr, _ = hm.convertIntoGlobalFrame(earth, railPos, (0, 0, 0), qr, (0, 0, 0), H[L.H_LAT], H[L.H_LON])
         railDir, _ = hm.q_rotate(qr, (0, 0, 1))
         H[L.H_RAIL_POS:L.H_RAIL_POS + 3] = railPos
         H[L.H_RAIL_DIR:L.H_RAIL_DIR + 3] = hm.v_normalize(railDir)
@@ -1173,5 +1188,5 @@ def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000) -> Model:
     meta = dict(stages=[dict(name=st["name"], components=[(c["name"], c["cls"]) for c in st["comps"]] +
                              ([("Auto-AddedZeroLengthBoatTail", "BoatTail")] if (st is stages[-1] and st["autoBT"] is not None) else []))
                         for st in stages],
-                initialInertia=rocketInertia0, method=method)
+                initialInertia=rocketInertia0, method=method, earth=earth)
     return Model(blob, meta)

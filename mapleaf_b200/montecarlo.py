@@ -23,7 +23,7 @@ from typing import List, Optional
 import numpy as np
 
 from . import hostmath as hm
-from .model import L, buildModel, initialStateLaunchTowerFrame
+from .model import L, buildModel, initialStateGlobalFrame
 from .simdef import SimDefinition, SubDictReader, parseVector
 
 __all__ = ["runMonteCarloSimulation", "MonteCarloLogger", "Vector", "MonteCarloResults", "laneInitialState"]
@@ -97,10 +97,8 @@ class MonteCarloResults:
 def laneInitialState(simDefinition: SimDefinition, model) -> List[float]:
     """Initial inertial-frame state of the CG for the current (sampled) Rocket.* values: rocket.py:251-291,416-421."""
     rk = SubDictReader("Rocket", simDefinition)
-    initPos, initVel, q0, w0 = initialStateLaunchTowerFrame(rk)
-    initPos = hm.v_add(initPos, (0, 0, model.header("H_ELEV")))
-    if model.header("H_RAIL_LEN") > 0:
-        w0 = (0.0, 0.0, 0.0)
+    initPos, initVel, q0, w0 = initialStateGlobalFrame(rk, model.meta["earth"], model.header("H_ELEV"), model.header("H_LAT"),
+                                                       model.header("H_LON"), model.header("H_RAIL_LEN") > 0)
     cgGlobal, q0n = hm.q_rotate(q0, model.meta["initialInertia"].CG)
     return list(hm.v_add(initPos, cgGlobal)) + list(initVel) + list(q0n) + list(w0)
 

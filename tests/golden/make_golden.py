@@ -21,6 +21,10 @@ What is recorded, and which reference code produced it:
                             FractionalJetDamping, AeroDamping, AeroForce, FixedForce (Rocket/RocketComponents.py:183-413)
   twostage_*.json ......... TwoStage.mapleaf: motor-burnout separation with delay, upper-stage ignition, automatic boat tail and
                             fineness update (Rocket/rocket.py:339-361,461-528), RK4 to apogee and RK45Adaptive to the ground
+  earth_*.json ............ TabulatedComponents.mapleaf flown over the Round and the WGS84 (J2) earth from 47.5 N, 112.25 W
+                            (ENV/EarthModelling.py:107-369, ENV/environment.py:105-181)
+  nasa_twostage.json ...... NASATwoStageOrbitalRocket.mapleaf, 200 s (BASELINE.json configs[3]; the reference's own regression case,
+                            BatchSims/NASAVerificationCases.mapleaf:264-278)
   rng.json ................ random.Random / PinkNoiseGenerator known answers (test_SimDefinition.py:118-151,
                             test_TurbulenceModelling.py:37-60)
 """
@@ -64,9 +68,13 @@ def runOne(sd):
 
 
 def flightRecord(f, traceEvery=0, keepDts=False):
-    land = f.getLandingLocation()
+    try:
+        land = f.getLandingLocation()
+        land = [land.X, land.Y, land.Z]
+    except ZeroDivisionError:      # Time end condition: the last step is ~1e-14 s long, dz == 0 (rocketFlight.py:65 divides by it)
+        land = [None, None, None]
     rec = dict(steps=len(f.times) - 1, final=stateRow(f.times[-1], f.rigidBodyStates[-1]),
-               results=[land.X, land.Y, land.Z, f.getApogee(), f.getMaxSpeed(), f.getFlightTime(), f.getMaxHorizontalVel()])
+               results=[*land, f.getApogee(), f.getMaxSpeed(), f.getFlightTime(), f.getMaxHorizontalVel()])
     if traceEvery:
         idx = list(range(0, len(f.times), traceEvery))
         rec["traceIdx"] = idx
@@ -214,7 +222,7 @@ def dump(name, obj):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["model", "rng", "windtunnel", "rk4_apogee", "rk4_ground", "rk45_pink", "rk45_gust", "tabulated", "twostage"]
+    which = sys.argv[1:] or ["model", "rng", "windtunnel", "rk4_apogee", "rk4_ground", "rk45_pink", "rk45_gust", "tabulated", "twostage", "earth"]
     mc = os.path.join(MY_DATA, "MonteCarlo.mapleaf")
     if "model" in which:
         dump("model_montecarlo.json", modelFields())
@@ -234,6 +242,12 @@ if __name__ == "__main__":
         two = os.path.join(MY_DATA, "TwoStage.mapleaf")
         dump("twostage_rk4.json", singleFlight(two, {}, traceEvery=50))
         dump("twostage_rk45_ground.json", singleFlight(two, {"SimControl.timeDiscretization": "RK45Adaptive", "SimControl.EndCondition": "Altitude"}, traceEvery=40, keepDts=True))
+    if "earth" in which:
+        tab = os.path.join(MY_DATA, "TabulatedComponents.mapleaf")
+        site = {"Environment.LaunchSite.latitude": "47.5", "Environment.LaunchSite.longitude": "-112.25", "Environment.LaunchSite.elevation": "350"}
+        dump("earth_round_rk4.json", singleFlight(tab, {"Environment.EarthModel": "Round", **site}))
+        dump("earth_wgs84_rk4.json", singleFlight(tab, {"Environment.EarthModel": "WGS84", **site}))
+        dump("nasa_twostage.json", singleFlight(os.path.join(MY_DATA, "NASATwoStageOrbitalRocket.mapleaf"), {}, traceEvery=40, keepDts=True))
     adaptive = os.path.join(MY_DATA, "MonteCarloAdaptive.mapleaf")
     if "rk45_pink" in which:
         dump("rk45_pink.json", monteCarlo(adaptive, {}, "2394781", 4, globalSeed=2394781, keepDts=True))

@@ -185,3 +185,33 @@ def test_two_stage_adaptive_lockstep(golden):
     assert o["counters"][0, 0] == r["steps"]
     assert np.abs(o["trace"][:, 0] - np.array(r["times"])).max() < 1e-9
     assert relErr(o["results"][0], r["results"]) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["earth_round_rk4.json", "earth_wgs84_rk4.json"])
+def test_round_and_wgs84_earth(golden, name):
+    """Earth-centred inertial frame: launch-site conversion, geodetic altitude (Newton iteration for the ellipsoid), ENU wind rotation,
+    earth-rotation wind term, inverse-square and J2 gravity (ENV/EarthModelling.py, ENV/environment.py:105-181)."""
+    g = golden(name)
+    m = buildFrom(g["definition"], g["overrides"])
+    r = g["runs"][0]
+    o = oracle.run(m.blob, 1, {}, traceLane=0, traceMaxRows=2000)
+    assert o["status"][0] == L.ST_OK and o["counters"][0, 0] == r["steps"]
+    assert stateErr(o["finals"][0], r["final"]) < 1e-13
+    for idx, row in zip(r["traceIdx"], r["trace"]):
+        assert stateErr(np.concatenate([o["trace"][idx, 1:14], [0]]), row) < 1e-13
+    assert relErr(o["results"][0, 3:7], r["results"][3:7]) < 1e-13
+
+
+def test_nasa_two_stage_orbital_rocket(golden):
+    """BASELINE.json configs[3] / the reference's own regression case (NASAVerificationCases.mapleaf:264-278): RK45Adaptive, WGS84 + J2,
+    tabulated aero and inertia, jet damping, separation 96.79 s after burnout, 200 s. Free-running: same 1043 accepted steps, same states."""
+    g = golden("nasa_twostage.json")
+    m = buildFrom(g["definition"], g["overrides"])
+    r = g["runs"][0]
+    o = oracle.run(m.blob, 1, {}, traceLane=0, traceMaxRows=2000)
+    assert o["counters"][0, 0] == r["steps"] == 1043
+    assert stateErr(o["finals"][0], r["final"]) < 1e-12
+    assert np.abs(o["trace"][:, 0] - np.array(r["times"])).max() < 1e-9
+    # the reference's recorded regression values for this case, its own 0.2 % tolerance (Batch.py:51-52)
+    for got, exp in zip(o["finals"][0, [0, 1, 3, 4]], (6598829.9, 637702.775, 2308.8505, 8475.945)):
+        assert abs(got - exp) <= 0.002 * abs(exp)
