@@ -98,6 +98,9 @@
    the Round model and H_EARTH_GM the gravitational parameter of the selected model */
 #define H_WGS_A 104
 #define H_WGS_E2 105
+/* doubles [0, H_SHARED_LEN) are staged in shared memory by the kernels; N-D interpolation tables of the control system (up to
+   hundreds of KB) follow and are read from global memory */
+#define H_SHARED_LEN 106
 #define H_SIZE 128
 
 /* integrator ids (H_INTEGRATOR) */
@@ -360,6 +363,41 @@
 /* FractionalJetDamping (:378-413) */
 #define JD_FRACTION 12
 #define JD_SIZE 13
+
+/* ---- control system record at H_CTRL_OFF (0: none): GNC/ControlSystems.py:45-211, MomentControllers.py:19-83, Actuators.py:43-139,
+   actuatedSystem.py:25-66 ------------------------------------------------------------------------------------------------------- */
+#define CS_UPDATE_DT 0        /* controlTimeStep = 1 / updateRate (0: run every step) */
+#define CS_TARGET_Q 1         /* Stabilizer target orientation (Navigation.py:15-24) */
+#define CS_MC_TYPE 5          /* 0: constant gains, 1: gains scheduled by a table */
+#define CS_GAINS 6            /* Pxy Ixy Dxy Pz Iz Dz */
+#define CS_GAIN_NKEYS 12
+#define CS_GAIN_KEYS 13       /* AKEY_* of each gain-table key column */
+#define CS_GAIN_INTERP_OFF 17
+#define CS_STAGE 18           /* controlled fin set: stage index, index in the stage's component list */
+#define CS_COMP 19
+#define CS_NACT 20
+#define CS_ACT_TAU 21         /* first-order actuator response time */
+#define CS_ACT_HASMIN 22
+#define CS_ACT_MIN 23
+#define CS_ACT_HASMAX 24
+#define CS_ACT_MAX 25
+#define CS_DEFL_NKEYS 26      /* aero keys in front of the three desired-moment keys of the deflection table */
+#define CS_DEFL_KEYS 27
+#define CS_DEFL_INTERP_OFF 31
+#define CS_FORCE_RK4 32       /* adaptive method + fixed update rate: RK4 during the controlled ascent (ControlSystems.py:126-135) */
+#define CS_TABLEAU2_OFF 33
+#define CS_SIZE 36
+#define CS_MAX_ACT 8
+/* N-D scattered linear interpolation (scipy LinearNDInterpolator + NearestNDInterpolator, Motion/Interpolation.py:109-124):
+   Delaunay triangulation computed on the host with scipy. Data after the 4 counts: points[npts][dim], values[npts][nval],
+   simplices[nsimp][dim+1] (point indices), transform[nsimp][dim+1][dim] (barycentric transform of each simplex, NaN if degenerate) */
+#define ND_DIM 0
+#define ND_NVAL 1
+#define ND_NPTS 2
+#define ND_NSIMP 3
+#define ND_DATA 4
+#define ND_MAX_DIM 6
+#define ND_MAX_VAL 8
 
 /* ---- per-lane input arrays (mlb_set_lanes arrayIds) ----------------------------------- */
 #define LANE_WIND 0          /* 3: Environment.ConstantMeanWind.velocity (ENU)        */

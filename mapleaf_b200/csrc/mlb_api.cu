@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) integrateLanes(const RunArg
             if (haveFinal) dt = finalDt;
             if (a.dtReplay && L.nSteps < a.nReplay) dt = a.dtReplay[L.nSteps];
         }
-        StepResult r = rocketTimeStep(B, L, ks, dt, run);
+        StepResult r = rocketTimeStep(B, a.blob, L, ks, dt, run);
         if (run) {
             dt = r.dt * r.factor;
             prevPos = lastPos; lastPos = L.s.pos;
@@ -216,6 +216,7 @@ struct mlb_handle {
     long long launches = 0;
     int nSlots = 0; size_t smemBytes = 0;
     int nSM = 148; int forceBlock = 0; int lastBlock = 0;
+    size_t sharedLen = 0;
 };
 
 static int laneArrayComponents(int id) { return id == LANE_WIND ? 3 : (id == LANE_INIT_STATE ? 13 : (id == LANE_PINK_SEED ? 3 : -1)); }
@@ -251,7 +252,8 @@ extern "C" int mlb_create(const void* model_blob, size_t n, int device, mlb_hand
     int method = (int)b[H_INTEGRATOR];
     int nRows = (int)b[H_TAB_NSTAGE_ROWS];
     h->nSlots = (method == INT_EULER) ? 1 : nRows + 1;
-    size_t blobPad = (len + 1) & ~(size_t)1;
+    h->sharedLen = (size_t)b[H_SHARED_LEN] > 0 && (size_t)b[H_SHARED_LEN] <= len ? (size_t)b[H_SHARED_LEN] : len;      /* the rest stays in global memory */
+    size_t blobPad = (h->sharedLen + 1) & ~(size_t)1;
     h->smemBytes = blobPad * sizeof(double);
     if (h->smemBytes > 227 * 1024) { delete h; return fail(MLB_ERR_UNSUPPORTED, "mlb_create: model block + stage storage exceed shared memory"); }
     CU(cudaMalloc(&h->d_blob, len * sizeof(double)));
@@ -318,7 +320,7 @@ extern "C" int mlb_run(mlb_handle* h, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     h->stream = s;
     RunArgs a;
-    a.blob = h->d_blob; a.blobLen = (int)h->blob.size(); a.blobPad = (int)((h->blob.size() + 1) & ~(size_t)1); a.nSlots = h->nSlots;
+    a.blob = h->d_blob; a.blobLen = (int)h->sharedLen; a.blobPad = (int)((h->sharedLen + 1) & ~(size_t)1); a.nSlots = h->nSlots;
     a.in.wind = h->d_lane[LANE_WIND]; a.in.initState = h->d_lane[LANE_INIT_STATE]; a.in.pinkSeed = h->d_lane[LANE_PINK_SEED]; a.in.nLanes = h->nLanes;
     a.results = h->d_results; a.finals = h->d_finals; a.status = h->d_status; a.counters = h->d_counters; a.mt = h->d_mt;
     a.trace = (h->traceLane >= 0 && h->traceLane < h->nLanes) ? h->d_trace : nullptr;
@@ -463,8 +465,8 @@ extern "C" int mlb_force_eval(mlb_handle* h, int64_t n, const double* states, co
     CU(cudaMemcpy(d_s, states, (size_t)n * 13 * sizeof(double), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(d_t, times, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
     if (winds) { CU(cudaMalloc(&d_w, (size_t)n * 3 * sizeof(double))); CU(cudaMemcpy(d_w, winds, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice)); }
-    size_t blobPad = (h->blob.size() + 1) & ~(size_t)1;
-    forceEvalKernel<<<(unsigned)((n + MLB_BLOCK - 1) / MLB_BLOCK), MLB_BLOCK, blobPad * sizeof(double)>>>(h->d_blob, (int)h->blob.size(), n, d_s, d_t, d_w, d_mt, d_o);
+    size_t blobPad = (h->sharedLen + 1) & ~(size_t)1;
+    forceEvalKernel<<<(unsigned)((n + MLB_BLOCK - 1) / MLB_BLOCK), MLB_BLOCK, blobPad * sizeof(double)>>>(h->d_blob, (int)h->sharedLen, n, d_s, d_t, d_w, d_mt, d_o);
     cudaError_t e = cudaDeviceSynchronize();
     if (e == cudaSuccess) e = cudaMemcpy(out, d_o, (size_t)n * 18 * sizeof(double), cudaMemcpyDeviceToHost);
     cudaFree(d_s); cudaFree(d_t); cudaFree(d_w); cudaFree(d_o); cudaFree(d_mt);

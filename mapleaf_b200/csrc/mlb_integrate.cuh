@@ -96,10 +96,17 @@ MLB_DEV bool pyIsClose(double a, double b) {                                    
    by the first stage, the classical and the adaptive stage composition and the adaptive retry loop, so the force model is
    instantiated once in the kernel. `active` false: the lane only keeps the CTA's barriers company. */
 MLB_DEV StepResult integrateStep(const double* B, Lane& L, const KStore& ks, State& y, double t, double dt, bool active) {
-    const int method = (int)B[H_INTEGRATOR];
+    /* A fixed-rate control system swaps an adaptive integrator for RK4 while it is in charge (ControlSystems.py:126-135); the
+       parachute switch restores the original one (rocket.py:700-726). So the method is a per-lane choice between two tableaus;
+       the stage loop below runs to the CTA-uniform maximum row count and lanes with fewer rows sit out the extra stages. */
+    const int method0 = (int)B[H_INTEGRATOR];
+    const bool rk4Lanes = B[H_CTRL_OFF] != 0 && B[(int)B[H_CTRL_OFF] + CS_FORCE_RK4] != 0;
+    const int nRows0 = (method0 == INT_EULER) ? 0 : (int)B[H_TAB_NSTAGE_ROWS];
+    const int nRowsLoop = rk4Lanes ? max(nRows0, 3) : nRows0;
+    const int method = L.forceRK4 ? INT_RK4 : method0;
     const bool adaptive = method >= INT_RK12A;
-    const double* tab = B + (int)B[H_TABLEAU_OFF];
-    const int nRows = (method == INT_EULER) ? 0 : (int)B[H_TAB_NSTAGE_ROWS];
+    const double* tab = B + (L.forceRK4 ? (int)B[(int)B[H_CTRL_OFF] + CS_TABLEAU2_OFF] : (int)B[H_TABLEAU_OFF]);
+    const int nRows = L.forceRK4 ? 3 : nRows0;
     const double target = B[H_AD_TARGET], minDt = B[H_AD_MINDT];
     StepResult r; r.factor = 1.0; r.err = 0.0; r.dt = dt;
     double err = 10000000;
@@ -111,9 +118,9 @@ MLB_DEV StepResult integrateStep(const double* B, Lane& L, const KStore& ks, Sta
             if (err != 10000000) L.nRejects++;
             dt = fmax(minDt, dt / 3);
         }
-        for (int i = -1; i < nRows; i++) {
+        for (int i = -1; i < nRowsLoop; i++) {
             /* slot 0 may already hold the last stage of the previous accepted step (first-same-as-last) */
-            const bool evalNow = attempting && !(i < 0 && adaptive && L.haveCache);
+            const bool evalNow = attempting && i < nRows && !(i < 0 && adaptive && L.haveCache);
             State evalY; double evalTime = t;
             if (evalNow) {
                 if (i < 0) evalY = y;
@@ -186,6 +193,7 @@ MLB_DEV StepResult integrateStep(const double* B, Lane& L, const KStore& ks, Sta
 }
 
 MLB_DEV bool isAdaptive(const double* B) { return (int)B[H_INTEGRATOR] >= INT_RK12A; }
+MLB_DEV bool laneAdaptive(const double* B, const Lane& L) { return !L.forceRK4 && isAdaptive(B); }
 
 /* ---------------------------------------------------------------------------------------------
  * Flight events
@@ -203,6 +211,7 @@ MLB_DEV void deployNextRecoveryStage(const double* B, Lane& L) {                
         L.underChute = true;
         L.dof3 = true; L.s.q = qIdentity(); L.s.w = v3(0, 0, 0);
         L.haveCache = false; L.pidLastError = 0; L.pidIntegral = 0;
+        L.forceRK4 = false;
     }
     if (L.recoveryStage < (int)C[RC_NSTAGES]) {
         const double* st = C + RC_STAGE0 + L.recoveryStage * RC_STAGE_STRIDE;
@@ -273,6 +282,99 @@ MLB_DEV void triggerEvents(const double* B, Lane& L, double& estTimeToNext, bool
     estTimeToNext = est; deterministic = det;
 }
 
+/* N-D scattered linear interpolation with nearest-neighbour fallback (scipy LinearNDInterpolator / NearestNDInterpolator behind
+   Motion/Interpolation.py:109-124). The Delaunay triangulation comes from scipy on the host; R points into GLOBAL memory (the
+   tables are too large for shared memory, every lane reads the same words: broadcast loads). Point location is a scan over
+   the simplices with scipy's inside tolerance; it runs once per control tick, not per derivative evaluation. */
+MLB_DEV void ndInterpolate(const double* __restrict__ R, const double* x, double* out) {
+    const int d = (int)R[ND_DIM], m = (int)R[ND_NVAL], npts = (int)R[ND_NPTS], ns = (int)R[ND_NSIMP];
+    const double* pts = R + ND_DATA; const double* vals = pts + npts * d; const double* simp = vals + npts * m; const double* T = simp + ns * (d + 1);
+    const double eps = 100 * 2.220446049250313e-16;
+    for (int s = 0; s < ns; s++) {
+        const double* Ts = T + s * (d + 1) * d;
+        if (Ts[0] != Ts[0]) continue;                                                       /* degenerate simplex */
+        double c[ND_MAX_DIM + 1]; double cLast = 1.0; bool inside = true;
+        for (int i = 0; i < d && inside; i++) {
+            double ci = 0;
+            for (int j = 0; j < d; j++) ci += Ts[d * i + j] * (x[j] - Ts[d * d + j]);
+            c[i] = ci; cLast -= ci;
+            inside = (ci >= -eps && ci <= 1 + eps);
+        }
+        if (!inside || !(cLast >= -eps && cLast <= 1 + eps)) continue;
+        c[d] = cLast;
+        for (int k = 0; k < m; k++) {
+            double v = 0;
+            for (int j = 0; j < d + 1; j++) v += c[j] * vals[(int)simp[s * (d + 1) + j] * m + k];
+            out[k] = v;
+        }
+        return;
+    }
+    int best = 0; double bestD = 1e300;                                                     /* outside the hull: nearest table row */
+    for (int p = 0; p < npts; p++) {
+        double dist = 0;
+        for (int j = 0; j < d; j++) { double t = pts[p * d + j] - x[j]; dist += t * t; }
+        if (dist < bestD) { bestD = dist; best = p; }
+    }
+    for (int k = 0; k < m; k++) out[k] = vals[best * m + k];
+}
+MLB_DEV double aeroKeyOf(const State& s, const Air& e, int key) {                           /* AeroParameters.stringToAeroFunctionMap */
+    switch (key) {
+        case AKEY_MACH: return len(s.vel - e.wind) / sqrt(1.4 * 287 * e.temp);
+        case AKEY_ALTITUDE: return e.asl;
+        case AKEY_UNITRE: return len(localFrameAirVel(s, e.wind)) * e.density / e.viscosity;
+        default: { V3 v = localFrameAirVel(s, e.wind); if (len(v) == 0) return 0; return angleBetween(v, v3(0, 0, -1)); }
+    }
+}
+/* Rocket._runControlSystem (rocket.py:646-656) -> RocketControlSystem.runControlLoopIfRequired (GNC/ControlSystems.py:170-211):
+   stabiliser target, orientation error as a rotation vector, (scheduled) PID gains, vector PID, deflection table, actuators.
+   G is the model block in global memory (interpolation tables). */
+MLB_DEV void runControlSystem(const double* B, const double* G, Lane& L) {
+    if (!L.hasControl || L.underChute) return;
+    const double* CS = B + (int)B[H_CTRL_OFF];
+    const double currentTime = L.time;
+    Air env = airProperties(B, L, L.s.pos, currentTime, false);
+    if (!((currentTime - L.ctrlLastRun) + 0.0000000001 >= CS[CS_UPDATE_DT])) return;
+    const double dt = currentTime - L.ctrlLastRun;
+    Q4 target = q4(CS[CS_TARGET_Q], CS[CS_TARGET_Q + 1], CS[CS_TARGET_Q + 2], CS[CS_TARGET_Q + 3]);
+    /* (target / orientation).toRotationVector() = orientation.inverse() * target (CythonQuaternion.pyx:121-126,160-162,219-226) */
+    double n = qNorm(L.s.q); double sc = 1.0 / (n * n);
+    Q4 inv = qConj(L.s.q);
+    inv = q4(inv.w * sc, inv.x * sc, inv.y * sc, inv.z * sc);
+    Q4 errQ = inv * target;
+    qNormalize(errQ);
+    double nn = sqrt(1 - errQ.w * errQ.w);
+    double angle = 2 * m_atan2(nn, errQ.w);
+    double err[3] = { 0, 0, 0 };
+    if (angle != 0) { err[0] = errQ.x * angle / nn; err[1] = errQ.y * angle / nn; err[2] = errQ.z * angle / nn; }
+    double g[ND_MAX_VAL];
+    if ((int)CS[CS_MC_TYPE] == 1) {
+        double keys[4]; const int nk = (int)CS[CS_GAIN_NKEYS];
+        for (int k = 0; k < nk; k++) keys[k] = aeroKeyOf(L.s, env, (int)CS[CS_GAIN_KEYS + k]);
+        ndInterpolate(G + (int)CS[CS_GAIN_INTERP_OFF], keys, g);
+    } else for (int k = 0; k < 6; k++) g[k] = CS[CS_GAINS + k];
+    double key[ND_MAX_DIM]; const int nk = (int)CS[CS_DEFL_NKEYS];
+    for (int k = 0; k < nk; k++) key[k] = aeroKeyOf(L.s, env, (int)CS[CS_DEFL_KEYS + k]);
+    for (int k = 0; k < 3; k++) {                           /* PIDController.getNewSetPoint, vector mode, no integral clamp (GNC/PID.py:27-51) */
+        const double P = (k < 2) ? g[0] : g[3], I = (k < 2) ? g[1] : g[4], D = (k < 2) ? g[2] : g[5];
+        double derivative = (err[k] - L.gncLastError[k]) / dt;
+        L.gncIntegral[k] = L.gncIntegral[k] + (err[k] + L.gncLastError[k]) * dt / 2;
+        L.gncLastError[k] = err[k];
+        key[nk + k] = P * err[k] + I * L.gncIntegral[k] + D * derivative;
+    }
+    double targets[ND_MAX_VAL];
+    ndInterpolate(G + (int)CS[CS_DEFL_INTERP_OFF], key, targets);
+    const int nAct = (int)CS[CS_NACT];
+    for (int i = 0; i < nAct; i++) {                        /* FirstOrderActuator.setTargetDeflection (Actuators.py:118-129) */
+        L.actLastDefl[i] = actuatorDeflection(B, L, i, currentTime);
+        L.actLastTime[i] = currentTime;
+        double t = targets[i];
+        if (CS[CS_ACT_HASMAX] != 0) t = fmin(t, CS[CS_ACT_MAX]);
+        if (CS[CS_ACT_HASMIN] != 0) t = fmax(t, CS[CS_ACT_MIN]);
+        L.actTarget[i] = t;
+    }
+    L.ctrlLastRun = currentTime;
+}
+
 MLB_DEV void railMotionConstraint(const double* B, Lane& L) {                                /* launchRail.py:58-81, environment.py:195-207 */
     if (!L.onRail) return;
     Q4 rot = qAxisAngle(v3(0, 0, 1), B[H_EARTH_ROT] * L.time);
@@ -287,15 +389,16 @@ MLB_DEV void railMotionConstraint(const double* B, Lane& L) {                   
     } else L.onRail = false;
 }
 
-MLB_DEV StepResult rocketTimeStep(const double* B, Lane& L, const KStore& ks, double dt, bool active) {   /* rocket.py:658-698 */
+MLB_DEV StepResult rocketTimeStep(const double* B, const double* G, Lane& L, const KStore& ks, double dt, bool active) {   /* rocket.py:658-698 */
     if (active) {
         railMotionConstraint(B, L);
         double est; bool det;
         triggerEvents(B, L, est, det);
-        if (isAdaptive(B) && est < dt) {
+        if (laneAdaptive(B, L) && est < dt) {
             if (det) dt = est + 1e-5;
             else dt = fmax(est / 1.5, B[H_EVENT_DT]);
         }
+        runControlSystem(B, G, L);
     }
     StepResult r = integrateStep(B, L, ks, L.s, L.time, dt, active);
     if (active) {
@@ -359,6 +462,11 @@ MLB_DEV void laneInit(const double* B, Lane& L, const LaneInputs& in, long long 
     }
     L.nStages = (int)B[H_NSTAGES];
     L.onRail = B[H_RAIL_LEN] > 0;
+    L.hasControl = B[H_CTRL_OFF] != 0;
+    L.forceRK4 = L.hasControl && B[(int)B[H_CTRL_OFF] + CS_FORCE_RK4] != 0;
+    L.ctrlLastRun = 0;                                      /* RocketControlSystem(initTime=0) */
+    for (int k = 0; k < 3; k++) { L.gncLastError[k] = 0; L.gncIntegral[k] = 0; }
+    for (int k = 0; k < CS_MAX_ACT; k++) { L.actLastDefl[k] = 0; L.actLastTime[k] = 0; L.actTarget[k] = 0; }
     for (int si = 0; si < MLB_MAX_STAGES; si++) { L.ignitionTime[si] = 0; L.engineShutOff[si] = -1; }
     for (int si = 0; si < L.nStages; si++) {
         const double* S = B + (int)B[H_STAGE_OFF + si];

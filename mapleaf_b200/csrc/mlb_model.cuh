@@ -39,6 +39,10 @@ struct Lane {
     State s; double time;
     V3 wind;                                    /* sampled Environment.ConstantMeanWind.velocity */
     bool dof3, underChute, onRail, haveLast, haveCache;
+    /* control system (GNC/*.py): loop timing, vector PID memory, first-order actuators; RK4 forced during the controlled ascent */
+    bool hasControl, forceRK4;
+    double ctrlLastRun, gncLastError[3], gncIntegral[3];
+    double actLastDefl[CS_MAX_ACT], actLastTime[CS_MAX_ACT], actTarget[CS_MAX_ACT];
     bool resorted;                              /* a stage has been dropped: inertia lists are in top-to-bottom order (rocket.py:476-479) */
     int recoveryStage, nStages, nEvents, turb;
     double lastVz, lastTime;                    /* event detector memory (simEventDetector.py:120-132) */
@@ -587,7 +591,15 @@ MLB_DEV void finStripSupersonic(const double* C, const double* aoa, int n, doubl
     force = f; moment = m;
 }
 
-MLB_DEV ForceMoment finSetForce(const double* B, Aero& a, const double* C, V3 CG, double thickK) {   /* Fins.py:263-358,463-551 */
+/* FirstOrderActuator.getDeflection (GNC/Actuators.py:14-29,131-132): analytic first-order lag towards the last target */
+MLB_DEV double actuatorDeflection(const double* B, const Lane& L, int i, double time) {
+    const double* CS = B + (int)B[H_CTRL_OFF];
+    double dt = time - L.actLastTime[i];
+    if (dt < 0) dt = 0;
+    double lastError = L.actTarget[i] - L.actLastDefl[i];
+    return L.actLastDefl[i] + lastError * (1 - m_exp(-dt / CS[CS_ACT_TAU]));
+}
+MLB_DEV ForceMoment finSetForce(const double* B, const Lane& L, Aero& a, const double* C, V3 CG, double thickK) {   /* Fins.py:263-358,463-551 */
     const double Mach = a.Mach, Aref = a.Aref, q = dynamicPressure(a);
     /* drag build-up common to all fins of the set (Fins.py:289-358) */
     double cf = skinFrictionCoefficient(a.unitRe, C[FS_MAC_LEN], Mach, C[FS_ROUGH], C[FS_CRIT_RE], C[FS_ROUGH_CF], a.fullyTurb, a.sfCorrRough);
@@ -615,6 +627,7 @@ MLB_DEV ForceMoment finSetForce(const double* B, Aero& a, const double* C, V3 CG
     const double stall = C[FS_STALL];
     const double* Ainv = B + (int)B[H_FIN_CUBIC_OFF];
     const int regime = (Mach <= 0.8) ? 0 : (Mach < 1.4 ? 1 : 2);
+    const bool actuated = (C[FS_ACTUATED] != 0) && L.hasControl;
     double cnA = 0, cnA1 = 0, cnA2 = 0; Busemann kM, k1, k2;
     if (regime == 0) cnA = finCnAlphaSubsonic(C, Mach);
     else if (regime == 2) kM = busemann(Mach);
@@ -627,6 +640,12 @@ MLB_DEV ForceMoment finSetForce(const double* B, Aero& a, const double* C, V3 CG
         /* deflected fin normal (Fins.py:479-480), drag direction and spanwise CP distance: constants of an un-actuated fin,
            computed by the host with the reference's arithmetic */
         V3 finNormal = ld3(C + FS_FIN_NORMAL + 3 * fi);
+        V3 axialDir = ld3(C + FS_AXIAL_DIR + 3 * fi);
+        if (actuated) {                                     /* Fins.py:264-268,479-480: the fin angle is the actuator's deflection now */
+            Q4 rot = qAxisAngle(span, actuatorDeflection(B, L, fi, a.time) * (MLB_PI / 180.0));
+            finNormal = qRotate(rot, v3(span.y, -span.x, 0));
+            axialDir = cross(span, finNormal);
+        }
         V3 ust = cross(v3(0, 0, a.w.z), span) * -1.0;
         double spanwiseCP = C[FS_SPANWISE_CP + fi];
         /* slice angles of attack (CythonFinFunctions.pyx:10-28): one asin per slice, reused by every strip sum below */
@@ -667,7 +686,7 @@ MLB_DEV ForceMoment finSetForce(const double* B, Aero& a, const double* C, V3 CG
         V3 normalForce = finNormal * (nf * q);
         mom *= q;
         double axialMag = dragToAxialFactor(aoa[mid]) * totalDrag * Aref * q;
-        V3 axialForce = ld3(C + FS_AXIAL_DIR + 3 * fi) * axialMag;
+        V3 axialForce = axialDir * axialMag;
         V3 globalCP = span * (C[FS_MAC_Y] + C[FS_BODY_R]) + (position - v3(0, 0, CPXPos));
         total = fmAdd(total, fm(normalForce + axialForce, globalCP, v3(0, 0, mom)));
     }
@@ -807,7 +826,7 @@ MLB_DEV ForceMoment appliedForce(const double* B, Lane& L, double time, State& s
                     case CT_BODYTUBE: f = bodyTubeForce(a, C, inertia.CG); break;
                     case CT_BOATTAIL: f = transitionForce(L, a, C, si, true); break;
                     case CT_TRANSITION: f = transitionForce(L, a, C, si, false); break;
-                    case CT_FINSET: f = finSetForce(B, a, C, inertia.CG, L.finThickK[finIdx & (MLB_MAX_FINSETS - 1)]); finIdx++; break;
+                    case CT_FINSET: f = finSetForce(B, L, a, C, inertia.CG, L.finThickK[finIdx & (MLB_MAX_FINSETS - 1)]); finIdx++; break;
                     case CT_MOTOR: f = fm(v3(0, 0, motorThrust(L, C, si, time)), v3(0, 0, 0), v3(0, 0, 0)); break;
                     case CT_FIXED_FORCE: f = fm(ld3(C + FF_FORCE), ld3(C + C_POS), ld3(C + FF_MOMENT)); break;
                     case CT_AERO_FORCE: f = forceFromCoefficients(a, C + AF_COEFFS, ld3(C + C_POS), C[AF_AREF], C[AF_LREF]); break;

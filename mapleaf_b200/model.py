@@ -696,6 +696,117 @@ def _buildJetDamping(r, stagePos):
     return rec, dict(position=(0.0, 0.0, 0.0), body=False)
 
 
+def _ndInterpolatorRecord(keys, values):
+    """Delaunay triangulation of the key points with scipy (the library the reference calls, Motion/Interpolation.py:109-124)."""
+    from scipy.interpolate import LinearNDInterpolator
+    keys = np.asarray(keys, dtype=np.float64)
+    values = np.asarray(values, dtype=np.float64)
+    if keys.shape[1] > L.ND_MAX_DIM or values.shape[1] > L.ND_MAX_VAL:
+        raise NotImplementedError("interpolation table with more than {} key or {} value columns".format(L.ND_MAX_DIM, L.ND_MAX_VAL))
+    tri = LinearNDInterpolator(keys, values).tri
+    rec = [keys.shape[1], values.shape[1], keys.shape[0], tri.simplices.shape[0]]
+    rec += [float(x) for x in keys.reshape(-1)] + [float(x) for x in values.reshape(-1)]
+    rec += [float(x) for x in tri.simplices.reshape(-1)] + [float(x) for x in tri.transform.reshape(-1)]
+    return rec
+
+
+def _buildControlSystem(sd, rk, stages, method, H, append):
+    cs = SubDictReader("Rocket.ControlSystem", sd)
+    rec = [0.0] * L.CS_SIZE
+    # Stabilizer (Navigation.py:15-24)
+    direction = hm.v_normalize(cs.getVector("desiredFlightDirection"))
+    rec[L.CS_TARGET_Q:L.CS_TARGET_Q + 4] = hm.q_from_axis_angle(hm.v_cross((0, 0, 1), direction), hm.v_angle((0, 0, 1), direction))
+    mcType = cs.getString("MomentController.Type")
+    if mcType == "ConstantGainPIDRocket":
+        rec[L.CS_MC_TYPE] = 0
+        rec[L.CS_GAINS:L.CS_GAINS + 6] = [cs.getFloat("MomentController." + k) for k in ("Pxy", "Ixy", "Dxy", "Pz", "Iz", "Dz")]
+    elif mcType == "ScheduledGainPIDRocket":
+        rec[L.CS_MC_TYPE] = 1
+        keyNames = cs.getString("MomentController.scheduledBy").split()
+        if len(keyNames) > 4:
+            raise NotImplementedError("gain table scheduled by more than 4 keys")
+        rec[L.CS_GAIN_NKEYS] = len(keyNames)
+        rec[L.CS_GAIN_KEYS:L.CS_GAIN_KEYS + len(keyNames)] = [_AERO_KEYS[k] for k in keyNames]
+    else:
+        raise ValueError("Moment Controller Type: {} not implemented. Try ScheduledGainPIDRocket or IdealMomentController".format(mcType))
+    updateRate = cs.getFloat("updateRate")
+    # controlled system: a FinSet (the only ActuatedSystem of the reference, Fins.py:45,87-91)
+    path = cs.getString("controlledSystem")
+    found = None
+    for si, st in enumerate(stages):
+        for ci, c in enumerate(st["comps"]):
+            if "Rocket.{}.{}".format(st["name"], c["name"]) == path:
+                found = (si, ci, c)
+    if found is None:
+        raise ValueError("Rocket Component: {} not found in {}".format(path, sd.fileName))
+    si, ci, comp = found
+    if comp["cls"] != "FinSet":
+        raise AttributeError("'{}' object has no attribute 'initializeActuators'".format(comp["cls"]))
+    rec[L.CS_STAGE], rec[L.CS_COMP] = si, ci
+    nAct = int(comp["rec"][L.FS_NFINS])
+    rec[L.CS_NACT] = nAct
+    act = SubDictReader(path + ".Actuators", sd)
+    if act.getString("responseModel") != "FirstOrder":
+        raise ValueError("Actuator response model {} not implemented. Try 'FirstOrder'".format(act.getString("responseModel")))
+    rec[L.CS_ACT_TAU] = act.getFloat("responseTime")
+    mx, mn = act.tryGetFloat("maxDeflection", defaultValue=None), act.tryGetFloat("minDeflection", defaultValue=None)
+    if mn is not None:
+        rec[L.CS_ACT_HASMIN], rec[L.CS_ACT_MIN] = 1.0, mn
+    if mx is not None:
+        rec[L.CS_ACT_HASMAX], rec[L.CS_ACT_MAX] = 1.0, mx
+    if act.getString("controller") != "TableInterpolating":
+        raise ValueError("Actuator controller: {} not implemented. Try TableInterpolating.")
+    cols = act.getString("deflectionKeyColumns").split()
+    noDesired = []
+    for k in cols:
+        if "Desired" not in k:
+            noDesired.append(k)
+        else:
+            break
+    for k in cols[len(noDesired):]:
+        if "Desired" not in k:
+            raise ValueError("'Desired' columns such as DesiredMx must come last in deflectionKeyColumns")
+    if len(cols) - len(noDesired) != 3 or len(noDesired) > 3:
+        raise NotImplementedError("deflection table keys must be up to 3 aero keys followed by DesiredMx DesiredMy DesiredMz")
+    rec[L.CS_DEFL_NKEYS] = len(noDesired)
+    rec[L.CS_DEFL_KEYS:L.CS_DEFL_KEYS + len(noDesired)] = [_AERO_KEYS[k] for k in noDesired]
+    # time stepping (ControlSystems.py:120-153)
+    if updateRate > 0:
+        controlTimeStep = 1 / updateRate
+        rec[L.CS_UPDATE_DT] = controlTimeStep
+        if "Adaptive" in method:
+            rec[L.CS_FORCE_RK4] = 1.0
+            rows, _ = butcherTableau("RK4")
+            flat = []
+            for row in rows:
+                flat.extend(row + [0.0] * (L.TABLEAU_STRIDE - len(row)))
+            rec[L.CS_TABLEAU2_OFF] = append(flat)
+        original = float(sd.getValue("SimControl.timeStep"))
+        if controlTimeStep / original != round(controlTimeStep / original):
+            recommended = controlTimeStep / max(1, round(controlTimeStep / original))
+            sd.setValue("SimControl.timeStep", str(recommended))      # the reference rewrites the definition, too (:147)
+            H[L.H_DT0] = recommended
+    return rec
+
+
+def _appendInterpolators(sd, rk, H, tail, append):
+    """The (large) Delaunay tables go behind H_SHARED_LEN; their offsets are patched into the control record."""
+    off = int(H[L.H_CTRL_OFF]) - L.H_SIZE
+    cs = SubDictReader("Rocket.ControlSystem", sd)
+    if tail[off + L.CS_MC_TYPE] == 1:
+        path = _resolvePath(cs, "MomentController.gainTableFilePath")
+        data = np.loadtxt(path, skiprows=1)
+        n = int(tail[off + L.CS_GAIN_NKEYS])
+        tail[off + L.CS_GAIN_INTERP_OFF] = append(_ndInterpolatorRecord(data[:, 0:n], data[:, n:n + 6]))
+    act = SubDictReader(cs.getString("controlledSystem") + ".Actuators", sd)
+    data = np.loadtxt(_resolvePath(act, "deflectionTablePath"), skiprows=1)
+    nKeys = int(tail[off + L.CS_DEFL_NKEYS]) + 3
+    nAct = int(tail[off + L.CS_NACT])
+    if data.shape[1] - nKeys != nAct:
+        raise ValueError("Number of actuators: {}, must match number of actuator deflection columns in deflection table: {}".format(nAct, data.shape[1] - nKeys))
+    tail[off + L.CS_DEFL_INTERP_OFF] = append(_ndInterpolatorRecord(data[:, 0:nKeys], data[:, nKeys:]))
+
+
 # ======================================================================================
 class Model:
     """Result of buildModel: `.blob` (np.float64 array) plus host-side metadata."""
@@ -940,8 +1051,9 @@ def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000) -> Model:
     addAutoBT = rk.getBool("Aero.addZeroLengthBoatTailsToAccountForBaseDrag")
     H[L.H_ADD_AUTO_BT] = 1.0 if addAutoBT else 0.0
     stageDicts = [d for d in rk.getImmediateSubDicts() if d not in ("Rocket.ControlSystem", "Rocket.HIL", "Rocket.Aero")]
-    if rk.tryGetString("ControlSystem.controlledSystem") is not None or "Rocket.ControlSystem" in rk.getImmediateSubDicts():
-        raise NotImplementedError("Rocket.ControlSystem (GNC) is not implemented by the B200 backend yet")
+    hasControl = rk.tryGetString("ControlSystem.controlledSystem") is not None
+    if rk.tryGetString("ControlSystem.MomentController.Type") == "IdealMomentController" and not hasControl and "Rocket.ControlSystem" in rk.getImmediateSubDicts():
+        raise NotImplementedError("IdealMomentController (rewrites the state between steps) is not implemented by the B200 backend")
     maxDiameter = 0
     for sdict in stageDicts:
         for cdict in sd.getImmediateSubDicts(sdict):
@@ -993,6 +1105,8 @@ def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000) -> Model:
                 rec, info = _buildJetDamping(cr, stagePos)
             else:
                 rec, info = _buildMass(cr, stagePos)
+            if hasControl and cls == "FinSet" and c == rk.getString("ControlSystem.controlledSystem"):
+                rec[L.FS_ACTUATED] = 1.0          # fin angles follow the actuators (Fins.py:264-268)
             info["name"] = cr.getDictName()
             info["cls"] = cls
             info["rec"] = rec
@@ -1145,6 +1259,13 @@ def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000) -> Model:
         if st["autoBT"] is not None:
             S[L.S_AUTO_BT_OFF] = append(st["autoBT"])
         H[L.H_STAGE_OFF + si] = append(S)
+
+    # ---- control system (rocket.py:210-217; GNC/ControlSystems.py:45-153) ----
+    H[L.H_SHARED_LEN] = L.H_SIZE + len(tail)          # everything so far is staged in shared memory
+    if hasControl:
+        H[L.H_CTRL_OFF] = append(_buildControlSystem(sd, rk, stages, method, H, append))
+        H[L.H_SHARED_LEN] = L.H_SIZE + len(tail)      # ... including the control record and the RK4 tableau
+        _appendInterpolators(sd, rk, H, tail, append)
 
     # ---- initial inertia -> CG shift of the integrated position (rocket.py:416-421) ----
     def stageInertia(st, t):

@@ -25,6 +25,8 @@ What is recorded, and which reference code produced it:
                             (ENV/EarthModelling.py:107-369, ENV/environment.py:105-181)
   nasa_twostage.json ...... NASATwoStageOrbitalRocket.mapleaf, 200 s (BASELINE.json configs[3]; the reference's own regression case,
                             BatchSims/NASAVerificationCases.mapleaf:264-278)
+  canards_*.json .......... Canards.mapleaf (BASELINE.json configs[2]): 100 Hz stabiliser + scheduled-gain PID + deflection table +
+                            first-order actuators (GNC/*.py), RK4 forced in the ascent, adaptive again under the parachute
   rng.json ................ random.Random / PinkNoiseGenerator known answers (test_SimDefinition.py:118-151,
                             test_TurbulenceModelling.py:37-60)
 """
@@ -222,7 +224,7 @@ def dump(name, obj):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["model", "rng", "windtunnel", "rk4_apogee", "rk4_ground", "rk45_pink", "rk45_gust", "tabulated", "twostage", "earth"]
+    which = sys.argv[1:] or ["model", "rng", "windtunnel", "rk4_apogee", "rk4_ground", "rk45_pink", "rk45_gust", "tabulated", "twostage", "earth", "canards"]
     mc = os.path.join(MY_DATA, "MonteCarlo.mapleaf")
     if "model" in which:
         dump("model_montecarlo.json", modelFields())
@@ -248,6 +250,10 @@ if __name__ == "__main__":
         dump("earth_round_rk4.json", singleFlight(tab, {"Environment.EarthModel": "Round", **site}))
         dump("earth_wgs84_rk4.json", singleFlight(tab, {"Environment.EarthModel": "WGS84", **site}))
         dump("nasa_twostage.json", singleFlight(os.path.join(MY_DATA, "NASATwoStageOrbitalRocket.mapleaf"), {}, traceEvery=40, keepDts=True))
+    if "canards" in which:
+        can = os.path.join(MY_DATA, "Canards.mapleaf")
+        dump("canards_apogee.json", singleFlight(can, {}, traceEvery=50))
+        dump("canards_ground.json", singleFlight(can, {"SimControl.EndCondition": "Altitude"}, traceEvery=100, keepDts=True))
     adaptive = os.path.join(MY_DATA, "MonteCarloAdaptive.mapleaf")
     if "rk45_pink" in which:
         dump("rk45_pink.json", monteCarlo(adaptive, {}, "2394781", 4, globalSeed=2394781, keepDts=True))

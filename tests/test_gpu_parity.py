@@ -358,3 +358,24 @@ def test_nasa_two_stage_orbital_rocket_vs_reference(backend, golden):
     for got, exp in zip(free["finals"][0, [0, 1, 3, 4]], (6598829.9, 637702.775, 2308.8505, 8475.945)):
         assert abs(got - exp) <= 0.002 * abs(exp)
     assert relErr(free["finals"][0, 0:3], r["final"][1:4]) < 1e-4
+
+
+def test_canard_control_system_vs_reference(backend, golden):
+    """BASELINE configs[2] on the GPU: controlled ascent at RK4 dt 0.01 (fixed-step gate), then to the ground (adaptive under chute)."""
+    g = golden("canards_apogee.json")
+    m = buildFrom(g["definition"], g["overrides"])
+    r = g["runs"][0]
+    o = gpuRun(backend, m, 1, {}, traceLane=0, traceRows=6000)
+    assert o["status"][0] == L.ST_OK and o["counters"][0, 0] == r["steps"]
+    assert stateErr(o["finals"][0], r["final"]) < FIXED_TOL
+    for idx, row in zip(r["traceIdx"], r["trace"]):
+        assert stateErr(np.concatenate([o["trace"][idx, 1:14], [0]]), row) < FIXED_TOL
+    assert relErr(o["results"][0, 3:7], r["results"][3:7]) < FIXED_TOL
+    g = golden("canards_ground.json")
+    m = buildFrom(g["definition"], g["overrides"])
+    r = g["runs"][0]
+    o = gpuRun(backend, m, 2, {})
+    assert (o["status"] == L.ST_OK).all()
+    assert abs(int(o["counters"][0, 0]) - r["steps"]) <= 60
+    assert abs(o["results"][0, 3] - r["results"][3]) < 1e-6                        # apogee is reached under RK4
+    assert abs(o["results"][0, 5] - r["results"][5]) < 0.5 and abs(o["results"][0, 1] - r["results"][1]) < 0.05

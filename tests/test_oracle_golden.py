@@ -215,3 +215,33 @@ def test_nasa_two_stage_orbital_rocket(golden):
     # the reference's recorded regression values for this case, its own 0.2 % tolerance (Batch.py:51-52)
     for got, exp in zip(o["finals"][0, [0, 1, 3, 4]], (6598829.9, 637702.775, 2308.8505, 8475.945)):
         assert abs(got - exp) <= 0.002 * abs(exp)
+
+
+@pytest.mark.parametrize("name", ["canards_apogee.json", "canards_ground.json"])
+def test_canard_control_system(golden, name):
+    """BASELINE.json configs[2]: 100 Hz stabiliser -> scheduled-gain vector PID -> 5-D deflection table (scipy Delaunay on the host)
+    -> four first-order actuators -> actuated fin angles; RK4 forced while the controller is in charge, RK45Adaptive again under
+    the parachute (GNC/*.py, Fins.py:264-268, rocket.py:646-656,700-726). Free-running, to apogee and to the ground."""
+    g = golden(name)
+    m = buildFrom(g["definition"], g["overrides"])
+    r = g["runs"][0]
+    o = oracle.run(m.blob, 1, {}, traceLane=0, traceMaxRows=6000)
+    assert o["status"][0] == L.ST_OK and o["counters"][0, 0] == r["steps"]
+    assert o["finals"][0, 13] == r["final"][0]
+    assert stateErr(o["finals"][0], r["final"]) < 1e-12
+    for idx, row in zip(r["traceIdx"], r["trace"]):
+        assert o["trace"][idx, 0] == row[0]
+        assert stateErr(np.concatenate([o["trace"][idx, 1:14], [0]]), row) < 1e-12
+    assert relErr(o["results"][0, 3:7], r["results"][3:7]) < 1e-12
+
+
+def test_control_record_and_time_step_rewrite():
+    m = buildFrom("Canards.mapleaf")
+    cs = m.blob[int(m.header("H_CTRL_OFF")):]
+    assert m.header("H_DT0") == 0.01 and cs[L.CS_UPDATE_DT] == 0.01 and cs[L.CS_FORCE_RK4] == 1     # ControlSystems.py:126-150
+    assert int(cs[L.CS_NACT]) == 4 and cs[L.CS_ACT_MIN] == -45 and cs[L.CS_ACT_MAX] == 45
+    names = [n for n, _ in m.meta["stages"][0]["components"]]
+    assert names[int(cs[L.CS_COMP])] == "Canards"
+    assert m.header("H_SHARED_LEN") < m.blob.size        # the Delaunay tables stay out of shared memory
+    nd = m.blob[int(cs[L.CS_DEFL_INTERP_OFF]):]
+    assert int(nd[L.ND_DIM]) == 5 and int(nd[L.ND_NVAL]) == 4 and int(nd[L.ND_NPTS]) == 60
