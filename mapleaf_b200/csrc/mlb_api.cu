@@ -37,7 +37,6 @@ static const int kShapeBlock[MLB_NUM_SHAPES] = { 128, 512, 1024 };
 #define TRACE_W 16
 #define MLB_NCOUNTERS 6
 
-struct LaneRun;
 struct RunArgs {
     const double* blob; int blobLen; int blobPad; int nSlots;
     LaneInputs in;
@@ -45,8 +44,6 @@ struct RunArgs {
     uint32_t* mt;
     double* trace; long long traceLane, traceMaxRows; long long* traceRows;
     const double* dtReplay; long long nReplay;
-    /* phase-sorted execution: lane snapshots in HBM, the queue of lanes that switched to the 3-DoF body, queue cursors */
-    struct LaneRun* snap; long long* queueB; unsigned long long* cursors;      /* cursors: [0] next fresh lane, [1] queue-B length, [2] next queue-B entry */
 };
 
 __device__ __forceinline__ void traceRow(const RunArgs& a, const Lane& L, long long& rows, double dt, double err) {
@@ -127,134 +124,6 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) integrateLanes(const RunArg
     if (tracing) *a.traceRows = rows;
 }
 
-
-/* A lane in flight: everything the Simulation.run loop carries between steps (SingleSimulations.py:81-139). */
-struct LaneRun {
-    Lane L;
-    double dt, apogee, maxSpeed, maxH, finalDt;
-    V3 prevPos, lastPos;
-    double fsal[12];            /* first-same-as-last derivative (slot 0 of the stage store) when the lane changes kernel */
-    long long lane;
-    int st; bool end, haveFinal;
-};
-
-__device__ __forceinline__ void laneBegin(const double* B, const RunArgs& a, LaneRun& R, long long lane) {
-    R.lane = lane;
-    laneInit(B, R.L, a.in, lane, a.mt, true);
-    R.dt = B[H_DT0];
-    R.apogee = -10000000; R.maxSpeed = 0; R.maxH = 0;
-    R.prevPos = R.L.s.pos; R.lastPos = R.L.s.pos;
-    R.st = ST_OK;
-    if (R.L.s.pos.z > R.apogee) R.apogee = R.L.s.pos.z;
-    R.maxSpeed = fmax(R.maxSpeed, len(R.L.s.vel));
-    R.maxH = fmax(R.maxH, sqrt(R.L.s.vel.x * R.L.s.vel.x + R.L.s.vel.y * R.L.s.vel.y));
-    R.end = true; R.haveFinal = false; R.finalDt = 0;
-    endDetector(B, R.L, R.dt, R.end, R.haveFinal, R.finalDt);
-}
-__device__ __forceinline__ void lanePostStep(const double* B, LaneRun& R, const StepResult& r) {
-    Lane& L = R.L;
-    R.dt = r.dt * r.factor;
-    R.prevPos = R.lastPos; R.lastPos = L.s.pos;
-    if (L.s.pos.z > R.apogee) R.apogee = L.s.pos.z;
-    double sp = len(L.s.vel); if (sp > R.maxSpeed) R.maxSpeed = sp;
-    double hv = sqrt(L.s.vel.x * L.s.vel.x + L.s.vel.y * L.s.vel.y); if (hv > R.maxH) R.maxH = hv;
-    if (!(L.s.pos.z == L.s.pos.z) || !(L.s.vel.x == L.s.vel.x)) { R.st = ST_NAN; R.end = true; }
-    else if (L.nSteps >= (long long)B[H_MAX_STEPS]) { R.st = ST_STEP_LIMIT; R.end = true; }
-    else endDetector(B, L, R.dt, R.end, R.haveFinal, R.finalDt);
-}
-__device__ __forceinline__ void laneWrite(const RunArgs& a, const LaneRun& Rn) {
-    const Lane& L = Rn.L; const long long lane = Rn.lane;
-    /* RocketFlight.getLandingLocation (rocketFlight.py:52-76): linear extrapolation of the last two positions to z = 0 */
-    double* R = a.results + lane * RES_SIZE;
-    double dz = Rn.lastPos.z - Rn.prevPos.z;
-    if (L.nSteps >= 1 && Rn.lastPos.z > dz * 2) {
-        double dxdz = (Rn.lastPos.x - Rn.prevPos.x) / dz, dydz = (Rn.lastPos.y - Rn.prevPos.y) / dz;
-        double dzLand = -Rn.lastPos.z;
-        R[RES_LAND_X] = Rn.lastPos.x + dxdz * dzLand; R[RES_LAND_Y] = Rn.lastPos.y + dydz * dzLand; R[RES_LAND_Z] = 0.0;
-    } else { R[RES_LAND_X] = Rn.lastPos.x; R[RES_LAND_Y] = Rn.lastPos.y; R[RES_LAND_Z] = Rn.lastPos.z; }
-    R[RES_APOGEE] = Rn.apogee; R[RES_MAX_SPEED] = Rn.maxSpeed; R[RES_FLIGHT_TIME] = L.time; R[RES_MAX_HVEL] = Rn.maxH;
-    double* F = a.finals + lane * FIN_SIZE;
-    F[0] = L.s.pos.x; F[1] = L.s.pos.y; F[2] = L.s.pos.z; F[3] = L.s.vel.x; F[4] = L.s.vel.y; F[5] = L.s.vel.z;
-    F[6] = L.s.q.w; F[7] = L.s.q.x; F[8] = L.s.q.y; F[9] = L.s.q.z; F[10] = L.s.w.x; F[11] = L.s.w.y; F[12] = L.s.w.z; F[13] = L.time;
-    a.status[lane] = Rn.st;
-    long long* cn = a.counters + lane * MLB_NCOUNTERS;
-    cn[0] = L.nSteps; cn[1] = L.nEvals; cn[2] = L.nRejects; cn[3] = L.nSteps3; cn[4] = L.nEvals3; cn[5] = L.nEvalsTransonic;
-}
-
-/* Phase-sorted execution for large batches (the lock-step kernel above wastes the lanes that wait for the slowest lane of
-   their CTA and mixes 6-DoF and under-chute lanes in one warp: measured 24 % at 1024 lanes per CTA).
-     lanePrologue ........ one thread per lane, no lock-step: inputs -> initial lane snapshot in HBM (CPython MT19937 seeding is a
-                           serial 60 k-instruction chain per generator: it must not run inside a convoy)
-     integratePhase<1> ... persistent CTAs, one per SM. A thread flies the 6-DoF part of a lane; when the lane ends or opens its
-                           parachute (3-DoF body) the thread stores the snapshot, queues the lane for phase 2 and pulls the next
-                           fresh lane: every warp stays full of 6-DoF lanes until the batch is exhausted.
-     integratePhase<2> ... same loop over the queue of under-chute lanes, to the ground. */
-__global__ void __launch_bounds__(128) lanePrologue(const RunArgs a) {
-    extern __shared__ double smem[];
-    double* B = smem;
-    for (int i = threadIdx.x; i < a.blobLen; i += blockDim.x) B[i] = a.blob[i];
-    __syncthreads();
-    const long long lane = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (lane >= a.in.nLanes) return;
-    LaneRun R;
-    laneBegin(B, a, R, lane);
-    for (int k = 0; k < 12; k++) R.fsal[k] = 0;
-    a.snap[lane] = R;
-}
-
-template <int BLOCK, int PHASE>
-__global__ void __launch_bounds__(BLOCK, 1) integratePhase(const RunArgs a) {
-    extern __shared__ double smem[];
-    double* B = smem;
-    for (int i = threadIdx.x; i < a.blobLen; i += blockDim.x) B[i] = a.blob[i];
-    __syncthreads();
-    double kLocal[MLB_K_SLOTS_MAX * 12];
-    KStore ks; ks.base = kLocal; ks.stride = 1;
-    LaneRun R;
-    bool have = false, drained = false;
-    const unsigned long long nFresh = (unsigned long long)a.in.nLanes;
-    const unsigned long long nQueued = (PHASE == 2) ? a.cursors[1] : 0;
-    for (;;) {
-        /* Pull the next lane of this phase. In the 6-DoF phase a WARP refills only when all its lanes are done, with 32 consecutive
-           fresh lanes: lanes of a warp then stay at the same point of the flight (same Mach regime, same motor phase), which is
-           what keeps a warp's control flow coherent; refilling thread by thread was measured 10 % slower than no refill at all
-           because some lane of every warp was always in the expensive transonic fin blend. Under the parachute the code path is
-           uniform, so there every thread refills on its own. */
-        bool pull = !have && !drained;
-        if (PHASE == 1) pull = __all_sync(0xffffffffu, !have) && !drained;
-        if (pull) {
-            long long idx = -1;
-            if (PHASE == 1) {
-                unsigned long long k0 = 0;
-                if ((threadIdx.x & 31) == 0) k0 = atomicAdd(&a.cursors[0], 32ULL);
-                k0 = __shfl_sync(0xffffffffu, k0, 0);
-                unsigned long long k = k0 + (threadIdx.x & 31);
-                if (k < nFresh) idx = (long long)k;
-            } else { unsigned long long k = atomicAdd(&a.cursors[2], 1ULL); if (k < nQueued) idx = a.queueB[k]; }
-            if (idx >= 0) {
-                R = a.snap[idx];
-                for (int k = 0; k < 12; k++) kLocal[k] = R.fsal[k];
-                have = true;
-                if (R.end) { laneWrite(a, R); have = false; }          /* ended before its first step */
-            } else drained = true;
-        }
-        if (!MLB_ANY(have || !drained)) break;
-        const bool run = have;
-        if (run && R.haveFinal) R.dt = R.finalDt;
-        StepResult r = rocketTimeStep(B, a.blob, R.L, ks, R.dt, run);
-        if (run) {
-            lanePostStep(B, R, r);
-            if (R.end) { laneWrite(a, R); have = false; }
-            else if (PHASE == 1 && R.L.dof3) {              /* parachute open: hand the lane to the 3-DoF phase */
-                for (int k = 0; k < 12; k++) R.fsal[k] = kLocal[k];
-                a.snap[R.lane] = R;
-                unsigned long long k = atomicAdd(&a.cursors[1], 1ULL);
-                a.queueB[k] = R.lane;
-                have = false;
-            }
-        }
-    }
-}
 
 __global__ void __launch_bounds__(MLB_BLOCK) forceEvalKernel(const double* blob, int blobLen, long long n, const double* states, const double* times,
                                                              const double* winds, uint32_t* mt, double* out) {
@@ -349,8 +218,6 @@ struct mlb_handle {
     int nSlots = 0; size_t smemBytes = 0;
     int nSM = 148; int forceBlock = 0; int lastBlock = 0;
     size_t sharedLen = 0;
-    LaneRun* d_snap = nullptr; long long* d_queueB = nullptr; unsigned long long* d_cursors = nullptr; long long snapLanes = 0;
-    int phaseMode = -1;          /* MLB_PHASES env: 0 never, 1 always (when no trace / replay), default: large batches */
 };
 
 static int laneArrayComponents(int id) { return id == LANE_WIND ? 3 : (id == LANE_INIT_STATE ? 13 : (id == LANE_PINK_SEED ? 3 : -1)); }
@@ -361,7 +228,6 @@ static void freeLanes(mlb_handle* h) {
     h->ownResults = true;
     cudaFree(h->d_finals); cudaFree(h->d_counters); cudaFree(h->d_mt);
     h->d_results = h->d_finals = nullptr; h->d_status = nullptr; h->d_counters = nullptr; h->d_mt = nullptr;
-    cudaFree(h->d_snap); cudaFree(h->d_queueB); cudaFree(h->d_cursors); h->d_snap = nullptr; h->d_queueB = nullptr; h->d_cursors = nullptr; h->snapLanes = 0;
     h->nLanes = 0; h->ran = false;
 }
 
@@ -398,10 +264,6 @@ extern "C" int mlb_create(const void* model_blob, size_t n, int device, mlb_hand
     CU(cudaFuncSetAttribute(integrateLanes<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
     { cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, device)); h->nSM = prop.multiProcessorCount; }
     { const char* e = getenv("MLB_BLOCK_SIZE"); h->forceBlock = e ? atoi(e) : 0; }
-    { const char* e = getenv("MLB_PHASES"); h->phaseMode = e ? atoi(e) : -1; }
-    CU(cudaFuncSetAttribute(integratePhase<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
-    CU(cudaFuncSetAttribute(integratePhase<1024, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
-    CU(cudaFuncSetAttribute(lanePrologue, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
     CU(cudaFuncSetAttribute(forceEvalKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(blobPad * sizeof(double))));
     CU(cudaEventCreate(&h->ev0)); CU(cudaEventCreate(&h->ev1));
     CU(cudaMalloc(&h->d_traceRows, sizeof(long long)));
@@ -473,33 +335,13 @@ extern "C" int mlb_run(mlb_handle* h, void* stream) {
     MLB_EXTRA_SHAPES(MLB_ALLOW)
     h->lastBlock = block;
     unsigned grid = (unsigned)((h->nLanes + block - 1) / block);
-    const bool hooks = a.trace != nullptr || a.dtReplay != nullptr;
-    const bool phases = !hooks && (h->phaseMode == 1 || (h->phaseMode != 0 && h->nLanes >= (long long)h->nSM * 1024 * 2 && h->forceBlock == 0));
     h->launches = 1;
-    if (phases) {
-        if (h->snapLanes != h->nLanes) {
-            cudaFree(h->d_snap); cudaFree(h->d_queueB); cudaFree(h->d_cursors);
-            CU(cudaMalloc(&h->d_snap, (size_t)h->nLanes * sizeof(LaneRun)));
-            CU(cudaMalloc(&h->d_queueB, (size_t)h->nLanes * sizeof(long long)));
-            CU(cudaMalloc(&h->d_cursors, 4 * sizeof(unsigned long long)));
-            h->snapLanes = h->nLanes;
-        }
-        a.snap = h->d_snap; a.queueB = h->d_queueB; a.cursors = h->d_cursors;
-        CU(cudaEventRecord(h->ev0, s));
-        CU(cudaMemsetAsync(h->d_cursors, 0, 4 * sizeof(unsigned long long), s));
-        lanePrologue<<<(unsigned)((h->nLanes + 127) / 128), 128, h->smemBytes, s>>>(a);
-        integratePhase<1024, 1><<<h->nSM, 1024, h->smemBytes, s>>>(a);
-        integratePhase<1024, 2><<<h->nSM, 1024, h->smemBytes, s>>>(a);
-        h->launches = 3; h->lastBlock = 1024;
-    } else {
-    a.snap = nullptr; a.queueB = nullptr; a.cursors = nullptr;
     CU(cudaEventRecord(h->ev0, s));
 #define MLB_LAUNCH(N) if (block == N) { cudaFuncSetAttribute(integrateLanes<N, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes); integrateLanes<N, 1><<<grid, N, h->smemBytes, s>>>(a); } else
     MLB_EXTRA_SHAPES(MLB_LAUNCH)
     if (block == 1024) integrateLanes<1024, 1><<<grid, 1024, h->smemBytes, s>>>(a);
     else if (block == 512) integrateLanes<512, 1><<<grid, 512, h->smemBytes, s>>>(a);
     else integrateLanes<128, 2><<<grid, 128, h->smemBytes, s>>>(a);
-    }
     CU(cudaGetLastError());
     CU(cudaEventRecord(h->ev1, s));
     h->ran = true;

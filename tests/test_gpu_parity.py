@@ -379,35 +379,3 @@ def test_canard_control_system_vs_reference(backend, golden):
     assert abs(int(o["counters"][0, 0]) - r["steps"]) <= 60
     assert abs(o["results"][0, 3] - r["results"][3]) < 1e-6                        # apogee is reached under RK4
     assert abs(o["results"][0, 5] - r["results"][5]) < 0.5 and abs(o["results"][0, 1] - r["results"][1]) < 0.05
-
-
-def test_phase_sorted_execution_matches_single_kernel(backend, monkeypatch):
-    """Large batches run as prologue + 6-DoF phase + under-chute phase with lane refill (mlb_api.cu: integratePhase). Which kernel
-    and thread flies a lane must not matter: fixed-step flights to the ground agree to 1e-12 with identical step counts (the
-    kernels are separate compilations of the same source, so not bit for bit); adaptive flights agree in step total and statistics."""
-    rng = np.random.default_rng(99)
-    n = 3000
-    w = rng.normal(size=(3, n)) * np.array([[5.0], [5.0], [0.5]]) + np.array([[2.0], [0.0], [0.0]])
-    seeds = np.vstack([rng.integers(0, 1000000, size=(2, n)), np.zeros((1, n))]).astype(float)
-    m2 = buildFrom("MonteCarlo.mapleaf", {"SimControl.EndCondition": "Altitude", "SimControl.EndConditionValue": "0"})
-    monkeypatch.setenv("MLB_PHASES", "0")
-    a2 = gpuRun(backend, m2, 600, {L.LANE_WIND: w[:, :600].copy()})
-    monkeypatch.setenv("MLB_PHASES", "1")
-    b2 = gpuRun(backend, m2, 600, {L.LANE_WIND: w[:, :600].copy()})
-    assert b2["totals"]["kernel_launches"] == 3 and a2["totals"]["kernel_launches"] == 1
-    assert (a2["status"] == L.ST_OK).all() and (b2["status"] == L.ST_OK).all()
-    assert np.array_equal(a2["counters"], b2["counters"])
-    for i in range(600):
-        assert relErr(b2["results"][i], a2["results"][i]) < 1e-10
-    m = buildFrom("MonteCarloAdaptive.mapleaf")
-    arrs = {L.LANE_WIND: w, L.LANE_PINK_SEED: seeds}
-    monkeypatch.setenv("MLB_PHASES", "0")
-    a = gpuRun(backend, m, n, arrs)
-    monkeypatch.setenv("MLB_PHASES", "1")
-    b = gpuRun(backend, m, n, arrs)
-    assert (a["status"] == L.ST_OK).all() and (b["status"] == L.ST_OK).all()
-    assert abs(int(a["counters"][:, 0].sum()) - int(b["counters"][:, 0].sum())) < 2e-3 * a["counters"][:, 0].sum()
-    for col in (0, 1, 3, 5):
-        sd = a["results"][:, col].std(ddof=1)
-        assert abs(a["results"][:, col].mean() - b["results"][:, col].mean()) <= 2e-3 * sd
-    assert np.median(np.abs(a["results"][:, 3] - b["results"][:, 3])) < 0.5
