@@ -239,7 +239,7 @@ if __name__ == "__main__":
     if "tabulated" in which:
         tab = os.path.join(MY_DATA, "TabulatedComponents.mapleaf")
         dump("tabulated_rk4.json", singleFlight(tab, {}))
-        dump("tabulated_rk45.json", singleFlight(tab, {"SimControl.timeDiscretization": "RK45Adaptive", "SimControl.EndConditionValue": "6"}, traceEvery=10))
+        dump("tabulated_rk45.json", singleFlight(tab, {"SimControl.timeDiscretization": "RK45Adaptive", "SimControl.EndConditionValue": "6"}, traceEvery=10, keepDts=True))
     if "twostage" in which:
         two = os.path.join(MY_DATA, "TwoStage.mapleaf")
         dump("twostage_rk4.json", singleFlight(two, {}, traceEvery=50))

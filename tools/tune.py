@@ -5,11 +5,9 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 VDIR = os.path.join(REPO, "mapleaf_b200", "lib", "variants")
 VARIANTS = {
-    "lock_b512x1_local": ["-DMLB_BLOCK=512", "-DMLB_MIN_BLOCKS=1", "-DMLB_K_LOCAL=1"],
-    "lock_b768x1_local": ["-DMLB_BLOCK=768", "-DMLB_MIN_BLOCKS=1", "-DMLB_K_LOCAL=1"],
-    "lock_b1024x1_local": ["-DMLB_BLOCK=1024", "-DMLB_MIN_BLOCKS=1", "-DMLB_K_LOCAL=1"],
-    "lock_b384x1_local": ["-DMLB_BLOCK=384", "-DMLB_MIN_BLOCKS=1", "-DMLB_K_LOCAL=1"],
-    "lock_b512x1_local_mathcall": ["-DMLB_BLOCK=512", "-DMLB_MIN_BLOCKS=1", "-DMLB_K_LOCAL=1", "-DMLB_MATH_NOINLINE=1"],
+    "d1": ["-DMLB_DERIV_NOINLINE=1"],
+    "d2": ["-DMLB_DERIV_NOINLINE=2"],
+    "d3": ["-DMLB_DERIV_NOINLINE=3"],
 }
 
 def build(names=None):
