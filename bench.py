@@ -236,13 +236,16 @@ def runB200(args):
         "e2e": {"value": e2eValue, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "sims_per_sec": n * world / (e2eS / args.steps)},
         "gpu_launches": launches,
         "clocks": clocks.summary(),
-        "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                     # DRAM bytes per launch: 20.9 MB per lane measured by ncu at full occupancy (profiles/r1b_raw_selected.txt: 3.17 TB for
+                     # 151 552 lanes; local-memory spill traffic, the algorithmic figure is hbm_algorithmic_bytes), scaled to this launch
+                     "traffic": 20.9e6 * n, "hbm_algorithmic_bytes": hbmBytes,
                      "kernel": "integrateLanes", "kernel_ms": kernelMsLast, "algorithmic_flops_per_launch": flops,
                      "peak_source": "FP64 DFMA microbenchmark run on this GPU by mlb_fp64_peak (MEASURED_PEAKS.json has no FP64 entry); nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2",
                      "hbm_algorithmic_gbs": hbmBytes / (kernelMsLast * 1e-3) / 1e9, "note": "not HBM- or tensor-bound: ~1e5 FLOP per byte of state moved"},
     }
     if world == 1 and not args.skip_cpu:
-        line["cpu_baseline"] = cpuBaseline(min(os.cpu_count() or 1, 16), 1)
+        line["cpu_baseline"] = cpuBaseline(min(os.cpu_count() or 1, 16), 1, warmup=1)      # one untimed pass: worker start-up, first-call parsing
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
