@@ -302,7 +302,12 @@
 #define FS_FIN_NORMAL 128
 #define FS_AXIAL_DIR 152
 #define FS_SPANWISE_CP 176
-#define FS_SIZE 184
+/* Mach-independent pieces of the transonic blend (Fins.py:508-528 evaluates its four strip sums at the fixed Mach numbers 0.8, 0.801,
+   1.4 and 1.401), computed once by the host with the reference's arithmetic */
+#define FS_TRANS_CNA 184     /* CN_alpha (Fins.py:26-34) at Mach 0.8 and 0.8 + 0.001 */
+#define FS_TRANS_K 186       /* Busemann K1, K2, K3 and Mach-cone slope (Fins.py:37-43,494-506) at Mach 1.4, then at 1.4 + 0.001 */
+#define FS_TRANS_W 194       /* per-slice Mach-cone weight fractionOut + 0.5 fractionIn (CythonFinFunctions.pyx:92-110): 16 at 1.4, 16 at 1.401 */
+#define FS_SIZE 226
 
 /* tabulated motor (Rocket/Propulsion.py:8-128). Table: 10 columns of MT_NROWS each, column-major,
    starting at C_P+MT_TABLE: time, thrust, oxWeight, fuelWeight, oxMOI xyz, fuelMOI xyz */

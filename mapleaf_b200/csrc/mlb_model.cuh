@@ -618,6 +618,27 @@ MLB_DEV void finStripSupersonic(const double* C, const double* aoa, int n, doubl
     force = f; moment = m;
 }
 
+/* The transonic blend's four strip sums in one pass (Fins.py:508-528): subsonic at CN_alpha(0.8), CN_alpha(0.801), Busemann at Mach 1.4 and
+   1.401. Everything Mach-dependent in them is a constant of the fin set (FS_TRANS_*); only the slice angles of attack vary. Each sum adds
+   its slices in order, as finStripSubsonic / finStripSupersonic do. */
+MLB_DEV void finStripTransonic(const double* C, const double* aoa, int n, double spanwiseCP, double* f, double* m) {
+    const double cnA1 = C[FS_TRANS_CNA], cnA2 = C[FS_TRANS_CNA + 1];
+    const double* K = C + FS_TRANS_K; const double* W = C + FS_TRANS_W;
+    double f0 = 0, m0 = 0, f1 = 0, m1 = 0, f2 = 0, m2 = 0, f3 = 0, m3 = 0;
+    for (int i = 0; i < n; i++) {
+        const double al = aoa[i], area = C[FS_SLICE_A + i], arm = spanwiseCP - C[FS_SLICE_R + i], al2 = al * al;
+        double sf = cnA1 * al * area; f0 += sf; m0 += sf * arm;
+        sf = cnA2 * al * area; f1 += sf; m1 += sf * arm;
+        double topCp = al * (K[0] + K[1] * al + K[2] * al2 - 0 * al2);
+        double bottomCp = -al * (K[0] + K[1] * (-al) + K[2] * ((-al) * (-al)) - 0 * al2);
+        sf = (topCp - bottomCp) * area; sf *= W[i]; f2 += sf; m2 += sf * arm;
+        topCp = al * (K[4] + K[5] * al + K[6] * al2 - 0 * al2);
+        bottomCp = -al * (K[4] + K[5] * (-al) + K[6] * ((-al) * (-al)) - 0 * al2);
+        sf = (topCp - bottomCp) * area; sf *= W[16 + i]; f3 += sf; m3 += sf * arm;
+    }
+    f[0] = f0; f[1] = f1; f[2] = f2; f[3] = f3; m[0] = m0; m[1] = m1; m[2] = m2; m[3] = m3;
+}
+
 /* FirstOrderActuator.getDeflection (GNC/Actuators.py:14-29,131-132): analytic first-order lag towards the last target */
 MLB_DEV double actuatorDeflection(const double* B, const Lane& L, int i, double time) {
     const double* CS = B + (int)B[H_CTRL_OFF];
@@ -626,6 +647,9 @@ MLB_DEV double actuatorDeflection(const double* B, const Lane& L, int i, double 
     double lastError = L.actTarget[i] - L.actLastDefl[i];
     return L.actLastDefl[i] + lastError * (1 - m_exp(-dt / CS[CS_ACT_TAU]));
 }
+#ifndef MLB_FIN_UNIFORM
+#define MLB_FIN_UNIFORM 1
+#endif
 MLB_COMP_FINS ForceMoment finSetForce(const double* B, const Lane& L, Aero& a, const double* C, V3 CG, double thickK) {   /* Fins.py:263-358,463-551 */
     const double Mach = a.Mach, Aref = a.Aref, q = dynamicPressure(a);
     /* drag build-up common to all fins of the set (Fins.py:289-358) */
@@ -655,10 +679,9 @@ MLB_COMP_FINS ForceMoment finSetForce(const double* B, const Lane& L, Aero& a, c
     const double* Ainv = B + (int)B[H_FIN_CUBIC_OFF];
     const int regime = (Mach <= 0.8) ? 0 : (Mach < 1.4 ? 1 : 2);
     const bool actuated = (C[FS_ACTUATED] != 0) && L.hasControl;
-    double cnA = 0, cnA1 = 0, cnA2 = 0; Busemann kM, k1, k2;
+    double cnA = 0; Busemann kM;
     if (regime == 0) cnA = finCnAlphaSubsonic(C, Mach);
     else if (regime == 2) kM = busemann(Mach);
-    else { cnA1 = finCnAlphaSubsonic(C, 0.8); cnA2 = finCnAlphaSubsonic(C, 0.8 + 0.001); k1 = busemann(1.4); k2 = busemann(1.4 + 0.001); }
 
     ForceMoment total = fm(v3(0, 0, 0), position, v3(0, 0, 0));
 #pragma unroll 1
@@ -682,7 +705,7 @@ MLB_COMP_FINS ForceMoment finSetForce(const double* B, const Lane& L, Aero& a, c
            so it vanishes for every inner slice too). All slices then see bit-identical velocities: one asin serves them all. */
         const double rOuter = C[FS_SLICE_R + nS - 1];
         const V3 vOuter = airVelRelativeToFin + ust * rOuter;
-        const bool uniform = (vOuter.x == airVelRelativeToFin.x) && (vOuter.y == airVelRelativeToFin.y) && (vOuter.z == airVelRelativeToFin.z)
+        const bool uniform = MLB_FIN_UNIFORM && (vOuter.x == airVelRelativeToFin.x) && (vOuter.y == airVelRelativeToFin.y) && (vOuter.z == airVelRelativeToFin.z)
                              && (C[FS_SLICE_R] <= rOuter);
         const int nAsin = uniform ? 1 : nS;
         for (int i = 0; i < nAsin; i++) {
@@ -702,13 +725,10 @@ MLB_COMP_FINS ForceMoment finSetForce(const double* B, const Lane& L, Aero& a, c
         if (regime == 0) finStripSubsonic(C, aoa, nS, spanwiseCP, cnA, nf, mom);
         else if (regime == 2) finStripSupersonic(C, aoa, nS, spanwiseCP, kM, nf, mom);
         else {                                                                              /* transonic cubic blend, Fins.py:508-528 */
-            double f1, m1, f12, m12, f2, m2, f22, m22;
-            finStripSubsonic(C, aoa, nS, spanwiseCP, cnA1, f1, m1);
-            finStripSubsonic(C, aoa, nS, spanwiseCP, cnA2, f12, m12);
-            finStripSupersonic(C, aoa, nS, spanwiseCP, k1, f2, m2);
-            finStripSupersonic(C, aoa, nS, spanwiseCP, k2, f22, m22);
-            nf = cubicBlend(Ainv, Mach, f1, f2, f12, f22, 0.001);
-            mom = cubicBlend(Ainv, Mach, m1, m2, m12, m22, 0.001);
+            double f[4], m[4];                                          /* [0] M 0.8, [1] M 0.801, [2] M 1.4, [3] M 1.401 */
+            finStripTransonic(C, aoa, nS, spanwiseCP, f, m);
+            nf = cubicBlend(Ainv, Mach, f[0], f[2], f[1], f[3], 0.001);
+            mom = cubicBlend(Ainv, Mach, m[0], m[2], m[1], m[3], 0.001);
         }
         V3 normalForce = finNormal * (nf * q);
         mom *= q;

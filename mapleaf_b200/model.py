@@ -433,6 +433,27 @@ def _finishFinSet(rec, fs, bodyRadius):
     rec[L.FS_XMAC_LE] = XMACLeadingEdge
     rec[L.FS_CP_POLY:L.FS_CP_POLY + 6] = [float(x) for x in poly]
     rec[L.FS_TIP_POS] = dZdS_LE * span
+    # Transonic blend constants: the four strip sums of Fins.py:508-528 use fixed Mach numbers, so CN_alpha, the Busemann coefficients
+    # and each slice's Mach-cone weight (CythonFinFunctions.pyx:92-110) do not depend on the flight state
+    def beta(Mach):
+        return sqrt(1 - Mach * Mach) if Mach <= 0.9 else sqrt(Mach * Mach - 1)
+    for j, Mach in enumerate((0.8, 0.8 + 0.001)):
+        t = beta(Mach) * (2 * (span * span) / planform) / math.cos(midChordSweep)
+        rec[L.FS_TRANS_CNA + j] = (2 * math.pi * (2 * (span * span) / planform)) / (2 + sqrt(4 + t * t))
+    gamma = 1.4
+    outerRadius = (nSlices - 1) * stepSize + stepSize * 0.5 + bodyRadius
+    for j, Mach in enumerate((1.4, 1.4 + 0.001)):
+        b = beta(Mach)
+        M2 = Mach * Mach; M4 = M2 * M2; M6 = M4 * M2; M8 = M4 * M4
+        b2 = b * b; b4 = b2 * b2; b7 = b4 * b2 * b
+        K = [2 / b, ((gamma + 1) * M4 - 4 * b2) / (4 * b4),
+             ((gamma + 1) * M8 + (2 * (gamma * gamma) - 7 * gamma - 5) * M6 + 10 * (gamma + 1) * M4 - 12 * M2 + 8) / (6 * b7),
+             1 / math.tan(math.asin(1 / Mach))]
+        rec[L.FS_TRANS_K + 4 * j:L.FS_TRANS_K + 4 * j + 4] = K
+        for i in range(nSlices):
+            machCone = (outerRadius - rec[L.FS_SLICE_R + i]) * K[3] + dZdS_LE * span
+            fractionOut = min(1.0, abs(machCone - rec[L.FS_SLICE_LE + i]) / rec[L.FS_SLICE_LEN + i])
+            rec[L.FS_TRANS_W + 16 * j + i] = fractionOut + 0.5 * (1 - fractionOut)
     rec[L.FS_CDTT_STAR] = CD_TT_star
     rec[L.FS_CRIT_RE], rec[L.FS_ROUGH_CF] = _skinFrictionConstants(rec[L.FS_ROUGH], MACLength)
     sep = 360 / numFins

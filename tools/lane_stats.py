@@ -22,3 +22,8 @@ for blk in (32, 128, 512, 1024):
     m6 = a6.max(axis=1); mt = at.max(axis=1); first3 = a6.min(axis=1)
     cost = (m6 * c6 + (m6 - first3) * c3 + (mt - m6) * c3) * blk
     print("group %5d: lock-step efficiency vs phase-sorted ideal %.3f   (max total steps / mean %.3f)" % (blk, (n6[:k] * c6 + n3[:k] * c3).sum() / cost.sum(), mt.mean() / n.mean()))
+print("6dof steps percentiles 1/10/50/90/99/max:", [int(np.percentile(n6, p)) for p in (1, 10, 50, 90, 99, 100)])
+print("3dof steps percentiles 1/10/50/90/99/max:", [int(np.percentile(n3, p)) for p in (1, 10, 50, 90, 99, 100)])
+w6 = n6[:lanes // 32 * 32].reshape(-1, 32)
+print("per-warp: mean(max n6)/mean(n6) = %.3f, mean(min n6)/mean(n6) = %.3f" % (w6.max(axis=1).mean() / n6.mean(), w6.min(axis=1).mean() / n6.mean()))
+np.save(os.path.join(REPO, "gpurun_out", "lane_counters.npy"), c)

@@ -5,9 +5,8 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 VDIR = os.path.join(REPO, "mapleaf_b200", "lib", "variants")
 VARIANTS = {
-    "d1": ["-DMLB_DERIV_NOINLINE=1"],
-    "d2": ["-DMLB_DERIV_NOINLINE=2"],
-    "d3": ["-DMLB_DERIV_NOINLINE=3"],
+    "cur": [],
+    "u0": ["-DMLB_FIN_UNIFORM=0"],
 }
 
 def build(names=None):
