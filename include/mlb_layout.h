@@ -101,6 +101,11 @@
 /* doubles [0, H_SHARED_LEN) are staged in shared memory by the kernels; N-D interpolation tables of the control system (up to
    hundreds of KB) follow and are read from global memory */
 #define H_SHARED_LEN 106
+/* Host-derived constants of the device path. Every quotient or cosine below has flight-independent operands; the host evaluates it once
+   with the reference's own operation order, the kernels multiply by it (or divide through the stored reciprocal with one correction
+   step, mlb_math.cuh divBy) instead of running a full FP64 division per derivative evaluation. The oracle ignores them. */
+#define H_RAREF 107           /* 1 / H_AREF */
+#define H_FINENESS_F 108      /* 1 + 0.5 / H_FINENESS[k] (AeroFunctions.py:150), k = stages remaining - 1; 4 entries */
 #define H_SIZE 128
 
 /* integrator ids (H_INTEGRATOR) */
@@ -227,7 +232,9 @@
 #define NC_ROUGH 25
 #define NC_CRIT_RE 26
 #define NC_ROUGH_CF 27
-#define NC_SIZE 28
+#define NC_K_WET 28       /* NC_WETTED / Aref (AeroFunctions.py:151) */
+#define NC_K_RAD 29       /* (NC_WETTED / NC_LENGTH) / (2 pi), the mean radius of :154 */
+#define NC_SIZE 30
 
 /* body tube (Rocket/bodyTube.py:13-33) */
 #define BT_LENGTH 12
@@ -238,7 +245,12 @@
 #define BT_ROUGH 19
 #define BT_CRIT_RE 20
 #define BT_ROUGH_CF 21
-#define BT_SIZE 22
+#define BT_K_WET 22
+#define BT_K_RAD 23
+#define BT_K_PLAN 24      /* BT_PLANFORM / Aref (bodyTube.py:46) */
+#define BT_DL 25          /* BT_LENGTH / 25 damping strips (bodyTube.py:71) */
+#define BT_STRIP_Z 26     /* z of the 25 damping strip centres in rocket coordinates: position.z + (-dL i - dL / 2) (bodyTube.py:74-77) */
+#define BT_SIZE 51
 
 /* boat tail / transition (Rocket/boatTail.py:12-99) */
 #define TR_TOP_AREA 12
@@ -257,7 +269,10 @@
 #define TR_END_D 31
 #define TR_CRIT_RE 32
 #define TR_ROUGH_CF 33
-#define TR_SIZE 34
+#define TR_K_WET 34
+#define TR_K_RAD 35
+#define TR_K_FRONT 36     /* TR_FRONTAL / Aref (boatTail.py:153,178) */
+#define TR_SIZE 37
 
 /* fin set (Rocket/Fins.py:45-262, 430-462) */
 #define FS_NFINS 12
@@ -307,7 +322,17 @@
 #define FS_TRANS_CNA 184     /* CN_alpha (Fins.py:26-34) at Mach 0.8 and 0.8 + 0.001 */
 #define FS_TRANS_K 186       /* Busemann K1, K2, K3 and Mach-cone slope (Fins.py:37-43,494-506) at Mach 1.4, then at 1.4 + 0.001 */
 #define FS_TRANS_W 194       /* per-slice Mach-cone weight fractionOut + 0.5 fractionIn (CythonFinFunctions.pyx:92-110): 16 at 1.4, 16 at 1.401 */
-#define FS_SIZE 226
+/* flight-independent factors of the fin drag build-up (Fins.py:289-358) and of CN_alpha (Fins.py:26-34) */
+#define FS_K_SKIN 226        /* FS_WETTED / Aref */
+#define FS_K_THICKF 227      /* 1 + 2 FS_THICK / FS_MAC_LEN */
+#define FS_K_LE 228          /* FS_LE_THICK FS_SPAN cos^2(FS_SWEEP) / Aref */
+#define FS_TC 229            /* FS_THICK / FS_ROOT */
+#define FS_K_PLAN 230        /* FS_PLANFORM / Aref */
+#define FS_COS_MID 231       /* cos(FS_MIDSWEEP) and its reciprocal */
+#define FS_RCOS_MID 232
+#define FS_AR2 233           /* 2 FS_SPAN^2 / FS_PLANFORM */
+#define FS_K_THICK_SUP 234   /* 2.3 FS_AR (FS_THICK / FS_MAC_LEN)^2, thickness drag above Mach 1 */
+#define FS_SIZE 235
 
 /* tabulated motor (Rocket/Propulsion.py:8-128). Table: 10 columns of MT_NROWS each, column-major,
    starting at C_P+MT_TABLE: time, thrust, oxWeight, fuelWeight, oxMOI xyz, fuelMOI xyz */

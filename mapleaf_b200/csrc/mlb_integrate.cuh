@@ -107,6 +107,7 @@ MLB_DEV StepResult integrateStep(const double* B, Lane& L, const KStore& ks, Sta
     const bool adaptive = method >= INT_RK12A;
     const double* tab = B + (L.forceRK4 ? (int)B[(int)B[H_CTRL_OFF] + CS_TABLEAU2_OFF] : (int)B[H_TABLEAU_OFF]);
     const int nRows = L.forceRK4 ? 3 : nRows0;
+    const int nResultRows = L.forceRK4 ? 1 : (int)B[H_TAB_NRESULT_ROWS];
     const double target = B[H_AD_TARGET], minDt = B[H_AD_MINDT];
     StepResult r; r.factor = 1.0; r.err = 0.0; r.dt = dt;
     double err = 10000000;
@@ -146,20 +147,21 @@ MLB_DEV StepResult integrateStep(const double* B, Lane& L, const KStore& ks, Sta
                 r.newValue = stateAdd(y, derivTimes(ks.get(0, dof3), dt, dof3), dof3);
                 attempting = false;
             } else {
-                const double* fr = tab + nRows * TABLEAU_STRIDE;
+                /* result-row weights as the reference's algebra applies them, 1 / (1 / c): constants, stored by the host after the rows */
+                const double* fr = tab + (nRows + nResultRows) * TABLEAU_STRIDE;
                 Deriv k0 = ks.get(0, dof3);
-                Deriv fd = derivScaled(k0, 1 / (1 / fr[0]), dof3);
+                Deriv fd = derivScaled(k0, fr[0], dof3);
                 if (!adaptive) {                                                            /* :233-236 */
-                    for (int i = 1; i < nRows + 1; i++) fd = derivAdd(fd, derivScaled(ks.get(i, dof3), 1 / (1 / fr[i]), dof3), dof3);
+                    for (int i = 1; i < nRows + 1; i++) fd = derivAdd(fd, derivScaled(ks.get(i, dof3), fr[i], dof3), dof3);
                     r.newValue = stateAdd(y, derivTimes(fd, dt, dof3), dof3);
                     attempting = false;
                 } else {
-                    const double* cr = tab + (nRows + 1) * TABLEAU_STRIDE;                  /* :434-447 */
-                    Deriv cd = derivScaled(k0, 1 / (1 / cr[0]), dof3);
+                    const double* cr = fr + TABLEAU_STRIDE;                                 /* :434-447 */
+                    Deriv cd = derivScaled(k0, cr[0], dof3);
                     for (int i = 1; i < nRows + 1; i++) {
                         Deriv ki = ks.get(i, dof3);
-                        fd = derivAdd(fd, derivScaled(ki, 1 / (1 / fr[i]), dof3), dof3);
-                        cd = derivAdd(cd, derivScaled(ki, 1 / (1 / cr[i]), dof3), dof3);
+                        fd = derivAdd(fd, derivScaled(ki, fr[i], dof3), dof3);
+                        cd = derivAdd(cd, derivScaled(ki, cr[i], dof3), dof3);
                     }
                     r.newValue = stateAdd(y, derivTimes(fd, dt, dof3), dof3);
                     State coarsePred = stateAdd(y, derivTimes(cd, dt, dof3), dof3);

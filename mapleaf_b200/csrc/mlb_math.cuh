@@ -58,6 +58,17 @@ MLB_DEV double divBy(double x, double n, double r) {
     double q = x * r;
     return fma(fma(-n, q, x), r, q);
 }
+/* 1 / x for a finite x well inside the normal range (callers guarantee it): the hardware seed and the two refinement steps of the
+   IEEE reciprocal sequence, without its range tests and slow-path call. The last step rounds an 80-bit-accurate value once. */
+MLB_DEV double rcpNormal(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    e = fma(e, e, e);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
 MLB_DEV V3 normalize(V3 a) {                                                               /* :118 — zero stays zero */
     double l = len(a);
     if (l > 0) { double r = 1.0 / l; return v3(divBy(a.x, l, r), divBy(a.y, l, r), divBy(a.z, l, r)); }

@@ -181,8 +181,9 @@ MLB_DEV void atmosphere(const double* B, double asl, Air& e) {
     double temp = Tb + lapse * altitudeAboveBase;
     double Pb = U[24 + baseIndex];
     double pressure;
-    if (lapse == 0) pressure = m_exp(-G * M * altitudeAboveBase / (R * Tb * 1000)) * Pb;
-    else pressure = m_pow((Tb + lapse * altitudeAboveBase) / Tb, -G * M / (R * lapse * 1000)) * Pb;
+    /* layer constants from the host: exponent -G M / (R lapse 1000), 1 / Tb, R Tb 1000 and its reciprocal (U rows 4-7) */
+    if (lapse == 0) pressure = m_exp(divBy(-G * M * altitudeAboveBase, U[48 + baseIndex], U[56 + baseIndex])) * Pb;
+    else pressure = m_pow(divBy(Tb + lapse * altitudeAboveBase, Tb, U[40 + baseIndex]), U[32 + baseIndex]) * Pb;
     double rho = M * pressure / (R * temp * 1000);
     double viscosity = 1.457e-6 * (temp * sqrt(temp)) / (temp + 110.4);                    /* temp**1.5 */
     if (H >= 86000) rho = 0.0;
@@ -358,6 +359,7 @@ MLB_DEV double skinFrictionCompressibility(double Mach, bool smooth);
 
 struct Aero {
     double Mach, totalAOA, q, airSpeed, unitRe, density, viscosity, asl, finenessRatio, Aref, time;
+    double rAref, finenessF;   /* 1 / Aref and 1 + 0.5 / finenessRatio, host-derived (H_RAREF, H_FINENESS_F) */
     bool qValid;        /* dynamic pressure is computed and cached at its FIRST use in an evaluation (AeroParameters.py:141-150) */
     double sinAOA, axialFactor, baseDrag, sfCorrRough;      /* functions of Mach / total AOA only, shared by every component */
     V3 lfav, normalDir, w;
@@ -379,7 +381,7 @@ MLB_DEV void aeroSetup(const double* B, const Lane& L, Aero& a, const State& s, 
     a.unitRe = a.airSpeed * e.density / e.viscosity;                                        /* :22-27 */
     a.finenessRatio = B[H_FINENESS + L.nStages - 1];
     a.fullyTurb = B[H_FULLY_TURB] != 0;
-    a.Aref = B[H_AREF];
+    a.Aref = B[H_AREF]; a.rAref = B[H_RAREF]; a.finenessF = B[H_FINENESS_F + L.nStages - 1];
     a.sinAOA = m_sin(a.totalAOA);
     a.axialFactor = dragToAxialFactor(a.totalAOA);
     a.baseDrag = baseDragCoefficient(a.Mach);
@@ -445,11 +447,10 @@ MLB_DEV double skinFrictionCoefficient(double unitRe, double length, double Mach
     return cf * (smooth ? skinFrictionCompressibility(Mach, true) : corrRough);
 }
 /* getCylindricalSkinFrictionDragCoefficientAndRollDampingMoment (:138-168) */
-MLB_DEV double cylinderSkinFriction(const Aero& a, double length, double roughness, double criticalRe, double roughCf, double wettedArea, V3& rollDamping) {
+MLB_DEV double cylinderSkinFriction(const Aero& a, double length, double roughness, double criticalRe, double roughCf, double wettedOverAref, double avgRadius, V3& rollDamping) {
     double cd = skinFrictionCoefficient(a.unitRe, length, a.Mach, roughness, criticalRe, roughCf, a.fullyTurb, a.sfCorrRough);
-    cd *= (1 + (0.5 / a.finenessRatio));
-    cd *= (wettedArea / a.Aref);
-    double avgRadius = (wettedArea / length) / (2 * MLB_PI);
+    cd *= a.finenessF;                                      /* (1 + (0.5 / finenessRatio)) */
+    cd *= wettedOverAref;                                   /* wettedArea / Aref; avgRadius = (wettedArea / length) / (2 pi): *_K_WET, *_K_RAD */
     double rollingSurfaceVel = avgRadius * a.w.z;
     double totalVelSquared = a.airSpeed * a.airSpeed + rollingSurfaceVel * rollingSurfaceVel;
     if (totalVelSquared == 0) { rollDamping = v3(0, 0, 0); return cd; }
@@ -480,7 +481,7 @@ MLB_DEV ForceMoment forceFromCdCN(Aero& a, double Cd, double CN, V3 CP, V3 momen
     V3 totalForce = ((v3(0, 0, -CA) + a.normalDir * CN) * a.Aref) * dynamicPressure(a);
     return fm(totalForce, CP, moment);
 }
-MLB_DEV double barrowmanCN(double sinAOA, double Aref, double top, double bottom) { return 2 * sinAOA * (bottom - top) / Aref; }   /* :284-289 */
+MLB_DEV double barrowmanCN(const Aero& a, double top, double bottom) { return divBy(2 * a.sinAOA * (bottom - top), a.Aref, a.rAref); }   /* :284-289 */
 MLB_DEV double conePressureCd(const double* sub, const double* trans, double halfAngle, double Mach) {   /* noseCone.py:199-212 */
     if (Mach < 1) return sub[0] * m_pow(Mach, sub[1]);
     if (Mach > 1 && Mach < 1.3) return trans[0] + trans[1] * Mach + trans[2] * (Mach * Mach) + trans[3] * (Mach * Mach * Mach);
@@ -492,19 +493,19 @@ MLB_DEV double conePressureCd(const double* sub, const double* trans, double hal
  * Components
  * ------------------------------------------------------------------------------------------- */
 MLB_COMP_NOSE ForceMoment noseConeForce(Aero& a, const double* C) {                         /* noseCone.py:173-197 */
-    double CN = barrowmanCN(a.sinAOA, a.Aref, 0, C[NC_BASE_AREA]);
+    double CN = barrowmanCN(a, 0, C[NC_BASE_AREA]);
     V3 roll;
-    double skin = cylinderSkinFriction(a, C[NC_LENGTH], C[NC_ROUGH], C[NC_CRIT_RE], C[NC_ROUGH_CF], C[NC_WETTED], roll);
-    double pressure = conePressureCd(C + NC_SUB, C + NC_TRANS, C[NC_HALF_ANGLE], a.Mach) * C[NC_BASE_AREA] / a.Aref;
+    double skin = cylinderSkinFriction(a, C[NC_LENGTH], C[NC_ROUGH], C[NC_CRIT_RE], C[NC_ROUGH_CF], C[NC_K_WET], C[NC_K_RAD], roll);
+    double pressure = divBy(conePressureCd(C + NC_SUB, C + NC_TRANS, C[NC_HALF_ANGLE], a.Mach) * C[NC_BASE_AREA], a.Aref, a.rAref);
     return forceFromCdCN(a, pressure + skin, CN, ld3(C + NC_CP), roll);
 }
 MLB_COMP_TUBE ForceMoment bodyTubeForce(Aero& a, const double* C, V3 CG) {                  /* bodyTube.py:35-97 */
     double CN = 1.1 * (a.sinAOA * a.sinAOA);
-    CN *= C[BT_PLANFORM] / a.Aref;
+    CN *= C[BT_K_PLAN];                                     /* BT_PLANFORM / Aref */
     V3 roll;
-    double skin = cylinderSkinFriction(a, C[BT_LENGTH], C[BT_ROUGH], C[BT_CRIT_RE], C[BT_ROUGH_CF], C[BT_WETTED], roll);
+    double skin = cylinderSkinFriction(a, C[BT_LENGTH], C[BT_ROUGH], C[BT_CRIT_RE], C[BT_ROUGH_CF], C[BT_K_WET], C[BT_K_RAD], roll);
     const int nSegments = 25;
-    double dL = C[BT_LENGTH] / nSegments;
+    double dL = C[BT_DL];                                   /* BT_LENGTH / nSegments */
     double dA = dL * C[BT_DIAM];
     V3 position = ld3(C + C_POS);
     V3 total = v3(0, 0, 0);
@@ -514,7 +515,7 @@ MLB_COMP_TUBE ForceMoment bodyTubeForce(Aero& a, const double* C, V3 CG) {      
            moment -psi x (v|v|) = (z sy, -z sx, 0): the same products as the general form with its exact-zero terms dropped */
 #pragma unroll 5
         for (int i = 0; i < nSegments; i++) {                                               /* longitudinal damping strips */
-            double z = (position.z + (-dL * i - dL / 2)) - CG.z;
+            double z = C[BT_STRIP_Z + i] - CG.z;            /* (position.z + (-dL i - dL / 2)) - CG.z */
             double vx = a.w.y * z, vy = -(a.w.x * z);
             double sx = vx * fabs(vx), sy = vy * fabs(vy);
             total.x += z * sy; total.y += -(z * sx);
@@ -522,7 +523,7 @@ MLB_COMP_TUBE ForceMoment bodyTubeForce(Aero& a, const double* C, V3 CG) {      
     } else {
 #pragma unroll 1
         for (int i = 0; i < nSegments; i++) {
-            V3 psi = (position + v3(0, 0, -dL * i - dL / 2)) - CG;
+            V3 psi = v3(position.x + 0, position.y + 0, C[BT_STRIP_Z + i]) - CG;
             V3 segVel = cross(a.w, psi);
             V3 sqVel = v3(segVel.x * fabs(segVel.x), segVel.y * fabs(segVel.y), segVel.z * fabs(segVel.z));
             total = total + (-cross(psi, sqVel));
@@ -533,28 +534,28 @@ MLB_COMP_TUBE ForceMoment bodyTubeForce(Aero& a, const double* C, V3 CG) {      
     return forceFromCdCN(a, skin, CN, ld3(C + BT_CP), total);
 }
 MLB_COMP_TAIL ForceMoment transitionForce(const Lane& L, Aero& a, const double* C, int stageIdx, bool isBoatTail) {   /* boatTail.py:127-217 */
-    double CN = barrowmanCN(a.sinAOA, a.Aref, C[TR_TOP_AREA], C[TR_BOTTOM_AREA]);
+    double CN = barrowmanCN(a, C[TR_TOP_AREA], C[TR_BOTTOM_AREA]);
     double cdp;
     if (isBoatTail) {
         double base = a.baseDrag;
         cdp = base * C[TR_CD_ADJ];
-        cdp *= C[TR_FRONTAL] / a.Aref;
+        cdp *= C[TR_K_FRONT];                               /* TR_FRONTAL / Aref */
         bool noEngine = (L.engineShutOff[stageIdx] < 0);
-        if (noEngine || a.time > L.engineShutOff[stageIdx]) cdp += base * C[TR_BOTTOM_AREA] / a.Aref;
+        if (noEngine || a.time > L.engineShutOff[stageIdx]) cdp += divBy(base * C[TR_BOTTOM_AREA], a.Aref, a.rAref);
     } else {
         if (C[TR_GROWING] == 0) cdp = a.baseDrag * C[TR_CD_ADJ];
         else cdp = conePressureCd(C + TR_SUB, C + TR_TRANS, C[TR_HALF_ANGLE], a.Mach);
-        cdp *= C[TR_FRONTAL] / a.Aref;
+        cdp *= C[TR_K_FRONT];                               /* TR_FRONTAL / Aref */
     }
     double skin = 0; V3 roll = v3(0, 0, 0);
-    if (C[TR_WETTED] != 0) skin = cylinderSkinFriction(a, C[TR_LENGTH], C[TR_ROUGH], C[TR_CRIT_RE], C[TR_ROUGH_CF], C[TR_WETTED], roll);
+    if (C[TR_WETTED] != 0) skin = cylinderSkinFriction(a, C[TR_LENGTH], C[TR_ROUGH], C[TR_CRIT_RE], C[TR_ROUGH_CF], C[TR_K_WET], C[TR_K_RAD], roll);
     return forceFromCdCN(a, cdp + skin, CN, ld3(C + TR_CP), roll);
 }
 
 MLB_DEV double finCnAlphaSubsonic(const double* C, double Mach) {                           /* Fins.py:26-34 */
     double beta = betaOf(Mach);
-    double AR = 2 * (C[FS_SPAN] * C[FS_SPAN]) / C[FS_PLANFORM];
-    double t = beta * AR / m_cos(C[FS_MIDSWEEP]);
+    double AR = C[FS_AR2];                                  /* 2 span^2 / planform */
+    double t = divBy(beta * AR, C[FS_COS_MID], C[FS_RCOS_MID]);
     return (2 * MLB_PI * AR) / (2 + sqrt(4 + t * t));
 }
 struct Busemann { double K1, K2, K3, negZPerRadius; };
@@ -654,20 +655,19 @@ MLB_COMP_FINS ForceMoment finSetForce(const double* B, const Lane& L, Aero& a, c
     const double Mach = a.Mach, Aref = a.Aref, q = dynamicPressure(a);
     /* drag build-up common to all fins of the set (Fins.py:289-358) */
     double cf = skinFrictionCoefficient(a.unitRe, C[FS_MAC_LEN], Mach, C[FS_ROUGH], C[FS_CRIT_RE], C[FS_ROUGH_CF], a.fullyTurb, a.sfCorrRough);
-    double skinDrag = cf * (C[FS_WETTED] / Aref);
-    skinDrag *= (1 + 2 * C[FS_THICK] / C[FS_MAC_LEN]);
+    double skinDrag = cf * C[FS_K_SKIN];                    /* the flight-independent factors are FS_K_* constants from the host */
+    skinDrag *= C[FS_K_THICKF];
     double leCd = (C[FS_LE_SHAPE] == 0) ? cylinderCrossFlowCd(Mach) : bluntBodyCd(Mach);
-    double cs = m_cos(C[FS_SWEEP]);
-    leCd *= C[FS_LE_THICK] * C[FS_SPAN] * (cs * cs) / Aref;
-    double teCd = a.baseDrag * C[FS_SPAN] * C[FS_TE_THICK] / Aref;
-    double tc = C[FS_THICK] / C[FS_ROOT];
-    double cm = m_cos(C[FS_MIDSWEEP]);
+    leCd *= C[FS_K_LE];
+    double teCd = divBy(a.baseDrag * C[FS_SPAN] * C[FS_TE_THICK], Aref, a.rAref);
+    double tc = C[FS_TC];
+    double cm = C[FS_COS_MID];
     double thicknessDrag;
     if (Mach <= 1) {
         double tc2 = tc * tc, d = thickK - (Mach * Mach) * (cm * cm);
         thicknessDrag = 4 * cf * (tc * cm + (30 * (tc2 * tc2) * (cm * cm)) / (d * sqrt(d)));
-    } else { double r = C[FS_THICK] / C[FS_MAC_LEN]; thicknessDrag = 2.3 * C[FS_AR] * (r * r); }
-    thicknessDrag *= C[FS_PLANFORM] / Aref;
+    } else thicknessDrag = C[FS_K_THICK_SUP];
+    thicknessDrag *= C[FS_K_PLAN];
     double totalDrag = (leCd + teCd + thicknessDrag) + skinDrag;
 
     V3 position = ld3(C + C_POS);
@@ -713,7 +713,7 @@ MLB_COMP_FINS ForceMoment finSetForce(const double* B, const Lane& L, Aero& a, c
             double finVelMag = len(finVelocity);
             double al = 0.0;
             if (finVelMag >= 0.1) {
-                double body = dot(finNormal, finVelocity) * (1 / finVelMag);
+                double body = dot(finNormal, finVelocity) * rcpNormal(finVelMag);      /* 1 / finVelMag, finVelMag >= 0.1 */
                 if (fabs(body - 1) < 1e-14) body = 1.0;
                 al = m_asin(body);
             }

@@ -133,7 +133,10 @@ MLB_HD_COLD static double pinkValue(PinkNoise& g, double time, double c0, double
     double lastVal = g.nextSlot ? g.last0 : g.last1;
     double secondLastVal = g.nextSlot ? g.last1 : g.last0;
     double secondLastValTime = g.lastValTime - timeStep;
-    double dValdt = (lastVal - secondLastVal) / timeStep;
+    /* (lastVal - secondLastVal) / timeStep with the exactly rounded reciprocal 1 / 0.05 = 20 and one correction step (Markstein): the
+       correctly rounded quotient, without the full division sequence */
+    const double diff = lastVal - secondLastVal, q = diff * 20.0;
+    double dValdt = fma(fma(-timeStep, q, diff), 20.0, q);
     return dValdt * (time - secondLastValTime) + secondLastVal;
 }
 

@@ -797,11 +797,8 @@ def _buildControlSystem(sd, rk, stages, method, H, append):
         rec[L.CS_UPDATE_DT] = controlTimeStep
         if "Adaptive" in method:
             rec[L.CS_FORCE_RK4] = 1.0
-            rows, _ = butcherTableau("RK4")
-            flat = []
-            for row in rows:
-                flat.extend(row + [0.0] * (L.TABLEAU_STRIDE - len(row)))
-            rec[L.CS_TABLEAU2_OFF] = append(flat)
+            rows, nRes = butcherTableau("RK4")
+            rec[L.CS_TABLEAU2_OFF] = append(_flattenTableau(rows, nRes))
         original = float(sd.getValue("SimControl.timeStep"))
         if controlTimeStep / original != round(controlTimeStep / original):
             recommended = controlTimeStep / max(1, round(controlTimeStep / original))
@@ -904,6 +901,54 @@ def initialStateGlobalFrame(rocketReader: SubDictReader, earth: str, elevation: 
     return initPos, initVel, q0, w0
 
 
+def _derivedConstants(rec, Aref):
+    """Flight-independent quotients of the component force routines (include/mlb_layout.h: *_K_*), evaluated in the reference's order."""
+    def quot(a, b):
+        return a / b if b != 0 else float("nan")
+    ctype = int(rec[L.C_TYPE])
+    if ctype == L.CT_NOSECONE:
+        rec[L.NC_K_WET] = quot(rec[L.NC_WETTED], Aref)
+        rec[L.NC_K_RAD] = quot(quot(rec[L.NC_WETTED], rec[L.NC_LENGTH]), 2 * math.pi)
+    elif ctype == L.CT_BODYTUBE:
+        rec[L.BT_K_WET] = quot(rec[L.BT_WETTED], Aref)
+        rec[L.BT_K_RAD] = quot(quot(rec[L.BT_WETTED], rec[L.BT_LENGTH]), 2 * math.pi)
+        rec[L.BT_K_PLAN] = quot(rec[L.BT_PLANFORM], Aref)
+        rec[L.BT_DL] = rec[L.BT_LENGTH] / 25
+        dL = rec[L.BT_DL]
+        for i in range(25):
+            rec[L.BT_STRIP_Z + i] = rec[L.C_POS + 2] + (-dL * i - dL / 2)
+    elif ctype in (L.CT_BOATTAIL, L.CT_TRANSITION):
+        rec[L.TR_K_WET] = quot(rec[L.TR_WETTED], Aref)
+        rec[L.TR_K_RAD] = quot(quot(rec[L.TR_WETTED], rec[L.TR_LENGTH]), 2 * math.pi)
+        rec[L.TR_K_FRONT] = quot(rec[L.TR_FRONTAL], Aref)
+    elif ctype == L.CT_FINSET:
+        rec[L.FS_K_SKIN] = quot(rec[L.FS_WETTED], Aref)
+        rec[L.FS_K_THICKF] = 1 + 2 * rec[L.FS_THICK] / rec[L.FS_MAC_LEN]
+        cs = math.cos(rec[L.FS_SWEEP])
+        rec[L.FS_K_LE] = quot(rec[L.FS_LE_THICK] * rec[L.FS_SPAN] * (cs * cs), Aref)
+        rec[L.FS_TC] = rec[L.FS_THICK] / rec[L.FS_ROOT]
+        rec[L.FS_K_PLAN] = quot(rec[L.FS_PLANFORM], Aref)
+        rec[L.FS_COS_MID] = math.cos(rec[L.FS_MIDSWEEP])
+        rec[L.FS_RCOS_MID] = 1 / rec[L.FS_COS_MID]
+        rec[L.FS_AR2] = 2 * (rec[L.FS_SPAN] * rec[L.FS_SPAN]) / rec[L.FS_PLANFORM]
+        r = rec[L.FS_THICK] / rec[L.FS_MAC_LEN]
+        rec[L.FS_K_THICK_SUP] = 2.3 * rec[L.FS_AR] * (r * r)
+    return rec
+
+
+def _flattenTableau(rows, nResult):
+    """Stage rows, result rows, then (device only) the result rows again as the weights the reference's object algebra ends up applying:
+    derivative * c is evaluated as derivative / (1 / c) and the division as * (1 / (1 / c)) (Integration.py:233-236,434-447)."""
+    flat = []
+    for row in rows:
+        flat.extend(row + [0.0] * (L.TABLEAU_STRIDE - len(row)))
+    with np.errstate(divide="ignore"):
+        for row in rows[len(rows) - nResult:]:
+            eff = [float(np.float64(1) / (np.float64(1) / np.float64(c))) for c in row]
+            flat.extend(eff + [0.0] * (L.TABLEAU_STRIDE - len(row)))
+    return flat
+
+
 def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000) -> Model:
     sd = simDefinition
     env = SubDictReader("Environment", sd)
@@ -927,10 +972,7 @@ def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000) -> Model:
     H[L.H_DT0] = float(sd.getValue("SimControl.timeStep"))
     rows, nResult = butcherTableau(method)
     if rows is not None:
-        flat = []
-        for row in rows:
-            flat.extend(row + [0.0] * (L.TABLEAU_STRIDE - len(row)))
-        H[L.H_TABLEAU_OFF] = append(flat)
+        H[L.H_TABLEAU_OFF] = append(_flattenTableau(rows, nResult))
         H[L.H_TAB_NSTAGE_ROWS] = len(rows) - nResult
         H[L.H_TAB_NRESULT_ROWS] = nResult
     if "Adapt" in method:
@@ -985,7 +1027,10 @@ def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000) -> Model:
     elif atm == "USStandardAtmosphere":
         H[L.H_ATM] = L.ATM_USSTD
         bh, lapse, temps, pres = usStandardAtmosphereBases()
-        H[L.H_USSTD_OFF] = append(bh + lapse + temps + pres)
+        # rows 4-7 (device only): pressure-ratio exponent -G M / (R lapse 1000), 1 / Tb, the isothermal divisor R Tb 1000 and its reciprocal
+        G, M, R = 9.80665, 28.9644, 8.31432
+        expo = [(-G * M / (R * lp * 1000)) if lp != 0 else 0.0 for lp in lapse]
+        H[L.H_USSTD_OFF] = append(bh + lapse + temps + pres + expo + [1 / t for t in temps] + [R * t * 1000 for t in temps] + [1 / (R * t * 1000) for t in temps])
     elif atm == "TabulatedAtmosphere":
         path = env.getString("TabulatedAtmosphere.filePath")
         table = np.loadtxt(path, skiprows=1)
@@ -1082,6 +1127,7 @@ def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000) -> Model:
                 maxDiameter = max(maxDiameter, float(sd.getValue(cdict + ".outerDiameter")))
     H[L.H_MAXDIAM] = maxDiameter
     H[L.H_AREF] = math.pi * maxDiameter ** 2 / 4
+    H[L.H_RAREF] = (1 / H[L.H_AREF]) if H[L.H_AREF] != 0 else float("inf")
 
     # ---- stages and components (stage.py:13-70; sort rules: stage.py:47-59, RocketComponents.py:131-143) ----
     stages = []
@@ -1223,6 +1269,8 @@ def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000) -> Model:
         if sub[-1]["autoBT"] is not None:
             md = max(md, maxDiameter)
         H[L.H_FINENESS + nRemaining - 1] = (length / md) if md != 0 else float("nan")
+        fr = H[L.H_FINENESS + nRemaining - 1]
+        H[L.H_FINENESS_F + nRemaining - 1] = (1 + (0.5 / fr)) if fr != 0 else float("inf")
 
     # ---- serialise stages ----
     H[L.H_NSTAGES] = len(stages)
@@ -1260,7 +1308,7 @@ def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000) -> Model:
         S[L.S_BURN_DURATION] = -1
         S[L.S_IGNITION0] = 0.0 if si == len(stages) - 1 else 1000000000
         for ci, c in enumerate(st["comps"]):
-            off = append(c["rec"])
+            off = append(_derivedConstants(c["rec"], H[L.H_AREF]))
             S[L.S_COMP_OFF + ci] = off
             if c["cls"] == "Motor":
                 S[L.S_MOTOR] = ci
@@ -1278,7 +1326,7 @@ def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000) -> Model:
         S[L.S_FIXED2_CG:L.S_FIXED2_CG + 3] = fixed2.CG
         S[L.S_FIXED2_MASS] = fixed2.mass
         if st["autoBT"] is not None:
-            S[L.S_AUTO_BT_OFF] = append(st["autoBT"])
+            S[L.S_AUTO_BT_OFF] = append(_derivedConstants(st["autoBT"], H[L.H_AREF]))
         H[L.H_STAGE_OFF + si] = append(S)
 
     # ---- control system (rocket.py:210-217; GNC/ControlSystems.py:45-153) ----
