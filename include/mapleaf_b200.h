@@ -66,7 +66,8 @@ const char* mlb_last_error(void);
 const char* mlb_version(void);
 
 /* Per-lane inputs. perLaneArrays[k] is a host array of [components(arrayIds[k])][nLanes] doubles, lane fastest
-   (LANE_WIND: 3, LANE_INIT_STATE: 13, LANE_PINK_SEED: 3). Arrays not given use the model block's value for every lane. */
+   (LANE_WIND: 3, LANE_INIT_STATE: 13, LANE_PINK_SEED: 3, LANE_MOTOR_ADJUST: 8 = impulseAdjustFactor and burnTimeAdjustFactor of the
+   motor of stages 0-3, Propulsion.py:38-40,109-128). Arrays not given use the model block's value for every lane. */
 int mlb_set_lanes(mlb_handle* h, int64_t nLanes, const double* const* perLaneArrays, const int* arrayIds, int nArrays);
 /* Same, with the arrays already resident in this device's memory (no copy is made; the caller keeps them alive). */
 int mlb_set_lanes_device(mlb_handle* h, int64_t nLanes, const double* const* devLaneArrays, const int* arrayIds, int nArrays);

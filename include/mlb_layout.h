@@ -106,6 +106,8 @@
    step, mlb_math.cuh divBy) instead of running a full FP64 division per derivative evaluation. The oracle ignores them. */
 #define H_RAREF 107           /* 1 / H_AREF */
 #define H_FINENESS_F 108      /* 1 + 0.5 / H_FINENESS[k] (AeroFunctions.py:150), k = stages remaining - 1; 4 entries */
+#define H_INIT_CG0 112        /* CG of the complete rocket at t = 0 in rocket coordinates: H_INIT_STATE position = H_NOSE_POS0 + rotate(q0, CG)
+                                 (rocket.py:251-291); lanes with their own motor factors have their own CG and re-derive it */
 #define H_SIZE 128
 
 /* integrator ids (H_INTEGRATOR) */
@@ -344,6 +346,14 @@
 #define MT_OX_W0 17
 #define MT_FUEL_W0 18
 #define MT_TABLE 19
+/* columns 10-13 serve per-lane motor adjust factors (LANE_MOTOR_ADJUST): time and thrust as read from the motor file, before
+   impulseAdjustFactor / burnTimeAdjustFactor (Propulsion.py:109-111), and the oxidiser / fuel flow rates the propellant weights are
+   integrated from (:113-128). Columns 0-3 hold the same quantities with the definition's own factors applied. */
+#define MT_NCOLS 14
+#define MT_COL_RAW_TIME 10
+#define MT_COL_RAW_THRUST 11
+#define MT_COL_OX_FLOW 12
+#define MT_COL_FUEL_FLOW 13
 
 /* recovery system (Rocket/Recovery.py:10-48): up to 4 chute stages of 5 doubles:
    trigger event type, trigger value, chute area, Cd, delay */
@@ -433,7 +443,9 @@
 #define LANE_WIND 0          /* 3: Environment.ConstantMeanWind.velocity (ENU)        */
 #define LANE_INIT_STATE 1    /* 13: pos, vel, quat, body-frame angular velocity         */
 #define LANE_PINK_SEED 2     /* 3: integer seeds of the pink-noise generators           */
-#define LANE_NUM_ARRAYS 3
+#define LANE_MOTOR_ADJUST 3  /* 8: impulseAdjustFactor, burnTimeAdjustFactor of the motor of stage 0, 1, 2, 3 (definition order)   */
+#define LANE_NUM_ARRAYS 4
+#define MLB_MAX_STAGES 4
 
 /* ---- per-lane outputs -------------------------------------------------------------------- */
 #define RES_LAND_X 0

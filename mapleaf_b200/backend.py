@@ -109,7 +109,7 @@ def _check(rc, what):
         raise ValueError("{}: {}".format(what, msg))
 
 
-_LANE_COMPONENTS = {L.LANE_WIND: 3, L.LANE_INIT_STATE: 13, L.LANE_PINK_SEED: 3}
+_LANE_COMPONENTS = {L.LANE_WIND: 3, L.LANE_INIT_STATE: 13, L.LANE_PINK_SEED: 3, L.LANE_MOTOR_ADJUST: 2 * L.MLB_MAX_STAGES}
 
 
 class TrajectoryBatch:

@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(MLB_BLOCK) forceEvalKernel(const double* blob,
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Lane L;
-    LaneInputs in; in.wind = nullptr; in.initState = nullptr; in.pinkSeed = nullptr; in.nLanes = 1;
+    LaneInputs in; in.wind = nullptr; in.initState = nullptr; in.pinkSeed = nullptr; in.motorAdjust = nullptr; in.nLanes = 1;
     laneInit(B, L, in, 0, mt ? mt + (size_t)i * 3 * 624 : nullptr, mt != nullptr);      /* each state gets its own generator block */
     if (winds) { L.wind = v3(winds[3 * i], winds[3 * i + 1], winds[3 * i + 2]); laneFinConstants(B, L); }
     const double* s13 = states + 13 * i;
@@ -203,8 +203,8 @@ struct mlb_handle {
     std::vector<double> blob;
     double* d_blob = nullptr;
     long long nLanes = 0;
-    double* d_lane[LANE_NUM_ARRAYS] = { nullptr, nullptr, nullptr };
-    bool ownLane[LANE_NUM_ARRAYS] = { false, false, false };
+    double* d_lane[LANE_NUM_ARRAYS] = { nullptr, nullptr, nullptr, nullptr };
+    bool ownLane[LANE_NUM_ARRAYS] = { false, false, false, false };
     bool ownResults = true;
     double* d_results = nullptr; double* d_finals = nullptr; int* d_status = nullptr; long long* d_counters = nullptr;
     uint32_t* d_mt = nullptr;
@@ -220,7 +220,7 @@ struct mlb_handle {
     size_t sharedLen = 0;
 };
 
-static int laneArrayComponents(int id) { return id == LANE_WIND ? 3 : (id == LANE_INIT_STATE ? 13 : (id == LANE_PINK_SEED ? 3 : -1)); }
+static int laneArrayComponents(int id) { return id == LANE_WIND ? 3 : (id == LANE_INIT_STATE ? 13 : (id == LANE_PINK_SEED ? 3 : (id == LANE_MOTOR_ADJUST ? 2 * MLB_MAX_STAGES : -1))); }
 
 static void freeLanes(mlb_handle* h) {
     for (int i = 0; i < LANE_NUM_ARRAYS; i++) { if (h->ownLane[i] && h->d_lane[i]) cudaFree(h->d_lane[i]); h->d_lane[i] = nullptr; h->ownLane[i] = false; }
@@ -322,7 +322,7 @@ extern "C" int mlb_run(mlb_handle* h, void* stream) {
     h->stream = s;
     RunArgs a;
     a.blob = h->d_blob; a.blobLen = (int)h->sharedLen; a.blobPad = (int)((h->sharedLen + 1) & ~(size_t)1); a.nSlots = h->nSlots;
-    a.in.wind = h->d_lane[LANE_WIND]; a.in.initState = h->d_lane[LANE_INIT_STATE]; a.in.pinkSeed = h->d_lane[LANE_PINK_SEED]; a.in.nLanes = h->nLanes;
+    a.in.wind = h->d_lane[LANE_WIND]; a.in.initState = h->d_lane[LANE_INIT_STATE]; a.in.pinkSeed = h->d_lane[LANE_PINK_SEED]; a.in.motorAdjust = h->d_lane[LANE_MOTOR_ADJUST]; a.in.nLanes = h->nLanes;
     a.results = h->d_results; a.finals = h->d_finals; a.status = h->d_status; a.counters = h->d_counters; a.mt = h->d_mt;
     a.trace = (h->traceLane >= 0 && h->traceLane < h->nLanes) ? h->d_trace : nullptr;
     a.traceLane = h->traceLane; a.traceMaxRows = h->traceMaxRows; a.traceRows = h->d_traceRows;
@@ -340,6 +340,9 @@ extern "C" int mlb_run(mlb_handle* h, void* stream) {
 #define MLB_LAUNCH(N) if (block == N) { cudaFuncSetAttribute(integrateLanes<N, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes); integrateLanes<N, 1><<<grid, N, h->smemBytes, s>>>(a); } else
     MLB_EXTRA_SHAPES(MLB_LAUNCH)
     if (block == 1024) integrateLanes<1024, 1><<<grid, 1024, h->smemBytes, s>>>(a);
+#ifdef MLB_TUNE_512X2
+    else if (block == 512) { cudaFuncSetAttribute(integrateLanes<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes); integrateLanes<512, 2><<<grid, 512, h->smemBytes, s>>>(a); }
+#endif
     else if (block == 512) integrateLanes<512, 1><<<grid, 512, h->smemBytes, s>>>(a);
     else integrateLanes<128, 2><<<grid, 128, h->smemBytes, s>>>(a);
     CU(cudaGetLastError());

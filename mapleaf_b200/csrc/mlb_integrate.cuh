@@ -139,6 +139,9 @@ MLB_DEV StepResult integrateStep(const double* B, Lane& L, const KStore& ks, Sta
                     }
                 }
             }
+#ifdef MLB_SYNC_STRIDE
+            if (((i + 1) % MLB_SYNC_STRIDE) == 0)
+#endif
             MLB_CONVOY_SYNC();
             if (evalNow) ks.put(i + 1, stateDerivative(B, L, evalTime, evalY, dof3), dof3);
         }
@@ -226,7 +229,14 @@ MLB_DEV void stageSeparation(const double* B, Lane& L) {                        
     L.resorted = true;
     const double* S0 = B + (int)B[H_STAGE_OFF];
     L.ignitionTime[0] = L.time;    /* stages[0].motor.updateIgnitionTime(currentTime) — the TOP stage's motor, as in the reference */
-    L.engineShutOff[0] = L.time + S0[S_BURN_DURATION];
+    /* ignitionTime + times[-1] (Propulsion.py:153-157): the table's last time AFTER the burn-time factor, unlike the value recorded at
+       construction (:102-107, S_BURN_DURATION) */
+    double burnTime = S0[S_BURN_DURATION];
+    if ((int)S0[S_MOTOR] >= 0) {
+        const double* C = B + (int)S0[S_COMP_OFF + (int)S0[S_MOTOR]]; const int n = (int)C[MT_NROWS];
+        burnTime = L.motorAdj ? C[MT_TABLE + MT_COL_RAW_TIME * n + n - 1] * L.motorBurn[0] : C[MT_TABLE + n - 1];
+    }
+    L.engineShutOff[0] = L.time + burnTime;
 }
 MLB_DEV void triggerEvents(const double* B, Lane& L, double& estTimeToNext, bool& deterministic) {   /* simEventDetector.py:64-118 */
     double est = 1e10; bool det = false;
@@ -426,7 +436,7 @@ MLB_DEV void endDetector(const double* B, const Lane& L, double dt, bool& end, b
 }
 
 /* Per-lane inputs, SoA over lanes ([component][lane], lane fastest) */
-struct LaneInputs { const double* wind; const double* initState; const double* pinkSeed; long long nLanes; };
+struct LaneInputs { const double* wind; const double* initState; const double* pinkSeed; const double* motorAdjust; long long nLanes; };
 
 /* fin-set constants that depend on the lane's sampled environment at t = 0 */
 MLB_DEV void laneFinConstants(const double* B, Lane& L) {
@@ -474,6 +484,25 @@ MLB_DEV void laneInit(const double* B, Lane& L, const LaneInputs& in, long long 
         const double* S = B + (int)B[H_STAGE_OFF + si];
         L.ignitionTime[si] = S[S_IGNITION0];
         L.engineShutOff[si] = S[S_BURN_DURATION];
+    }
+    L.motorAdj = in.motorAdjust != nullptr;
+    for (int si = 0; si < MLB_MAX_STAGES; si++) { L.motorImp[si] = 1; L.motorBurn[si] = 1; L.motorOxW0[si] = 0; L.motorFuelW0[si] = 0; }
+    if (L.motorAdj) for (int si = 0; si < L.nStages; si++) {
+        const double* S = B + (int)B[H_STAGE_OFF + si];
+        if ((int)S[S_MOTOR] < 0) continue;
+        const double* C = B + (int)S[S_COMP_OFF + (int)S[S_MOTOR]]; const int n = (int)C[MT_NROWS]; const double* T = C + MT_TABLE;
+        L.motorImp[si] = in.motorAdjust[(2 * si) * in.nLanes + lane];
+        L.motorBurn[si] = in.motorAdjust[(2 * si + 1) * in.nLanes + lane];
+        L.motorOxW0[si] = motorWeightFromEnd(T + MT_COL_RAW_TIME * n, T + MT_COL_OX_FLOW * n, n, 0, L.motorBurn[si]);
+        L.motorFuelW0[si] = motorWeightFromEnd(T + MT_COL_RAW_TIME * n, T + MT_COL_FUEL_FLOW * n, n, 0, L.motorBurn[si]);
+    }
+    if (L.motorAdj) {
+        /* the state's position is the CG's (rocket.py:251-291,416-421) and the propellant weights move the CG: launch position of the
+           nose + rotate(q0, this lane's CG at t = 0). With a sampled initial state as well, the nose position is recovered from it. */
+        L.resorted = false;
+        double massSum; const Inertia I0 = rocketInertia(B, L, 0.0, &massSum);
+        const V3 nose = in.initState ? (L.s.pos - qRotateUnit(L.s.q, ld3(B + H_INIT_CG0))) : ld3(B + H_NOSE_POS0);
+        L.s.pos = nose + qRotateUnit(L.s.q, I0.CG);
     }
     /* RecoverySystem.__init__ -> _deployNextStage(): chute stage 0, subscribes the first trigger */
     L.recoveryStage = -1;

@@ -53,7 +53,7 @@ namespace mlb {
 #define MLB_COMP_FINS __device__ __forceinline__
 #endif
 
-#define MLB_MAX_STAGES 4
+/* MLB_MAX_STAGES: include/mlb_layout.h */
 #define MLB_MAX_FINSETS 4
 
 struct ForceMoment { V3 force, location, moment; };      /* Motion/forceMomentSystem.py */
@@ -75,6 +75,10 @@ struct Lane {
     double lastVz, lastTime;                    /* event detector memory (simEventDetector.py:120-132) */
     double pidLastError, pidIntegral;           /* step-size PID (GNC/PID.py:27-51) */
     double ignitionTime[MLB_MAX_STAGES], engineShutOff[MLB_MAX_STAGES];
+    /* sampled motor adjust factors (LANE_MOTOR_ADJUST; Propulsion.py:38-40,109-128): the motor tables of this lane are the file's
+       columns rescaled on the fly, the initial propellant weights are integrated once at lane start */
+    bool motorAdj;
+    double motorImp[MLB_MAX_STAGES], motorBurn[MLB_MAX_STAGES], motorOxW0[MLB_MAX_STAGES], motorFuelW0[MLB_MAX_STAGES];
     double finThickK[MLB_MAX_FINSETS];          /* Fins.py:198-210, depends on the sampled wind */
     Event events[MLB_MAX_EVENTS];
     PinkNoise png[3];
@@ -308,6 +312,49 @@ MLB_DEV Inertia motorInertia(const double* C, double t) {                       
     }
     return combineInertias(part, 2);
 }
+/* The same motor with per-lane adjust factors (Propulsion.py:109-128): times are rawTime * burnTimeAdjustFactor, the propellant weight
+   at table row k is the trapezoid sum of flowRate over the ADJUSTED times from the last row back to k, accumulated in the reference's
+   order (last interval first), so it is rebuilt here from the end of the table down to the interval that brackets t. */
+MLB_DEV int bisectRightScaled(const double* X, int n, double x, double scale) {
+    int lo = 0, hi = n;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (x < X[mid] * scale) hi = mid; else lo = mid + 1; }
+    return lo;
+}
+MLB_DEV double motorWeightFromEnd(const double* rawT, const double* flow, int n, int k, double burn) {      /* weights[k], :119-128 */
+    double sum = 0;
+    for (int i = n - 1; i > k; i--) { double deltaT = rawT[i] * burn - rawT[i - 1] * burn; sum += deltaT * (flow[i - 1] + flow[i]) / 2; }
+    return sum;
+}
+MLB_DEV Inertia motorInertiaAdjusted(const double* C, double t, double burn, double oxW0, double fuelW0) {
+    int n = (int)C[MT_NROWS]; const double* T = C + MT_TABLE; const double* rawT = T + MT_COL_RAW_TIME * n;
+    Inertia part[2];                                                                        /* [fuel, ox] (ox + fuel) */
+    int i = bisectRightScaled(rawT, n, t, burn);
+    for (int p = 0; p < 2; p++) {
+        double W0 = p ? oxW0 : fuelW0;
+        part[p].MOI = v3(0, 0, 0); part[p].CG = v3(0, 0, 0); part[p].mass = 0;
+        if (W0 != 0) {
+            const double* flow = T + (p ? MT_COL_OX_FLOW : MT_COL_FUEL_FLOW) * n;
+            const double* Mcol = T + (p ? 4 : 7) * n;
+            double w; V3 moi;
+            if (i >= n) { w = 0; moi = v3(Mcol[n - 1], Mcol[2 * n - 1], Mcol[3 * n - 1]); }            /* weights[-1] = 0 */
+            else if (i < 1) { w = W0; moi = v3(Mcol[0], Mcol[n], Mcol[2 * n]); }
+            else {
+                double wHi = motorWeightFromEnd(rawT, flow, n, i, burn);
+                double x0 = rawT[i - 1] * burn, x1 = rawT[i] * burn;
+                double wLo = wHi + (x1 - x0) * (flow[i - 1] + flow[i]) / 2;                 /* one more interval: weights[i - 1] */
+                w = (wHi - wLo) * (t - x0) / (x1 - x0) + wLo;
+                V3 lg = v3(Mcol[i], Mcol[n + i], Mcol[2 * n + i]), sm = v3(Mcol[i - 1], Mcol[n + i - 1], Mcol[2 * n + i - 1]);
+                moi = vdiv((lg - sm) * (t - x0), (x1 - x0)) + sm;
+            }
+            double frac = 1 - (w / W0);
+            double cg0 = p ? C[MT_OX_CG0] : C[MT_FUEL_CG0], cg1 = p ? C[MT_OX_CG1] : C[MT_FUEL_CG1];
+            part[p].MOI = moi;
+            part[p].CG = v3(0, 0, cg0 * (1 - frac) + cg1 * frac);
+            part[p].mass = w;
+        }
+    }
+    return combineInertias(part, 2);
+}
 /* TabulatedInertia.getInertia (RocketComponents.py:369-372): time-tabulated mass, CG, MOI */
 MLB_DEV Inertia tabulatedInertia(const double* C, double time) {
     int n = (int)C[TI_NROWS]; const double* T = C + TI_TABLE;
@@ -332,7 +379,10 @@ MLB_DEV Inertia stageInertia(const double* B, const Lane& L, int si, double time
     const int nVar = (int)S[S_NVAR];
     for (int k = 0; k < nVar; k++) {                       /* variable-mass components, in the order the reference combines them */
         const double* C = B + (int)S[S_COMP_OFF + (int)S[(L.resorted ? S_VAR2_IDX : S_VAR_IDX) + k]];
-        if ((int)C[C_TYPE] == CT_MOTOR) list[n++] = motorInertia(C, fmax(0.0, time - L.ignitionTime[si]));
+        if ((int)C[C_TYPE] == CT_MOTOR) {
+            double tIgn = fmax(0.0, time - L.ignitionTime[si]);
+            list[n++] = L.motorAdj ? motorInertiaAdjusted(C, tIgn, L.motorBurn[si], L.motorOxW0[si], L.motorFuelW0[si]) : motorInertia(C, tIgn);
+        }
         else list[n++] = tabulatedInertia(C, time);
     }
     r = combineInertias(list, n);
@@ -801,6 +851,16 @@ MLB_DEV ForceMoment jetDampingForce(const double* B, const Lane& L, const Aero& 
 MLB_DEV double motorThrust(const Lane& L, const double* C, int si, double time) {           /* Propulsion.py:138-151 */
     double t = fmax(0.0, time - L.ignitionTime[si]);
     int n = (int)C[MT_NROWS]; const double* T = C + MT_TABLE;
+    if (L.motorAdj) {                                       /* thrust * impulseAdjustFactor / burnTimeAdjustFactor over time * burnTimeAdjustFactor */
+        const double* rawT = T + MT_COL_RAW_TIME * n; const double* rawF = T + MT_COL_RAW_THRUST * n;
+        const double imp = L.motorImp[si], burn = L.motorBurn[si];
+        if (t < 0 || t > rawT[n - 1] * burn) return 0;
+        int i = bisectRightScaled(rawT, n, t, burn);
+        if (i >= n) return rawF[n - 1] * imp / burn;
+        if (i < 1) return rawF[0] * imp / burn;
+        double y1 = rawF[i] * imp / burn, y0 = rawF[i - 1] * imp / burn, x0 = rawT[i - 1] * burn, x1 = rawT[i] * burn;
+        return (y1 - y0) * (t - x0) / (x1 - x0) + y0;
+    }
     if (t < 0 || t > T[n - 1]) return 0;
     return linInterp(T, T + n, n, t);
 }

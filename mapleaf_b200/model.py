@@ -490,6 +490,7 @@ def parseMotorFile(path, stagePosZ, impulseAdjustFactor=1.0, burnTimeAdjustFacto
         d = ln.index(")", c) + 1
         fuelMOIs.append(parseVector(ln[c:d]))
     burnDuration0 = times[-1]      # stage.engineShutOffTime is recorded BEFORE the burn-time factor is applied
+    rawTimes, rawThrust = list(times), list(thrust)
     thrust = [t * impulseAdjustFactor / burnTimeAdjustFactor for t in thrust]
     times = [t * burnTimeAdjustFactor for t in times]
     initOx = 0
@@ -503,7 +504,7 @@ def parseMotorFile(path, stagePosZ, impulseAdjustFactor=1.0, burnTimeAdjustFacto
         initFuel += dT * (fuelFlow[i - 1] + fuelFlow[i]) / 2
         fuelW.insert(0, initFuel)
     return dict(times=times, thrust=thrust, oxW=oxW, fuelW=fuelW, oxMOIs=oxMOIs, fuelMOIs=fuelMOIs, cg=cg,
-                initOx=initOx, initFuel=initFuel, engineShutOff=burnDuration0)
+                initOx=initOx, initFuel=initFuel, engineShutOff=burnDuration0, rawTimes=rawTimes, rawThrust=rawThrust, oxFlow=oxFlow, fuelFlow=fuelFlow)
 
 
 def motorInertia(m, tSinceIgnition) -> Inertia:
@@ -540,7 +541,7 @@ def _buildMotor(r, stagePos):
         path = found
     m = parseMotorFile(path, stagePos[2], impulse, burn)
     n = len(m["times"])
-    size = L.C_P + L.MT_TABLE - L.C_P + 10 * n
+    size = L.MT_TABLE + L.MT_NCOLS * n
     rec = [0.0] * size
     rec[L.C_TYPE] = L.CT_MOTOR
     rec[L.C_LEN] = size
@@ -550,12 +551,12 @@ def _buildMotor(r, stagePos):
     rec[L.MT_FUEL_W0] = m["initFuel"]
     t = L.MT_TABLE
     cols = [m["times"], m["thrust"], m["oxW"], m["fuelW"]] + [[v[k] for v in m["oxMOIs"]] for k in range(3)] + \
-           [[v[k] for v in m["fuelMOIs"]] for k in range(3)]
+           [[v[k] for v in m["fuelMOIs"]] for k in range(3)] + [m["rawTimes"], m["rawThrust"], m["oxFlow"], m["fuelFlow"]]
     for c, col in enumerate(cols):
         rec[t + c * n:t + (c + 1) * n] = col
     init = motorInertia(m, 0)
     rec[L.C_POS:L.C_POS + 3] = init.CG      # motor "position" = its initial CG (Propulsion.py:47-49)
-    return rec, dict(position=init.CG, motor=m, body=False)
+    return rec, dict(position=init.CG, motor=m, body=False, motorFactors=(impulse, burn), path=r.simDefDictPathToReadFrom)
 
 
 _TRIGGERS = {"Apogee": L.EV_APOGEE, "Altitude": L.EV_DESCENDING_ALT, "Time": L.EV_TIME_REACHED}
@@ -1358,6 +1359,7 @@ def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000) -> Model:
     cgGlobal, q0n = hm.q_rotate(q0, rocketInertia0.CG)
     posCG = hm.v_add(initPos, cgGlobal)
     H[L.H_NOSE_POS0:L.H_NOSE_POS0 + 3] = initPos
+    H[L.H_INIT_CG0:L.H_INIT_CG0 + 3] = rocketInertia0.CG
     H[L.H_INIT_STATE:L.H_INIT_STATE + 13] = list(posCG) + list(initVel) + list(q0n) + list(w0)
 
     # ---- end condition (SingleSimulations.py:205-248) ----
@@ -1378,5 +1380,7 @@ def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000) -> Model:
     meta = dict(stages=[dict(name=st["name"], components=[(c["name"], c["cls"]) for c in st["comps"]] +
                              ([("Auto-AddedZeroLengthBoatTail", "BoatTail")] if (st is stages[-1] and st["autoBT"] is not None) else []))
                         for st in stages],
-                initialInertia=rocketInertia0, method=method, earth=earth)
+                initialInertia=rocketInertia0, method=method, earth=earth,
+                # per stage: definition path and (impulseAdjustFactor, burnTimeAdjustFactor) of its motor, for LANE_MOTOR_ADJUST
+                motors=[next((dict(path=c["path"], factors=c["motorFactors"]) for c in st["comps"] if c["cls"] == "Motor"), None) for st in stages])
     return Model(blob, meta)

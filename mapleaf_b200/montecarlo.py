@@ -13,7 +13,7 @@ Sampling is the reference's: one `random.Random` owned by the SimDefinition, re-
 (IO/simDefinition.py:471-532), pink-noise seeds from the global `random` module, two (1D: one, 3D: three) per run
 (ENV/TurbulenceModelling.py:191-195). The Monte Carlo log has the same lines in the same order.
 What differs: all runs are sampled first and then flown together, so sampled keys must be ones the kernels take per
-lane (wind, initial state); any other `_stdDev` key raises NotImplementedError naming it. There is no CPU fallback.
+lane (wind, initial state, motor adjust factors); any other `_stdDev` key raises NotImplementedError naming it. There is no CPU fallback.
 """
 import os
 import random
@@ -124,12 +124,23 @@ def _prepSim(simDefinition, echo=True):
     return nRuns, mCLogger, outputLists
 
 
-def _checkSampledKeys(simDefinition):
+def _motorKeys(model):
+    """{definition key: row of LANE_MOTOR_ADJUST} for the impulse / burn-time adjust factors of every stage's motor."""
+    keys = {}
+    for si, motor in enumerate(model.meta["motors"] if model is not None else []):
+        if motor is not None:
+            keys[motor["path"] + ".impulseAdjustFactor"] = 2 * si
+            keys[motor["path"] + ".burnTimeAdjustFactor"] = 2 * si + 1
+    return keys
+
+
+def _checkSampledKeys(simDefinition, model=None):
     keys = simDefinition.probabilisticKeys()
-    bad = [k for k in keys if k != _WIND_KEY and k not in _INIT_STATE_KEYS]
+    motorKeys = _motorKeys(model)
+    bad = [k for k in keys if k != _WIND_KEY and k not in _INIT_STATE_KEYS and k not in motorKeys]
     if bad:
-        raise NotImplementedError("Monte Carlo sampling of {} is not implemented by the B200 backend: per-lane inputs are {} and {}".format(
-            ", ".join(bad), _WIND_KEY, ", ".join(sorted(_INIT_STATE_KEYS))))
+        raise NotImplementedError("Monte Carlo sampling of {} is not implemented by the B200 backend: per-lane inputs are {}, {} and the motors' "
+                                  "impulseAdjustFactor / burnTimeAdjustFactor".format(", ".join(bad), _WIND_KEY, ", ".join(sorted(_INIT_STATE_KEYS))))
     if any(k in _INIT_STATE_KEYS for k in keys) and float(simDefinition.getValue("Environment.LaunchSite.railLength")) > 0 \
             and "Rocket.initialDirection" in keys:
         raise NotImplementedError("Sampling Rocket.initialDirection with a launch rail (the rail direction is part of the model block)")
@@ -138,7 +149,9 @@ def _checkSampledKeys(simDefinition):
 
 def sampleRuns(simDefinition, nRuns, mCLogger, model):
     """Draws every run's inputs in the reference's order (MonteCarlo.py:64-72) and returns the per-lane arrays."""
-    keys = _checkSampledKeys(simDefinition)
+    keys = _checkSampledKeys(simDefinition, model)
+    motorKeys = _motorKeys(model)
+    sampleMotor = any(k in motorKeys for k in keys)
     sampleWind = _WIND_KEY in keys
     sampleState = any(k in _INIT_STATE_KEYS for k in keys)
     turb = int(model.header("H_TURB"))
@@ -147,6 +160,7 @@ def sampleRuns(simDefinition, nRuns, mCLogger, model):
     wind = np.empty((3, nRuns)) if sampleWind else None
     state = np.empty((13, nRuns)) if sampleState else None
     seeds = np.zeros((3, nRuns)) if nGen else None
+    motor = np.ones((2 * L.MLB_MAX_STAGES, nRuns)) if sampleMotor else None
     for i in range(nRuns):
         mCLogger.log("\nMonte Carlo Run #{}".format(i + 1))
         simDefinition.resampleProbabilisticValues()
@@ -154,6 +168,9 @@ def sampleRuns(simDefinition, nRuns, mCLogger, model):
             wind[:, i] = parseVector(simDefinition.getValue(_WIND_KEY))
         if sampleState:
             state[:, i] = laneInitialState(simDefinition, model)
+        if sampleMotor:
+            for key, row in motorKeys.items():
+                motor[row, i] = float(simDefinition.getValue(key))
         for g in range(nGen):
             # PinkNoiseGenerator.__init__ draws from the *global* random module when no seed key is given
             seeds[g, i] = model.blob[L.H_PINK_SEED + g] if (hasSeed >> g) & 1 else random.randrange(1000000)
@@ -164,6 +181,8 @@ def sampleRuns(simDefinition, nRuns, mCLogger, model):
         arrays[L.LANE_INIT_STATE] = state
     if nGen:
         arrays[L.LANE_PINK_SEED] = seeds
+    if sampleMotor:
+        arrays[L.LANE_MOTOR_ADJUST] = motor
     return arrays
 
 

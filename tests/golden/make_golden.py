@@ -27,6 +27,9 @@ What is recorded, and which reference code produced it:
                             BatchSims/NASAVerificationCases.mapleaf:264-278)
   canards_*.json .......... Canards.mapleaf (BASELINE.json configs[2]): 100 Hz stabiliser + scheduled-gain PID + deflection table +
                             first-order actuators (GNC/*.py), RK4 forced in the ascent, adaptive again under the parachute
+  motoradj_*.json ......... motor impulseAdjustFactor / burnTimeAdjustFactor (Rocket/Propulsion.py:38-40,102-128,153-157): set in the
+                            definition for a single-stage and a two-stage flight, and sampled (`_stdDev`) in a 3-run Monte Carlo loop
+                            like the reference's Jake1_MonteCarlo.mapleaf example
   rng.json ................ random.Random / PinkNoiseGenerator known answers (test_SimDefinition.py:118-151,
                             test_TurbulenceModelling.py:37-60)
 """
@@ -87,7 +90,7 @@ def flightRecord(f, traceEvery=0, keepDts=False):
     return rec
 
 
-def monteCarlo(defFile, overrides, seed, nRuns, globalSeed=None, traceEvery=0, keepDts=False):
+def monteCarlo(defFile, overrides, seed, nRuns, globalSeed=None, traceEvery=0, keepDts=False, motorKeys=()):
     """Same sampling order as Main.main -> runMonteCarloSimulation single-threaded (MonteCarlo.py:64-76)."""
     if globalSeed is not None:
         random.seed(globalSeed)          # the pink-noise seeds come from the *global* random module
@@ -110,6 +113,7 @@ def monteCarlo(defFile, overrides, seed, nRuns, globalSeed=None, traceEvery=0, k
         random.setstate(after)
         rec = flightRecord(f, traceEvery if i == 0 else 0, keepDts and i == 0)
         rec["wind"] = wind
+        rec["motor"] = [float(sd.getValue(k)) for k in motorKeys]
         rec["pinkSeeds"] = seeds
         runs.append(rec)
         print("  run", i + 1, "steps", rec["steps"], "apogee", rec["results"][3], flush=True)
@@ -224,7 +228,7 @@ def dump(name, obj):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["model", "rng", "windtunnel", "rk4_apogee", "rk4_ground", "rk45_pink", "rk45_gust", "tabulated", "twostage", "earth", "canards"]
+    which = sys.argv[1:] or ["model", "rng", "windtunnel", "rk4_apogee", "rk4_ground", "rk45_pink", "rk45_gust", "tabulated", "twostage", "earth", "canards", "motoradj"]
     mc = os.path.join(MY_DATA, "MonteCarlo.mapleaf")
     if "model" in which:
         dump("model_montecarlo.json", modelFields())
@@ -254,6 +258,15 @@ if __name__ == "__main__":
         can = os.path.join(MY_DATA, "Canards.mapleaf")
         dump("canards_apogee.json", singleFlight(can, {}, traceEvery=50))
         dump("canards_ground.json", singleFlight(can, {"SimControl.EndCondition": "Altitude"}, traceEvery=100, keepDts=True))
+    if "motoradj" in which:
+        m = "Rocket.Sustainer.Motor."
+        dump("motoradj_rk4.json", singleFlight(mc, {m + "impulseAdjustFactor": "1.0421", m + "burnTimeAdjustFactor": "0.9137"}, traceEvery=200))
+        two = os.path.join(MY_DATA, "TwoStage.mapleaf")
+        dump("motoradj_twostage.json", singleFlight(two, {"Rocket.Booster.Motor.impulseAdjustFactor": "0.97", "Rocket.Booster.Motor.burnTimeAdjustFactor": "1.12",
+                                                          "Rocket.Sustainer.Motor.impulseAdjustFactor": "1.05", "Rocket.Sustainer.Motor.burnTimeAdjustFactor": "0.88"}, traceEvery=50))
+        dump("motoradj_mc.json", monteCarlo(mc, {m + "impulseAdjustFactor": "1.0", m + "impulseAdjustFactor_stdDev": "0.02331",
+                                                     m + "burnTimeAdjustFactor": "1.0", m + "burnTimeAdjustFactor_stdDev": "0.10679"}, "2394781", 3,
+                                            motorKeys=(m + "impulseAdjustFactor", m + "burnTimeAdjustFactor")))
     adaptive = os.path.join(MY_DATA, "MonteCarloAdaptive.mapleaf")
     if "rk45_pink" in which:
         dump("rk45_pink.json", monteCarlo(adaptive, {}, "2394781", 4, globalSeed=2394781, keepDts=True))

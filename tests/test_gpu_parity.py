@@ -383,3 +383,56 @@ def test_canard_control_system_vs_reference(backend, golden):
     assert abs(int(o["counters"][0, 0]) - r["steps"]) <= 0.1 * r["steps"]        # the adaptive part under the parachute decorrelates
     assert abs(o["results"][0, 3] - r["results"][3]) < 1e-6                        # apogee is reached under RK4
     assert abs(o["results"][0, 5] - r["results"][5]) < 0.5 and abs(o["results"][0, 1] - r["results"][1]) < 0.05
+
+
+def motorAdjustLanes(factorsPerLane):
+    a = np.ones((2 * L.MLB_MAX_STAGES, len(factorsPerLane)))
+    for lane, f in enumerate(factorsPerLane):
+        for si, (imp, burn) in f.items():
+            a[2 * si, lane], a[2 * si + 1, lane] = imp, burn
+    return a
+
+
+@pytest.mark.parametrize("name", ["motoradj_rk4.json", "motoradj_twostage.json"])
+def test_motor_adjust_factors_vs_reference(backend, golden, name):
+    """Motor impulse / burn-time adjust factors (Propulsion.py:38-40,102-128,153-157) against the reference flight: factors in the
+    definition (host-built table) and as a per-lane input on the unadjusted model (tables rescaled on the fly in the kernel)."""
+    g = golden(name)
+    r = g["runs"][0]
+    baked = buildFrom(g["definition"], g["overrides"])
+    plain = buildFrom(g["definition"])
+    factors = {si: (float(g["overrides"][mo["path"] + ".impulseAdjustFactor"]), float(g["overrides"][mo["path"] + ".burnTimeAdjustFactor"]))
+               for si, mo in enumerate(plain.meta["motors"])}
+    for o in (gpuRun(backend, baked, 1, {}, traceLane=0, traceRows=4000),
+              gpuRun(backend, plain, 1, {L.LANE_MOTOR_ADJUST: motorAdjustLanes([factors])}, traceLane=0, traceRows=4000)):
+        assert o["status"][0] == L.ST_OK and o["counters"][0, 0] == r["steps"]
+        assert stateErr(o["finals"][0], r["final"]) < FIXED_TOL
+        assert relErr(o["results"][0, 3:7], r["results"][3:7]) < FIXED_TOL
+        for idx, row in zip(r["traceIdx"], r["trace"]):
+            assert stateErr(np.concatenate([o["trace"][idx, 1:14], [0]]), row) < FIXED_TOL
+
+
+def test_sampled_motor_adjust_factors_match_oracle(backend, golden):
+    """A batch in which every lane has its own wind and its own motor factors on both stages (sigma 2 % impulse, 10 % burn time, the
+    magnitudes of the reference's Jake1_MonteCarlo.mapleaf), plus the three reference-flown lanes of the sampled fixture."""
+    from oracle import oracle
+    g = golden("motoradj_mc.json")
+    m = buildFrom(g["definition"])
+    lanes = [{0: tuple(r["motor"])} for r in g["runs"]]
+    o = gpuRun(backend, m, 3, {L.LANE_WIND: winds(g["runs"]), L.LANE_MOTOR_ADJUST: motorAdjustLanes(lanes)})
+    for i, r in enumerate(g["runs"]):
+        assert o["counters"][i, 0] == r["steps"] and stateErr(o["finals"][i], r["final"]) < FIXED_TOL
+    two = buildFrom("TwoStage.mapleaf")
+    rng = np.random.default_rng(7)
+    n = 96
+    adj = np.ones((2 * L.MLB_MAX_STAGES, n))
+    adj[[0, 2]] = rng.normal(1.0, 0.02, size=(2, n)); adj[[1, 3]] = rng.normal(1.0, 0.10, size=(2, n))
+    w = rng.normal(size=(3, n)) * np.array([[3.0], [3.0], [0.3]])
+    arrays = {L.LANE_WIND: w, L.LANE_MOTOR_ADJUST: adj}
+    gq = gpuRun(backend, two, n, arrays)
+    c = oracle.run(two.blob, n, arrays)
+    assert (gq["status"] == c["status"]).all() and (gq["counters"][:, 0] == c["counters"][:, 0]).all()
+    for i in range(n):
+        ref = np.concatenate([[c["finals"][i, 13]], c["finals"][i, :13]])
+        assert stateErr(gq["finals"][i], ref) < FIXED_TOL
+        assert relErr(gq["results"][i, 3:7], c["results"][i, 3:7]) < FIXED_TOL

@@ -135,10 +135,26 @@ def test_runner_pink_noise_seeds_follow_the_global_stream(monkeypatch, tmp_path,
 
 
 def test_runner_rejects_sampled_keys_it_cannot_vary_per_lane(tmp_path):
-    sd = montecarloDefinition(tmp_path, nRuns=2, **{"Rocket.Sustainer.Motor.impulseAdjustFactor": "1.0",
-                                                     "Rocket.Sustainer.Motor.impulseAdjustFactor_stdDev": "0.02"})
-    with pytest.raises(NotImplementedError, match="impulseAdjustFactor"):
-        montecarlo._checkSampledKeys(sd)
+    sd = montecarloDefinition(tmp_path, nRuns=2, **{"Rocket.Sustainer.UpperBodyTube.mass_stdDev": "0.02"})
+    with pytest.raises(NotImplementedError, match="UpperBodyTube.mass"):
+        montecarlo._checkSampledKeys(sd, buildModel(sd))
+
+
+def test_runner_samples_motor_adjust_factors(monkeypatch, tmp_path, golden):
+    """`_stdDev` on a motor's impulseAdjustFactor / burnTimeAdjustFactor (the reference's Jake1_MonteCarlo.mapleaf): drawn after the
+    wind, in dictionary order, logged like the reference, and flown per lane."""
+    g = golden("motoradj_mc.json")
+    monkeypatch.setattr(backend, "TrajectoryBatch", OracleBatch)
+    sd = montecarloDefinition(tmp_path, nRuns=3)
+    for k, v in g["overrides"].items():          # after construction, as tests/golden/make_golden.py does: draw set 1 sampled the wind only
+        sd.setValue(k, v)
+    out = montecarlo.runMonteCarloSimulation(simDefinition=sd, silent=True)
+    for i, ref in enumerate(g["runs"]):
+        assert np.allclose(out.results[i, 3:7], ref["results"][3:7], rtol=1e-12)
+    body = open(out.logPath).read().splitlines()
+    i1 = body.index("Monte Carlo Run #1")
+    assert body[i1 + 2] == "Sampling scalar parameter: Rocket.Sustainer.Motor.impulseAdjustFactor, value: {:1.3f}".format(g["runs"][0]["motor"][0])
+    assert body[i1 + 3] == "Sampling scalar parameter: Rocket.Sustainer.Motor.burnTimeAdjustFactor, value: {:1.3f}".format(g["runs"][0]["motor"][1])
 
 
 def test_sampled_initial_state_matches_model_builder(tmp_path):

@@ -245,3 +245,53 @@ def test_control_record_and_time_step_rewrite():
     assert m.header("H_SHARED_LEN") < m.blob.size        # the Delaunay tables stay out of shared memory
     nd = m.blob[int(cs[L.CS_DEFL_INTERP_OFF]):]
     assert int(nd[L.ND_DIM]) == 5 and int(nd[L.ND_NVAL]) == 4 and int(nd[L.ND_NPTS]) == 60
+
+
+def motorAdjustLanes(model, factorsPerLane):
+    """LANE_MOTOR_ADJUST array [8, nLanes] from {stage index: (impulseAdjustFactor, burnTimeAdjustFactor)} per lane."""
+    a = np.ones((2 * L.MLB_MAX_STAGES, len(factorsPerLane)))
+    for lane, f in enumerate(factorsPerLane):
+        for si, (imp, burn) in f.items():
+            a[2 * si, lane], a[2 * si + 1, lane] = imp, burn
+    return a
+
+
+@pytest.mark.parametrize("name", ["motoradj_rk4.json", "motoradj_twostage.json"])
+def test_motor_adjust_factors(golden, name):
+    """impulseAdjustFactor / burnTimeAdjustFactor (Propulsion.py:38-40,102-128,153-157), two ways: written into the definition (the
+    host builds the adjusted table) and as a per-lane input on the unadjusted model (the per-sample table is rebuilt at lane start).
+    Both must reproduce the reference flight; the burnout-separation time uses the UNadjusted burn time, the upper-stage shut-off the
+    adjusted one (two-stage case: 0.5 s separation delay, factors 1.12 / 0.88)."""
+    g = golden(name)
+    r = g["runs"][0]
+    baked = buildFrom(g["definition"], g["overrides"])
+    plain = buildFrom(g["definition"])
+    factors = {}
+    for si, motor in enumerate(plain.meta["motors"]):
+        factors[si] = (float(g["overrides"][motor["path"] + ".impulseAdjustFactor"]), float(g["overrides"][motor["path"] + ".burnTimeAdjustFactor"]))
+    assert baked.meta["motors"][0]["factors"] == factors[0]
+    for o in (oracle.run(baked.blob, 1, {}, traceLane=0, traceMaxRows=4000),
+              oracle.run(plain.blob, 1, {L.LANE_MOTOR_ADJUST: motorAdjustLanes(plain, [factors])}, traceLane=0, traceMaxRows=4000)):
+        assert o["status"][0] == L.ST_OK and o["counters"][0, 0] == r["steps"]
+        assert stateErr(o["finals"][0], r["final"]) < 1e-12
+        assert relErr(o["results"][0, 3:7], r["results"][3:7]) < 1e-12
+        for idx, row in zip(r["traceIdx"], r["trace"]):
+            assert o["trace"][idx, 0] == row[0]
+            assert stateErr(np.concatenate([o["trace"][idx, 1:14], [0]]), row) < 1e-12
+
+
+def test_sampled_motor_adjust_factors_per_lane(golden):
+    """The reference's Monte Carlo loop with `_stdDev` on the motor factors (its Jake1_MonteCarlo.mapleaf example does this): one
+    batch, each lane with its own wind and factors, lanes with unit factors alongside."""
+    g = golden("motoradj_mc.json")
+    m = buildFrom(g["definition"])
+    runs = g["runs"]
+    lanes = [{0: tuple(r["motor"])} for r in runs] + [{}]
+    wind = np.concatenate([lanesFromRuns(runs), np.array([[2.0], [0.0], [0.0]])], axis=1)
+    o = oracle.run(m.blob, len(lanes), {L.LANE_WIND: wind, L.LANE_MOTOR_ADJUST: motorAdjustLanes(m, lanes)})
+    for i, r in enumerate(runs):
+        assert o["counters"][i, 0] == r["steps"]
+        assert stateErr(o["finals"][i], r["final"]) < 1e-12
+        assert relErr(o["results"][i, 3:7], r["results"][3:7]) < 1e-12
+    base = oracle.run(m.blob, 1, {L.LANE_WIND: wind[:, -1:]})
+    assert (o["finals"][-1] == base["finals"][0]).all()          # unit factors: identical to the table built by the host

@@ -5,8 +5,9 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 VDIR = os.path.join(REPO, "mapleaf_b200", "lib", "variants")
 VARIANTS = {
-    "cur": [],
-    "u0": ["-DMLB_FIN_UNIFORM=0"],
+    "s2": ["-DMLB_SYNC_STRIDE=2"],
+    "s3": ["-DMLB_SYNC_STRIDE=3"],
+    "x2": ["-DMLB_TUNE_512X2"],
 }
 
 def build(names=None):
