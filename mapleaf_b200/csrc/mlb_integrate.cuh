@@ -227,6 +227,7 @@ MLB_DEV void stageSeparation(const double* B, Lane& L) {                        
     if (L.nStages <= 1) return;
     L.nStages -= 1;                /* the bottom stage leaves; boat-tail ownership and fineness ratio follow the stage count */
     L.resorted = true;
+    L.inertiaCached = false;       /* fewer stages, and the next motor is about to ignite */
     const double* S0 = B + (int)B[H_STAGE_OFF];
     L.ignitionTime[0] = L.time;    /* stages[0].motor.updateIgnitionTime(currentTime) — the TOP stage's motor, as in the reference */
     /* ignitionTime + times[-1] (Propulsion.py:153-157): the table's last time AFTER the burn-time factor, unlike the value recorded at
@@ -485,6 +486,7 @@ MLB_DEV void laneInit(const double* B, Lane& L, const LaneInputs& in, long long 
         L.ignitionTime[si] = S[S_IGNITION0];
         L.engineShutOff[si] = S[S_BURN_DURATION];
     }
+    L.inertiaCached = false;
     L.motorAdj = in.motorAdjust != nullptr;
     for (int si = 0; si < MLB_MAX_STAGES; si++) { L.motorImp[si] = 1; L.motorBurn[si] = 1; L.motorOxW0[si] = 0; L.motorFuelW0[si] = 0; }
     if (L.motorAdj) for (int si = 0; si < L.nStages; si++) {

@@ -78,6 +78,9 @@ struct Lane {
     /* sampled motor adjust factors (LANE_MOTOR_ADJUST; Propulsion.py:38-40,109-128): the motor tables of this lane are the file's
        columns rescaled on the fly, the initial propellant weights are integrated once at lane start */
     bool motorAdj;
+    /* the rocket's inertia once every motor has burnt out and every inertia table has run past its last row: a constant until the next
+       stage separation (rocketInertiaFrozen), kept here instead of being recombined at every derivative evaluation */
+    bool inertiaCached; Inertia inertiaC; double massSumC;
     double motorImp[MLB_MAX_STAGES], motorBurn[MLB_MAX_STAGES], motorOxW0[MLB_MAX_STAGES], motorFuelW0[MLB_MAX_STAGES];
     double finThickK[MLB_MAX_FINSETS];          /* Fins.py:198-210, depends on the sampled wind */
     Event events[MLB_MAX_EVENTS];
@@ -398,6 +401,29 @@ MLB_DEV Inertia rocketInertia(const double* B, const Lane& L, double time, doubl
     for (int si = 0; si < L.nStages; si++) { list[n] = stageInertia(B, L, si, time); m += list[n].mass; n++; }
     *massSum = m;                                                                           /* CompositeObject.getMass: plain sum over stages */
     return combineInertias(list, n);
+}
+
+/* True when no variable-mass component of the remaining stages can change any more at `time` or later: a motor returns its last table
+   row for timeSinceIgnition >= times[-1] (Propulsion.py:171-204 through linInterp's end clamp, Interpolation.py:22-25), a TabulatedInertia
+   its last row for time >= its last time. The tests are the clamps' own comparisons, so the frozen value is bit-identical. */
+MLB_DEV bool rocketInertiaFrozen(const double* B, const Lane& L, double time) {
+    for (int si = 0; si < L.nStages; si++) {
+        const double* S = B + (int)B[H_STAGE_OFF + si];
+        if ((int)S[S_OVR_FLAGS] == (OVR_CG | OVR_MASS | OVR_MOI)) continue;
+        const int nVar = (int)S[S_NVAR];
+        for (int k = 0; k < nVar; k++) {
+            const double* C = B + (int)S[S_COMP_OFF + (int)S[S_VAR_IDX + k]];
+            if ((int)C[C_TYPE] == CT_MOTOR) {
+                const int n = (int)C[MT_NROWS]; const double* T = C + MT_TABLE;
+                const double tEnd = L.motorAdj ? T[MT_COL_RAW_TIME * n + n - 1] * L.motorBurn[si] : T[n - 1];
+                if (!(fmax(0.0, time - L.ignitionTime[si]) >= tEnd)) return false;
+            } else {
+                const int n = (int)C[TI_NROWS];
+                if (!(time >= C[TI_TABLE + n - 1])) return false;
+            }
+        }
+    }
+    return true;
 }
 
 /* ---------------------------------------------------------------------------------------------
@@ -911,7 +937,10 @@ MLB_DEV ForceMoment appliedForce(const double* B, Lane& L, double time, State& s
     if (dof3) L.nEvals3++;
     Air e = airProperties(B, L, s.pos, time, L.underChute && B[H_TURB_OFF_CHUTE] != 0);
     if (L.underChute && B[H_TURB_OFF_CHUTE] != 0) e.wind = e.meanWind;
-    inertia = rocketInertia(B, L, time, &massSum);
+    if (rocketInertiaFrozen(B, L, time)) {
+        if (!L.inertiaCached) { L.inertiaC = rocketInertia(B, L, time, &L.massSumC); L.inertiaCached = true; }
+        inertia = L.inertiaC; massSum = L.massSumC;
+    } else inertia = rocketInertia(B, L, time, &massSum);
     ForceMoment comp;
     if (!L.underChute) {
         Aero a;
@@ -973,7 +1002,7 @@ MLB_DEV Deriv stateDerivative(const double* B, Lane& L, double time, State& s, b
     }
     /* CG migration velocity by forward difference of the inertia model (RigidBodies.py:91-97) */
     V3 CGVel_local = v3(0, 0, 0);
-    if (B[H_INERTIA_CONST] == 0) {
+    if (B[H_INERTIA_CONST] == 0 && !rocketInertiaFrozen(B, L, time)) {      /* frozen: both inertias are the same value, the difference is +0 */
         double m2; Inertia inertia2 = rocketInertia(B, L, time + 1e-8, &m2);
         CGVel_local = vdiv(inertia2.CG - inertia.CG, 1e-8);
     }

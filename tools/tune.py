@@ -5,9 +5,8 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 VDIR = os.path.join(REPO, "mapleaf_b200", "lib", "variants")
 VARIANTS = {
-    "s2": ["-DMLB_SYNC_STRIDE=2"],
-    "s3": ["-DMLB_SYNC_STRIDE=3"],
-    "x2": ["-DMLB_TUNE_512X2"],
+    "cur": [],
+    "is1": ["-DMLB_INNER_SYNC=1"],
 }
 
 def build(names=None):
