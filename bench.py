@@ -41,12 +41,14 @@ METRIC = "MC trajectory-steps/sec (FP64)"
 UNIT = "trajectory-steps/s"
 SEED = "2394781"
 
-# algorithmic FP64 work per unit (add/sub/mul/div/sqrt/compare = 1, FMA = 2, transcendental call = 1)
-FLOP_EVAL_6DOF = 4.5e3          # one Rocket._getAppliedForce + rigid-body derivative, Mach <= 0.8 or >= 1.4
-FLOP_EVAL_6DOF_TRANSONIC = 1.1e4
-FLOP_EVAL_3DOF = 525.0          # under parachute (2.1e3 per RK4 step / 4)
-FLOP_STEP_ALGEBRA_6DOF = 2.0e3  # RK45 stage composition, two solution rows, error norm (2.9e4 - 6 x 4.5e3)
-FLOP_STEP_ALGEBRA_3DOF = 250.0
+# algorithmic FP64 work per unit (add/sub/mul/div/sqrt/compare = 1, a transcendental call = 1). EXACT counts of the
+# reference's arithmetic, from the CPU oracle compiled with an op-counting scalar (oracle/opcount.hpp, tools/count_flops.py, 64 sampled lanes
+# of this workload: 8.8e8 add, 9.7e8 mul, 1.0e8 div, 4.6e7 sqrt, 1.3e8 compare, 6.4e7 transcendental); tests/test_host_runner.py re-counts them.
+FLOP_EVAL_6DOF = 4533.0             # one Rocket._getAppliedForce + rigid-body derivative, Mach <= 0.8 or >= 1.4
+FLOP_EVAL_6DOF_TRANSONIC = 11147.0  # the transonic fin blend evaluates four strip sums (Fins.py:508-528)
+FLOP_EVAL_3DOF = 521.6              # under parachute
+FLOP_STEP_ALGEBRA_6DOF = 3617.0     # rest of an RK45 attempt: stage composition, two solution rows, error norm, events, step-size PID
+FLOP_STEP_ALGEBRA_3DOF = 576.2
 
 
 def sampleInputs(first, n):

@@ -30,6 +30,42 @@ def lib():
     return _lib
 
 
+_OPLIB = os.path.join(_DIR, "_build", "libmapleaf_oracle_opcount.so")
+_oplib = None
+
+
+def opcountLib():
+    """The oracle compiled with an op-counting scalar in place of double (oracle/opcount.hpp): exact algorithmic FLOP counts."""
+    global _oplib
+    if _oplib is None:
+        srcs = [os.path.join(_DIR, f) for f in ("opcount_build.cpp", "opcount.hpp", "mapleaf_oracle.c")] + [os.path.join(_DIR, "..", "include", "mlb_layout.h")]
+        if not os.path.exists(_OPLIB) or os.path.getmtime(_OPLIB) < max(os.path.getmtime(f) for f in srcs):
+            os.makedirs(os.path.dirname(_OPLIB), exist_ok=True)
+            subprocess.check_call(["g++", "-O2", "-fPIC", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fpermissive", "-w", "-shared",
+                                   "-o", _OPLIB, srcs[0], "-lm"])
+        _oplib = ctypes.CDLL(_OPLIB)
+        _oplib.oracle_run.restype = ctypes.c_int
+    return _oplib
+
+
+def runCounted(blob, nLanes, laneArrays=None):
+    """oracle.run through the op-counting build. Returns (results dict, op counts dict)."""
+    global _lib
+    saved, _lib = _lib, opcountLib()
+    try:
+        _lib.oracle_opcount_reset()
+        out = run(blob, nLanes, laneArrays)
+        c = np.zeros(17, dtype=np.uint64)
+        _lib.oracle_opcount_get(_p(c, ctypes.c_uint64))
+    finally:
+        _lib = saved
+    names = ["eval_6dof", "eval_6dof_transonic", "eval_3dof", "step_rest_6dof", "step_rest_3dof"]
+    ops = dict(add=int(c[0]), mul=int(c[1]), div=int(c[2]), sqrt=int(c[3]), compare=int(c[4]), transcendental=int(c[5]), uncounted=int(c[6]),
+               buckets={n: dict(flops=int(c[7 + 2 * k]), count=int(c[8 + 2 * k])) for k, n in enumerate(names)})
+    ops["flops"] = sum(int(x) for x in c[:6])
+    return out, ops
+
+
 def _p(a, t=ctypes.c_double):
     return a.ctypes.data_as(ctypes.POINTER(t)) if a is not None else None
 

@@ -206,3 +206,25 @@ def test_two_rank_gather_restores_sample_order(tmp_path):
         assert np.array_equal(np.load(tmp_path / "res{}.npy".format(rank)), full)
         mom = np.load(tmp_path / "mom{}.npy".format(rank))
         assert mom[0] == 8 and np.allclose(mom[1:8], full.mean(axis=0), rtol=1e-12) and np.allclose(mom[8:], full.std(axis=0, ddof=1), rtol=1e-10)
+
+
+def test_bench_flop_constants_are_the_oracle_op_counts():
+    """bench.py's algorithmic FLOP figures (the roofline numerator) are exact op counts of the oracle (oracle/opcount.hpp): re-count on two
+    lanes of the bench workload; the op-counting build must also reproduce the plain oracle bit for bit."""
+    import bench
+    from oracle import oracle
+    sd = SimDefinition(bench.DEFINITION, silent=True, disableDistributionSampling=True)
+    m = buildModel(sd)
+    wind, seeds = np.array([[3.0, -1.0], [1.5, 4.0], [0.2, -0.3]]), np.array([[11.0, 5.0], [7.0, 123456.0], [0.0, 0.0]])
+    arrays = {L.LANE_WIND: wind, L.LANE_PINK_SEED: seeds}
+    out, ops = oracle.runCounted(m.blob, 2, arrays)
+    plain = oracle.run(m.blob, 2, arrays)
+    assert (out["finals"] == plain["finals"]).all() and (out["counters"] == plain["counters"]).all()
+    per = {k: v["flops"] / v["count"] for k, v in ops["buckets"].items()}
+    for key, const in (("eval_6dof", bench.FLOP_EVAL_6DOF), ("eval_6dof_transonic", bench.FLOP_EVAL_6DOF_TRANSONIC), ("eval_3dof", bench.FLOP_EVAL_3DOF),
+                       ("step_rest_6dof", bench.FLOP_STEP_ALGEBRA_6DOF), ("step_rest_3dof", bench.FLOP_STEP_ALGEBRA_3DOF)):
+        assert abs(per[key] - const) <= 0.01 * const, (key, per[key], const)
+    c = dict(derivative_evals=int(out["counters"][:, 1].sum()), derivative_evals_3dof=ops["buckets"]["eval_3dof"]["count"],
+             derivative_evals_transonic=ops["buckets"]["eval_6dof_transonic"]["count"], steps=int(out["counters"][:, 0].sum()),
+             steps_3dof=ops["buckets"]["step_rest_3dof"]["count"], rejected_steps=int(out["counters"][:, 2].sum()))
+    assert abs(bench.algorithmicFlops(c) - ops["flops"]) <= 0.01 * ops["flops"]          # the bench formula reproduces the total
