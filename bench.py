@@ -239,9 +239,10 @@ def runB200(args):
         "gpu_launches": launches,
         "clocks": clocks.summary(),
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     # DRAM bytes per launch: 20.9 MB per lane measured by ncu at full occupancy (profiles/r1b_raw_selected.txt: 3.17 TB for
-                     # 151 552 lanes; local-memory spill traffic, the algorithmic figure is hbm_algorithmic_bytes), scaled to this launch
-                     "traffic": 20.9e6 * n, "hbm_algorithmic_bytes": hbmBytes,
+                     # DRAM bytes per launch: 18.4 MB per lane measured by ncu at full occupancy (profiles/r1d_full_occupancy_metrics.csv:
+                     # 1.36 TB read + 1.43 TB written for 151 552 lanes; local-memory spill traffic, the algorithmic figure is
+                     # hbm_algorithmic_bytes), scaled to this launch
+                     "traffic": 18.4e6 * n, "hbm_algorithmic_bytes": hbmBytes,
                      "kernel": "integrateLanes", "kernel_ms": kernelMsLast, "algorithmic_flops_per_launch": flops,
                      "peak_source": "FP64 DFMA microbenchmark run on this GPU by mlb_fp64_peak (MEASURED_PEAKS.json has no FP64 entry); nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2",
                      "hbm_algorithmic_gbs": hbmBytes / (kernelMsLast * 1e-3) / 1e9, "note": "not HBM- or tensor-bound: ~1e5 FLOP per byte of state moved"},

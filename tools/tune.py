@@ -26,12 +26,14 @@ def build(names=None):
                 print(name, "|", lines[i + 2].strip(), "|", lines[i + 3].strip())
         if p.returncode: print(name, "FAILED\n", txt[-2000:])
 
-def runOne(lib, lanes, definition):
+def runOne(lib, lanes, definition, overrides=()):
     os.environ["MLB_LIB"] = lib
     import numpy as np
     import bench
     from mapleaf_b200 import L, SimDefinition, backend, buildModel
     sd = SimDefinition(os.path.join(REPO, "mapleaf_b200", "data", "Simulations", definition), silent=True, disableDistributionSampling=True)
+    for kv in overrides:
+        k, v = kv.split("=", 1); sd.setValue(k, v)
     m = buildModel(sd)
     wind, seeds = bench.sampleInputs(0, lanes)
     with backend.TrajectoryBatch(m.blob) as b:
@@ -40,13 +42,13 @@ def runOne(lib, lanes, definition):
         b.run(); b.sync()
         c = b.counters()
     print(json.dumps({"lib": os.path.basename(lib), "def": definition, "lanes": lanes, "ms": c["last_run_ms"], "steps_per_s": c["steps"] / c["last_run_ms"] * 1e3,
-                      "steps": c["steps"], "ok": c["lanes_ok"]}), flush=True)
+                      "steps": c["steps"], "ok": c["lanes_ok"], "steps_3dof": c["steps_3dof"], "evals": c["derivative_evals"], "overrides": list(overrides)}), flush=True)
 
 if __name__ == "__main__":
     if sys.argv[1] == "build":
         build(sys.argv[2:])
     elif sys.argv[1] == "one":
-        runOne(sys.argv[2], int(sys.argv[3]), sys.argv[4])
+        runOne(sys.argv[2], int(sys.argv[3]), sys.argv[4], sys.argv[5:])
     else:
         lanes = int(sys.argv[2]) if len(sys.argv) > 2 else 151552
         defs = sys.argv[3:] or ["MonteCarloAdaptive.mapleaf"]
