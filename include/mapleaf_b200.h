@@ -96,8 +96,18 @@ int mlb_set_result_buffers(mlb_handle* h, void* results, void* status);
    out[0] = count, then for each of the 7 columns: mean, M2 (sum of squared deviations). 15 doubles. */
 int mlb_moments(mlb_handle* h, double* out15);
 
+/* Flight paths of lanes [firstLane, firstLane + nLanes): what RocketFlight.times / rigidBodyStates hold for those samples
+   (IO/rocketFlight.py:12-25), the input of `MonteCarlo.output flightPaths` (MonteCarlo.py:60-62, Plotting._keepNTimeSteps). Rows of 16
+   doubles: time, position 3, velocity 3, quaternion 4, body-frame angular velocity 3, step size taken, error estimate. Row 0 is the initial
+   state; then the state after every `every`-th accepted step; the final state is always the last row. A lane whose buffer fills up drops
+   every other stored row and doubles its stride, so any flight ends as maxRowsPerLane/2 .. maxRowsPerLane evenly strided states
+   (112 B of state per kept step: the HBM-write-bound companion of the trajectory kernel). Call before mlb_run; firstLane < 0 switches
+   the log off. mlb_get_flight_log: rows = nLanes x maxRowsPerLane x 16 doubles, rowsPerLane = nLanes counts. */
+int mlb_set_flight_log(mlb_handle* h, int64_t firstLane, int64_t nLanes, int64_t every, int64_t maxRowsPerLane);
+int mlb_get_flight_log(mlb_handle* h, double* rows, int64_t* rowsPerLane);
+
 /* Test / analysis hooks */
-/* record every step of one lane: rows of 16 doubles (time, pos3, vel3, quat4, angvel3, dt taken, error estimate) */
+/* the first maxRows steps of one lane, every step (later steps are not recorded): mlb_set_flight_log(h, lane, 1, 0, maxRows) */
 int mlb_set_trace(mlb_handle* h, int64_t lane, int64_t maxRows);
 int mlb_get_trace(mlb_handle* h, double* rows, int64_t* nRows);
 /* force the first n step sizes of every lane (lock-step replay of a recorded adaptive step sequence) */

@@ -81,6 +81,8 @@ def lib():
     l.mlb_device_results.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp)]
     l.mlb_set_result_buffers.argtypes = [vp, vp, vp]
     l.mlb_moments.argtypes = [vp, dp]
+    l.mlb_set_flight_log.argtypes = [vp, i64, i64, i64, i64]
+    l.mlb_get_flight_log.argtypes = [vp, dp, ctypes.POINTER(ctypes.c_int64)]
     l.mlb_set_trace.argtypes = [vp, i64, i64]
     l.mlb_get_trace.argtypes = [vp, dp, ctypes.POINTER(ctypes.c_int64)]
     l.mlb_set_dt_replay.argtypes = [vp, dp, i64]
@@ -93,7 +95,7 @@ def lib():
 
 
 EXPORTED_SYMBOLS = ["mlb_create", "mlb_destroy", "mlb_last_error", "mlb_version", "mlb_set_lanes", "mlb_set_lanes_device", "mlb_run", "mlb_sync",
-                    "mlb_results", "mlb_finals", "mlb_counters", "mlb_lane_counters", "mlb_device_results", "mlb_set_result_buffers", "mlb_moments", "mlb_set_trace",
+                    "mlb_results", "mlb_finals", "mlb_counters", "mlb_lane_counters", "mlb_device_results", "mlb_set_result_buffers", "mlb_moments", "mlb_set_flight_log", "mlb_get_flight_log", "mlb_set_trace",
                     "mlb_get_trace", "mlb_set_dt_replay", "mlb_force_eval", "mlb_host_gauss_stream", "mlb_host_randrange_stream", "mlb_fp64_peak"]
 
 
@@ -205,6 +207,19 @@ class TrajectoryBatch:
         out = np.empty(15)
         _check(lib().mlb_moments(self._h, _dp(out)), "mlb_moments")
         return out[0], out[1::2].copy(), out[2::2].copy()
+
+    def setFlightLog(self, firstLane: int, nLanes: int, every: int = 1, maxRowsPerLane: int = 2048):
+        """Record the flight paths of lanes [firstLane, firstLane + nLanes) during the next run (see mlb_set_flight_log)."""
+        _check(lib().mlb_set_flight_log(self._h, firstLane, nLanes, every, maxRowsPerLane), "mlb_set_flight_log")
+        self._flightLog = (nLanes, maxRowsPerLane)
+
+    def flightLog(self):
+        """List of [rows_i, 16] arrays, one per logged lane: time, pos, vel, quaternion, angular velocity, dt, error estimate."""
+        n, m = self._flightLog
+        rows = np.empty((n, m, TRACE_W))
+        counts = np.zeros(n, dtype=np.int64)
+        _check(lib().mlb_get_flight_log(self._h, _dp(rows), counts.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))), "mlb_get_flight_log")
+        return [rows[i, :counts[i]].copy() for i in range(n)]
 
     def setTrace(self, lane: int, maxRows: int):
         _check(lib().mlb_set_trace(self._h, lane, maxRows), "mlb_set_trace")

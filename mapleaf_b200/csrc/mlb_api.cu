@@ -42,13 +42,26 @@ struct RunArgs {
     LaneInputs in;
     double* results; double* finals; int* status; long long* counters;
     uint32_t* mt;
-    double* trace; long long traceLane, traceMaxRows; long long* traceRows;
+    double* trace; long long traceLane, traceCount, traceMaxRows, traceEvery; long long* traceRows;     /* flight log of lanes [traceLane, traceLane + traceCount) */
     const double* dtReplay; long long nReplay;
 };
 
-__device__ __forceinline__ void traceRow(const RunArgs& a, const Lane& L, long long& rows, double dt, double err) {
-    if (rows >= a.traceMaxRows) return;
-    double* T = a.trace + rows * TRACE_W;
+/* One row of a lane's flight log (RocketFlight.times / rigidBodyStates, IO/rocketFlight.py:12-25). The log keeps every `stride`-th
+   accepted step; when the lane's buffer is full it drops every other stored row and doubles the stride, so a flight of any length
+   ends up as maxRows/2 .. maxRows evenly strided states. `last`: the final state is always stored. */
+__device__ __noinline__ void traceRow(const RunArgs& a, double* base, const Lane& L, long long& rows, long long& stride, double dt, double err, bool last) {
+    if (a.traceEvery == 0) { if (rows >= a.traceMaxRows) return; }                          /* mlb_set_trace: the first maxRows steps, then stop */
+    else if (!last && (L.nSteps % stride) != 0) return;
+    if (rows >= a.traceMaxRows) {
+        if (a.traceMaxRows < 4) { if (!last) return; rows = a.traceMaxRows - 1; }
+        else {
+            const long long keep = (a.traceMaxRows + 1) / 2;
+            for (long long i = 1; i < keep; i++) for (int k = 0; k < TRACE_W; k++) base[i * TRACE_W + k] = base[2 * i * TRACE_W + k];
+            rows = keep; stride *= 2;
+            if (!last && (L.nSteps % stride) != 0) return;
+        }
+    }
+    double* T = base + rows * TRACE_W;
     T[0] = L.time; T[1] = L.s.pos.x; T[2] = L.s.pos.y; T[3] = L.s.pos.z; T[4] = L.s.vel.x; T[5] = L.s.vel.y; T[6] = L.s.vel.z;
     T[7] = L.s.q.w; T[8] = L.s.q.x; T[9] = L.s.q.y; T[10] = L.s.q.z; T[11] = L.s.w.x; T[12] = L.s.w.y; T[13] = L.s.w.z;
     T[14] = dt; T[15] = err; rows++;
@@ -74,14 +87,15 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) integrateLanes(const RunArg
     V3 prevPos = L.s.pos, lastPos = L.s.pos;
     const long long maxSteps = (long long)B[H_MAX_STEPS];
     int st = ST_OK;
-    const bool tracing = (a.trace != nullptr && inRange && lane == a.traceLane);
-    long long rows = 0;
+    const bool tracing = (a.trace != nullptr && inRange && lane >= a.traceLane && lane < a.traceLane + a.traceCount);
+    double* const traceBase = tracing ? a.trace + (size_t)(lane - a.traceLane) * a.traceMaxRows * TRACE_W : nullptr;
+    long long rows = 0, traceStride = a.traceEvery > 0 ? a.traceEvery : 1;
 
     /* RocketFlight reductions (rocketFlight.py:27-50), kept as running values */
     if (L.s.pos.z > apogee) apogee = L.s.pos.z;
     maxSpeed = fmax(maxSpeed, len(L.s.vel));
     maxH = fmax(maxH, sqrt(L.s.vel.x * L.s.vel.x + L.s.vel.y * L.s.vel.y));
-    if (tracing) traceRow(a, L, rows, 0.0, 0.0);
+    if (tracing) traceRow(a, traceBase, L, rows, traceStride, 0.0, 0.0, false);
 
     bool end = true, haveFinal = false; double finalDt = 0;
     if (inRange) endDetector(B, L, dt, end, haveFinal, finalDt);
@@ -98,10 +112,10 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) integrateLanes(const RunArg
             if (L.s.pos.z > apogee) apogee = L.s.pos.z;
             double sp = len(L.s.vel); if (sp > maxSpeed) maxSpeed = sp;
             double hv = sqrt(L.s.vel.x * L.s.vel.x + L.s.vel.y * L.s.vel.y); if (hv > maxH) maxH = hv;
-            if (tracing) traceRow(a, L, rows, r.dt, r.err);
             if (!(L.s.pos.z == L.s.pos.z) || !(L.s.vel.x == L.s.vel.x)) { st = ST_NAN; end = true; }
             else if (L.nSteps >= maxSteps) { st = ST_STEP_LIMIT; end = true; }
             else endDetector(B, L, dt, end, haveFinal, finalDt);
+            if (tracing) traceRow(a, traceBase, L, rows, traceStride, r.dt, r.err, end);
         }
     }
     if (!inRange) return;
@@ -121,7 +135,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) integrateLanes(const RunArg
     a.status[lane] = st;
     long long* cn = a.counters + lane * MLB_NCOUNTERS;
     cn[0] = L.nSteps; cn[1] = L.nEvals; cn[2] = L.nRejects; cn[3] = L.nSteps3; cn[4] = L.nEvals3; cn[5] = L.nEvalsTransonic;
-    if (tracing) *a.traceRows = rows;
+    if (tracing) a.traceRows[lane - a.traceLane] = rows;
 }
 
 
@@ -208,7 +222,7 @@ struct mlb_handle {
     bool ownResults = true;
     double* d_results = nullptr; double* d_finals = nullptr; int* d_status = nullptr; long long* d_counters = nullptr;
     uint32_t* d_mt = nullptr;
-    double* d_trace = nullptr; long long traceLane = -1, traceMaxRows = 0; long long* d_traceRows = nullptr;
+    double* d_trace = nullptr; long long traceLane = -1, traceCount = 0, traceMaxRows = 0, traceEvery = 1; long long* d_traceRows = nullptr;
     double* d_replay = nullptr; long long nReplay = 0;
     double* d_partials = nullptr; double* d_moments = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -266,8 +280,6 @@ extern "C" int mlb_create(const void* model_blob, size_t n, int device, mlb_hand
     { const char* e = getenv("MLB_BLOCK_SIZE"); h->forceBlock = e ? atoi(e) : 0; }
     CU(cudaFuncSetAttribute(forceEvalKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(blobPad * sizeof(double))));
     CU(cudaEventCreate(&h->ev0)); CU(cudaEventCreate(&h->ev1));
-    CU(cudaMalloc(&h->d_traceRows, sizeof(long long)));
-    CU(cudaMemset(h->d_traceRows, 0, sizeof(long long)));
     CU(cudaMalloc(&h->d_partials, 148 * 15 * sizeof(double)));
     CU(cudaMalloc(&h->d_moments, 15 * sizeof(double)));
     *out = h;
@@ -325,7 +337,8 @@ extern "C" int mlb_run(mlb_handle* h, void* stream) {
     a.in.wind = h->d_lane[LANE_WIND]; a.in.initState = h->d_lane[LANE_INIT_STATE]; a.in.pinkSeed = h->d_lane[LANE_PINK_SEED]; a.in.motorAdjust = h->d_lane[LANE_MOTOR_ADJUST]; a.in.nLanes = h->nLanes;
     a.results = h->d_results; a.finals = h->d_finals; a.status = h->d_status; a.counters = h->d_counters; a.mt = h->d_mt;
     a.trace = (h->traceLane >= 0 && h->traceLane < h->nLanes) ? h->d_trace : nullptr;
-    a.traceLane = h->traceLane; a.traceMaxRows = h->traceMaxRows; a.traceRows = h->d_traceRows;
+    a.traceLane = h->traceLane; a.traceCount = h->traceCount; a.traceMaxRows = h->traceMaxRows; a.traceEvery = h->traceEvery; a.traceRows = h->d_traceRows;
+    if (a.trace) CU(cudaMemsetAsync(h->d_traceRows, 0, (size_t)h->traceCount * sizeof(long long), s));
     a.dtReplay = h->d_replay; a.nReplay = h->nReplay;
     /* largest CTA shape that still gives every SM a CTA (MLB_BLOCK_SIZE overrides, for tuning) */
     int block = 128;
@@ -427,22 +440,33 @@ extern "C" int mlb_moments(mlb_handle* h, double* out15) {
     return MLB_OK;
 }
 
-extern "C" int mlb_set_trace(mlb_handle* h, int64_t lane, int64_t maxRows) {
+extern "C" int mlb_set_flight_log(mlb_handle* h, int64_t firstLane, int64_t nLanes, int64_t every, int64_t maxRowsPerLane) {
     if (!h) return fail(MLB_ERR_ARG, "null handle");
     CU(cudaSetDevice(h->device));
-    cudaFree(h->d_trace); h->d_trace = nullptr;
-    h->traceLane = -1; h->traceMaxRows = 0;
-    if (lane >= 0 && maxRows > 0) {
-        CU(cudaMalloc(&h->d_trace, (size_t)maxRows * TRACE_W * sizeof(double)));
-        h->traceLane = lane; h->traceMaxRows = maxRows;
+    cudaFree(h->d_trace); h->d_trace = nullptr; cudaFree(h->d_traceRows); h->d_traceRows = nullptr;
+    h->traceLane = -1; h->traceCount = 0; h->traceMaxRows = 0; h->traceEvery = 1;
+    if (firstLane >= 0 && nLanes > 0 && maxRowsPerLane > 0) {
+        if (every < 0) return fail(MLB_ERR_ARG, "mlb_set_flight_log: every must be >= 1 (0: every step, stop when the buffer is full)");
+        CU(cudaMalloc(&h->d_trace, (size_t)nLanes * maxRowsPerLane * TRACE_W * sizeof(double)));
+        CU(cudaMalloc(&h->d_traceRows, (size_t)nLanes * sizeof(long long)));
+        CU(cudaMemset(h->d_traceRows, 0, (size_t)nLanes * sizeof(long long)));
+        h->traceLane = firstLane; h->traceCount = nLanes; h->traceMaxRows = maxRowsPerLane; h->traceEvery = every;
     }
-    CU(cudaMemset(h->d_traceRows, 0, sizeof(long long)));
     return MLB_OK;
 }
+extern "C" int mlb_get_flight_log(mlb_handle* h, double* rows, int64_t* rowsPerLane) {
+    int rc = needRun(h, "mlb_get_flight_log"); if (rc) return rc;
+    if (!h->d_trace || h->traceCount <= 0) return fail(MLB_ERR_STATE, "mlb_get_flight_log: no flight log was requested before the run");
+    static_assert(sizeof(long long) == sizeof(int64_t), "row counters are copied as int64");
+    if (rowsPerLane) CU(cudaMemcpy(rowsPerLane, h->d_traceRows, (size_t)h->traceCount * sizeof(long long), cudaMemcpyDeviceToHost));
+    if (rows) CU(cudaMemcpy(rows, h->d_trace, (size_t)h->traceCount * h->traceMaxRows * TRACE_W * sizeof(double), cudaMemcpyDeviceToHost));
+    return MLB_OK;
+}
+extern "C" int mlb_set_trace(mlb_handle* h, int64_t lane, int64_t maxRows) { return mlb_set_flight_log(h, lane, 1, 0, maxRows); }
 extern "C" int mlb_get_trace(mlb_handle* h, double* rows, int64_t* nRows) {
     int rc = needRun(h, "mlb_get_trace"); if (rc) return rc;
     long long n = 0;
-    CU(cudaMemcpy(&n, h->d_traceRows, sizeof(long long), cudaMemcpyDeviceToHost));
+    if (h->d_traceRows) CU(cudaMemcpy(&n, h->d_traceRows, sizeof(long long), cudaMemcpyDeviceToHost));
     if (nRows) *nRows = n;
     if (rows && n > 0 && h->d_trace) CU(cudaMemcpy(rows, h->d_trace, (size_t)n * TRACE_W * sizeof(double), cudaMemcpyDeviceToHost));
     return MLB_OK;

@@ -94,6 +94,32 @@ class MonteCarloResults:
         self.landingLocations, self.apogees, self.maxSpeeds, self.flightTimes, self.maxHorizontalVels, self.flights = outputLists
 
 
+_FLIGHT_PATH_LIMIT = 2000      # runs whose paths are kept (256 KB of device memory each while the batch runs)
+_FLIGHT_PATH_ROWS = 2048       # strided states kept per flight on the device: 1024-2048 of them, whatever the flight's length
+_FLIGHT_PATH_FRAMES = 900      # MonteCarlo.py:60-62: Plotting._keepNTimeSteps(flight, 900)
+
+
+class FlightPath:
+    """What the reference keeps of a flight for `MonteCarlo.output flightPaths` (RocketFlight after Plotting._keepNTimeSteps(flight, 900),
+    IO/Plotting.py:320-375): 900 frames evenly spaced in time. Positions, velocities and angular velocities are interpolated linearly
+    like the reference's; the orientation is the normalised linear blend of the neighbouring quaternions (the reference uses slerp) and the
+    source is the device's strided flight log (every 1st, 2nd, 4th ... accepted step) rather than every step."""
+
+    def __init__(self, times, positions, velocities, orientations, angularVelocities):
+        self.times, self.positions, self.velocities = times, positions, velocities
+        self.orientations, self.angularVelocities = orientations, angularVelocities
+
+    @classmethod
+    def fromLog(cls, rows, nFrames=_FLIGHT_PATH_FRAMES):
+        t = rows[:, 0]
+        newTimes = np.linspace(0, t[-1], num=nFrames)
+        cols = np.stack([np.interp(newTimes, t, rows[:, k]) for k in range(1, 14)], axis=1)
+        q = cols[:, 6:10]
+        n = np.linalg.norm(q, axis=1, keepdims=True)
+        q = np.where(n > 0, q / np.where(n > 0, n, 1), np.array([1.0, 0, 0, 0]))
+        return cls(newTimes, cols[:, 0:3], cols[:, 3:6], q, cols[:, 10:13])
+
+
 def laneInitialState(simDefinition: SimDefinition, model) -> List[float]:
     """Initial inertial-frame state of the CG for the current (sampled) Rocket.* values: rocket.py:251-291,416-421."""
     rk = SubDictReader("Rocket", simDefinition)
@@ -191,8 +217,9 @@ def _runSimulations_B200(simDefinition, nRuns, outputLists, mCLogger, silent=Fal
     from . import backend
     landingLocations, apogees, maxSpeeds, flightTimes, maxHorizontalVels, flights = outputLists
     resultsToOutput = simDefinition.getValue("MonteCarlo.output")
-    if "flightPaths" in resultsToOutput:
-        mCLogger.log("NOTE: MonteCarlo.output flightPaths is not produced by the B200 backend (per-step trajectories stay on the device)")
+    wantPaths = "flightPaths" in resultsToOutput
+    if wantPaths and nRuns > _FLIGHT_PATH_LIMIT:
+        mCLogger.log("NOTE: MonteCarlo.output flightPaths: flight paths are kept for the first {} of {} runs".format(_FLIGHT_PATH_LIMIT, nRuns))
     model = buildModel(simDefinition)
     arrays = sampleRuns(simDefinition, nRuns, mCLogger, model)
 
@@ -204,6 +231,9 @@ def _runSimulations_B200(simDefinition, nRuns, outputLists, mCLogger, silent=Fal
         lo, hi = bounds[g], bounds[g + 1]
         b = backend.TrajectoryBatch(model.blob, device=device + g)
         b.setLanes(hi - lo, {k: np.ascontiguousarray(a[:, lo:hi]) for k, a in arrays.items()})
+        nLogged = max(0, min(hi, _FLIGHT_PATH_LIMIT) - lo) if wantPaths else 0
+        if nLogged:
+            b.setFlightLog(0, nLogged, 1, _FLIGHT_PATH_ROWS)
         b.run()                                   # asynchronous: all GPUs integrate concurrently
         batches.append(b)
     results = np.empty((nRuns, L.RES_SIZE))
@@ -213,6 +243,8 @@ def _runSimulations_B200(simDefinition, nRuns, outputLists, mCLogger, silent=Fal
         r, s = b.results()
         results[bounds[g]:bounds[g + 1]], status[bounds[g]:bounds[g + 1]] = r, s
         counters.append(b.counters())
+        if wantPaths and bounds[g] < _FLIGHT_PATH_LIMIT:
+            flights.extend(FlightPath.fromLog(rows) for rows in b.flightLog())
         b.close()
 
     failed = np.nonzero(status != L.ST_OK)[0]

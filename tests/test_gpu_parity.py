@@ -436,3 +436,41 @@ def test_sampled_motor_adjust_factors_match_oracle(backend, golden):
         ref = np.concatenate([[c["finals"][i, 13]], c["finals"][i, :13]])
         assert stateErr(gq["finals"][i], ref) < FIXED_TOL
         assert relErr(gq["results"][i, 3:7], c["results"][i, 3:7]) < FIXED_TOL
+
+
+def test_flight_log_matches_oracle_traces_and_decimates(backend):
+    """mlb_set_flight_log: the paths of a range of lanes (RocketFlight.times / rigidBodyStates). Full stride: every row equals the oracle's
+    trace of that lane. Small buffer: the log keeps every 2^k-th step, between maxRows/2 and maxRows rows, first row the initial state,
+    last row the final state."""
+    from oracle import oracle
+    m = buildFrom("MonteCarlo.mapleaf")
+    rng = np.random.default_rng(5)
+    n = 40
+    w = rng.normal(size=(3, n)) * 5 + np.array([[2.0], [0.0], [0.0]])
+    with backend.TrajectoryBatch(m.blob) as b:
+        b.setLanes(n, {L.LANE_WIND: w})
+        b.setFlightLog(33, 4, 1, 4000)
+        b.run()
+        full = b.flightLog()
+        finals = b.finals()
+        b.setFlightLog(0, n, 1, 100)
+        b.run()
+        small = b.flightLog()
+        steps = b.laneCounters()[:, 0]
+    for k, rows in enumerate(full):
+        lane = 33 + k
+        tr = oracle.run(m.blob, n, {L.LANE_WIND: w}, traceLane=lane, traceMaxRows=4000)["trace"]
+        assert rows.shape == tr.shape
+        assert np.array_equal(rows[:, 0], tr[:, 0])
+        for i in range(0, len(tr), 97):
+            assert stateErr(np.concatenate([rows[i, 1:14], [0]]), np.concatenate([[0], tr[i, 1:14]])) < FIXED_TOL
+        assert np.array_equal(rows[-1, 1:14], finals[lane, :13]) and rows[-1, 0] == finals[lane, 13]
+    ref = {33 + k: rows for k, rows in enumerate(full)}
+    for lane, rows in enumerate(small):
+        assert 50 <= len(rows) <= 100
+        assert rows[0, 0] == 0 and rows[-1, 0] == finals[lane, 13] and np.array_equal(rows[-1, 1:14], finals[lane, :13])
+        stride = int(round((rows[1, 0] - rows[0, 0]) / 0.01))           # fixed 0.01 s steps: rows are `stride` steps apart
+        assert stride in (32, 64) and (steps[lane] // stride) + 1 + (1 if steps[lane] % stride else 0) == len(rows)
+        if lane in ref:
+            body = rows[:-1] if steps[lane] % stride else rows
+            assert np.array_equal(body, ref[lane][::stride][:len(body)])

@@ -34,6 +34,14 @@ class OracleBatch:
     def results(self):
         return self.out["results"], self.out["status"]
 
+    def setFlightLog(self, firstLane, nLanes, every=1, maxRowsPerLane=2048):
+        self.logged = (firstLane, nLanes, maxRowsPerLane)
+
+    def flightLog(self):
+        from oracle import oracle
+        first, n, maxRows = self.logged
+        return [oracle.run(self.blob, self.n, self.arrays, traceLane=first + i, traceMaxRows=maxRows)["trace"] for i in range(n)]
+
     def counters(self):
         c = self.out["counters"]
         return dict(lanes=self.n, steps=int(c[:, 0].sum()), derivative_evals=int(c[:, 1].sum()), rejected_steps=int(c[:, 2].sum()))
@@ -228,3 +236,20 @@ def test_bench_flop_constants_are_the_oracle_op_counts():
              derivative_evals_transonic=ops["buckets"]["eval_6dof_transonic"]["count"], steps=int(out["counters"][:, 0].sum()),
              steps_3dof=ops["buckets"]["step_rest_3dof"]["count"], rejected_steps=int(out["counters"][:, 2].sum()))
     assert abs(bench.algorithmicFlops(c) - ops["flops"]) <= 0.01 * ops["flops"]          # the bench formula reproduces the total
+
+
+def test_runner_flight_paths_output(monkeypatch, tmp_path, golden):
+    """`MonteCarlo.output flightPaths` (MonteCarlo.py:60-62): every run's path, 900 frames evenly spaced in time, ending where the run ended."""
+    g = golden("rk4_apogee.json")
+    monkeypatch.setattr(backend, "TrajectoryBatch", OracleBatch)
+    monkeypatch.setattr(montecarlo, "_FLIGHT_PATH_ROWS", 4000)
+    sd = montecarloDefinition(tmp_path, nRuns=2, **{"MonteCarlo.output": "flightPaths apogees"})
+    out = montecarlo.runMonteCarloSimulation(simDefinition=sd, silent=True)
+    assert len(out.flights) == 2
+    for i, f in enumerate(out.flights):
+        ref = g["runs"][i]
+        assert f.times.shape == (900,) and f.positions.shape == (900, 3) and f.orientations.shape == (900, 4)
+        assert f.times[0] == 0 and abs(f.times[-1] - ref["final"][0]) < 1e-12
+        assert np.allclose(f.positions[-1], ref["final"][1:4], rtol=1e-12) and np.allclose(f.velocities[-1], ref["final"][4:7], rtol=1e-9, atol=1e-9)
+        assert abs(f.positions[:, 2].max() - ref["results"][3]) < 1e-3 * ref["results"][3]          # apogee is the last frame here
+        assert np.allclose(np.linalg.norm(f.orientations, axis=1), 1.0)

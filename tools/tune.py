@@ -5,8 +5,7 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 VDIR = os.path.join(REPO, "mapleaf_b200", "lib", "variants")
 VARIANTS = {
-    "cur": [],
-    "is1": ["-DMLB_INNER_SYNC=1"],
+    "shapes": ["-DMLB_TUNE_SHAPES"],
 }
 
 def build(names=None):
