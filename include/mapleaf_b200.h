@@ -124,6 +124,12 @@ int mlb_host_gauss_stream(const uint32_t* key, int keyLen, int64_t skip, const d
 
 /* random.randrange(n) stream of the same generator (pink-noise seeds: ENV/TurbulenceModelling.py:191-195) */
 int mlb_host_randrange_stream(const uint32_t* key, int keyLen, int64_t skip, uint32_t n, int64_t nDraws, double* out);
+/* Both streams continued from a live CPython generator (random.Random.getstate()): the 624 state words, the position and the cached
+   second Gaussian are read and updated in place, so the Python object can be set to the advanced state afterwards. This is what lets
+   the Monte Carlo runner draw 10^6 runs' inputs at C speed while the SimDefinition's own generator stays the single source of the
+   stream (IO/simDefinition.py:216,471-532; ENV/TurbulenceModelling.py:191-195 for the seeds drawn from the global `random` module). */
+int mlb_host_gauss_from_state(uint32_t* state624, int* pos, int* hasNext, double* next, const double* mu, const double* sigma, int nPer, int64_t nDraws, double* out);
+int mlb_host_randrange_from_state(uint32_t* state624, int* pos, uint32_t n, int64_t nDraws, double* out);
 
 /* Measured FP64 FMA throughput of `device` in TFLOP/s (independent DFMA chains on every SM): the denominator of the
    FP64 roofline this path is reported against. */

@@ -89,6 +89,9 @@ def lib():
     l.mlb_force_eval.argtypes = [vp, i64, dp, dp, dp, dp]
     l.mlb_host_gauss_stream.argtypes = [ctypes.POINTER(ctypes.c_uint32), ctypes.c_int, i64, dp, dp, ctypes.c_int, i64, dp]
     l.mlb_host_randrange_stream.argtypes = [ctypes.POINTER(ctypes.c_uint32), ctypes.c_int, i64, ctypes.c_uint32, i64, dp]
+    ip = ctypes.POINTER(ctypes.c_int)
+    l.mlb_host_gauss_from_state.argtypes = [ctypes.POINTER(ctypes.c_uint32), ip, ip, ctypes.POINTER(ctypes.c_double), dp, dp, ctypes.c_int, i64, dp]
+    l.mlb_host_randrange_from_state.argtypes = [ctypes.POINTER(ctypes.c_uint32), ip, ctypes.c_uint32, i64, dp]
     l.mlb_fp64_peak.argtypes = [ctypes.c_int, dp]
     _lib = l
     return l
@@ -96,7 +99,7 @@ def lib():
 
 EXPORTED_SYMBOLS = ["mlb_create", "mlb_destroy", "mlb_last_error", "mlb_version", "mlb_set_lanes", "mlb_set_lanes_device", "mlb_run", "mlb_sync",
                     "mlb_results", "mlb_finals", "mlb_counters", "mlb_lane_counters", "mlb_device_results", "mlb_set_result_buffers", "mlb_moments", "mlb_set_flight_log", "mlb_get_flight_log", "mlb_set_trace",
-                    "mlb_get_trace", "mlb_set_dt_replay", "mlb_force_eval", "mlb_host_gauss_stream", "mlb_host_randrange_stream", "mlb_fp64_peak"]
+                    "mlb_get_trace", "mlb_set_dt_replay", "mlb_force_eval", "mlb_host_gauss_stream", "mlb_host_randrange_stream", "mlb_host_gauss_from_state", "mlb_host_randrange_from_state", "mlb_fp64_peak"]
 
 
 def _dp(a):
@@ -279,6 +282,37 @@ def hostRandrangeStream(seed, n: int, nDraws: int, skipDraws: int = 0) -> np.nda
     out = np.empty(nDraws)
     _check(lib().mlb_host_randrange_stream(key.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), key.size, skipDraws, n, nDraws, _dp(out)),
            "mlb_host_randrange_stream")
+    return out
+
+
+def _pyRandomState(rng):
+    version, internal, gaussNext = rng.getstate()
+    words = np.array(internal[:624], dtype=np.uint32)
+    return version, words, ctypes.c_int(internal[624]), gaussNext
+
+
+def gaussFromGenerator(rng, mu, sigma, nSamples: int) -> np.ndarray:
+    """nSamples rows of rng.gauss(mu[j], sigma[j]) for a random.Random (or the `random` module), drawn by the C++ sampler; the generator
+    is left exactly where nSamples * len(mu) Python-level gauss() calls would have left it."""
+    mu = np.ascontiguousarray(np.atleast_1d(mu), dtype=np.float64)
+    sigma = np.ascontiguousarray(np.atleast_1d(sigma), dtype=np.float64)
+    version, words, pos, gaussNext = _pyRandomState(rng)
+    hasNext = ctypes.c_int(0 if gaussNext is None else 1)
+    nxt = ctypes.c_double(0.0 if gaussNext is None else gaussNext)
+    out = np.empty((nSamples, mu.size))
+    _check(lib().mlb_host_gauss_from_state(words.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), ctypes.byref(pos), ctypes.byref(hasNext), ctypes.byref(nxt),
+                                          _dp(mu), _dp(sigma), mu.size, nSamples * mu.size, _dp(out)), "mlb_host_gauss_from_state")
+    rng.setstate((version, tuple(int(w) for w in words) + (pos.value,), nxt.value if hasNext.value else None))
+    return out
+
+
+def randrangeFromGenerator(rng, n: int, nDraws: int) -> np.ndarray:
+    """nDraws values of rng.randrange(n), drawn by the C++ sampler; the generator is advanced as Python would have advanced it."""
+    version, words, pos, gaussNext = _pyRandomState(rng)
+    out = np.empty(nDraws)
+    _check(lib().mlb_host_randrange_from_state(words.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), ctypes.byref(pos), n, nDraws, _dp(out)),
+           "mlb_host_randrange_from_state")
+    rng.setstate((version, tuple(int(w) for w in words) + (pos.value,), gaussNext))
     return out
 
 

@@ -530,6 +530,29 @@ extern "C" int mlb_host_randrange_stream(const uint32_t* key, int keyLen, int64_
     return MLB_OK;
 }
 
+/* The same two streams continued from a live CPython generator: `state` = the 624 words of random.Random.getstate()[1][:624], *pos its
+   last element, hasNext / next the cached second Gaussian (getstate()[2]). All four are updated in place, so the caller hands the
+   advanced state back with setstate() and the Python object carries on as if it had made the draws itself. */
+extern "C" int mlb_host_gauss_from_state(uint32_t* state, int* pos, int* hasNext, double* next, const double* mu, const double* sigma, int nPer, int64_t nDraws, double* out) {
+    if (!state || !pos || !hasNext || !next || !mu || !sigma || nPer <= 0 || nDraws < 0 || !out) return fail(MLB_ERR_ARG, "mlb_host_gauss_from_state: bad arguments");
+    PyRandom r; r.mt = state; r.idx = *pos; r.hasNext = *hasNext; r.next = *next;
+    for (int64_t i = 0; i < nDraws; i++) out[i] = pyRandomGauss(r, mu[i % nPer], sigma[i % nPer]);
+    *pos = r.idx; *hasNext = r.hasNext; *next = r.next;
+    return MLB_OK;
+}
+extern "C" int mlb_host_randrange_from_state(uint32_t* state, int* pos, uint32_t n, int64_t nDraws, double* out) {
+    if (!state || !pos || n == 0 || nDraws < 0 || !out) return fail(MLB_ERR_ARG, "mlb_host_randrange_from_state: bad arguments");
+    PyRandom r; r.mt = state; r.idx = *pos; r.hasNext = 0; r.next = 0;
+    int k = 0; for (uint32_t v = n; v; v >>= 1) k++;
+    for (int64_t i = 0; i < nDraws; i++) {
+        uint32_t v = mtGenrand(r) >> (32 - k);
+        while (v >= n) v = mtGenrand(r) >> (32 - k);
+        out[i] = (double)v;
+    }
+    *pos = r.idx;
+    return MLB_OK;
+}
+
 /* FP64 pipe ceiling of this GPU, measured: 16 independent DFMA chains per thread, every SM full. The roofline
    denominator of the trajectory kernels (MEASURED_PEAKS.json carries HBM and bf16 tensor figures only). */
 __global__ void __launch_bounds__(256) fp64PeakKernel(double* out, int iters, double a, double b) {

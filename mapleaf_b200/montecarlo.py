@@ -24,7 +24,7 @@ import numpy as np
 
 from . import hostmath as hm
 from .model import L, buildModel, initialStateGlobalFrame
-from .simdef import SimDefinition, SubDictReader, parseVector
+from .simdef import SimDefinition, SubDictReader, formatVector, parseVector
 
 __all__ = ["runMonteCarloSimulation", "MonteCarloLogger", "Vector", "MonteCarloResults", "laneInitialState"]
 
@@ -81,8 +81,7 @@ class MonteCarloLogger:
                 n += 1
                 filePath = fileBaseName + str(n) + ".txt"
         with open(filePath, "w+") as f:
-            for line in self.monteCarloLog:
-                f.write(line if (len(line) > 0 and line[-1] == "\n") else line + "\n")
+            f.write("".join(line if (len(line) > 0 and line[-1] == "\n") else line + "\n" for line in self.monteCarloLog))
         return filePath
 
 
@@ -183,6 +182,8 @@ def sampleRuns(simDefinition, nRuns, mCLogger, model):
     turb = int(model.header("H_TURB"))
     nGen = {L.TURB_PINK1D: 1, L.TURB_PINK2D: 2, L.TURB_PINK3D: 3}.get(turb, 0)
     hasSeed = int(model.header("H_PINK_HAS_SEED"))
+    if not sampleState and not simDefinition.disableDistributionSampling and nRuns >= _VECTORIZED_SAMPLING_FROM:
+        return _sampleRunsVectorized(simDefinition, nRuns, mCLogger, model, keys, motorKeys, nGen, hasSeed)
     wind = np.empty((3, nRuns)) if sampleWind else None
     state = np.empty((13, nRuns)) if sampleState else None
     seeds = np.zeros((3, nRuns)) if nGen else None
@@ -209,6 +210,68 @@ def sampleRuns(simDefinition, nRuns, mCLogger, model):
         arrays[L.LANE_PINK_SEED] = seeds
     if sampleMotor:
         arrays[L.LANE_MOTOR_ADJUST] = motor
+    return arrays
+
+
+_VECTORIZED_SAMPLING_FROM = 64      # runs; below this the per-run Python loop is as fast
+
+
+def _sampleRunsVectorized(simDefinition, nRuns, mCLogger, model, keys, motorKeys, nGen, hasSeed):
+    """sampleRuns for 10^5+ runs: the same draws from the same two generators (the SimDefinition's own `rng` for the `_stdDev` keys, the
+    global `random` module for the pink-noise seeds), made by the C++ CPython-exact sampler (mlb_host_gauss_from_state /
+    mlb_host_randrange_from_state) instead of nRuns passes of resampleProbabilisticValues; the generators, the dictionary and the Monte
+    Carlo log end up as the per-run loop leaves them (IO/simDefinition.py:471-532, MonteCarlo.py:64-72)."""
+    from . import backend
+    D = simDefinition.dict
+    mus, sigmas, spans = [], [], []            # one (mu, sigma) per drawn component, in draw order; spans: (key, first column, width)
+    for key in keys:
+        meanString = D.setdefault(key + "_mean", D[key])
+        try:
+            m, sd = [float(meanString)], [float(D[key + "_stdDev"])]
+        except ValueError:
+            m, sd = list(parseVector(meanString)), list(parseVector(D[key + "_stdDev"]))
+        spans.append((key, len(mus), len(m)))
+        mus += m
+        sigmas += sd
+    draws = backend.gaussFromGenerator(simDefinition.rng, mus, sigmas, nRuns) if mus else np.empty((nRuns, 0))
+    arrays = {}
+    perRunLines = []
+    for key, c0, w in spans:
+        v = draws[:, c0:c0 + w]
+        if w == 1:
+            D[key] = str(float(v[-1, 0]))
+            perRunLines.append(["Sampling scalar parameter: {}, value: {:1.3f}".format(key, x) for x in v[:, 0].tolist()])
+        else:
+            D[key] = formatVector(v[-1].tolist())
+            perRunLines.append(["Sampling vector parameter: {}, value: ({:1.3f} {:1.3f} {:1.3f})".format(key, *x) for x in v.tolist()])
+        if key == _WIND_KEY:
+            arrays[L.LANE_WIND] = np.ascontiguousarray(v.T)
+        else:
+            motor = arrays.setdefault(L.LANE_MOTOR_ADJUST, np.ones((2 * L.MLB_MAX_STAGES, nRuns)))
+            motor[motorKeys[key]] = v[:, 0]
+    if L.LANE_MOTOR_ADJUST in arrays:              # motors whose factors are not sampled keep the definition's values
+        for key, row in motorKeys.items():
+            if key not in keys:
+                arrays[L.LANE_MOTOR_ADJUST][row] = float(simDefinition.getValue(key))
+    if nGen:
+        seeds = np.zeros((3, nRuns))
+        free = [g for g in range(nGen) if not (hasSeed >> g) & 1]
+        if free:
+            drawn = backend.randrangeFromGenerator(random, 1000000, len(free) * nRuns).reshape(nRuns, len(free))
+            for j, g in enumerate(free):
+                seeds[g] = drawn[:, j]
+        for g in range(nGen):
+            if (hasSeed >> g) & 1:
+                seeds[g] = model.blob[L.H_PINK_SEED + g]
+        arrays[L.LANE_PINK_SEED] = seeds
+    log = mCLogger.log
+    # resampleProbabilisticValues reports to the definition's own logger, else to the console unless silent (simDefinition.py:528-532)
+    sampleLog = simDefinition.monteCarloLogger.log if simDefinition.monteCarloLogger is not None else (None if simDefinition.silent else print)
+    for i in range(nRuns):
+        log("\nMonte Carlo Run #{}".format(i + 1))
+        if sampleLog is not None:
+            for lines in perRunLines:
+                sampleLog(lines[i])
     return arrays
 
 
@@ -276,7 +339,7 @@ def summarizeVectorResult(vectorList, name="Landing location", monteCarloLogger=
     out = ["{}s:   X       Y        Z".format(name)]
     x, y, z = [], [], []
     for i, loc in enumerate(vectorList):
-        out.append("Simulation #{}:   {:>7.1f}".format(i + 1, loc))
+        out.append("Simulation #{}:   {:>7.1f} {:>7.1f} {:>7.1f}".format(i + 1, loc.X, loc.Y, loc.Z))       # "{:>7.1f}".format(Vector)
         x.append(loc.X), y.append(loc.Y), z.append(loc.Z)
     out.append("")
     out.append("Mean {}: ({:>8.1f} {:>8.1f} {:>8.1f})".format(name, _mean(x), _mean(y), _mean(z)))

@@ -253,3 +253,32 @@ def test_runner_flight_paths_output(monkeypatch, tmp_path, golden):
         assert np.allclose(f.positions[-1], ref["final"][1:4], rtol=1e-12) and np.allclose(f.velocities[-1], ref["final"][4:7], rtol=1e-9, atol=1e-9)
         assert abs(f.positions[:, 2].max() - ref["results"][3]) < 1e-3 * ref["results"][3]          # apogee is the last frame here
         assert np.allclose(np.linalg.norm(f.orientations, axis=1), 1.0)
+
+
+def test_vectorized_sampling_is_the_per_run_loop(monkeypatch, tmp_path):
+    """The C++ sampler continuing the SimDefinition's own generator and the global `random` module (mlb_host_*_from_state) reproduces the
+    per-run Python loop: same per-lane arrays, same log, same dictionary, and both generators left in the same state."""
+    def prepared():
+        sd = SimDefinition(os.path.join(DATA, "MonteCarloAdaptive.mapleaf"), silent=True, disableDistributionSampling=True)
+        sd.setValue("MonteCarlo.randomSeed", "2394781")
+        sd.setValue("Rocket.Sustainer.Motor.impulseAdjustFactor", "1.0")
+        sd.setValue("Rocket.Sustainer.Motor.impulseAdjustFactor_stdDev", "0.02331")
+        sd = SimDefinition(dictionary=dict(sd.dict), silent=True)
+        return sd, buildModel(sd)
+    n = 300
+    out = []
+    for threshold in (10 ** 9, 1):
+        monkeypatch.setattr(montecarlo, "_VECTORIZED_SAMPLING_FROM", threshold)
+        sd, model = prepared()
+        random.seed(99)
+        log = montecarlo.MonteCarloLogger(echo=False)
+        sd.monteCarloLogger = log          # as _prepSim does
+        arrays = montecarlo.sampleRuns(sd, n, log, model)
+        sd.monteCarloLogger = None
+        out.append((arrays, list(log.monteCarloLog[4:]), dict(sd.dict), sd.rng.getstate(), random.getstate(), sd.rng.gauss(0, 1), random.random()))
+    slow, fast = out
+    assert sorted(slow[0]) == sorted(fast[0]) == [L.LANE_WIND, L.LANE_PINK_SEED, L.LANE_MOTOR_ADJUST]
+    for k in slow[0]:
+        assert np.array_equal(slow[0][k], fast[0][k])
+    assert slow[1] == fast[1] and slow[2] == fast[2]
+    assert slow[3] == fast[3] and slow[4] == fast[4] and slow[5:] == fast[5:]
