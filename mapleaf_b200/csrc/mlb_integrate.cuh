@@ -298,12 +298,18 @@ MLB_DEV void triggerEvents(const double* B, Lane& L, double& estTimeToNext, bool
 /* N-D scattered linear interpolation with nearest-neighbour fallback (scipy LinearNDInterpolator / NearestNDInterpolator behind
    Motion/Interpolation.py:109-124). The Delaunay triangulation comes from scipy on the host; R points into GLOBAL memory (the
    tables are too large for shared memory, every lane reads the same words: broadcast loads). Point location is a scan over
-   the simplices with scipy's inside tolerance; it runs once per control tick, not per derivative evaluation. */
-MLB_DEV void ndInterpolate(const double* __restrict__ R, const double* x, double* out) {
+   the simplices with scipy's inside tolerance; it runs once per control tick, not per derivative evaluation. `hint`: the simplex
+   that held the lane's previous query. Between two ticks of a 100 Hz loop the query barely moves, so the hint is tested first and
+   accepted only when the point is STRICTLY inside it (every barycentric coordinate at least 1e-6 from 0 and 1): no other simplex of a
+   triangulation can then contain the point, even within the tolerance, so the scan would have returned this simplex and these weights. */
+MLB_DEV void ndInterpolate(const double* __restrict__ R, const double* x, double* out, int& hint) {
     const int d = (int)R[ND_DIM], m = (int)R[ND_NVAL], npts = (int)R[ND_NPTS], ns = (int)R[ND_NSIMP];
     const double* pts = R + ND_DATA; const double* vals = pts + npts * d; const double* simp = vals + npts * m; const double* T = simp + ns * (d + 1);
     const double eps = 100 * 2.220446049250313e-16;
-    for (int s = 0; s < ns; s++) {
+    const bool tryHint = (hint >= 0 && hint < ns);
+    for (int it = tryHint ? -1 : 0; it < ns; it++) {
+        const int s = (it < 0) ? hint : it;
+        const double lo = (it < 0) ? 1e-6 : -eps, hi = (it < 0) ? 1 - 1e-6 : 1 + eps;
         const double* Ts = T + s * (d + 1) * d;
         if (Ts[0] != Ts[0]) continue;                                                       /* degenerate simplex */
         double c[ND_MAX_DIM + 1]; double cLast = 1.0; bool inside = true;
@@ -311,10 +317,11 @@ MLB_DEV void ndInterpolate(const double* __restrict__ R, const double* x, double
             double ci = 0;
             for (int j = 0; j < d; j++) ci += Ts[d * i + j] * (x[j] - Ts[d * d + j]);
             c[i] = ci; cLast -= ci;
-            inside = (ci >= -eps && ci <= 1 + eps);
+            inside = (ci >= lo && ci <= hi);
         }
-        if (!inside || !(cLast >= -eps && cLast <= 1 + eps)) continue;
+        if (!inside || !(cLast >= lo && cLast <= hi)) continue;
         c[d] = cLast;
+        hint = s;
         for (int k = 0; k < m; k++) {
             double v = 0;
             for (int j = 0; j < d + 1; j++) v += c[j] * vals[(int)simp[s * (d + 1) + j] * m + k];
@@ -363,7 +370,7 @@ MLB_DEV void runControlSystem(const double* B, const double* G, Lane& L) {
     if ((int)CS[CS_MC_TYPE] == 1) {
         double keys[4]; const int nk = (int)CS[CS_GAIN_NKEYS];
         for (int k = 0; k < nk; k++) keys[k] = aeroKeyOf(L.s, env, (int)CS[CS_GAIN_KEYS + k]);
-        ndInterpolate(G + (int)CS[CS_GAIN_INTERP_OFF], keys, g);
+        ndInterpolate(G + (int)CS[CS_GAIN_INTERP_OFF], keys, g, L.ndHint[0]);
     } else for (int k = 0; k < 6; k++) g[k] = CS[CS_GAINS + k];
     double key[ND_MAX_DIM]; const int nk = (int)CS[CS_DEFL_NKEYS];
     for (int k = 0; k < nk; k++) key[k] = aeroKeyOf(L.s, env, (int)CS[CS_DEFL_KEYS + k]);
@@ -375,7 +382,7 @@ MLB_DEV void runControlSystem(const double* B, const double* G, Lane& L) {
         key[nk + k] = P * err[k] + I * L.gncIntegral[k] + D * derivative;
     }
     double targets[ND_MAX_VAL];
-    ndInterpolate(G + (int)CS[CS_DEFL_INTERP_OFF], key, targets);
+    ndInterpolate(G + (int)CS[CS_DEFL_INTERP_OFF], key, targets, L.ndHint[1]);
     const int nAct = (int)CS[CS_NACT];
     for (int i = 0; i < nAct; i++) {                        /* FirstOrderActuator.setTargetDeflection (Actuators.py:118-129) */
         L.actLastDefl[i] = actuatorDeflection(B, L, i, currentTime);
@@ -479,6 +486,7 @@ MLB_DEV void laneInit(const double* B, Lane& L, const LaneInputs& in, long long 
     L.forceRK4 = L.hasControl && B[(int)B[H_CTRL_OFF] + CS_FORCE_RK4] != 0;
     L.ctrlLastRun = 0;                                      /* RocketControlSystem(initTime=0) */
     for (int k = 0; k < 3; k++) { L.gncLastError[k] = 0; L.gncIntegral[k] = 0; }
+    L.ndHint[0] = -1; L.ndHint[1] = -1;
     for (int k = 0; k < CS_MAX_ACT; k++) { L.actLastDefl[k] = 0; L.actLastTime[k] = 0; L.actTarget[k] = 0; }
     for (int si = 0; si < MLB_MAX_STAGES; si++) { L.ignitionTime[si] = 0; L.engineShutOff[si] = -1; }
     for (int si = 0; si < L.nStages; si++) {
