@@ -302,7 +302,7 @@ MLB_DEV void triggerEvents(const double* B, Lane& L, double& estTimeToNext, bool
    that held the lane's previous query. Between two ticks of a 100 Hz loop the query barely moves, so the hint is tested first and
    accepted only when the point is STRICTLY inside it (every barycentric coordinate at least 1e-6 from 0 and 1): no other simplex of a
    triangulation can then contain the point, even within the tolerance, so the scan would have returned this simplex and these weights. */
-MLB_DEV void ndInterpolate(const double* __restrict__ R, const double* x, double* out, int& hint) {
+MLB_COLD_NDTABLE void ndInterpolate(const double* __restrict__ R, const double* x, double* out, int& hint) {
     const int d = (int)R[ND_DIM], m = (int)R[ND_NVAL], npts = (int)R[ND_NPTS], ns = (int)R[ND_NSIMP];
     const double* pts = R + ND_DATA; const double* vals = pts + npts * d; const double* simp = vals + npts * m; const double* T = simp + ns * (d + 1);
     const double eps = 100 * 2.220446049250313e-16;
@@ -348,7 +348,7 @@ MLB_DEV double aeroKeyOf(const State& s, const Air& e, int key) {               
 /* Rocket._runControlSystem (rocket.py:646-656) -> RocketControlSystem.runControlLoopIfRequired (GNC/ControlSystems.py:170-211):
    stabiliser target, orientation error as a rotation vector, (scheduled) PID gains, vector PID, deflection table, actuators.
    G is the model block in global memory (interpolation tables). */
-MLB_DEV void runControlSystem(const double* B, const double* G, Lane& L) {
+MLB_COLD_CONTROL void runControlSystem(const double* B, const double* G, Lane& L) {
     if (!L.hasControl || L.underChute) return;
     const double* CS = B + (int)B[H_CTRL_OFF];
     const double currentTime = L.time;

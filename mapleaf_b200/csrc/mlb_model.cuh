@@ -128,7 +128,7 @@ MLB_DEV V3 linInterpV(const double* X, const double* Yx, const double* Yy, const
    sphere (:147-160), Newton-Raphson on the latitude parameter for the ellipsoid (:305-341). Angles in radians here. */
 struct Geodetic { double lat, lon, height; };
 MLB_DEV bool earthIsRound(const double* B) { int m = (int)B[H_EARTH]; return m == EARTH_ROUND || m == EARTH_WGS84; }
-MLB_DEV Geodetic cartesianToGeodetic(const double* B, V3 pos) {
+MLB_COLD_GEODETIC Geodetic cartesianToGeodetic(const double* B, V3 pos) {
     Geodetic g;
     const double x = pos.x, y = pos.y, z = pos.z;
     const double p = sqrt(x * x + y * y);
@@ -395,7 +395,7 @@ MLB_DEV Inertia stageInertia(const double* B, const Lane& L, int si, double time
     if (flags & OVR_MASS) r.mass = S[S_OVR_MASS];
     return r;
 }
-MLB_DEV Inertia rocketInertia(const double* B, const Lane& L, double time, double* massSum) {
+MLB_COLD_INERTIA Inertia rocketInertia(const double* B, const Lane& L, double time, double* massSum) {
     Inertia list[MLB_MAX_STAGES + 1]; int n = 0;
     list[n].MOI = v3(0, 0, 0); list[n].CG = v3(0, 0, 0); list[n].mass = 0; n++;            /* rocket-level fixed-mass component (empty) */
     double m = 0;
@@ -864,7 +864,7 @@ MLB_DEV ForceMoment tabulatedAeroForce(Aero& a, const double* C) {              
     }
     return forceFromCoefficients(a, coeffs, ld3(C + C_POS), C[TA_AREF], C[TA_LREF]);
 }
-MLB_DEV Inertia rocketInertia(const double* B, const Lane& L, double time, double* massSum);
+MLB_COLD_INERTIA Inertia rocketInertia(const double* B, const Lane& L, double time, double* massSum);
 MLB_DEV ForceMoment jetDampingForce(const double* B, const Lane& L, const Aero& a, const double* C, int si, const Inertia& current) {   /* :392-410 */
     if (a.time > L.ignitionTime[si] && a.time < L.engineShutOff[si]) {
         double m; const double dt = 0.001;

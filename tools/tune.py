@@ -5,7 +5,9 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 VDIR = os.path.join(REPO, "mapleaf_b200", "lib", "variants")
 VARIANTS = {
-    "shapes": ["-DMLB_TUNE_SHAPES"],
+    "c0": ["-DMLB_COLD_MASK=0"],
+    "c1": ["-DMLB_COLD_MASK=1"],
+    "c15": ["-DMLB_COLD_MASK=15"],
 }
 
 def build(names=None):
