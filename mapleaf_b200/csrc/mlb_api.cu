@@ -353,6 +353,9 @@ extern "C" int mlb_run(mlb_handle* h, void* stream) {
 #define MLB_LAUNCH(N) if (block == N) { cudaFuncSetAttribute(integrateLanes<N, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes); integrateLanes<N, 1><<<grid, N, h->smemBytes, s>>>(a); } else
     MLB_EXTRA_SHAPES(MLB_LAUNCH)
     if (block == 1024) integrateLanes<1024, 1><<<grid, 1024, h->smemBytes, s>>>(a);
+#ifdef MLB_TUNE_640X2          /* 1280 lanes per SM at 48 registers: MLB_BLOCK_SIZE=512 selects it in this build */
+    else if (block == 512) { cudaFuncSetAttribute(integrateLanes<640, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes); grid = (unsigned)((h->nLanes + 639) / 640); integrateLanes<640, 2><<<grid, 640, h->smemBytes, s>>>(a); }
+#endif
 #ifdef MLB_TUNE_512X2
     else if (block == 512) { cudaFuncSetAttribute(integrateLanes<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes); integrateLanes<512, 2><<<grid, 512, h->smemBytes, s>>>(a); }
 #endif

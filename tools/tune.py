@@ -5,9 +5,7 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 VDIR = os.path.join(REPO, "mapleaf_b200", "lib", "variants")
 VARIANTS = {
-    "c0": ["-DMLB_COLD_MASK=0"],
-    "c1": ["-DMLB_COLD_MASK=1"],
-    "c15": ["-DMLB_COLD_MASK=15"],
+    "x640": ["-DMLB_TUNE_640X2"],
 }
 
 def build(names=None):
