@@ -340,9 +340,19 @@ extern "C" int mlb_run(mlb_handle* h, void* stream) {
     a.traceLane = h->traceLane; a.traceCount = h->traceCount; a.traceMaxRows = h->traceMaxRows; a.traceEvery = h->traceEvery; a.traceRows = h->d_traceRows;
     if (a.trace) CU(cudaMemsetAsync(h->d_traceRows, 0, (size_t)h->traceCount * sizeof(long long), s));
     a.dtReplay = h->d_replay; a.nReplay = h->nReplay;
-    /* largest CTA shape that still gives every SM a CTA (MLB_BLOCK_SIZE overrides, for tuning) */
-    int block = 128;
-    for (int k = 0; k < MLB_NUM_SHAPES; k++) if (h->nLanes >= (long long)h->nSM * kShapeBlock[k]) block = kShapeBlock[k];
+    /* CTA shape: the one with the smallest (waves of CTAs) x (measured duration of one wave of that shape). One wave of the bench
+       workload takes 0.43 / 0.52 / 0.95 s for the 128x2 / 512 / 1024 shapes and holds 256 / 512 / 1024 lanes per SM: large batches
+       want the largest convoy, a batch that leaves SMs empty in one shape may fill them in a smaller one, and a batch just over one
+       wave is better off in a larger shape than in two waves of a smaller one (10^5 lanes: 1.27 s in the 1024 shape, 1.46 s in the
+       512 shape). MLB_BLOCK_SIZE overrides, for tuning. */
+    int block = 128; double bestCost = 1e300;
+    static const double kShapeWaveTime[MLB_NUM_SHAPES] = { 0.43, 0.52, 0.95 };
+    for (int k = 0; k < MLB_NUM_SHAPES; k++) {
+        const long long ctas = (h->nLanes + kShapeBlock[k] - 1) / kShapeBlock[k];
+        const long long slots = (long long)h->nSM * (kShapeBlock[k] == 128 ? 2 : 1);
+        const double cost = (double)((ctas + slots - 1) / slots) * kShapeWaveTime[k];
+        if (cost < bestCost) { bestCost = cost; block = kShapeBlock[k]; }
+    }
     if (h->forceBlock == 128 || h->forceBlock == 512 || h->forceBlock == 1024) block = h->forceBlock;
 #define MLB_ALLOW(N) if (h->forceBlock == N) block = N;
     MLB_EXTRA_SHAPES(MLB_ALLOW)
