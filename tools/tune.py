@@ -5,7 +5,10 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 VDIR = os.path.join(REPO, "mapleaf_b200", "lib", "variants")
 VARIANTS = {
-    "x640": ["-DMLB_TUNE_640X2"],
+    "p_c8": ["-DMLB_PINK_INLINE", "-DMLB_COMP_NOINLINE=8"],
+    "p_c12": ["-DMLB_PINK_INLINE", "-DMLB_COMP_NOINLINE=12"],
+    "p_c0": ["-DMLB_PINK_INLINE", "-DMLB_COMP_NOINLINE=0"],
+    "p_c15": ["-DMLB_PINK_INLINE"],
 }
 
 def build(names=None):
