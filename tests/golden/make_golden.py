@@ -14,6 +14,7 @@ What is recorded, and which reference code produced it:
   rk4_apogee.json ......... `runMonteCarloSimulation`-style loop (SimulationRunners/MonteCarlo.py:64-76),
                             seed "2394781", 8 runs, RK4 dt 0.01, EndCondition Apogee
   rk4_ground.json ......... same, 3 runs, EndCondition Altitude 0 (BASELINE.md first parity anchor)
+  rk78_gust.json .......... RK78Adaptive (Dormand-Prince 8(7)13M, no first-same-as-last) with the sine gust, to apogee, 2 runs
   rk45_pink.json .......... RK45Adaptive + PID, Hellman wind, PinkNoise2D (derived config 2), 4 runs
   windtunnel.json ......... WindTunnelSimulation.runSweep force evaluations (SingleSimulations.py:444-475)
                             + the reference's recorded regression values (BatchSims/regressionTests.mapleaf:1-27)
@@ -228,7 +229,7 @@ def dump(name, obj):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["model", "rng", "windtunnel", "rk4_apogee", "rk4_ground", "rk45_pink", "rk45_gust", "tabulated", "twostage", "earth", "canards", "motoradj"]
+    which = sys.argv[1:] or ["model", "rng", "windtunnel", "rk4_apogee", "rk4_ground", "rk45_pink", "rk45_gust", "tabulated", "twostage", "earth", "canards", "motoradj", "rk78"]
     mc = os.path.join(MY_DATA, "MonteCarlo.mapleaf")
     if "model" in which:
         dump("model_montecarlo.json", modelFields())
@@ -270,6 +271,9 @@ if __name__ == "__main__":
     adaptive = os.path.join(MY_DATA, "MonteCarloAdaptive.mapleaf")
     if "rk45_pink" in which:
         dump("rk45_pink.json", monteCarlo(adaptive, {}, "2394781", 4, globalSeed=2394781, keepDts=True))
+    if "rk78" in which:
+        dump("rk78_gust.json", monteCarlo(adaptive, {"Environment.TurbulenceModel": "customSineGust", "Environment.MeanWindModel": "Constant",
+                                                     "SimControl.EndCondition": "Apogee", "SimControl.timeDiscretization": "RK78Adaptive"}, "2394781", 2, keepDts=True))
     if "rk45_gust" in which:
         dump("rk45_gust.json", monteCarlo(adaptive, {"Environment.TurbulenceModel": "customSineGust", "Environment.MeanWindModel": "Constant",
                                                      "SimControl.EndCondition": "Apogee"}, "2394781", 2, keepDts=True))

@@ -474,3 +474,27 @@ def test_flight_log_matches_oracle_traces_and_decimates(backend):
         if lane in ref:
             body = rows[:-1] if steps[lane] % stride else rows
             assert np.array_equal(body, ref[lane][::stride][:len(body)])
+
+
+def test_rk78_adaptive_vs_reference(backend, golden):
+    """RK78Adaptive on the device (13 stage slots per lane): lock-step replay of the reference's accepted step sizes, and the free-running
+    flight inside the lane's own sensitivity band."""
+    g = golden("rk78_gust.json")
+    m = buildFrom(g["definition"], g["overrides"])
+    runs = g["runs"]
+    r0 = runs[0]
+    n = len(r0["dts"])
+    rep = gpuRun(backend, m, 1, {L.LANE_WIND: winds([r0])}, traceLane=0, traceRows=n + 2, dtReplay=r0["dts"])
+    k = min(n, len(rep["trace"]) - 1)
+    assert k >= n - 2
+    assert np.abs(rep["trace"][1:k + 1, 0] - np.array(r0["times"])[1:k + 1]).max() < 1e-9
+    assert rep["counters"][0, 0] == r0["steps"] and stateErr(rep["finals"][0], r0["final"]) < 1e-6
+    arrs = {L.LANE_WIND: winds(runs)}
+    o = gpuRun(backend, m, len(runs), arrs)
+    assert (o["status"] == L.ST_OK).all()
+    band = selfSensitivityBand(m, arrs, len(runs))
+    for i, r in enumerate(runs):
+        tol = 5 * band[i] + np.array([0.05, 0.02, 0.005, 3])
+        assert abs(o["results"][i, 3] - r["results"][3]) <= tol[0], (o["results"][i, 3], r["results"][3], band[i])
+        assert abs(int(o["counters"][i, 0]) - r["steps"]) <= tol[3]
+        assert o["counters"][i, 1] >= 13 * o["counters"][i, 0]

@@ -295,3 +295,21 @@ def test_sampled_motor_adjust_factors_per_lane(golden):
         assert relErr(o["results"][i, 3:7], r["results"][3:7]) < 1e-12
     base = oracle.run(m.blob, 1, {L.LANE_WIND: wind[:, -1:]})
     assert (o["finals"][-1] == base["finals"][0]).all()          # unit factors: identical to the table built by the host
+
+
+def test_rk78_adaptive_gust(golden):
+    """RK78Adaptive (Dormand-Prince 8(7)13M: 13 evaluations per attempt, no first-same-as-last; Integration.py:279-297) through the sine
+    gust to apogee: same accepted-step counts and results as the reference (observed bit-identical), and the lock-step replay of its
+    accepted step sizes reproduces every step time."""
+    g = golden("rk78_gust.json")
+    m = buildFrom(g["definition"], g["overrides"])
+    runs = g["runs"]
+    assert m.header("H_TAB_NSTAGE_ROWS") == 12 and m.header("H_TAB_NRESULT_ROWS") == 2
+    o = oracle.run(m.blob, len(runs), {L.LANE_WIND: lanesFromRuns(runs)})
+    for i, r in enumerate(runs):
+        assert o["counters"][i, 0] == r["steps"] and o["counters"][i, 1] >= 13 * r["steps"]
+        assert stateErr(o["finals"][i], r["final"]) < 1e-12
+        assert relErr(o["results"][i, 3:7], r["results"][3:7]) < 1e-12
+    r0 = runs[0]
+    rep = oracle.run(m.blob, 1, {L.LANE_WIND: lanesFromRuns(runs[:1])}, traceLane=0, traceMaxRows=3000, dtReplay=r0["dts"])
+    assert np.abs(rep["trace"][:, 0] - np.array(r0["times"])).max() < 1e-12
