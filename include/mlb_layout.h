@@ -389,7 +389,10 @@
 #define TA_NROWS 15
 #define TA_NVALS 16
 #define TA_COEFF_IDX 17
-#define TA_TABLE 22
+#define TA_NKEYS 22       /* key columns of the table; 1: TA_KEY + the 1-D table at TA_TABLE (MAPLEAF.Motion.linInterp) */
+#define TA_KEYS 23        /* >1: the AKEY_* id of every key column, in column order (up to ND_MAX_DIM) */
+#define TA_ND_OFF 29      /* >1: model-block offset of the scattered-interpolation record (ND_*), behind H_SHARED_LEN in global memory */
+#define TA_TABLE 30
 #define AKEY_MACH 0
 #define AKEY_ALTITUDE 1
 #define AKEY_UNITRE 2

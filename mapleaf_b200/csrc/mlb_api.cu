@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) integrateLanes(const RunArg
 
     Lane L;
     laneInit(B, L, a.in, inRange ? lane : 0, inRange ? a.mt : nullptr, inRange);
+    L.G = a.blob;
     double dt = B[H_DT0];
     double apogee = -10000000, maxSpeed = 0, maxH = 0;
     V3 prevPos = L.s.pos, lastPos = L.s.pos;
@@ -150,6 +151,7 @@ __global__ void __launch_bounds__(MLB_BLOCK) forceEvalKernel(const double* blob,
     Lane L;
     LaneInputs in; in.wind = nullptr; in.initState = nullptr; in.pinkSeed = nullptr; in.motorAdjust = nullptr; in.nLanes = 1;
     laneInit(B, L, in, 0, mt ? mt + (size_t)i * 3 * 624 : nullptr, mt != nullptr);      /* each state gets its own generator block */
+    L.G = blob;
     if (winds) { L.wind = v3(winds[3 * i], winds[3 * i + 1], winds[3 * i + 2]); laneFinConstants(B, L); }
     const double* s13 = states + 13 * i;
     State s; s.pos = v3(s13[0], s13[1], s13[2]); s.vel = v3(s13[3], s13[4], s13[5]);

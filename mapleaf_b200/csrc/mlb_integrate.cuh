@@ -295,48 +295,6 @@ MLB_DEV void triggerEvents(const double* B, Lane& L, double& estTimeToNext, bool
     estTimeToNext = est; deterministic = det;
 }
 
-/* N-D scattered linear interpolation with nearest-neighbour fallback (scipy LinearNDInterpolator / NearestNDInterpolator behind
-   Motion/Interpolation.py:109-124). The Delaunay triangulation comes from scipy on the host; R points into GLOBAL memory (the
-   tables are too large for shared memory, every lane reads the same words: broadcast loads). Point location is a scan over
-   the simplices with scipy's inside tolerance; it runs once per control tick, not per derivative evaluation. `hint`: the simplex
-   that held the lane's previous query. Between two ticks of a 100 Hz loop the query barely moves, so the hint is tested first and
-   accepted only when the point is STRICTLY inside it (every barycentric coordinate at least 1e-6 from 0 and 1): no other simplex of a
-   triangulation can then contain the point, even within the tolerance, so the scan would have returned this simplex and these weights. */
-MLB_COLD_NDTABLE void ndInterpolate(const double* __restrict__ R, const double* x, double* out, int& hint) {
-    const int d = (int)R[ND_DIM], m = (int)R[ND_NVAL], npts = (int)R[ND_NPTS], ns = (int)R[ND_NSIMP];
-    const double* pts = R + ND_DATA; const double* vals = pts + npts * d; const double* simp = vals + npts * m; const double* T = simp + ns * (d + 1);
-    const double eps = 100 * 2.220446049250313e-16;
-    const bool tryHint = (hint >= 0 && hint < ns);
-    for (int it = tryHint ? -1 : 0; it < ns; it++) {
-        const int s = (it < 0) ? hint : it;
-        const double lo = (it < 0) ? 1e-6 : -eps, hi = (it < 0) ? 1 - 1e-6 : 1 + eps;
-        const double* Ts = T + s * (d + 1) * d;
-        if (Ts[0] != Ts[0]) continue;                                                       /* degenerate simplex */
-        double c[ND_MAX_DIM + 1]; double cLast = 1.0; bool inside = true;
-        for (int i = 0; i < d && inside; i++) {
-            double ci = 0;
-            for (int j = 0; j < d; j++) ci += Ts[d * i + j] * (x[j] - Ts[d * d + j]);
-            c[i] = ci; cLast -= ci;
-            inside = (ci >= lo && ci <= hi);
-        }
-        if (!inside || !(cLast >= lo && cLast <= hi)) continue;
-        c[d] = cLast;
-        hint = s;
-        for (int k = 0; k < m; k++) {
-            double v = 0;
-            for (int j = 0; j < d + 1; j++) v += c[j] * vals[(int)simp[s * (d + 1) + j] * m + k];
-            out[k] = v;
-        }
-        return;
-    }
-    int best = 0; double bestD = 1e300;                                                     /* outside the hull: nearest table row */
-    for (int p = 0; p < npts; p++) {
-        double dist = 0;
-        for (int j = 0; j < d; j++) { double t = pts[p * d + j] - x[j]; dist += t * t; }
-        if (dist < bestD) { bestD = dist; best = p; }
-    }
-    for (int k = 0; k < m; k++) out[k] = vals[best * m + k];
-}
 MLB_DEV double aeroKeyOf(const State& s, const Air& e, int key) {                           /* AeroParameters.stringToAeroFunctionMap */
     switch (key) {
         case AKEY_MACH: return len(s.vel - e.wind) / sqrt(1.4 * 287 * e.temp);

@@ -78,6 +78,7 @@ struct Lane {
     double ignitionTime[MLB_MAX_STAGES], engineShutOff[MLB_MAX_STAGES];
     /* sampled motor adjust factors (LANE_MOTOR_ADJUST; Propulsion.py:38-40,109-128): the motor tables of this lane are the file's
        columns rescaled on the fly, the initial propellant weights are integrated once at lane start */
+    const double* G;                            /* the whole model block in global memory (interpolation records behind H_SHARED_LEN) */
     bool motorAdj;
     /* the rocket's inertia once every motor has burnt out and every inertia table has run past its last row: a constant until the next
        stage separation (rocketInertiaFrozen), kept here instead of being recombined at every derivative evaluation */
@@ -843,7 +844,75 @@ MLB_DEV ForceMoment aeroDampingForce(Aero& a, const double* C) {                
     coeffs[4] = dot(ld3(C + AD_ZCOEFFS), a.w) * redimConst;
     return forceFromCoefficients(a, coeffs, v3(0, 0, 0), C[AD_AREF], C[AD_LREF]);
 }
-MLB_DEV ForceMoment tabulatedAeroForce(Aero& a, const double* C) {                          /* RocketComponents.py:322-345, one key column */
+/* N-D scattered linear interpolation with nearest-neighbour fallback (scipy LinearNDInterpolator / NearestNDInterpolator behind
+   Motion/Interpolation.py:109-124). The Delaunay triangulation comes from scipy on the host; R points into GLOBAL memory (the
+   tables are too large for shared memory, every lane reads the same words: broadcast loads). Point location is a scan over
+   the simplices with scipy's inside tolerance; it runs once per control tick, not per derivative evaluation. `hint`: the simplex
+   that held the lane's previous query. Between two ticks of a 100 Hz loop the query barely moves, so the hint is tested first and
+   accepted only when the point is STRICTLY inside it (every barycentric coordinate at least 1e-6 from 0 and 1): no other simplex of a
+   triangulation can then contain the point, even within the tolerance, so the scan would have returned this simplex and these weights. */
+MLB_COLD_NDTABLE void ndInterpolate(const double* __restrict__ R, const double* x, double* out, int& hint) {
+    const int d = (int)R[ND_DIM], m = (int)R[ND_NVAL], npts = (int)R[ND_NPTS], ns = (int)R[ND_NSIMP];
+    const double* pts = R + ND_DATA; const double* vals = pts + npts * d; const double* simp = vals + npts * m; const double* T = simp + ns * (d + 1);
+    const double eps = 100 * 2.220446049250313e-16;
+    const bool tryHint = (hint >= 0 && hint < ns);
+    for (int it = tryHint ? -1 : 0; it < ns; it++) {
+        const int s = (it < 0) ? hint : it;
+        const double lo = (it < 0) ? 1e-6 : -eps, hi = (it < 0) ? 1 - 1e-6 : 1 + eps;
+        const double* Ts = T + s * (d + 1) * d;
+        if (Ts[0] != Ts[0]) continue;                                                       /* degenerate simplex */
+        double c[ND_MAX_DIM + 1]; double cLast = 1.0; bool inside = true;
+        for (int i = 0; i < d && inside; i++) {
+            double ci = 0;
+            for (int j = 0; j < d; j++) ci += Ts[d * i + j] * (x[j] - Ts[d * d + j]);
+            c[i] = ci; cLast -= ci;
+            inside = (ci >= lo && ci <= hi);
+        }
+        if (!inside || !(cLast >= lo && cLast <= hi)) continue;
+        c[d] = cLast;
+        hint = s;
+        for (int k = 0; k < m; k++) {
+            double v = 0;
+            for (int j = 0; j < d + 1; j++) v += c[j] * vals[(int)simp[s * (d + 1) + j] * m + k];
+            out[k] = v;
+        }
+        return;
+    }
+    int best = 0; double bestD = 1e300;                                                     /* outside the hull: nearest table row */
+    for (int p = 0; p < npts; p++) {
+        double dist = 0;
+        for (int j = 0; j < d; j++) { double t = pts[p * d + j] - x[j]; dist += t * t; }
+        if (dist < bestD) { bestD = dist; best = p; }
+    }
+    for (int k = 0; k < m; k++) out[k] = vals[best * m + k];
+}
+MLB_DEV double aeroKeyValue(Aero& a, int id) {                                              /* AeroParameters.stringToAeroFunctionMap */
+    switch (id) {
+        case AKEY_MACH: return a.Mach;
+        case AKEY_ALTITUDE: return a.asl;
+        case AKEY_UNITRE: return a.unitRe * 1;
+        case AKEY_TOTALAOA: return a.totalAOA;
+        case AKEY_ROLLANGLE: return aeroRollAngle(a);
+        case AKEY_AOA: return aeroAOA(a);
+        default: return aeroAOSS(a);
+    }
+}
+MLB_DEV ForceMoment tabulatedAeroForce(const Lane& L, Aero& a, const double* C) {           /* RocketComponents.py:322-345 */
+    if ((int)C[TA_NKEYS] > 1) {
+        /* several key columns: scattered linear interpolation with nearest-neighbour fallback (:316-320,331); the keys are evaluated in
+           column order (AOA / AOSS mutate the cached air velocity for the keys and components after them, App. A #8) */
+        const int nk = (int)C[TA_NKEYS], nv = (int)C[TA_NVALS];
+        double keys[ND_MAX_DIM], vals[ND_MAX_VAL];
+        for (int k = 0; k < nk; k++) keys[k] = aeroKeyValue(a, (int)C[TA_KEYS + k]);
+        int hint = -1;
+        ndInterpolate(L.G + (int)C[TA_ND_OFF], keys, vals, hint);
+        double coeffs[5] = { 0.0, 0.0, 0.0, 0.0, 0.0 };
+        for (int c = 0; c < nv; c++) {
+            int k = (int)C[TA_COEFF_IDX + c];
+            if (k == 0) coeffs[0] = vals[c]; else if (k == 1) coeffs[1] = vals[c]; else if (k == 2) coeffs[2] = vals[c]; else if (k == 3) coeffs[3] = vals[c]; else coeffs[4] = vals[c];
+        }
+        return forceFromCoefficients(a, coeffs, ld3(C + C_POS), C[TA_AREF], C[TA_LREF]);
+    }
     double key;
     switch ((int)C[TA_KEY]) {
         case AKEY_MACH: key = a.Mach; break;
@@ -968,7 +1037,7 @@ MLB_DEV ForceMoment appliedForce(const double* B, Lane& L, double time, State& s
                     case CT_FIXED_FORCE: f = fm(ld3(C + FF_FORCE), ld3(C + C_POS), ld3(C + FF_MOMENT)); break;
                     case CT_AERO_FORCE: f = forceFromCoefficients(a, C + AF_COEFFS, ld3(C + C_POS), C[AF_AREF], C[AF_LREF]); break;
                     case CT_AERO_DAMPING: f = aeroDampingForce(a, C); break;
-                    case CT_TAB_AERO: f = tabulatedAeroForce(a, C); break;
+                    case CT_TAB_AERO: f = tabulatedAeroForce(L, a, C); break;
                     case CT_JET_DAMPING: f = jetDampingForce(B, L, a, C, si, inertia); break;
                     default: f = fmZero(); break;                                          /* FixedMass / RecoverySystem: zero force */
                 }

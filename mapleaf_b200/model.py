@@ -684,17 +684,31 @@ def _buildTabulatedAeroForce(r, stagePos):
             raise ValueError("ERROR: One of the following columns: {} did not match any of the expected columns names: Keys: {}, values: {}. \
                     Or was in the wrong order. All key columns must come BEFORE value columns.".format(columnNames, list(_AERO_KEYS), _AERO_COEFFS))
         coeffIdx.append(_AERO_COEFFS.index(name))
-    if len(keys) != 1:
-        raise NotImplementedError("TabulatedAeroForce tables with {} key columns (scattered N-D interpolation) are not implemented by the B200 backend".format(len(keys)))
+    if len(keys) < 1 or len(keys) > L.ND_MAX_DIM:
+        raise NotImplementedError("TabulatedAeroForce tables with {} key columns are not implemented by the B200 backend".format(len(keys)))
     data = np.loadtxt(path, delimiter=",", skiprows=1)
     if data.ndim == 1:
         data = data.reshape(1, -1)
-    n, nVals = data.shape[0], data.shape[1] - 1
+    nKeys = len(keys)
+    n, nVals = data.shape[0], data.shape[1] - nKeys
+    if nKeys > 1:
+        # scattered linear interpolation over several keys (NoNaNLinearNDInterpolator, RocketComponents.py:316-320): the Delaunay record
+        # is appended behind the shared part of the block once that is complete; its offset is patched into TA_ND_OFF
+        rec = _zeroInertiaRecord(L.CT_TAB_AERO, L.TA_TABLE, position)
+        rec[L.TA_AREF] = r.getFloat("Aref")
+        rec[L.TA_LREF] = r.getFloat("Lref")
+        rec[L.TA_KEY] = keys[0]
+        rec[L.TA_NKEYS] = nKeys
+        rec[L.TA_KEYS:L.TA_KEYS + nKeys] = keys
+        rec[L.TA_NVALS] = nVals
+        rec[L.TA_COEFF_IDX:L.TA_COEFF_IDX + 5] = coeffIdx + [-1] * (5 - len(coeffIdx))
+        return rec, dict(position=position, body=False, ndTable=(data[:, 0:nKeys], data[:, nKeys:]))
     size = L.TA_TABLE + n * (1 + nVals)
     rec = _zeroInertiaRecord(L.CT_TAB_AERO, size, position)
     rec[L.TA_AREF] = r.getFloat("Aref")
     rec[L.TA_LREF] = r.getFloat("Lref")
     rec[L.TA_KEY] = keys[0]
+    rec[L.TA_NKEYS] = 1
     rec[L.TA_NROWS] = n
     rec[L.TA_NVALS] = nVals
     rec[L.TA_COEFF_IDX:L.TA_COEFF_IDX + 5] = coeffIdx + [-1] * (5 - len(coeffIdx))
@@ -1335,6 +1349,7 @@ def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000) -> Model:
         for ci, c in enumerate(st["comps"]):
             off = append(_derivedConstants(c["rec"], H[L.H_AREF]))
             S[L.S_COMP_OFF + ci] = off
+            c["blobOffset"] = off
             if c["cls"] == "Motor":
                 S[L.S_MOTOR] = ci
                 S[L.S_BURN_DURATION] = c["motor"]["engineShutOff"]
@@ -1360,6 +1375,10 @@ def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000) -> Model:
         H[L.H_CTRL_OFF] = append(_buildControlSystem(sd, rk, stages, method, H, append))
         H[L.H_SHARED_LEN] = L.H_SIZE + len(tail)      # ... including the control record and the RK4 tableau
         _appendInterpolators(sd, rk, H, tail, append)
+    for st in stages:                                  # multi-key aero tables: Delaunay records in the global part of the block
+        for c in st["comps"]:
+            if c.get("ndTable") is not None:
+                tail[c["blobOffset"] - L.H_SIZE + L.TA_ND_OFF] = append(_ndInterpolatorRecord(*c["ndTable"]))
 
     # ---- initial inertia -> CG shift of the integrated position (rocket.py:416-421) ----
     def stageInertia(st, t):

@@ -20,6 +20,8 @@ What is recorded, and which reference code produced it:
                             + the reference's recorded regression values (BatchSims/regressionTests.mapleaf:1-27)
   tabulated_rk4/rk45.json . TabulatedComponents.mapleaf: TabulatedInertia, TabulatedAeroForce (TotalAOA / AOA / AOSS / Mach keys),
                             FractionalJetDamping, AeroDamping, AeroForce, FixedForce (Rocket/RocketComponents.py:183-413)
+  tabulated2d_rk4.json .... TabulatedComponents2D.mapleaf: TabulatedAeroForce tables with 2 and 3 key columns (scipy LinearNDInterpolator with
+                            nearest-neighbour fallback behind NoNaNLinearNDInterpolator, Motion/Interpolation.py:109-124)
   twostage_*.json ......... TwoStage.mapleaf: motor-burnout separation with delay, upper-stage ignition, automatic boat tail and
                             fineness update (Rocket/rocket.py:339-361,461-528), RK4 to apogee and RK45Adaptive to the ground
   earth_*.json ............ TabulatedComponents.mapleaf flown over the Round and the WGS84 (J2) earth from 47.5 N, 112.25 W
@@ -244,6 +246,7 @@ if __name__ == "__main__":
     if "tabulated" in which:
         tab = os.path.join(MY_DATA, "TabulatedComponents.mapleaf")
         dump("tabulated_rk4.json", singleFlight(tab, {}))
+        dump("tabulated2d_rk4.json", singleFlight(os.path.join(MY_DATA, "TabulatedComponents2D.mapleaf"), {}))
         dump("tabulated_rk45.json", singleFlight(tab, {"SimControl.timeDiscretization": "RK45Adaptive", "SimControl.EndConditionValue": "6"}, traceEvery=10, keepDts=True))
     if "twostage" in which:
         two = os.path.join(MY_DATA, "TwoStage.mapleaf")

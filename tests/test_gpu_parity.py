@@ -283,9 +283,11 @@ def test_runner_end_to_end_matches_reference_run(backend, golden, tmp_path):
     assert "Monte Carlo Run #3" in log and "Mean Landing location" in log and "Mean Max horizontal speed" in log
 
 
-def test_tabulated_components_fixed_step_vs_reference(backend, golden):
-    """SURVEY §8 row a19 on the GPU: tabulated inertia / aero tables, jet damping, aero damping, constant-coefficient and fixed forces."""
-    g = golden("tabulated_rk4.json")
+@pytest.mark.parametrize("name", ["tabulated_rk4.json", "tabulated2d_rk4.json"])
+def test_tabulated_components_fixed_step_vs_reference(backend, golden, name):
+    """SURVEY §8 row a19 on the GPU: tabulated inertia / aero tables (1 key: linInterp; 2 and 3 keys: scattered N-D interpolation from the
+    global-memory part of the model block), jet damping, aero damping, constant-coefficient and fixed forces."""
+    g = golden(name)
     m = buildFrom(g["definition"], g["overrides"])
     r = g["runs"][0]
     o = gpuRun(backend, m, 1, {}, traceLane=0, traceRows=2000)

@@ -135,10 +135,11 @@ def test_step_limit_status():
     assert o["status"][0] == L.ST_STEP_LIMIT and o["counters"][0, 0] == 100
 
 
-@pytest.mark.parametrize("name", ["tabulated_rk4.json", "tabulated_rk45.json"])
+@pytest.mark.parametrize("name", ["tabulated_rk4.json", "tabulated_rk45.json", "tabulated2d_rk4.json"])
 def test_tabulated_and_force_only_components(golden, name):
     """TabulatedInertia, TabulatedAeroForce (TotalAOA / AOA / AOSS / Mach keys, including the cached-vector mutation of
-    getAOA / getAOSS), FractionalJetDamping, AeroDamping, AeroForce, Force: one tumbling flight, fixed-step and adaptive."""
+    getAOA / getAOSS), FractionalJetDamping, AeroDamping, AeroForce, Force: one tumbling flight, fixed-step and adaptive; and the same
+    flight with 2- and 3-key aero tables (scattered N-D interpolation on scipy's triangulation, nearest neighbour outside the hull)."""
     g = golden(name)
     m = buildFrom(g["definition"], g["overrides"])
     r = g["runs"][0]
