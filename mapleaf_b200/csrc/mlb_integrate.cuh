@@ -314,6 +314,15 @@ MLB_COLD_CONTROL void runControlSystem(const double* B, const double* G, Lane& L
     if (!((currentTime - L.ctrlLastRun) + 0.0000000001 >= CS[CS_UPDATE_DT])) return;
     const double dt = currentTime - L.ctrlLastRun;
     Q4 target = q4(CS[CS_TARGET_Q], CS[CS_TARGET_Q + 1], CS[CS_TARGET_Q + 2], CS[CS_TARGET_Q + 3]);
+    if ((int)CS[CS_MC_TYPE] == 2) {
+        /* IdealMomentController (MomentControllers.py:85-93): the orientation becomes the target, the angular velocity zero. The
+           reference assigns the navigator's quaternion OBJECT, so in-place normalisations of the state's orientation during the step
+           reach the target of the following steps: the lane keeps its own copy and takes it back when the step replaces the state. */
+        if (!L.haveTargetQ) { L.targetQ = target; L.haveTargetQ = true; }
+        L.s.q = L.targetQ; L.s.w = v3(0, 0, 0); L.qAliased = true;
+        L.ctrlLastRun = currentTime;
+        return;
+    }
     /* (target / orientation).toRotationVector() = orientation.inverse() * target (CythonQuaternion.pyx:121-126,160-162,219-226) */
     double n = qNorm(L.s.q); double sc = 1.0 / (n * n);
     Q4 inv = qConj(L.s.q);
@@ -382,6 +391,7 @@ MLB_DEV StepResult rocketTimeStep(const double* B, const double* G, Lane& L, con
     if (active) {
         if (L.dof3) L.nSteps3++;
         L.time += r.dt;
+        if (L.qAliased) { L.targetQ = L.s.q; L.qAliased = false; }
         L.s = r.newValue;
         L.nSteps++;
     }
@@ -445,6 +455,7 @@ MLB_DEV void laneInit(const double* B, Lane& L, const LaneInputs& in, long long 
     L.ctrlLastRun = 0;                                      /* RocketControlSystem(initTime=0) */
     for (int k = 0; k < 3; k++) { L.gncLastError[k] = 0; L.gncIntegral[k] = 0; }
     L.ndHint[0] = -1; L.ndHint[1] = -1;
+    L.haveTargetQ = false; L.qAliased = false; L.targetQ = qIdentity();
     for (int k = 0; k < CS_MAX_ACT; k++) { L.actLastDefl[k] = 0; L.actLastTime[k] = 0; L.actTarget[k] = 0; }
     for (int si = 0; si < MLB_MAX_STAGES; si++) { L.ignitionTime[si] = 0; L.engineShutOff[si] = -1; }
     for (int si = 0; si < L.nStages; si++) {

@@ -69,6 +69,7 @@ struct Lane {
     /* control system (GNC/*.py): loop timing, vector PID memory, first-order actuators; RK4 forced during the controlled ascent */
     bool hasControl, forceRK4;
     double ctrlLastRun, gncLastError[3], gncIntegral[3];
+    Q4 targetQ; bool haveTargetQ, qAliased;     /* IdealMomentController: the navigator's target quaternion as the reference's object aliasing leaves it */
     int ndHint[2];                              /* simplex that held the previous gain-table / deflection-table query (ndInterpolate) */
     double actLastDefl[CS_MAX_ACT], actLastTime[CS_MAX_ACT], actTarget[CS_MAX_ACT];
     bool resorted;                              /* a stage has been dropped: inertia lists are in top-to-bottom order (rocket.py:476-479) */

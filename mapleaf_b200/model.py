@@ -787,6 +787,12 @@ def _buildControlSystem(sd, rk, stages, method, H, append):
             raise NotImplementedError("gain table scheduled by more than 4 keys")
         rec[L.CS_GAIN_NKEYS] = len(keyNames)
         rec[L.CS_GAIN_KEYS:L.CS_GAIN_KEYS + len(keyNames)] = [_AERO_KEYS[k] for k in keyNames]
+    elif mcType == "IdealMomentController":
+        # MomentControllers.py:85-93: every time step the orientation becomes the target orientation and the angular velocity zero; no
+        # controlled system, no actuators, update rate 0 = once per step (ControlSystems.py:79-100,120-122)
+        rec[L.CS_MC_TYPE] = 2
+        rec[L.CS_STAGE], rec[L.CS_COMP] = -1, -1
+        return rec
     else:
         raise ValueError("Moment Controller Type: {} not implemented. Try ScheduledGainPIDRocket or IdealMomentController".format(mcType))
     updateRate = cs.getFloat("updateRate")
@@ -1156,9 +1162,11 @@ def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000) -> Model:
     addAutoBT = rk.getBool("Aero.addZeroLengthBoatTailsToAccountForBaseDrag")
     H[L.H_ADD_AUTO_BT] = 1.0 if addAutoBT else 0.0
     stageDicts = [d for d in rk.getImmediateSubDicts() if d not in ("Rocket.ControlSystem", "Rocket.HIL", "Rocket.Aero")]
-    hasControl = rk.tryGetString("ControlSystem.controlledSystem") is not None
-    if rk.tryGetString("ControlSystem.MomentController.Type") == "IdealMomentController" and not hasControl and "Rocket.ControlSystem" in rk.getImmediateSubDicts():
-        raise NotImplementedError("IdealMomentController (rewrites the state between steps) is not implemented by the B200 backend")
+    # rocket.py:210-217: a control system exists when a controlled system is named OR the moment controller is the ideal one (which has
+    # no controlled system: ControlSystems.py:85-100)
+    idealControl = rk.tryGetString("ControlSystem.MomentController.Type") == "IdealMomentController"
+    hasActuatedSystem = rk.tryGetString("ControlSystem.controlledSystem") is not None and not idealControl
+    hasControl = hasActuatedSystem or idealControl
     maxDiameter = 0
     for sdict in stageDicts:
         for cdict in sd.getImmediateSubDicts(sdict):
@@ -1211,7 +1219,7 @@ def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000) -> Model:
                 rec, info = _buildJetDamping(cr, stagePos)
             else:
                 rec, info = _buildMass(cr, stagePos)
-            if hasControl and cls == "FinSet" and c == rk.getString("ControlSystem.controlledSystem"):
+            if hasActuatedSystem and cls == "FinSet" and c == rk.getString("ControlSystem.controlledSystem"):
                 rec[L.FS_ACTUATED] = 1.0          # fin angles follow the actuators (Fins.py:264-268)
             info["name"] = cr.getDictName()
             info["cls"] = cls
@@ -1374,7 +1382,8 @@ def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000) -> Model:
     if hasControl:
         H[L.H_CTRL_OFF] = append(_buildControlSystem(sd, rk, stages, method, H, append))
         H[L.H_SHARED_LEN] = L.H_SIZE + len(tail)      # ... including the control record and the RK4 tableau
-        _appendInterpolators(sd, rk, H, tail, append)
+        if hasActuatedSystem:
+            _appendInterpolators(sd, rk, H, tail, append)
     for st in stages:                                  # multi-key aero tables: Delaunay records in the global part of the block
         for c in st["comps"]:
             if c.get("ndTable") is not None:

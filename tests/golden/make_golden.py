@@ -14,6 +14,8 @@ What is recorded, and which reference code produced it:
   rk4_apogee.json ......... `runMonteCarloSimulation`-style loop (SimulationRunners/MonteCarlo.py:64-76),
                             seed "2394781", 8 runs, RK4 dt 0.01, EndCondition Apogee
   rk4_ground.json ......... same, 3 runs, EndCondition Altitude 0 (BASELINE.md first parity anchor)
+  ideal_rk4/rk45.json ..... IdealMomentController (GNC/MomentControllers.py:85-93): orientation forced to a tilted target every step, zero angular
+                            velocity; fixed-step and adaptive (the adaptive integrator keeps its first-same-as-last derivative across the rewrite)
   rk78_gust.json .......... RK78Adaptive (Dormand-Prince 8(7)13M, no first-same-as-last) with the sine gust, to apogee, 2 runs
   rk45_pink.json .......... RK45Adaptive + PID, Hellman wind, PinkNoise2D (derived config 2), 4 runs
   windtunnel.json ......... WindTunnelSimulation.runSweep force evaluations (SingleSimulations.py:444-475)
@@ -231,7 +233,7 @@ def dump(name, obj):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["model", "rng", "windtunnel", "rk4_apogee", "rk4_ground", "rk45_pink", "rk45_gust", "tabulated", "twostage", "earth", "canards", "motoradj", "rk78"]
+    which = sys.argv[1:] or ["model", "rng", "windtunnel", "rk4_apogee", "rk4_ground", "rk45_pink", "rk45_gust", "tabulated", "twostage", "earth", "canards", "motoradj", "rk78", "ideal"]
     mc = os.path.join(MY_DATA, "MonteCarlo.mapleaf")
     if "model" in which:
         dump("model_montecarlo.json", modelFields())
@@ -274,6 +276,11 @@ if __name__ == "__main__":
     adaptive = os.path.join(MY_DATA, "MonteCarloAdaptive.mapleaf")
     if "rk45_pink" in which:
         dump("rk45_pink.json", monteCarlo(adaptive, {}, "2394781", 4, globalSeed=2394781, keepDts=True))
+    if "ideal" in which:
+        ideal = {"Rocket.ControlSystem.MomentController.Type": "IdealMomentController", "Rocket.ControlSystem.desiredFlightDirection": "(0.2 0.1 1)",
+                 "Environment.ConstantMeanWind.velocity": "(6 -3 0)"}
+        dump("ideal_rk4.json", singleFlight(mc, ideal, traceEvery=200))
+        dump("ideal_rk45.json", singleFlight(mc, {**ideal, "SimControl.timeDiscretization": "RK45Adaptive"}, traceEvery=20, keepDts=True))
     if "rk78" in which:
         dump("rk78_gust.json", monteCarlo(adaptive, {"Environment.TurbulenceModel": "customSineGust", "Environment.MeanWindModel": "Constant",
                                                      "SimControl.EndCondition": "Apogee", "SimControl.timeDiscretization": "RK78Adaptive"}, "2394781", 2, keepDts=True))

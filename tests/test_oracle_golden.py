@@ -314,3 +314,23 @@ def test_rk78_adaptive_gust(golden):
     r0 = runs[0]
     rep = oracle.run(m.blob, 1, {L.LANE_WIND: lanesFromRuns(runs[:1])}, traceLane=0, traceMaxRows=3000, dtReplay=r0["dts"])
     assert np.abs(rep["trace"][:, 0] - np.array(r0["times"])).max() < 1e-12
+
+
+@pytest.mark.parametrize("name", ["ideal_rk4.json", "ideal_rk45.json"])
+def test_ideal_moment_controller(golden, name):
+    """IdealMomentController (GNC/MomentControllers.py:85-93; ControlSystems.py:73-100): every time step the orientation is overwritten
+    with the navigator's (tilted) target and the angular velocity with zero. The reference assigns the target quaternion OBJECT, so the
+    in-place normalisations of the step reach the next steps' target; the adaptive integrator keeps its first-same-as-last derivative
+    across the rewrite. Observed bit-identical to the reference, fixed-step and free-running adaptive."""
+    g = golden(name)
+    r = g["runs"][0]
+    m = buildFrom(g["definition"], g["overrides"])
+    assert m.blob[int(m.header("H_CTRL_OFF")) + L.CS_MC_TYPE] == 2
+    o = oracle.run(m.blob, 1, {}, traceLane=0, traceMaxRows=5000)
+    assert o["status"][0] == L.ST_OK and o["counters"][0, 0] == r["steps"]
+    assert stateErr(o["finals"][0], r["final"]) < 1e-12 and relErr(o["results"][0, 3:7], r["results"][3:7]) < 1e-12
+    # the reference's flight log holds the state OBJECTS, and the controller rewrites each one's orientation / angular velocity at the start
+    # of the following step: only position and velocity of a logged row are what the integrator produced
+    for idx, row in zip(r["traceIdx"], r["trace"]):
+        assert abs(o["trace"][idx, 0] - row[0]) < 1e-12
+        assert relErr(o["trace"][idx, 1:4], row[1:4]) < 1e-12 and relErr(o["trace"][idx, 4:7], row[4:7]) < 1e-12
