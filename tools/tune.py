@@ -4,11 +4,11 @@ import json, os, subprocess, sys, time
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 VDIR = os.path.join(REPO, "mapleaf_b200", "lib", "variants")
+# name -> extra nvcc flags; edit for the experiment at hand (see DESIGN.md for the switches: MLB_COMP_NOINLINE, MLB_COLD_MASK,
+# MLB_SYNC_STRIDE, MLB_TUNE_SHAPES, MLB_TUNE_512X2, MLB_TUNE_640X2, MLB_MATH_NOINLINE, MLB_LOCKSTEP, MLB_FIN_UNIFORM)
 VARIANTS = {
-    "p_c8": ["-DMLB_PINK_INLINE", "-DMLB_COMP_NOINLINE=8"],
-    "p_c12": ["-DMLB_PINK_INLINE", "-DMLB_COMP_NOINLINE=12"],
-    "p_c0": ["-DMLB_PINK_INLINE", "-DMLB_COMP_NOINLINE=0"],
-    "p_c15": ["-DMLB_PINK_INLINE"],
+    "default": [],
+    "cold15": ["-DMLB_COLD_MASK=15"],
 }
 
 def build(names=None):
