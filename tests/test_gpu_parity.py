@@ -522,3 +522,27 @@ def test_ideal_moment_controller_vs_reference(backend, golden):
     assert rep["counters"][0, 0] == r["steps"]
     assert np.abs(rep["trace"][:, 0] - np.array(r["times"])[:len(rep["trace"])]).max() < 1e-9
     assert stateErr(rep["finals"][0], r["final"]) < 1e-6
+
+
+def test_runner_large_batch_with_flight_paths(backend, golden, tmp_path):
+    """runMonteCarloSimulation with 200 runs on the GPU: inputs drawn by the C++ sampler (>= 64 runs), the first runs equal to the
+    reference's first runs, `MonteCarlo.output flightPaths` filled from the device's flight log."""
+    from mapleaf_b200 import runMonteCarloSimulation
+    g = golden("rk4_apogee.json")
+    sd = SimDefinition(os.path.join(DATA, g["definition"]), silent=True, disableDistributionSampling=True)
+    sd.setValue("MonteCarlo.randomSeed", g["randomSeed"])
+    sd.setValue("MonteCarlo.numberRuns", "200")
+    sd.setValue("MonteCarlo.output", "flightPaths landingLocations apogees")
+    sd = SimDefinition(dictionary=dict(sd.dict), silent=True)
+    sd.fileName = str(tmp_path / "MonteCarlo.mapleaf")
+    out = runMonteCarloSimulation(simDefinition=sd, silent=True)
+    assert (out.status == L.ST_OK).all() and len(out.apogees) == 200 and len(out.flights) == 200
+    for i, r in enumerate(g["runs"]):
+        assert relErr(out.results[i, 3:7], r["results"][3:7]) < FIXED_TOL
+        f = out.flights[i]
+        assert f.times.shape == (900,) and abs(f.times[-1] - r["final"][0]) < 1e-9
+        assert relErr(f.positions[-1], r["final"][1:4]) < FIXED_TOL
+    body = open(out.logPath).read().splitlines()
+    assert body.count("Monte Carlo Run #200") == 1
+    i1 = body.index("Monte Carlo Run #1")
+    assert body[i1 + 1] == "Sampling vector parameter: Environment.ConstantMeanWind.velocity, value: ({:1.3f} {:1.3f} {:1.3f})".format(*g["runs"][0]["wind"])
