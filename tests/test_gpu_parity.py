@@ -546,3 +546,31 @@ def test_runner_large_batch_with_flight_paths(backend, golden, tmp_path):
     assert body.count("Monte Carlo Run #200") == 1
     i1 = body.index("Monte Carlo Run #1")
     assert body[i1 + 1] == "Sampling vector parameter: Environment.ConstantMeanWind.velocity, value: ({:1.3f} {:1.3f} {:1.3f})".format(*g["runs"][0]["wind"])
+
+
+def test_handle_reuse_across_batch_sizes(backend):
+    """One handle, three batches of different sizes (device buffers are re-sized by mlb_set_lanes), a flight log switched on and off, and
+    a ragged size that does not fill its last CTA: the lanes common to all batches give identical results every time."""
+    m = buildFrom("MonteCarloAdaptive.mapleaf")
+    rng = np.random.default_rng(11)
+    nBig = 2500
+    w = rng.normal(size=(3, nBig)) * np.array([[5.0], [5.0], [0.5]]) + np.array([[2.0], [0.0], [0.0]])
+    seeds = np.zeros((3, nBig)); seeds[:2] = rng.integers(0, 1000000, size=(2, nBig))
+    outs = []
+    with backend.TrajectoryBatch(m.blob) as b:
+        for n, log in ((100, False), (nBig, True), (7, False), (1031, False)):
+            b.setLanes(n, {L.LANE_WIND: np.ascontiguousarray(w[:, :n]), L.LANE_PINK_SEED: np.ascontiguousarray(seeds[:, :n])})
+            b.setFlightLog(0 if log else -1, 5 if log else 0, 1, 256)
+            b.run()
+            res, st = b.results()
+            assert (st == L.ST_OK).all() and res.shape == (n, 7)
+            outs.append(res)
+            if log:
+                paths = b.flightLog()
+                assert len(paths) == 5 and all(128 <= len(p) <= 256 for p in paths)
+                assert all(p[-1, 0] == res[i, L.RES_FLIGHT_TIME] for i, p in enumerate(paths))
+            c = b.counters()
+            assert c["lanes"] == n and c["lanes_ok"] == n
+    for res in outs:
+        k = min(len(res), 7)
+        assert np.array_equal(res[:k], outs[1][:k])
