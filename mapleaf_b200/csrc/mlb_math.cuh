@@ -150,7 +150,12 @@ MLB_DEV double qRotationAngle(Q4& q) {                                          
     return 2 * m_atan2(sqrt(1 - q.w * q.w), q.w);
 }
 MLB_DEV V3 qRotationAxis(Q4& q) {                                                          /* :197 */
-    if (fabs(qRotationAngle(q)) > 0) {
+    /* `if abs(self.rotationAngle()) > 0`: the angle 2 atan2(sqrt(1 - w^2), w) is only tested against zero here. With t = 1 - w^2 it is
+       non-zero exactly when t > 0 (atan2 of a positive sine) or t == 0 and w < 0 (atan2(+0, negative) = pi); t < 0 makes it NaN and the
+       test false. Same branch, same in-place normalisation, without the second arctangent and square root of every angle rescaling. */
+    qNormalize(q);
+    const double t = 1 - q.w * q.w;
+    if (t > 0 || (t == 0 && q.w < 0)) {
         double n = sqrt(qNorm(q) - q.w * q.w);
         double r = 1.0 / n;
         return v3(divBy(q.x, n, r), divBy(q.y, n, r), divBy(q.z, n, r));
