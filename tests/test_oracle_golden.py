@@ -334,3 +334,15 @@ def test_ideal_moment_controller(golden, name):
     for idx, row in zip(r["traceIdx"], r["trace"]):
         assert abs(o["trace"][idx, 0] - row[0]) < 1e-12
         assert relErr(o["trace"][idx, 1:4], row[1:4]) < 1e-12 and relErr(o["trace"][idx, 4:7], row[4:7]) < 1e-12
+
+
+def test_reference_regression_case_timestep_adaptation_demo():
+    """A golden the reference ships itself (regressionTests.mapleaf:87-114, checked by its batch runner at 0.2 %): RK45Adaptive + PID with
+    the case's own coefficients, a 20 m launch rail, PinkNoise2D with fixed seeds, motor impulse and burn time both doubled, 45 s of flight."""
+    from conftest import TIMESTEP_ADAPTATION_DEMO, TIMESTEP_ADAPTATION_DEMO_EXPECTED as exp
+    m = buildFrom("MonteCarloAdaptive.mapleaf", TIMESTEP_ADAPTATION_DEMO)
+    assert m.header("H_RAIL_LEN") == 20 and m.meta["motors"][0]["factors"] == (2.0, 2.0)
+    o = oracle.run(m.blob, 1, {})
+    assert o["status"][0] == L.ST_OK
+    assert abs(o["finals"][0, 13] - exp["Time"]) < 1e-9
+    assert abs(o["finals"][0, 0] - exp["PositionX"]) <= exp["percentTolerance"] / 100 * abs(exp["PositionX"])
