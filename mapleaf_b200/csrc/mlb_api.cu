@@ -25,8 +25,8 @@ using namespace mlb;
 
 #define MLB_BLOCK 128               /* threads per CTA of the small helper kernels */
 #define MLB_K_SLOTS_MAX 14          /* RK78: 13 stages + first-same-as-last */
-/* The integrate kernel is built for three CTA shapes. Larger CTAs make larger convoys (see mlb_integrate.cuh) and are
-   faster as long as every SM gets a CTA; registers per lane shrink accordingly (255 / 128 / 64). */
+/* The integrate kernel is built for three CTA shapes. Larger CTAs make larger convoys (see mlb_integrate.cuh) and more lanes per SM;
+   registers per lane shrink accordingly (255 / 128 / 64). mlb_run picks the shape with the fewest (waves x wave time). */
 #define MLB_NUM_SHAPES 3
 static const int kShapeBlock[MLB_NUM_SHAPES] = { 128, 512, 1024 };
 #ifdef MLB_TUNE_SHAPES
