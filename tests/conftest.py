@@ -46,3 +46,22 @@ TIMESTEP_ADAPTATION_DEMO = {
     "Rocket.Sustainer.Motor.impulseAdjustFactor": "2", "Rocket.Sustainer.Motor.burnTimeAdjustFactor": "2",
 }
 TIMESTEP_ADAPTATION_DEMO_EXPECTED = {"PositionX": -141.033, "Time": 45.0, "percentTolerance": 0.2}
+
+
+REGRESSION_CASES = ["B4-4SimpleRocketCase", "C6-3SimpleRocketCase", "HaisunaataCase", "RollingRocketCase"]
+
+
+def regressionCase(name):
+    """(model block, expected [x, y, z, vx, vy, vz]) of one of the reference's own flight regression cases
+    (MAPLEAF/Examples/BatchSims/OpenRocketCases.mapleaf:63-214), flattened by tests/golden/make_regression_blobs.py."""
+    import numpy as np
+    from mapleaf_b200 import L
+    z = np.load(os.path.join(GOLDEN, "regression_blobs.npz"))
+    if list(z["layoutVersion"]) != [L.MLB_VERSION, L.H_SIZE, L.FS_SIZE, L.S_SIZE, L.TA_TABLE, L.CS_SIZE]:
+        pytest.skip("regression_blobs.npz was flattened with another model-block layout: re-run tests/golden/make_regression_blobs.py")
+    return z[name + "/blob"], z[name + "/expected"]
+
+
+def regressionErrors(final, expected):
+    """The reference's batch-runner check (SimulationRunners/Batch.py:488-520): percent error, absolute where the expectation is 0."""
+    return [abs(a - b) / abs(b) * 100 if b != 0 else abs(a) for a, b in zip(final, expected)]

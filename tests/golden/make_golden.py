@@ -35,6 +35,8 @@ What is recorded, and which reference code produced it:
   motoradj_*.json ......... motor impulseAdjustFactor / burnTimeAdjustFactor (Rocket/Propulsion.py:38-40,102-128,153-157): set in the
                             definition for a single-stage and a two-stage flight, and sampled (`_stdDev`) in a 3-run Monte Carlo loop
                             like the reference's Jake1_MonteCarlo.mapleaf example
+  regression_blobs.npz .... (tests/golden/make_regression_blobs.py) the reference's own flight regression cases as flattened model blocks +
+                            the final values the reference records for them
   rng.json ................ random.Random / PinkNoiseGenerator known answers (test_SimDefinition.py:118-151,
                             test_TurbulenceModelling.py:37-60)
 """

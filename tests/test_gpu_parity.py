@@ -593,3 +593,21 @@ def test_reference_regression_case_timestep_adaptation_demo(backend):
         xs.append(p["finals"][0, 0]); zs.append(p["finals"][0, 2])
     bandX, bandZ = max(xs) - min(xs), max(zs) - min(zs)
     assert abs(o["finals"][0, 0] - c["finals"][0, 0]) <= 3 * bandX + 0.05 and abs(o["finals"][0, 2] - c["finals"][0, 2]) <= 3 * bandZ + 0.5
+
+
+@pytest.mark.parametrize("name", __import__("conftest").REGRESSION_CASES)
+def test_reference_flight_regression_cases(backend, name):
+    """The reference's own flight regression goldens (OpenRocketCases.mapleaf:63-214, 0.2 % in its batch runner) on the device: within 0.05 %
+    of the recorded values and <= 1e-9 from the oracle (fixed-step RK4)."""
+    from conftest import regressionCase, regressionErrors
+    from oracle import oracle
+
+    class M:
+        pass
+    m = M()
+    m.blob, expected = regressionCase(name)
+    o = gpuRun(backend, m, 1, {})
+    c = oracle.run(m.blob, 1, {})
+    assert o["status"][0] == L.ST_OK and o["counters"][0, 0] == c["counters"][0, 0]
+    assert max(regressionErrors(o["finals"][0][:6], expected)) < 0.05
+    assert stateErr(o["finals"][0], np.concatenate([[c["finals"][0, 13]], c["finals"][0, :13]])) < FIXED_TOL

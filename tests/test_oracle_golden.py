@@ -346,3 +346,15 @@ def test_reference_regression_case_timestep_adaptation_demo():
     assert o["status"][0] == L.ST_OK
     assert abs(o["finals"][0, 13] - exp["Time"]) < 1e-9
     assert abs(o["finals"][0, 0] - exp["PositionX"]) <= exp["percentTolerance"] / 100 * abs(exp["PositionX"])
+
+
+@pytest.mark.parametrize("name", __import__("conftest").REGRESSION_CASES)
+def test_reference_flight_regression_cases(name):
+    """Goldens the reference ships and checks at 0.2 % (OpenRocketCases.mapleaf:63-214): two Estes-motor model rockets to apogee, a
+    sounding rocket with a boat tail and a nose-cone-to-tube transition (Haisunaata), and a rolling rocket with canted fins flown for 6 s.
+    The recorded values are printed to 4-7 digits; the oracle reproduces them to that precision (observed <= 0.04 %)."""
+    from conftest import regressionCase, regressionErrors
+    blob, expected = regressionCase(name)
+    o = oracle.run(blob, 1, {})
+    assert o["status"][0] == L.ST_OK
+    assert max(regressionErrors(o["finals"][0][:6], expected)) < 0.05
