@@ -48,12 +48,13 @@ TIMESTEP_ADAPTATION_DEMO = {
 TIMESTEP_ADAPTATION_DEMO_EXPECTED = {"PositionX": -141.033, "Time": 45.0, "percentTolerance": 0.2}
 
 
-REGRESSION_CASES = ["B4-4SimpleRocketCase", "C6-3SimpleRocketCase", "HaisunaataCase", "RollingRocketCase"]
+REGRESSION_CASES = ["B4-4SimpleRocketCase", "C6-3SimpleRocketCase", "HaisunaataCase", "RollingRocketCase", "NASADraglessSphere", "NASACdSphere_RoundEarth",
+                    "NASACdSphere_WGS84", "NASACdSphere_WGS84Wind", "NASADampedBrick"]
 
 
 def regressionCase(name):
     """(model block, expected [x, y, z, vx, vy, vz]) of one of the reference's own flight regression cases
-    (MAPLEAF/Examples/BatchSims/OpenRocketCases.mapleaf:63-214), flattened by tests/golden/make_regression_blobs.py."""
+    (MAPLEAF/Examples/BatchSims/OpenRocketCases.mapleaf:63-214, NASAVerificationCases.mapleaf:9-262), flattened by tests/golden/make_regression_blobs.py."""
     import numpy as np
     from mapleaf_b200 import L
     z = np.load(os.path.join(GOLDEN, "regression_blobs.npz"))

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """
 Flattens the reference's own flight regression cases (MAPLEAF/Examples/BatchSims/OpenRocketCases.mapleaf:63-214: B4-4 / C6-3
-SimpleRocketCase, HaisunaataCase, RollingRocketCase) into model blocks with this repo's builder and stores them, with the final values the
+SimpleRocketCase, HaisunaataCase, RollingRocketCase; NASAVerificationCases.mapleaf:9-262: sphere and brick cases) into model blocks with this repo's builder and stores them, with the final values the
 reference records for them, in tests/golden/regression_blobs.npz. The input decks themselves (Jake1.mapleaf, Haisunaata.mapleaf, the Estes
 motor tables) stay in /root/reference: what is committed is the derived model block in this repo's own layout (include/mlb_layout.h).
 Re-run after a layout change (the tests skip blobs whose H_VERSION / length no longer match):
@@ -36,6 +36,18 @@ CASES = {      # name: (deck, ParameterOverrides, ExpectedFinalValues: position 
                               "Rocket.Sustainer.AltimeterMass.mass": "0.03", "SimControl.EndCondition": "Time", "SimControl.EndConditionValue": "6",
                               "SimControl.timeStep": "0.005"}, [-9.898, 1.51, 123.546, -1.6056, 0.2942, -0.3942]),
 }
+# NASA verification cases (MAPLEAF/Examples/BatchSims/NASAVerificationCases.mapleaf:9-262, from NASA/TM-2015-218675 check cases): a sphere
+# dropped from 9144 m over the round / WGS84 earth without and with drag and wind, a tumbling brick with aerodynamic damping; 30 s
+S = os.path.join(REF, "MAPLEAF/Examples/Simulations/NASASphere.mapleaf")
+B = os.path.join(REF, "MAPLEAF/Examples/Simulations/NASABrick.mapleaf")
+CASES.update({
+    "NASADraglessSphere": (S, {"Rocket.Stage.AeroForce.Cd": "0.0"}, [6382876.054, 13969.82281, 0.0, -293.7167128, 465.4464411, 0.0]),
+    "NASACdSphere_RoundEarth": (S, {"Environment.EarthModel": "Round"}, [6375952.953, 13954.22714, 0.0, -264.5117166, 464.9271675, 0.0]),
+    "NASACdSphere_WGS84": (S, {}, [6383085.212, 13969.82655, 0.0, -264.3698185, 465.4472786, 0.0]),
+    "NASACdSphere_WGS84Wind": (S, {"Environment.MeanWindModel": "Constant", "Environment.ConstantMeanWind.velocity": "(6.096 0 0)"},
+                               [6383085.4118580, 13978.2005101, 0.0, -264.3589523, 466.3203626, 0.0]),
+    "NASADampedBrick": (B, {}, [6382876.054, 13969.82281, 0.0, -293.7167128, 465.4464411, 0.0]),
+})
 out = {}
 for name, (deck, overrides, expected) in CASES.items():
     sd = SimDefinition(deck, silent=True, disableDistributionSampling=True)

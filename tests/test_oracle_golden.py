@@ -351,7 +351,9 @@ def test_reference_regression_case_timestep_adaptation_demo():
 @pytest.mark.parametrize("name", __import__("conftest").REGRESSION_CASES)
 def test_reference_flight_regression_cases(name):
     """Goldens the reference ships and checks at 0.2 % (OpenRocketCases.mapleaf:63-214): two Estes-motor model rockets to apogee, a
-    sounding rocket with a boat tail and a nose-cone-to-tube transition (Haisunaata), and a rolling rocket with canted fins flown for 6 s.
+    sounding rocket with a boat tail and a nose-cone-to-tube transition (Haisunaata), a rolling rocket with canted fins flown for 6 s; and
+    the NASA check cases (NASAVerificationCases.mapleaf:9-262): a sphere dropped over the round / WGS84 earth with and without drag and wind, a
+    damped tumbling brick.
     The recorded values are printed to 4-7 digits; the oracle reproduces them to that precision (observed <= 0.04 %)."""
     from conftest import regressionCase, regressionErrors
     blob, expected = regressionCase(name)
