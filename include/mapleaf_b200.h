@@ -56,7 +56,10 @@ typedef struct {
     int64_t lanes_ok, lanes_step_limit, lanes_nan;
     int64_t kernel_launches;    /* CUDA kernels launched by the last mlb_run */
     double last_run_ms;         /* device time of the last mlb_run (CUDA events on the launch stream) */
-    double dominant_kernel_ms;  /* of which: the integrate kernel */
+    double dominant_kernel_ms;  /* of which: the free-flight (6-DoF) kernel, all its generations */
+    double chute_kernel_ms;     /* of which: the under-chute (3-DoF) kernel */
+    int64_t flight_block;       /* CTA shape of the free-flight kernel in the last run */
+    int64_t flight_generations; /* launches of the free-flight kernel in the last run */
 } mlb_counters_t;
 
 /* model_blob: the FP64 model block (include/mlb_layout.h), n = its size in BYTES */

@@ -29,7 +29,8 @@ class Counters(ctypes.Structure):
     _fields_ = [("lanes", ctypes.c_int64), ("steps", ctypes.c_int64), ("derivative_evals", ctypes.c_int64), ("rejected_steps", ctypes.c_int64),
                 ("steps_3dof", ctypes.c_int64), ("derivative_evals_3dof", ctypes.c_int64), ("derivative_evals_transonic", ctypes.c_int64),
                 ("lanes_ok", ctypes.c_int64), ("lanes_step_limit", ctypes.c_int64), ("lanes_nan", ctypes.c_int64),
-                ("kernel_launches", ctypes.c_int64), ("last_run_ms", ctypes.c_double), ("dominant_kernel_ms", ctypes.c_double)]
+                ("kernel_launches", ctypes.c_int64), ("last_run_ms", ctypes.c_double), ("dominant_kernel_ms", ctypes.c_double),
+                ("chute_kernel_ms", ctypes.c_double), ("flight_block", ctypes.c_int64), ("flight_generations", ctypes.c_int64)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

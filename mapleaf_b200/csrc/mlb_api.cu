@@ -1,15 +1,22 @@
 /*
  * mlb_api.cu — trajectory kernels and the C ABI of libmapleaf_b200.so (include/mapleaf_b200.h).
  *
- * Kernels (sm_100a, FP64, one lane = one sampled rocket = one thread):
- *   integrateLanes ... lane prologue (sampled inputs -> initial state, pink-noise generators, per-lane fin constants),
- *                      then the whole flight: events, RK stages with the full force model fused in, end condition,
- *                      running reductions; writes 7 result doubles + final state + status + counters per lane.
- *                      The model block is staged in shared memory once per CTA; RK stage derivatives live in shared
- *                      memory columns (mlb_integrate.cuh).
- *   forceEvalKernel .. one Rocket._getAppliedForce per thread (wind-tunnel known-answer path).
- *   momentsKernel .... per-column count / mean / M2 of the result block (Chan's pairwise combination), the
- *                      per-GPU half of the dispersion statistics.
+ * Kernels (sm_100a, FP64, one lane = one sampled rocket = one thread). A run is a fixed, data-independent sequence of launches;
+ * between launches a lane lives in its LaneRec in HBM (written once per launch, ~1.7 KB):
+ *   initLanes ......... lane prologue: sampled inputs -> initial state, CPython-exact MT19937 seeding of the pink-noise generators,
+ *                       per-lane fin constants, event subscriptions.
+ *   flightLanes<B> .... FREE FLIGHT (6-DoF): events, RK stages with the whole component build-up force model fused in, convoy
+ *                       execution (one barrier per derivative evaluation, see mlb_integrate.cuh). Launched MLB_GENERATIONS times: a
+ *                       CTA whose live lanes drop below a fraction of what it started with hands the stragglers to the next
+ *                       generation's queue and retires, so lock-step tails are re-packed into full CTAs of lanes that are at the
+ *                       same point of their flights. A lane leaves for good when its end condition fires (results written) or when
+ *                       its first parachute opens (queued for chuteLanes).
+ *   chuteLanes ........ UNDER PARACHUTE (3-DoF): the same integrator compiled without the component force model; small enough for the
+ *                       instruction cache, so it runs free of barriers with more registers per lane.
+ *   forceEvalKernel ... one Rocket._getAppliedForce per thread (wind-tunnel known-answer path).
+ *   momentsPartial/Final  per-column count / mean / M2 of the result block (Chan's pairwise combination), the per-GPU half of the
+ *                       dispersion statistics.
+ * The model block is staged in shared memory once per CTA; RK stage derivatives live in per-thread local memory.
  */
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -25,17 +32,34 @@ using namespace mlb;
 
 #define MLB_BLOCK 128               /* threads per CTA of the small helper kernels */
 #define MLB_K_SLOTS_MAX 14          /* RK78: 13 stages + first-same-as-last */
-/* The integrate kernel is built for three CTA shapes. Larger CTAs make larger convoys (see mlb_integrate.cuh) and more lanes per SM;
-   registers per lane shrink accordingly (255 / 128 / 64). mlb_run picks the shape with the fewest (waves x wave time). */
-#define MLB_NUM_SHAPES 3
-static const int kShapeBlock[MLB_NUM_SHAPES] = { 128, 512, 1024 };
-#ifdef MLB_TUNE_SHAPES
-#define MLB_EXTRA_SHAPES(X) X(256) X(384) X(640) X(768) X(896)
-#else
-#define MLB_EXTRA_SHAPES(X)
+/* The free-flight kernel is built for three CTA shapes. Larger CTAs make larger convoys (see mlb_integrate.cuh) and more lanes per SM;
+   registers per lane shrink accordingly (255 / 128 / 64). mlb_run picks the largest shape that still gives every SM a CTA. */
+#ifndef MLB_CHUTE_BLOCK
+#define MLB_CHUTE_BLOCK 128         /* under-chute kernel: CTA size and CTAs per SM (registers per lane = 65536 / (block x CTAs)) */
+#endif
+#ifndef MLB_CHUTE_CTAS
+#define MLB_CHUTE_CTAS 4
+#endif
+#ifndef MLB_GENERATIONS
+#define MLB_GENERATIONS 6           /* launches of the free-flight kernel per run; the last one runs its lanes to the end */
 #endif
 #define TRACE_W 16
 #define MLB_NCOUNTERS 6
+
+/* A lane between two launches. Everything the time loop carries from step to step. */
+struct LaneRec {
+    Lane L;
+    double k0[12];                  /* first-same-as-last derivative (slot 0 of the stage store) */
+    double dt, finalDt;
+    double apogee, maxSpeed, maxH;  /* RocketFlight reductions (rocketFlight.py:27-50), kept as running values */
+    V3 prevPos, lastPos;
+    long long rows, traceStride;    /* flight log */
+    int st;
+    int flags;                      /* REC_* */
+};
+#define REC_END 1
+#define REC_HAVE_FINAL 2
+#define REC_PRE_DONE 4              /* left the free-flight kernel after the first half of Rocket.timeStep (see rocketTimeStep) */
 
 struct RunArgs {
     const double* blob; int blobLen; int blobPad; int nSlots;
@@ -44,6 +68,12 @@ struct RunArgs {
     uint32_t* mt;
     double* trace; long long traceLane, traceCount, traceMaxRows, traceEvery; long long* traceRows;     /* flight log of lanes [traceLane, traceLane + traceCount) */
     const double* dtReplay; long long nReplay;
+    LaneRec* recs;
+    /* lane queues: entries are lane indices. qIn == nullptr: the identity over [0, nLanes) */
+    const int* qIn; const int* qInCount;
+    int* qNext; int* qNextCount;          /* stragglers of this generation (free flight) */
+    int* qChute; int* qChuteCount;        /* lanes whose first parachute has opened */
+    int bailPermille;                     /* a free-flight CTA retires when fewer than this share of its initial lanes are still flying; 0: never */
 };
 
 /* One row of a lane's flight log (RocketFlight.times / rigidBodyStates, IO/rocketFlight.py:12-25). The log keeps every `stride`-th
@@ -67,64 +97,43 @@ __device__ __noinline__ void traceRow(const RunArgs& a, double* base, const Lane
     T[14] = dt; T[15] = err; rows++;
 }
 
-template <int BLOCK, int MIN_BLOCKS>
-__global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) integrateLanes(const RunArgs a) {
+MLB_DEV bool laneTraced(const RunArgs& a, long long lane) { return a.trace != nullptr && lane >= a.traceLane && lane < a.traceLane + a.traceCount; }
+
+/* Lane prologue: Simulation.__init__ .. the first endDetector call of Simulation.run (SingleSimulations.py:89-101). */
+__global__ void __launch_bounds__(MLB_BLOCK) initLanes(const RunArgs a) {
     extern __shared__ double smem[];
     double* B = smem;
     for (int i = threadIdx.x; i < a.blobLen; i += blockDim.x) B[i] = a.blob[i];
     __syncthreads();
     const long long lane = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool inRange = lane < a.in.nLanes;          /* out-of-range threads stay: they take part in the CTA's barriers */
-    /* RK stage derivatives: per-thread local memory (L1-resident, hardware-interleaved across the warp), indexed
-       dynamically by the tableau loops */
-    double kLocal[MLB_K_SLOTS_MAX * 12];
-    KStore ks; ks.base = kLocal; ks.stride = 1;
-
+    if (lane >= a.in.nLanes) return;
+    LaneRec& R = a.recs[lane];
     Lane L;
-    laneInit(B, L, a.in, inRange ? lane : 0, inRange ? a.mt : nullptr, inRange);
+    laneInit(B, L, a.in, lane, a.mt, true);
     L.G = a.blob;
-    double dt = B[H_DT0];
-    double apogee = -10000000, maxSpeed = 0, maxH = 0;
-    V3 prevPos = L.s.pos, lastPos = L.s.pos;
-    const long long maxSteps = (long long)B[H_MAX_STEPS];
-    int st = ST_OK;
-    const bool tracing = (a.trace != nullptr && inRange && lane >= a.traceLane && lane < a.traceLane + a.traceCount);
-    double* const traceBase = tracing ? a.trace + (size_t)(lane - a.traceLane) * a.traceMaxRows * TRACE_W : nullptr;
-    long long rows = 0, traceStride = a.traceEvery > 0 ? a.traceEvery : 1;
+    R.dt = B[H_DT0]; R.finalDt = 0;
+    R.apogee = -10000000; R.maxSpeed = 0; R.maxH = 0;
+    R.prevPos = L.s.pos; R.lastPos = L.s.pos;
+    R.st = ST_OK;
+    if (L.s.pos.z > R.apogee) R.apogee = L.s.pos.z;
+    R.maxSpeed = fmax(R.maxSpeed, len(L.s.vel));
+    R.maxH = fmax(R.maxH, sqrt(L.s.vel.x * L.s.vel.x + L.s.vel.y * L.s.vel.y));
+    long long rows = 0, stride = a.traceEvery > 0 ? a.traceEvery : 1;
+    if (laneTraced(a, lane)) traceRow(a, a.trace + (size_t)(lane - a.traceLane) * a.traceMaxRows * TRACE_W, L, rows, stride, 0.0, 0.0, false);
+    R.rows = rows; R.traceStride = stride;
+    bool end, haveFinal; double finalDt;
+    endDetector(B, L, R.dt, end, haveFinal, finalDt);
+    R.finalDt = finalDt;
+    R.flags = (end ? REC_END : 0) | (haveFinal ? REC_HAVE_FINAL : 0);
+    for (int k = 0; k < 12; k++) R.k0[k] = 0;
+    R.L = L;
+}
 
-    /* RocketFlight reductions (rocketFlight.py:27-50), kept as running values */
-    if (L.s.pos.z > apogee) apogee = L.s.pos.z;
-    maxSpeed = fmax(maxSpeed, len(L.s.vel));
-    maxH = fmax(maxH, sqrt(L.s.vel.x * L.s.vel.x + L.s.vel.y * L.s.vel.y));
-    if (tracing) traceRow(a, traceBase, L, rows, traceStride, 0.0, 0.0, false);
-
-    bool end = true, haveFinal = false; double finalDt = 0;
-    if (inRange) endDetector(B, L, dt, end, haveFinal, finalDt);
-    while (MLB_ANY(!end)) {                                                                 /* SingleSimulations.py:102-139 */
-        const bool run = !end;
-        if (run) {
-            if (haveFinal) dt = finalDt;
-            if (a.dtReplay && L.nSteps < a.nReplay) dt = a.dtReplay[L.nSteps];
-        }
-        StepResult r = rocketTimeStep(B, a.blob, L, ks, dt, run);
-        if (run) {
-            dt = r.dt * r.factor;
-            prevPos = lastPos; lastPos = L.s.pos;
-            if (L.s.pos.z > apogee) apogee = L.s.pos.z;
-            double sp = len(L.s.vel); if (sp > maxSpeed) maxSpeed = sp;
-            double hv = sqrt(L.s.vel.x * L.s.vel.x + L.s.vel.y * L.s.vel.y); if (hv > maxH) maxH = hv;
-            if (!(L.s.pos.z == L.s.pos.z) || !(L.s.vel.x == L.s.vel.x)) { st = ST_NAN; end = true; }
-            else if (L.nSteps >= maxSteps) { st = ST_STEP_LIMIT; end = true; }
-            else endDetector(B, L, dt, end, haveFinal, finalDt);
-            if (tracing) traceRow(a, traceBase, L, rows, traceStride, r.dt, r.err, end);
-        }
-    }
-    if (!inRange) return;
-
-    /* RocketFlight.getLandingLocation (rocketFlight.py:52-76): linear extrapolation of the last two positions to z = 0 */
+/* RocketFlight.getLandingLocation (rocketFlight.py:52-76) and the other per-flight outputs */
+MLB_DEV void finishLane(const RunArgs& a, long long lane, const Lane& L, V3 prevPos, V3 lastPos, double apogee, double maxSpeed, double maxH, int st, long long rows) {
     double* R = a.results + lane * RES_SIZE;
     double dz = lastPos.z - prevPos.z;
-    if (L.nSteps >= 1 && lastPos.z > dz * 2) {
+    if (L.nSteps >= 1 && lastPos.z > dz * 2) {                /* linear extrapolation of the last two positions to z = 0 */
         double dxdz = (lastPos.x - prevPos.x) / dz, dydz = (lastPos.y - prevPos.y) / dz;
         double dzLand = -lastPos.z;
         R[RES_LAND_X] = lastPos.x + dxdz * dzLand; R[RES_LAND_Y] = lastPos.y + dydz * dzLand; R[RES_LAND_Z] = 0.0;
@@ -136,7 +145,116 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) integrateLanes(const RunArg
     a.status[lane] = st;
     long long* cn = a.counters + lane * MLB_NCOUNTERS;
     cn[0] = L.nSteps; cn[1] = L.nEvals; cn[2] = L.nRejects; cn[3] = L.nSteps3; cn[4] = L.nEvals3; cn[5] = L.nEvalsTransonic;
-    if (tracing) a.traceRows[lane - a.traceLane] = rows;
+    if (laneTraced(a, lane)) a.traceRows[lane - a.traceLane] = rows;
+}
+
+/* The Simulation.run loop (SingleSimulations.py:102-139) of one flight phase. PH 0: free flight, convoy execution, CTA-uniform control
+   flow (out-of-range and finished threads stay and keep the barriers company). PH 1: under parachute, every thread on its own. */
+template <int PH, bool CONVOY>
+MLB_DEV void flightLoop(const RunArgs& a, const double* B) {
+    const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long count = a.qIn ? (long long)*a.qInCount : a.in.nLanes;
+    if ((long long)blockIdx.x * blockDim.x >= count) return;          /* CTA-uniform: nothing queued for this CTA */
+    const bool inRange = slot < count;
+    const long long lane = inRange ? (a.qIn ? (long long)a.qIn[slot] : slot) : 0;
+    /* RK stage derivatives: per-thread local memory, indexed dynamically by the tableau loops */
+    double kLocal[MLB_K_SLOTS_MAX * (PH == 1 ? 6 : 12)];
+    KStore ks; ks.base = kLocal; ks.slotStride = (PH == 1 ? 6 : 12);
+
+    LaneRec* const rec = a.recs + lane;
+    Lane L;
+    double dt = 0, finalDt = 0, apogee = 0, maxSpeed = 0, maxH = 0;
+    V3 prevPos = v3(0, 0, 0), lastPos = v3(0, 0, 0);
+    long long rows = 0, traceStride = 1;
+    int st = ST_OK;
+    bool end = true, haveFinal = false, skipPre = false, left = false;
+    if (inRange) {
+        L = rec->L;
+        dt = rec->dt; finalDt = rec->finalDt; apogee = rec->apogee; maxSpeed = rec->maxSpeed; maxH = rec->maxH;
+        prevPos = rec->prevPos; lastPos = rec->lastPos; rows = rec->rows; traceStride = rec->traceStride; st = rec->st;
+        end = (rec->flags & REC_END) != 0; haveFinal = (rec->flags & REC_HAVE_FINAL) != 0; skipPre = (rec->flags & REC_PRE_DONE) != 0;
+        if (L.haveCache) for (int k = 0; k < (PH == 1 ? 6 : 12); k++) kLocal[k] = rec->k0[k];
+        L.G = a.blob;
+    } else L.forceRK4 = false;          /* threads past the end of the queue only keep the barriers company: the one lane field that path reads */
+    const bool tracing = inRange && laneTraced(a, lane);
+    double* const traceBase = tracing ? a.trace + (size_t)(lane - a.traceLane) * a.traceMaxRows * TRACE_W : nullptr;
+    const long long maxSteps = (long long)B[H_MAX_STEPS];
+
+    int bailBelow = 0;
+    if (CONVOY && a.bailPermille > 0) {
+        const long long inCta = min((long long)blockDim.x, count - (long long)blockIdx.x * blockDim.x);
+        bailBelow = (int)((inCta * a.bailPermille + 999) / 1000);
+    }
+    for (;;) {
+        const bool run = !end && !left;
+        if (CONVOY) { const int flying = __syncthreads_count(run); if (flying == 0 || flying < bailBelow) break; }
+        else if (!run) break;
+        if (run && !skipPre) {
+            if (haveFinal) dt = finalDt;
+            if (a.dtReplay && L.nSteps < a.nReplay) dt = a.dtReplay[L.nSteps];
+        }
+        StepResult r = rocketTimeStep<PH, CONVOY>(B, a.blob, L, ks, dt, run, skipPre, left);
+        skipPre = false;
+        if (run && !left) {
+            dt = r.dt * r.factor;
+            prevPos = lastPos; lastPos = L.s.pos;
+            if (L.s.pos.z > apogee) apogee = L.s.pos.z;
+            double sp = len(L.s.vel); if (sp > maxSpeed) maxSpeed = sp;
+            double hv = sqrt(L.s.vel.x * L.s.vel.x + L.s.vel.y * L.s.vel.y); if (hv > maxH) maxH = hv;
+            if (!(L.s.pos.z == L.s.pos.z) || !(L.s.vel.x == L.s.vel.x)) { st = ST_NAN; end = true; }
+            else if (L.nSteps >= maxSteps) { st = ST_STEP_LIMIT; end = true; }
+            else endDetector(B, L, dt, end, haveFinal, finalDt);
+            if (tracing) traceRow(a, traceBase, L, rows, traceStride, r.dt, r.err, end);
+        }
+    }
+
+    /* hand-over: finished lanes write their results; the others go back to HBM and into the queue of the kernel that continues them */
+    const bool toChute = inRange && !end && left;
+    const bool toNext = inRange && !end && !left;
+    if (inRange && end) finishLane(a, lane, L, prevPos, lastPos, apogee, maxSpeed, maxH, st, rows);
+    if (toChute || toNext) {
+        rec->L = L;
+        rec->dt = dt; rec->finalDt = finalDt; rec->apogee = apogee; rec->maxSpeed = maxSpeed; rec->maxH = maxH;
+        rec->prevPos = prevPos; rec->lastPos = lastPos; rec->rows = rows; rec->traceStride = traceStride; rec->st = st;
+        rec->flags = (haveFinal ? REC_HAVE_FINAL : 0) | (left ? REC_PRE_DONE : 0);
+        if (L.haveCache) for (int k = 0; k < (PH == 1 ? 6 : 12); k++) rec->k0[k] = kLocal[k];
+    }
+    if (CONVOY) {
+        /* one atomic per CTA and queue: warp ballots, then the warp totals through shared memory */
+        __shared__ int warpBase[2][32];
+        __shared__ int ctaBase[2];
+        const int w = threadIdx.x >> 5, ln = threadIdx.x & 31, nWarps = (blockDim.x + 31) >> 5;
+        const unsigned mNext = __ballot_sync(0xffffffffu, toNext), mChute = __ballot_sync(0xffffffffu, toChute);
+        if (ln == 0) { warpBase[0][w] = __popc(mNext); warpBase[1][w] = __popc(mChute); }
+        __syncthreads();
+        if (threadIdx.x < 2) {
+            int sum = 0;
+            for (int i = 0; i < nWarps; i++) { int c = warpBase[threadIdx.x][i]; warpBase[threadIdx.x][i] = sum; sum += c; }
+            int* counter = threadIdx.x == 0 ? a.qNextCount : a.qChuteCount;
+            ctaBase[threadIdx.x] = (sum > 0 && counter) ? atomicAdd(counter, sum) : 0;
+        }
+        __syncthreads();
+        const unsigned below = (1u << ln) - 1u;
+        if (toNext && a.qNext) a.qNext[ctaBase[0] + warpBase[0][w] + __popc(mNext & below)] = (int)lane;
+        if (toChute && a.qChute) a.qChute[ctaBase[1] + warpBase[1][w] + __popc(mChute & below)] = (int)lane;
+    }
+}
+
+template <int BLOCK, int MIN_BLOCKS>
+__global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) flightLanes(const RunArgs a) {
+    extern __shared__ double smem[];
+    double* B = smem;
+    for (int i = threadIdx.x; i < a.blobLen; i += blockDim.x) B[i] = a.blob[i];
+    __syncthreads();
+    flightLoop<0, true>(a, B);
+}
+
+__global__ void __launch_bounds__(MLB_CHUTE_BLOCK, MLB_CHUTE_CTAS) chuteLanes(const RunArgs a) {
+    extern __shared__ double smem[];
+    double* B = smem;
+    for (int i = threadIdx.x; i < a.blobLen; i += blockDim.x) B[i] = a.blob[i];
+    __syncthreads();
+    flightLoop<1, false>(a, B);
 }
 
 
@@ -158,7 +276,7 @@ __global__ void __launch_bounds__(MLB_BLOCK) forceEvalKernel(const double* blob,
     s.q = q4(s13[6], s13[7], s13[8], s13[9]); s.w = v3(s13[10], s13[11], s13[12]);
     ForceProbe p; Inertia inertia; double massSum;
     p.Mach = 0; p.density = 0; p.wind = v3(0, 0, 0);
-    ForceMoment f = appliedForce(B, L, times[i], s, false, inertia, massSum, &p);
+    ForceMoment f = appliedForce<0>(B, L, times[i], s, inertia, massSum, &p);
     double* o = out + 18 * i;
     o[0] = f.force.x; o[1] = f.force.y; o[2] = f.force.z; o[3] = f.moment.x; o[4] = f.moment.y; o[5] = f.moment.z;
     o[6] = p.aero.force.x; o[7] = p.aero.force.y; o[8] = p.aero.force.z; o[9] = p.Mach; o[10] = p.density;
@@ -219,36 +337,60 @@ struct mlb_handle {
     std::vector<double> blob;
     double* d_blob = nullptr;
     long long nLanes = 0;
+    long long capLanes = 0;             /* lanes the per-lane device buffers below are sized for (kept across mlb_set_lanes calls) */
     double* d_lane[LANE_NUM_ARRAYS] = { nullptr, nullptr, nullptr, nullptr };
-    bool ownLane[LANE_NUM_ARRAYS] = { false, false, false, false };
+    size_t laneBytes[LANE_NUM_ARRAYS] = { 0, 0, 0, 0 };        /* capacity of the library-owned copies */
+    double* d_laneOwned[LANE_NUM_ARRAYS] = { nullptr, nullptr, nullptr, nullptr };
     bool ownResults = true;
     double* d_results = nullptr; double* d_finals = nullptr; int* d_status = nullptr; long long* d_counters = nullptr;
+    double* d_resultsOwned = nullptr; int* d_statusOwned = nullptr;
     uint32_t* d_mt = nullptr;
+    LaneRec* d_recs = nullptr;
+    int* d_queue[3] = { nullptr, nullptr, nullptr };      /* two straggler queues (ping-pong) and the under-chute queue */
+    int* d_queueCount = nullptr;                          /* MLB_GENERATIONS + 1 counters */
     double* d_trace = nullptr; long long traceLane = -1, traceCount = 0, traceMaxRows = 0, traceEvery = 1; long long* d_traceRows = nullptr;
     double* d_replay = nullptr; long long nReplay = 0;
     double* d_partials = nullptr; double* d_moments = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evFlight0 = nullptr, evFlight1 = nullptr;
     cudaStream_t stream = nullptr;
     bool ran = false;
     long long launches = 0;
     int nSlots = 0; size_t smemBytes = 0;
-    int nSM = 148; int forceBlock = 0; int lastBlock = 0;
+    int nSM = 148; int forceBlock = 0; int lastBlock = 0; int bailPermille = 500; int generations = MLB_GENERATIONS;
     size_t sharedLen = 0;
 };
 
 static int laneArrayComponents(int id) { return id == LANE_WIND ? 3 : (id == LANE_INIT_STATE ? 13 : (id == LANE_PINK_SEED ? 3 : (id == LANE_MOTOR_ADJUST ? 2 * MLB_MAX_STAGES : -1))); }
 
 static void freeLanes(mlb_handle* h) {
-    for (int i = 0; i < LANE_NUM_ARRAYS; i++) { if (h->ownLane[i] && h->d_lane[i]) cudaFree(h->d_lane[i]); h->d_lane[i] = nullptr; h->ownLane[i] = false; }
-    if (h->ownResults) { cudaFree(h->d_results); cudaFree(h->d_status); }
-    h->ownResults = true;
-    cudaFree(h->d_finals); cudaFree(h->d_counters); cudaFree(h->d_mt);
-    h->d_results = h->d_finals = nullptr; h->d_status = nullptr; h->d_counters = nullptr; h->d_mt = nullptr;
-    h->nLanes = 0; h->ran = false;
+    for (int i = 0; i < LANE_NUM_ARRAYS; i++) { cudaFree(h->d_laneOwned[i]); h->d_laneOwned[i] = nullptr; h->laneBytes[i] = 0; h->d_lane[i] = nullptr; }
+    cudaFree(h->d_resultsOwned); cudaFree(h->d_statusOwned);
+    h->d_resultsOwned = nullptr; h->d_statusOwned = nullptr; h->ownResults = true;
+    cudaFree(h->d_finals); cudaFree(h->d_counters); cudaFree(h->d_mt); cudaFree(h->d_recs);
+    for (int i = 0; i < 3; i++) { cudaFree(h->d_queue[i]); h->d_queue[i] = nullptr; }
+    h->d_results = h->d_finals = nullptr; h->d_status = nullptr; h->d_counters = nullptr; h->d_mt = nullptr; h->d_recs = nullptr;
+    h->nLanes = 0; h->capLanes = 0; h->ran = false;
 }
 
 extern "C" const char* mlb_last_error(void) { return g_err.c_str(); }
-extern "C" const char* mlb_version(void) { return "mapleaf_b200 0.1 (sm_100a)"; }
+extern "C" const char* mlb_version(void) { return "mapleaf_b200 0.2 (sm_100a)"; }
+
+static int createOnDevice(mlb_handle* h, const double* b, size_t len) {
+    CU(cudaMalloc(&h->d_blob, len * sizeof(double)));
+    CU(cudaMemcpy(h->d_blob, b, len * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaFuncSetAttribute(flightLanes<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
+    CU(cudaFuncSetAttribute(flightLanes<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
+    CU(cudaFuncSetAttribute(flightLanes<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
+    CU(cudaFuncSetAttribute(chuteLanes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
+    CU(cudaFuncSetAttribute(initLanes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
+    CU(cudaFuncSetAttribute(forceEvalKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
+    { cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, h->device)); h->nSM = prop.multiProcessorCount; }
+    CU(cudaEventCreate(&h->ev0)); CU(cudaEventCreate(&h->ev1)); CU(cudaEventCreate(&h->evFlight0)); CU(cudaEventCreate(&h->evFlight1));
+    CU(cudaMalloc(&h->d_partials, 148 * 15 * sizeof(double)));
+    CU(cudaMalloc(&h->d_moments, 15 * sizeof(double)));
+    CU(cudaMalloc(&h->d_queueCount, (MLB_GENERATIONS + 2) * sizeof(int)));
+    return MLB_OK;
+}
 
 extern "C" int mlb_create(const void* model_blob, size_t n, int device, mlb_handle** out) {
     if (!model_blob || !out || n < H_SIZE * sizeof(double) || n % sizeof(double)) return fail(MLB_ERR_ARG, "mlb_create: model block missing or too short");
@@ -272,18 +414,12 @@ extern "C" int mlb_create(const void* model_blob, size_t n, int device, mlb_hand
     h->sharedLen = (size_t)b[H_SHARED_LEN] > 0 && (size_t)b[H_SHARED_LEN] <= len ? (size_t)b[H_SHARED_LEN] : len;      /* the rest stays in global memory */
     size_t blobPad = (h->sharedLen + 1) & ~(size_t)1;
     h->smemBytes = blobPad * sizeof(double);
-    if (h->smemBytes > 227 * 1024) { delete h; return fail(MLB_ERR_UNSUPPORTED, "mlb_create: model block + stage storage exceed shared memory"); }
-    CU(cudaMalloc(&h->d_blob, len * sizeof(double)));
-    CU(cudaMemcpy(h->d_blob, b, len * sizeof(double), cudaMemcpyHostToDevice));
-    CU(cudaFuncSetAttribute(integrateLanes<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
-    CU(cudaFuncSetAttribute(integrateLanes<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
-    CU(cudaFuncSetAttribute(integrateLanes<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
-    { cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, device)); h->nSM = prop.multiProcessorCount; }
+    if (h->smemBytes > 226 * 1024) { delete h; return fail(MLB_ERR_UNSUPPORTED, "mlb_create: the shared part of the model block exceeds shared memory"); }
     { const char* e = getenv("MLB_BLOCK_SIZE"); h->forceBlock = e ? atoi(e) : 0; }
-    CU(cudaFuncSetAttribute(forceEvalKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(blobPad * sizeof(double))));
-    CU(cudaEventCreate(&h->ev0)); CU(cudaEventCreate(&h->ev1));
-    CU(cudaMalloc(&h->d_partials, 148 * 15 * sizeof(double)));
-    CU(cudaMalloc(&h->d_moments, 15 * sizeof(double)));
+    { const char* e = getenv("MLB_BAIL_PERMILLE"); if (e) h->bailPermille = atoi(e); }
+    { const char* e = getenv("MLB_NUM_GENERATIONS"); if (e) { int g = atoi(e); if (g >= 1 && g <= MLB_GENERATIONS) h->generations = g; } }
+    int rc = createOnDevice(h, b, len);
+    if (rc != MLB_OK) { mlb_destroy(h); return rc; }       /* g_err keeps the message of the failed call */
     *out = h;
     return MLB_OK;
 }
@@ -292,41 +428,71 @@ extern "C" void mlb_destroy(mlb_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     freeLanes(h);
-    cudaFree(h->d_blob); cudaFree(h->d_trace); cudaFree(h->d_traceRows); cudaFree(h->d_replay); cudaFree(h->d_partials); cudaFree(h->d_moments);
+    cudaFree(h->d_blob); cudaFree(h->d_trace); cudaFree(h->d_traceRows); cudaFree(h->d_replay); cudaFree(h->d_partials); cudaFree(h->d_moments); cudaFree(h->d_queueCount);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->evFlight0) cudaEventDestroy(h->evFlight0);
+    if (h->evFlight1) cudaEventDestroy(h->evFlight1);
     delete h;
+}
+
+/* Per-lane device buffers are sized once for the largest batch seen and kept: a Monte Carlo driver that calls mlb_set_lanes with a
+   fresh sample block of the same size every pass re-uses them (at 10^6 lanes the generator states alone are 7.5 GB). */
+static int reserveLanes(mlb_handle* h, long long nLanes) {
+    if (nLanes <= h->capLanes) return MLB_OK;
+    cudaFree(h->d_resultsOwned); cudaFree(h->d_statusOwned); cudaFree(h->d_finals); cudaFree(h->d_counters); cudaFree(h->d_mt); cudaFree(h->d_recs);
+    for (int i = 0; i < 3; i++) { cudaFree(h->d_queue[i]); h->d_queue[i] = nullptr; }
+    h->d_resultsOwned = nullptr; h->d_statusOwned = nullptr; h->d_finals = nullptr; h->d_counters = nullptr; h->d_mt = nullptr; h->d_recs = nullptr;
+    h->capLanes = 0;
+    if (nLanes > 0x7fffffffLL) return fail(MLB_ERR_UNSUPPORTED, "mlb_set_lanes: more than 2^31 - 1 lanes per handle");
+    CU(cudaMalloc(&h->d_resultsOwned, (size_t)nLanes * RES_SIZE * sizeof(double)));
+    CU(cudaMalloc(&h->d_finals, (size_t)nLanes * FIN_SIZE * sizeof(double)));
+    CU(cudaMalloc(&h->d_statusOwned, (size_t)nLanes * sizeof(int)));
+    CU(cudaMalloc(&h->d_counters, (size_t)nLanes * MLB_NCOUNTERS * sizeof(long long)));
+    CU(cudaMalloc(&h->d_recs, (size_t)nLanes * sizeof(LaneRec)));
+    for (int i = 0; i < 3; i++) CU(cudaMalloc(&h->d_queue[i], (size_t)nLanes * sizeof(int)));
+    int turb = (int)h->blob[H_TURB];
+    if (turb >= TURB_PINK1D && turb <= TURB_PINK3D) CU(cudaMalloc(&h->d_mt, (size_t)nLanes * 3 * 624 * sizeof(uint32_t)));
+    h->capLanes = nLanes;
+    return MLB_OK;
 }
 
 static int setLanes(mlb_handle* h, int64_t nLanes, const double* const* arrays, const int* ids, int nArrays, bool onDevice) {
     if (!h) return fail(MLB_ERR_ARG, "null handle");
     if (nLanes <= 0) return fail(MLB_ERR_ARG, "mlb_set_lanes: nLanes must be positive");
     if (nArrays < 0 || (nArrays > 0 && (!arrays || !ids))) return fail(MLB_ERR_ARG, "mlb_set_lanes: array list missing");
-    CU(cudaSetDevice(h->device));
-    freeLanes(h);
-    h->nLanes = nLanes;
     for (int k = 0; k < nArrays; k++) {
-        int comps = laneArrayComponents(ids[k]);
-        if (comps < 0) return fail(MLB_ERR_ARG, "mlb_set_lanes: unknown array id");
+        if (laneArrayComponents(ids[k]) < 0) return fail(MLB_ERR_ARG, "mlb_set_lanes: unknown array id");
         if (!arrays[k]) return fail(MLB_ERR_ARG, "mlb_set_lanes: null array");
-        if (onDevice) { h->d_lane[ids[k]] = (double*)arrays[k]; h->ownLane[ids[k]] = false; }
-        else {
-            size_t bytes = (size_t)comps * nLanes * sizeof(double);
-            CU(cudaMalloc(&h->d_lane[ids[k]], bytes));
-            h->ownLane[ids[k]] = true;
-            CU(cudaMemcpy(h->d_lane[ids[k]], arrays[k], bytes, cudaMemcpyHostToDevice));
-        }
     }
-    CU(cudaMalloc(&h->d_results, (size_t)nLanes * RES_SIZE * sizeof(double)));
-    CU(cudaMalloc(&h->d_finals, (size_t)nLanes * FIN_SIZE * sizeof(double)));
-    CU(cudaMalloc(&h->d_status, (size_t)nLanes * sizeof(int)));
-    CU(cudaMalloc(&h->d_counters, (size_t)nLanes * MLB_NCOUNTERS * sizeof(long long)));
-    int turb = (int)h->blob[H_TURB];
-    if (turb >= TURB_PINK1D && turb <= TURB_PINK3D) CU(cudaMalloc(&h->d_mt, (size_t)nLanes * 3 * 624 * sizeof(uint32_t)));
+    CU(cudaSetDevice(h->device));
+    h->nLanes = 0; h->ran = false;                         /* the handle has no runnable batch until everything below has succeeded */
+    int rc = reserveLanes(h, nLanes);
+    if (rc != MLB_OK) { freeLanes(h); return rc; }
+    for (int i = 0; i < LANE_NUM_ARRAYS; i++) h->d_lane[i] = nullptr;
+    for (int k = 0; k < nArrays; k++) {
+        const int id = ids[k];
+        if (onDevice) { h->d_lane[id] = (double*)arrays[k]; continue; }
+        size_t bytes = (size_t)laneArrayComponents(id) * nLanes * sizeof(double);
+        if (bytes > h->laneBytes[id]) {
+            cudaFree(h->d_laneOwned[id]); h->d_laneOwned[id] = nullptr; h->laneBytes[id] = 0;
+            cudaError_t e = cudaMalloc(&h->d_laneOwned[id], bytes);
+            if (e != cudaSuccess) { freeLanes(h); return fail(MLB_ERR_CUDA, std::string("mlb_set_lanes: cudaMalloc: ") + cudaGetErrorString(e)); }
+            h->laneBytes[id] = bytes;
+        }
+        cudaError_t e = cudaMemcpy(h->d_laneOwned[id], arrays[k], bytes, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { freeLanes(h); return fail(MLB_ERR_CUDA, std::string("mlb_set_lanes: cudaMemcpy: ") + cudaGetErrorString(e)); }
+        h->d_lane[id] = h->d_laneOwned[id];
+    }
+    h->d_results = h->d_resultsOwned; h->d_status = h->d_statusOwned; h->ownResults = true;
+    h->nLanes = nLanes;
     return MLB_OK;
 }
 extern "C" int mlb_set_lanes(mlb_handle* h, int64_t nLanes, const double* const* arrays, const int* ids, int nArrays) { return setLanes(h, nLanes, arrays, ids, nArrays, false); }
 extern "C" int mlb_set_lanes_device(mlb_handle* h, int64_t nLanes, const double* const* arrays, const int* ids, int nArrays) { return setLanes(h, nLanes, arrays, ids, nArrays, true); }
+
+template <int BLOCK, int MIN_BLOCKS>
+static void launchFlight(const RunArgs& a, unsigned grid, size_t smem, cudaStream_t s) { flightLanes<BLOCK, MIN_BLOCKS><<<grid, BLOCK, smem, s>>>(a); }
 
 extern "C" int mlb_run(mlb_handle* h, void* stream) {
     if (!h) return fail(MLB_ERR_ARG, "null handle");
@@ -342,37 +508,42 @@ extern "C" int mlb_run(mlb_handle* h, void* stream) {
     a.traceLane = h->traceLane; a.traceCount = h->traceCount; a.traceMaxRows = h->traceMaxRows; a.traceEvery = h->traceEvery; a.traceRows = h->d_traceRows;
     if (a.trace) CU(cudaMemsetAsync(h->d_traceRows, 0, (size_t)h->traceCount * sizeof(long long), s));
     a.dtReplay = h->d_replay; a.nReplay = h->nReplay;
-    /* CTA shape: the one with the smallest (waves of CTAs) x (measured duration of one wave of that shape). One wave of the bench
-       workload takes 0.43 / 0.52 / 0.95 s for the 128x2 / 512 / 1024 shapes and holds 256 / 512 / 1024 lanes per SM: large batches
-       want the largest convoy, a batch that leaves SMs empty in one shape may fill them in a smaller one, and a batch just over one
-       wave is better off in a larger shape than in two waves of a smaller one (10^5 lanes: 1.27 s in the 1024 shape, 1.46 s in the
-       512 shape). MLB_BLOCK_SIZE overrides, for tuning. */
-    int block = 128; double bestCost = 1e300;
-    static const double kShapeWaveTime[MLB_NUM_SHAPES] = { 0.43, 0.52, 0.95 };
-    for (int k = 0; k < MLB_NUM_SHAPES; k++) {
-        const long long ctas = (h->nLanes + kShapeBlock[k] - 1) / kShapeBlock[k];
-        const long long slots = (long long)h->nSM * (kShapeBlock[k] == 128 ? 2 : 1);
-        const double cost = (double)((ctas + slots - 1) / slots) * kShapeWaveTime[k];
-        if (cost < bestCost) { bestCost = cost; block = kShapeBlock[k]; }
-    }
+    a.recs = h->d_recs;
+    a.qIn = nullptr; a.qInCount = nullptr; a.qNext = nullptr; a.qNextCount = nullptr; a.qChute = h->d_queue[2]; a.qChuteCount = h->d_queueCount + MLB_GENERATIONS; a.bailPermille = 0;
+    /* CTA shape of the free-flight kernel: the largest convoy that still gives every SM a CTA (1024 lanes per SM at 64 registers,
+       512 at 128, 2 x 128 at 255). MLB_BLOCK_SIZE overrides, for tuning. */
+    int block = 128;
+    if (h->nLanes >= 512LL * h->nSM) block = 512;
+    if (h->nLanes >= 1024LL * h->nSM) block = 1024;
     if (h->forceBlock == 128 || h->forceBlock == 512 || h->forceBlock == 1024) block = h->forceBlock;
-#define MLB_ALLOW(N) if (h->forceBlock == N) block = N;
-    MLB_EXTRA_SHAPES(MLB_ALLOW)
     h->lastBlock = block;
-    unsigned grid = (unsigned)((h->nLanes + block - 1) / block);
-    h->launches = 1;
+    const unsigned grid = (unsigned)((h->nLanes + block - 1) / block);
+    h->launches = 0;
     CU(cudaEventRecord(h->ev0, s));
-#define MLB_LAUNCH(N) if (block == N) { cudaFuncSetAttribute(integrateLanes<N, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes); integrateLanes<N, 1><<<grid, N, h->smemBytes, s>>>(a); } else
-    MLB_EXTRA_SHAPES(MLB_LAUNCH)
-    if (block == 1024) integrateLanes<1024, 1><<<grid, 1024, h->smemBytes, s>>>(a);
-#ifdef MLB_TUNE_640X2          /* 1280 lanes per SM at 48 registers: MLB_BLOCK_SIZE=512 selects it in this build */
-    else if (block == 512) { cudaFuncSetAttribute(integrateLanes<640, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes); grid = (unsigned)((h->nLanes + 639) / 640); integrateLanes<640, 2><<<grid, 640, h->smemBytes, s>>>(a); }
-#endif
-#ifdef MLB_TUNE_512X2
-    else if (block == 512) { cudaFuncSetAttribute(integrateLanes<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes); integrateLanes<512, 2><<<grid, 512, h->smemBytes, s>>>(a); }
-#endif
-    else if (block == 512) integrateLanes<512, 1><<<grid, 512, h->smemBytes, s>>>(a);
-    else integrateLanes<128, 2><<<grid, 128, h->smemBytes, s>>>(a);
+    CU(cudaMemsetAsync(h->d_queueCount, 0, (MLB_GENERATIONS + 2) * sizeof(int), s));
+    initLanes<<<(unsigned)((h->nLanes + MLB_BLOCK - 1) / MLB_BLOCK), MLB_BLOCK, h->smemBytes, s>>>(a);
+    h->launches++;
+    CU(cudaGetLastError());
+    /* Free flight, MLB_GENERATIONS launches over ping-pong straggler queues. Every launch is sized for the whole batch (CTAs past the end
+       of their queue exit at once), so the sequence needs no host round trip. */
+    CU(cudaEventRecord(h->evFlight0, s));
+    const int G = h->generations;
+    for (int g = 0; g < G; g++) {
+        a.qIn = g == 0 ? nullptr : h->d_queue[(g - 1) & 1];
+        a.qInCount = g == 0 ? nullptr : h->d_queueCount + (g - 1);
+        a.qNext = h->d_queue[g & 1]; a.qNextCount = h->d_queueCount + g;
+        a.bailPermille = (g == G - 1) ? 0 : h->bailPermille;
+        if (block == 1024) launchFlight<1024, 1>(a, grid, h->smemBytes, s);
+        else if (block == 512) launchFlight<512, 1>(a, grid, h->smemBytes, s);
+        else launchFlight<128, 2>(a, grid, h->smemBytes, s);
+        h->launches++;
+        CU(cudaGetLastError());
+    }
+    CU(cudaEventRecord(h->evFlight1, s));
+    /* Under parachute: everything the free-flight launches queued */
+    a.qIn = h->d_queue[2]; a.qInCount = h->d_queueCount + MLB_GENERATIONS; a.qNext = nullptr; a.qNextCount = nullptr; a.qChute = nullptr; a.qChuteCount = nullptr; a.bailPermille = 0;
+    chuteLanes<<<(unsigned)((h->nLanes + MLB_CHUTE_BLOCK - 1) / MLB_CHUTE_BLOCK), MLB_CHUTE_BLOCK, h->smemBytes, s>>>(a);
+    h->launches++;
     CU(cudaGetLastError());
     CU(cudaEventRecord(h->ev1, s));
     h->ran = true;
@@ -424,9 +595,12 @@ extern "C" int mlb_counters(mlb_handle* h, mlb_counters_t* out) {
         out->steps_3dof += ci[3]; out->derivative_evals_3dof += ci[4]; out->derivative_evals_transonic += ci[5];
         if (st[i] == ST_OK) out->lanes_ok++; else if (st[i] == ST_STEP_LIMIT) out->lanes_step_limit++; else if (st[i] == ST_NAN) out->lanes_nan++;
     }
-    float ms = 0;
+    float ms = 0, msFlight = 0, msChute = 0;
     CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-    out->last_run_ms = ms; out->dominant_kernel_ms = ms; out->kernel_launches = h->launches;
+    CU(cudaEventElapsedTime(&msFlight, h->evFlight0, h->evFlight1));
+    CU(cudaEventElapsedTime(&msChute, h->evFlight1, h->ev1));
+    out->last_run_ms = ms; out->dominant_kernel_ms = msFlight; out->kernel_launches = h->launches;
+    out->chute_kernel_ms = msChute; out->flight_block = h->lastBlock; out->flight_generations = h->generations;
     return MLB_OK;
 }
 extern "C" int mlb_device_results(mlb_handle* h, void** results, void** status) {
@@ -439,7 +613,6 @@ extern "C" int mlb_set_result_buffers(mlb_handle* h, void* results, void* status
     if (!h || h->nLanes <= 0) return fail(MLB_ERR_STATE, "mlb_set_result_buffers: call mlb_set_lanes first");
     if (!results || !status) return fail(MLB_ERR_ARG, "mlb_set_result_buffers: null buffer");
     CU(cudaSetDevice(h->device));
-    if (h->ownResults) { cudaFree(h->d_results); cudaFree(h->d_status); }
     h->d_results = (double*)results; h->d_status = (int*)status; h->ownResults = false; h->ran = false;
     return MLB_OK;
 }
@@ -508,8 +681,7 @@ extern "C" int mlb_force_eval(mlb_handle* h, int64_t n, const double* states, co
     CU(cudaMemcpy(d_s, states, (size_t)n * 13 * sizeof(double), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(d_t, times, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
     if (winds) { CU(cudaMalloc(&d_w, (size_t)n * 3 * sizeof(double))); CU(cudaMemcpy(d_w, winds, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice)); }
-    size_t blobPad = (h->sharedLen + 1) & ~(size_t)1;
-    forceEvalKernel<<<(unsigned)((n + MLB_BLOCK - 1) / MLB_BLOCK), MLB_BLOCK, blobPad * sizeof(double)>>>(h->d_blob, (int)h->sharedLen, n, d_s, d_t, d_w, d_mt, d_o);
+    forceEvalKernel<<<(unsigned)((n + MLB_BLOCK - 1) / MLB_BLOCK), MLB_BLOCK, h->smemBytes>>>(h->d_blob, (int)h->sharedLen, n, d_s, d_t, d_w, d_mt, d_o);
     cudaError_t e = cudaDeviceSynchronize();
     if (e == cudaSuccess) e = cudaMemcpy(out, d_o, (size_t)n * 18 * sizeof(double), cudaMemcpyDeviceToHost);
     cudaFree(d_s); cudaFree(d_t); cudaFree(d_w); cudaFree(d_o); cudaFree(d_mt);

@@ -14,9 +14,12 @@
  * classical one sums stage derivatives weighted by 1/(1/(a dt)) and converts the sum to a rotation once; the
  * adaptive one converts every stage derivative to a rotation, composes them and rescales the composed angle.
  *
- * Stage derivatives k_i live in shared memory, one column per thread ([slot][component][thread], 8-byte
- * words of consecutive threads are consecutive: no bank conflicts), so the tableau loops can index them
- * dynamically without forcing 84+ doubles per lane into local memory.
+ * Stage derivatives k_i live in per-thread local memory (KStore: [slot][component], indexed dynamically by the
+ * tableau loops; the hardware interleaves local memory across the warp, so a slot access is coalesced).
+ *
+ * Every routine here is compiled once per flight phase (template parameter PH, see appliedForce): PH 0 is the
+ * 6-DoF free-flight code with the convoy barriers, PH 1 the 3-DoF under-chute code, which is small enough to run
+ * free (no barriers, CONVOY false).
  */
 #pragma once
 #include "mlb_model.cuh"
@@ -24,23 +27,23 @@
 namespace mlb {
 
 struct KStore {
-    double* base; int stride;
+    double* base; int slotStride;          /* 12 doubles per slot; 6 in the 3-DoF kernel, which never touches the rotational half */
     MLB_DEV void put(int slot, const Deriv& d, bool dof3) const {
-        double* p = base + (size_t)slot * 12 * stride;
-        p[0] = d.vel.x; p[stride] = d.vel.y; p[2 * stride] = d.vel.z;
-        p[3 * stride] = d.acc.x; p[4 * stride] = d.acc.y; p[5 * stride] = d.acc.z;
+        double* p = base + slot * slotStride;
+        p[0] = d.vel.x; p[1] = d.vel.y; p[2] = d.vel.z;
+        p[3] = d.acc.x; p[4] = d.acc.y; p[5] = d.acc.z;
         if (dof3) return;
-        p[6 * stride] = d.angvel.x; p[7 * stride] = d.angvel.y; p[8 * stride] = d.angvel.z;
-        p[9 * stride] = d.angacc.x; p[10 * stride] = d.angacc.y; p[11 * stride] = d.angacc.z;
+        p[6] = d.angvel.x; p[7] = d.angvel.y; p[8] = d.angvel.z;
+        p[9] = d.angacc.x; p[10] = d.angacc.y; p[11] = d.angacc.z;
     }
     MLB_DEV Deriv get(int slot, bool dof3) const {
-        const double* p = base + (size_t)slot * 12 * stride;
+        const double* p = base + slot * slotStride;
         Deriv d;
-        d.vel = v3(p[0], p[stride], p[2 * stride]);
-        d.acc = v3(p[3 * stride], p[4 * stride], p[5 * stride]);
+        d.vel = v3(p[0], p[1], p[2]);
+        d.acc = v3(p[3], p[4], p[5]);
         if (dof3) { d.angvel = v3(0, 0, 0); d.angacc = v3(0, 0, 0); return d; }
-        d.angvel = v3(p[6 * stride], p[7 * stride], p[8 * stride]);
-        d.angacc = v3(p[9 * stride], p[10 * stride], p[11 * stride]);
+        d.angvel = v3(p[6], p[7], p[8]);
+        d.angacc = v3(p[9], p[10], p[11]);
         return d;
     }
 };
@@ -76,25 +79,19 @@ MLB_DEV bool pyIsClose(double a, double b) {                                    
     return (diff <= fabs(1e-9 * b)) || (diff <= fabs(1e-9 * a));
 }
 
-/* Convoy execution. The force model is ~10^4 SASS instructions per evaluation, several times the SM's instruction
+/* Convoy execution. The 6-DoF force model is ~10^4 SASS instructions per evaluation, several times the SM's instruction
    cache, and warps that drift apart each stream it from L2 on their own (measured: 74 % of warp cycles stalled on
-   instruction fetch, ICC hit rate 46 %). With MLB_LOCKSTEP the CTA's warps re-group at a barrier before every
+   instruction fetch, ICC hit rate 46 %). In the convoy kernels the CTA's warps re-group at a barrier before every
    derivative evaluation, so one warp's fetch serves the others. All control flow around the barriers is CTA-uniform:
-   lanes that have nothing to do in a stage / attempt / step stay in the loops with `active` false. */
-#ifndef MLB_LOCKSTEP
-#define MLB_LOCKSTEP 1
-#endif
-#if MLB_LOCKSTEP
-#define MLB_CONVOY_SYNC() __syncthreads()
-#define MLB_ANY(pred) __syncthreads_or(pred)
-#else
-#define MLB_CONVOY_SYNC()
-#define MLB_ANY(pred) (pred)
-#endif
+   lanes that have nothing to do in a stage / attempt / step stay in the loops with `active` false. The under-chute
+   kernel (CONVOY false) fits the instruction cache and runs without barriers: every predicate is then the thread's own. */
+template <bool CONVOY> MLB_DEV void convoySync() { if (CONVOY) __syncthreads(); }
+template <bool CONVOY> MLB_DEV bool convoyAny(bool pred) { return CONVOY ? (__syncthreads_or(pred) != 0) : pred; }
 
 /* One Runge-Kutta step of either family. The stage loop has ONE call site of the (large) state-derivative code, shared
    by the first stage, the classical and the adaptive stage composition and the adaptive retry loop, so the force model is
    instantiated once in the kernel. `active` false: the lane only keeps the CTA's barriers company. */
+template <int PH, bool CONVOY>
 MLB_DEV StepResult integrateStep(const double* B, Lane& L, const KStore& ks, State& y, double t, double dt, bool active) {
     /* A fixed-rate control system swaps an adaptive integrator for RK4 while it is in charge (ControlSystems.py:126-135); the
        parachute switch restores the original one (rocket.py:700-726). So the method is a per-lane choice between two tableaus;
@@ -114,7 +111,7 @@ MLB_DEV StepResult integrateStep(const double* B, Lane& L, const KStore& ks, Sta
     if (adaptive) dt *= 3;                                                                  /* Integration.py:335: first attempt = requested dt */
     bool attempting = active;
     for (;;) {
-        const bool dof3 = L.dof3;
+        constexpr bool dof3 = (PH == 1);
         if (attempting && adaptive) {
             if (err != 10000000) L.nRejects++;
             dt = fmax(minDt, dt / 3);
@@ -139,11 +136,8 @@ MLB_DEV StepResult integrateStep(const double* B, Lane& L, const KStore& ks, Sta
                     }
                 }
             }
-#ifdef MLB_SYNC_STRIDE
-            if (((i + 1) % MLB_SYNC_STRIDE) == 0)
-#endif
-            MLB_CONVOY_SYNC();
-            if (evalNow) ks.put(i + 1, stateDerivative(B, L, evalTime, evalY, dof3), dof3);
+            convoySync<CONVOY>();
+            if (evalNow) ks.put(i + 1, stateDerivative<PH>(B, L, evalTime, evalY), dof3);
         }
         if (attempting) {
             if (method == INT_EULER) {                                                      /* :192-195 */
@@ -175,13 +169,13 @@ MLB_DEV StepResult integrateStep(const double* B, Lane& L, const KStore& ks, Sta
                 }
             }
         }
-        if (!MLB_ANY(attempting)) break;
+        if (!convoyAny<CONVOY>(attempting)) break;
     }
     r.dt = dt;
     if (!active || !adaptive) return r;
     /* accepted adaptive step: FSAL cache, step-size controller (:349-389) */
     if (method == INT_RK45A || method == INT_RK23A) {
-        ks.put(0, ks.get(nRows, L.dof3), L.dof3);            /* becomes k_0 of the next step (attempts never overwrite slot 0) */
+        ks.put(0, ks.get(nRows, PH == 1), PH == 1);          /* becomes k_0 of the next step (attempts never overwrite slot 0) */
         L.haveCache = true;
     }
     const double maxDt = B[H_AD_MAXDT];
@@ -376,8 +370,12 @@ MLB_DEV void railMotionConstraint(const double* B, Lane& L) {                   
     } else L.onRail = false;
 }
 
-MLB_DEV StepResult rocketTimeStep(const double* B, const double* G, Lane& L, const KStore& ks, double dt, bool active) {   /* rocket.py:658-698 */
-    if (active) {
+/* Rocket.timeStep (rocket.py:658-698) in two halves. The first (rail constraint, event detector, step clamp near events, control
+   loop) can deploy the first parachute, which turns the lane into a 3-DoF body: a lane of the free-flight kernel then leaves
+   (`left`) with the first half done and its step size already clamped, and the under-chute kernel resumes it with `skipPre`. */
+template <int PH, bool CONVOY>
+MLB_DEV StepResult rocketTimeStep(const double* B, const double* G, Lane& L, const KStore& ks, double& dt, bool active, bool skipPre, bool& left) {
+    if (active && !skipPre) {
         railMotionConstraint(B, L);
         double est; bool det;
         triggerEvents(B, L, est, det);
@@ -385,11 +383,12 @@ MLB_DEV StepResult rocketTimeStep(const double* B, const double* G, Lane& L, con
             if (det) dt = est + 1e-5;
             else dt = fmax(est / 1.5, B[H_EVENT_DT]);
         }
-        runControlSystem(B, G, L);
+        if (PH == 0) runControlSystem(B, G, L);             /* `not self.isUnderChute` (rocket.py:646-656) */
+        if (L.dof3 != (PH == 1)) { left = true; active = false; }
     }
-    StepResult r = integrateStep(B, L, ks, L.s, L.time, dt, active);
+    StepResult r = integrateStep<PH, CONVOY>(B, L, ks, L.s, L.time, dt, active);
     if (active) {
-        if (L.dof3) L.nSteps3++;
+        if (PH == 1) L.nSteps3++;
         L.time += r.dt;
         if (L.qAliased) { L.targetQ = L.s.q; L.qAliased = false; }
         L.s = r.newValue;

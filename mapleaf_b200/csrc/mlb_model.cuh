@@ -1003,17 +1003,22 @@ MLB_DEV ForceMoment launchRailForce(const double* B, const Lane& L, const State&
 
 struct ForceProbe { ForceMoment total, aero; Inertia inertia; double Mach, density; V3 wind; };
 
-MLB_DEV ForceMoment appliedForce(const double* B, Lane& L, double time, State& s, bool dof3, Inertia& inertia, double& massSum, ForceProbe* probe) {
+/* PH: the flight phase the caller is compiled for. 0 = free flight (6-DoF body, component build-up aerodynamics), 1 = under a parachute
+   (3-DoF body, recovery-system drag only: rocket.py:531-547,700-726). The two are set together by the first chute deployment
+   (deployNextRecoveryStage) and never revert, so each trajectory kernel carries only its own half of the force model. */
+template <int PH>
+MLB_DEV ForceMoment appliedForce(const double* B, Lane& L, double time, State& s, Inertia& inertia, double& massSum, ForceProbe* probe) {
+    constexpr bool dof3 = (PH == 1), underChute = (PH == 1);
     L.nEvals++;
     if (dof3) L.nEvals3++;
-    Air e = airProperties(B, L, s.pos, time, L.underChute && B[H_TURB_OFF_CHUTE] != 0);
-    if (L.underChute && B[H_TURB_OFF_CHUTE] != 0) e.wind = e.meanWind;
+    Air e = airProperties(B, L, s.pos, time, underChute && B[H_TURB_OFF_CHUTE] != 0);
+    if (underChute && B[H_TURB_OFF_CHUTE] != 0) e.wind = e.meanWind;
     if (rocketInertiaFrozen(B, L, time)) {
         if (!L.inertiaCached) { L.inertiaC = rocketInertia(B, L, time, &L.massSumC); L.inertiaCached = true; }
         inertia = L.inertiaC; massSum = L.massSumC;
     } else inertia = rocketInertia(B, L, time, &massSum);
     ForceMoment comp;
-    if (!L.underChute) {
+    if (!underChute) {
         Aero a;
         aeroSetup(B, L, a, s, e, time);
         if (a.Mach > 0.8 && a.Mach < 1.4) L.nEvalsTransonic++;
@@ -1061,10 +1066,12 @@ MLB_DEV ForceMoment appliedForce(const double* B, Lane& L, double time, State& s
     return total;
 }
 
-MLB_DEV Deriv stateDerivative(const double* B, Lane& L, double time, State& s, bool dof3) {
+template <int PH>
+MLB_DEV Deriv stateDerivative(const double* B, Lane& L, double time, State& s) {
+    constexpr bool dof3 = (PH == 1);
     Deriv d;
     Inertia inertia; double massSum;
-    ForceMoment f = appliedForce(B, L, time, s, dof3, inertia, massSum, nullptr);
+    ForceMoment f = appliedForce<PH>(B, L, time, s, inertia, massSum, nullptr);
     if (dof3) {                                                                             /* RigidBodies.py:41-47 */
         d.vel = s.vel;
         d.acc = vdiv(f.force, massSum);

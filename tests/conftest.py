@@ -59,7 +59,7 @@ def regressionCase(name):
     from mapleaf_b200 import L
     z = np.load(os.path.join(GOLDEN, "regression_blobs.npz"))
     if list(z["layoutVersion"]) != [L.MLB_VERSION, L.H_SIZE, L.FS_SIZE, L.S_SIZE, L.TA_TABLE, L.CS_SIZE]:
-        pytest.skip("regression_blobs.npz was flattened with another model-block layout: re-run tests/golden/make_regression_blobs.py")
+        pytest.fail("regression_blobs.npz was flattened with another model-block layout: re-run tests/golden/make_regression_blobs.py")
     return z[name + "/blob"], z[name + "/expected"]
 
 
