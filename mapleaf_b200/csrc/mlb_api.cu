@@ -34,6 +34,11 @@ using namespace mlb;
 #define MLB_K_SLOTS_MAX 14          /* RK78: 13 stages + first-same-as-last */
 /* The free-flight kernel is built for three CTA shapes. Larger CTAs make larger convoys (see mlb_integrate.cuh) and more lanes per SM;
    registers per lane shrink accordingly (255 / 128 / 64). mlb_run picks the largest shape that still gives every SM a CTA. */
+/* (CTA size, CTAs per SM) of every instantiation; MLB_BLOCK_SIZE selects one by its CTA size. Tuning builds replace the list:
+   a header with `#define MLB_FLIGHT_SHAPES(X) X(768,1) X(640,1)` passed with -include (tools/tune.py) */
+#ifndef MLB_FLIGHT_SHAPES
+#define MLB_FLIGHT_SHAPES(X) X(128, 2) X(512, 1) X(1024, 1)
+#endif
 #ifndef MLB_CHUTE_BLOCK
 #define MLB_CHUTE_BLOCK 128         /* under-chute kernel: CTA size and CTAs per SM (registers per lane = 65536 / (block x CTAs)) */
 #endif
@@ -378,9 +383,8 @@ extern "C" const char* mlb_version(void) { return "mapleaf_b200 0.2 (sm_100a)"; 
 static int createOnDevice(mlb_handle* h, const double* b, size_t len) {
     CU(cudaMalloc(&h->d_blob, len * sizeof(double)));
     CU(cudaMemcpy(h->d_blob, b, len * sizeof(double), cudaMemcpyHostToDevice));
-    CU(cudaFuncSetAttribute(flightLanes<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
-    CU(cudaFuncSetAttribute(flightLanes<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
-    CU(cudaFuncSetAttribute(flightLanes<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
+#define MLB_SET_SMEM(N, M) CU((cudaFuncSetAttribute(flightLanes<N, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes)));
+    MLB_FLIGHT_SHAPES(MLB_SET_SMEM)
     CU(cudaFuncSetAttribute(chuteLanes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
     CU(cudaFuncSetAttribute(initLanes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
     CU(cudaFuncSetAttribute(forceEvalKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
@@ -491,9 +495,6 @@ static int setLanes(mlb_handle* h, int64_t nLanes, const double* const* arrays, 
 extern "C" int mlb_set_lanes(mlb_handle* h, int64_t nLanes, const double* const* arrays, const int* ids, int nArrays) { return setLanes(h, nLanes, arrays, ids, nArrays, false); }
 extern "C" int mlb_set_lanes_device(mlb_handle* h, int64_t nLanes, const double* const* arrays, const int* ids, int nArrays) { return setLanes(h, nLanes, arrays, ids, nArrays, true); }
 
-template <int BLOCK, int MIN_BLOCKS>
-static void launchFlight(const RunArgs& a, unsigned grid, size_t smem, cudaStream_t s) { flightLanes<BLOCK, MIN_BLOCKS><<<grid, BLOCK, smem, s>>>(a); }
-
 extern "C" int mlb_run(mlb_handle* h, void* stream) {
     if (!h) return fail(MLB_ERR_ARG, "null handle");
     if (h->nLanes <= 0) return fail(MLB_ERR_STATE, "mlb_run: call mlb_set_lanes first");
@@ -515,7 +516,8 @@ extern "C" int mlb_run(mlb_handle* h, void* stream) {
     int block = 128;
     if (h->nLanes >= 512LL * h->nSM) block = 512;
     if (h->nLanes >= 1024LL * h->nSM) block = 1024;
-    if (h->forceBlock == 128 || h->forceBlock == 512 || h->forceBlock == 1024) block = h->forceBlock;
+#define MLB_ALLOW_SHAPE(N, M) if (h->forceBlock == N) block = N;
+    MLB_FLIGHT_SHAPES(MLB_ALLOW_SHAPE)
     h->lastBlock = block;
     const unsigned grid = (unsigned)((h->nLanes + block - 1) / block);
     h->launches = 0;
@@ -533,9 +535,8 @@ extern "C" int mlb_run(mlb_handle* h, void* stream) {
         a.qInCount = g == 0 ? nullptr : h->d_queueCount + (g - 1);
         a.qNext = h->d_queue[g & 1]; a.qNextCount = h->d_queueCount + g;
         a.bailPermille = (g == G - 1) ? 0 : h->bailPermille;
-        if (block == 1024) launchFlight<1024, 1>(a, grid, h->smemBytes, s);
-        else if (block == 512) launchFlight<512, 1>(a, grid, h->smemBytes, s);
-        else launchFlight<128, 2>(a, grid, h->smemBytes, s);
+#define MLB_LAUNCH_SHAPE(N, M) if (block == N) flightLanes<N, M><<<grid, N, h->smemBytes, s>>>(a);
+        MLB_FLIGHT_SHAPES(MLB_LAUNCH_SHAPE)
         h->launches++;
         CU(cudaGetLastError());
     }

@@ -730,6 +730,9 @@ MLB_DEV double actuatorDeflection(const double* B, const Lane& L, int i, double 
 #ifndef MLB_FIN_UNIFORM
 #define MLB_FIN_UNIFORM 1
 #endif
+#ifndef MLB_FIN_LINEAR
+#define MLB_FIN_LINEAR 1
+#endif
 MLB_COMP_FINS ForceMoment finSetForce(const double* B, const Lane& L, Aero& a, const double* C, V3 CG, double thickK) {   /* Fins.py:263-358,463-551 */
     const double Mach = a.Mach, Aref = a.Aref, q = dynamicPressure(a);
     /* drag build-up common to all fins of the set (Fins.py:289-358) */
@@ -786,7 +789,35 @@ MLB_COMP_FINS ForceMoment finSetForce(const double* B, const Lane& L, Aero& a, c
         const V3 vOuter = airVelRelativeToFin + ust * rOuter;
         const bool uniform = MLB_FIN_UNIFORM && (vOuter.x == airVelRelativeToFin.x) && (vOuter.y == airVelRelativeToFin.y) && (vOuter.z == airVelRelativeToFin.z)
                              && (C[FS_SLICE_R] <= rOuter);
-        const int nAsin = uniform ? 1 : nS;
+        /* Almost the same holds while the spin term is merely tiny next to the air speed (roll rates that grow out of rounding noise on a
+           rocket without fin cant, 1e-13 of the air speed in the bench workload): the slice angle is then its value on the axis plus a
+           term linear in the slice radius, alpha(r) = asin(b0) + r (db/dr) / sqrt(1 - b0^2) with b(r) = n.(A + U r) / |A + U r|. The
+           neglected second-order term is below (|U| r / |A|)^2 <= 1e-18 rad, under the last bit of the arcsine the reference takes per
+           slice. This is the GPU path's one departure from the reference's operation sequence in the force model; it replaces nine of
+           ten arcsine / square-root / reciprocal chains per fin, and because warps mix rolling-noise lanes with exactly non-rolling
+           ones, those chains used to run for every warp at a third of its lanes (profiles/r2a). Fin cant, real roll and stalled or
+           near-perpendicular flow take the per-slice path below. */
+        bool linear = false;
+        if (MLB_FIN_LINEAR) {                               /* exactly non-rolling lanes too: one code path for the whole warp */
+            const double m2 = dot(airVelRelativeToFin, airVelRelativeToFin), u2 = dot(ust, ust);
+            if (m2 > 0.04 && u2 * (rOuter * rOuter) < 1e-18 * m2 && C[FS_SLICE_R] >= 0 && C[FS_SLICE_R] <= rOuter) {
+                const double m0 = sqrt(m2), rm = rcpNormal(m0);
+                double b0 = dot(finNormal, airVelRelativeToFin) * rm;
+                const double c2 = 1 - b0 * b0;
+                if (c2 > 1e-4) {
+                    const double al0 = m_asin(b0);
+                    const double dbdr = (dot(finNormal, ust) - b0 * (dot(airVelRelativeToFin, ust) * rm)) * rm;
+                    const double dadr = dbdr / sqrt(c2);
+                    for (int i = 0; i < nS; i++) {
+                        double al = fma(dadr, C[FS_SLICE_R + i], al0);
+                        if (fabs(al) > stall) al *= fabs(stall / al);
+                        aoa[i] = al;
+                    }
+                    linear = true;
+                }
+            }
+        }
+        const int nAsin = linear ? 0 : (uniform ? 1 : nS);
         for (int i = 0; i < nAsin; i++) {
             V3 finVelocity = airVelRelativeToFin + ust * C[FS_SLICE_R + i];
             double finVelMag = len(finVelocity);
@@ -799,7 +830,7 @@ MLB_COMP_FINS ForceMoment finSetForce(const double* B, const Lane& L, Aero& a, c
             if (fabs(al) > stall) al *= fabs(stall / al);
             aoa[i] = al;
         }
-        if (uniform) for (int i = 1; i < nS; i++) aoa[i] = aoa[0];
+        if (uniform && !linear) for (int i = 1; i < nS; i++) aoa[i] = aoa[0];
         double nf, mom;
         if (regime == 0) finStripSubsonic(C, aoa, nS, spanwiseCP, cnA, nf, mom);
         else if (regime == 2) finStripSupersonic(C, aoa, nS, spanwiseCP, kM, nf, mom);
@@ -1066,8 +1097,16 @@ MLB_DEV ForceMoment appliedForce(const double* B, Lane& L, double time, State& s
     return total;
 }
 
+#ifndef MLB_DERIV_NOINLINE
+#define MLB_DERIV_NOINLINE 0
+#endif
+#if MLB_DERIV_NOINLINE
+#define MLB_DERIV_FN static __device__ __noinline__
+#else
+#define MLB_DERIV_FN MLB_DEV
+#endif
 template <int PH>
-MLB_DEV Deriv stateDerivative(const double* B, Lane& L, double time, State& s) {
+MLB_DERIV_FN Deriv stateDerivative(const double* B, Lane& L, double time, State& s) {
     constexpr bool dof3 = (PH == 1);
     Deriv d;
     Inertia inertia; double massSum;

@@ -1030,9 +1030,9 @@ def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000) -> Model:
         elif controller == "elementary":
             H[L.H_AD_CTRL] = L.CTRL_ELEMENTARY
             H[L.H_AD_SAFETY] = ad.getFloat("Elementary.safetyFactor")
-        elif controller == "Constant":
-            H[L.H_AD_CTRL] = L.CTRL_CONSTANT
         else:
+            # "Constant" included: the reference's integratorFactory leaves safetyFactor unbound for it and the rocket cannot be
+            # constructed (Integration.py:74-93); AdaptiveIntegrator itself raises this message for it (:352-357)
             raise ValueError("Adaptive Integrator requires non-constant step size controller such as 'PID' or 'elementary'")
         H[L.H_AD_TARGET] = ad.getFloat("targetError")
         H[L.H_AD_MINF] = ad.getFloat("minFactor")

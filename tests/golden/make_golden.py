@@ -37,6 +37,10 @@ What is recorded, and which reference code produced it:
                             like the reference's Jake1_MonteCarlo.mapleaf example
   regression_blobs.npz .... (tests/golden/make_regression_blobs.py) the reference's own flight regression cases as flattened model blocks +
                             the final values the reference records for them
+  opt_*.json .............. one short flight per option the backend accepts and no other fixture exercises: TabulatedAtmosphere
+                            (ENV/AtmosphereModelling.py:79-96), CustomWindProfile / InterpolatedWind (ENV/MeanWindModelling.py:165-196),
+                            PinkNoise1D / 3D with fixed seeds (ENV/TurbulenceModelling.py:100-131), Euler / RK2Midpoint / RK2Heun / RK4_3/8
+                            (Motion/Integration.py:144-187,189-236), RK12Adaptive / RK23Adaptive (:238-330), the `elementary` step-size controller (:359-382), ConstantGainPIDRocket (GNC/MomentControllers.py:58-83)
   rng.json ................ random.Random / PinkNoiseGenerator known answers (test_SimDefinition.py:118-151,
                             test_TurbulenceModelling.py:37-60)
 """
@@ -276,6 +280,40 @@ if __name__ == "__main__":
                                                      m + "burnTimeAdjustFactor": "1.0", m + "burnTimeAdjustFactor_stdDev": "0.10679"}, "2394781", 3,
                                             motorKeys=(m + "impulseAdjustFactor", m + "burnTimeAdjustFactor")))
     adaptive = os.path.join(MY_DATA, "MonteCarloAdaptive.mapleaf")
+    if "options" in which:
+        envDir = os.path.join(REPO, "mapleaf_b200", "data", "Environment")
+        wind = {"Environment.ConstantMeanWind.velocity": "(4 -2.5 0.3)"}
+        # The reference's TabulatedAtmosphere hands numpy scalars to the Cython vector algebra, which numpy >= 2 turns into ndarrays
+        # (TypeError in forceMomentSystem.getAt on the first step). Shim for this one fixture: the same four interpolated values as
+        # Python floats (np.float64 -> float is exact), nothing else touched.
+        from MAPLEAF.ENV import AtmosphereModelling
+        _orig = AtmosphereModelling.TabulatedAtmosphere.getAirProperties
+        AtmosphereModelling.TabulatedAtmosphere.getAirProperties = lambda self, h, _=None: [float(x) for x in _orig(self, h)]
+        dump("opt_atm_tabulated.json", singleFlight(mc, {**wind, "Environment.AtmosphericPropertiesModel": "TabulatedAtmosphere",
+                                                        "Environment.TabulatedAtmosphere.filePath": os.path.join(envDir, "atmosphereTable.txt")}, traceEvery=200))
+        dump("opt_wind_profile.json", singleFlight(mc, {"Environment.MeanWindModel": "CustomWindProfile",
+                                                       "Environment.CustomWindProfile.filePath": os.path.join(envDir, "windProfile.txt")}, traceEvery=200))
+        pink = {**wind, "Environment.MeanWindModel": "Constant", "SimControl.timeDiscretization": "RK4", "SimControl.timeStep": "0.02", "SimControl.EndCondition": "Apogee",
+                "Environment.PinkNoiseModel.randomSeed1": "63583", "Environment.PinkNoiseModel.randomSeed2": "4021", "Environment.PinkNoiseModel.randomSeed3": "77"}
+        dump("opt_pink1d.json", singleFlight(adaptive, {**pink, "Environment.TurbulenceModel": "PinkNoise1D"}, traceEvery=100))
+        dump("opt_pink3d.json", singleFlight(adaptive, {**pink, "Environment.TurbulenceModel": "PinkNoise3D"}, traceEvery=100))
+        dump("opt_pink3d_rk45.json", singleFlight(adaptive, {**pink, "Environment.TurbulenceModel": "PinkNoise3D", "SimControl.timeDiscretization": "RK45Adaptive",
+                                                            "SimControl.timeStep": "0.01", "SimControl.EndCondition": "Time", "SimControl.EndConditionValue": "8"}, traceEvery=20, keepDts=True))
+        short = {**wind, "SimControl.EndCondition": "Time", "SimControl.EndConditionValue": "4", "SimControl.timeStep": "0.01"}
+        for name, method in (("euler", "Euler"), ("rk2mid", "RK2Midpoint"), ("rk2heun", "RK2Heun"), ("rk4_38", "RK4_3/8")):
+            dump("opt_%s.json" % name, singleFlight(mc, {**short, "SimControl.timeDiscretization": method}, traceEvery=100))
+        gust = {"Environment.TurbulenceModel": "customSineGust", "Environment.MeanWindModel": "Constant", "SimControl.EndCondition": "Apogee", **wind}
+        dump("opt_rk12a.json", singleFlight(adaptive, {**gust, "SimControl.timeDiscretization": "RK12Adaptive", "SimControl.EndCondition": "Time", "SimControl.EndConditionValue": "3"},
+                                            traceEvery=50, keepDts=True))
+        dump("opt_rk23a.json", singleFlight(adaptive, {**gust, "SimControl.timeDiscretization": "RK23Adaptive", "SimControl.EndCondition": "Time", "SimControl.EndConditionValue": "12"},
+                                            traceEvery=50, keepDts=True))
+        dump("opt_ctrl_elementary.json", singleFlight(adaptive, {**gust, "SimControl.TimeStepAdaptation.controller": "elementary"}, traceEvery=20, keepDts=True))
+        # controller "Constant" cannot be flown: integratorFactory leaves safetyFactor unbound for it (Integration.py:74-93, UnboundLocalError
+        # while the rocket is constructed), so the backend rejects it as well
+        can = os.path.join(MY_DATA, "Canards.mapleaf")
+        mcK = "Rocket.ControlSystem.MomentController."
+        dump("opt_constgain_pid.json", singleFlight(can, {mcK + "Type": "ConstantGainPIDRocket", mcK + "Pxy": "4", mcK + "Ixy": "0.5", mcK + "Dxy": "1.2",
+                                                         mcK + "Pz": "0.5", mcK + "Iz": "0.1", mcK + "Dz": "0.2"}, traceEvery=50))
     if "rk45_pink" in which:
         dump("rk45_pink.json", monteCarlo(adaptive, {}, "2394781", 4, globalSeed=2394781, keepDts=True))
     if "ideal" in which:

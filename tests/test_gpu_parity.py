@@ -611,3 +611,47 @@ def test_reference_flight_regression_cases(backend, name):
     assert o["status"][0] == L.ST_OK and o["counters"][0, 0] == c["counters"][0, 0]
     assert max(regressionErrors(o["finals"][0][:6], expected)) < 0.05
     assert stateErr(o["finals"][0], np.concatenate([[c["finals"][0, 13]], c["finals"][0, :13]])) < FIXED_TOL
+
+
+# ---- one short flight per option the backend accepts (fixtures: tests/golden/make_golden.py `options`) ----
+def optionOverrides(g):
+    from conftest import REPO
+    out = dict(g["overrides"])
+    for k, v in out.items():
+        if k.endswith("filePath"):
+            out[k] = os.path.join(REPO, "mapleaf_b200", "data", "Environment", os.path.basename(v))
+    return out
+
+
+@pytest.mark.parametrize("name", ["opt_atm_tabulated.json", "opt_wind_profile.json", "opt_pink1d.json", "opt_pink3d.json", "opt_euler.json", "opt_rk2mid.json",
+                                  "opt_rk2heun.json", "opt_rk4_38.json", "opt_constgain_pid.json"])
+def test_option_fixed_step_vs_reference(backend, golden, name):
+    """TabulatedAtmosphere, CustomWindProfile, PinkNoise1D / 3D (fixed seeds), Euler / RK2Midpoint / RK2Heun / RK4_3/8 and the
+    ConstantGainPIDRocket controller on the GPU: same step count as the reference flight, final state and sampled states <= 1e-9."""
+    g = golden(name)
+    m = buildFrom(g["definition"], optionOverrides(g))
+    r = g["runs"][0]
+    o = gpuRun(backend, m, 1, {}, traceLane=0, traceRows=4000)
+    assert o["status"][0] == L.ST_OK and o["counters"][0, 0] == r["steps"]
+    assert abs(o["finals"][0, 13] - r["final"][0]) < 1e-9
+    assert stateErr(o["finals"][0], r["final"]) < FIXED_TOL
+    assert relErr(o["results"][0, 3:7], r["results"][3:7]) < FIXED_TOL
+    for idx, row in zip(r["traceIdx"], r["trace"]):
+        assert stateErr(np.concatenate([o["trace"][idx, 1:14], [0]]), row) < FIXED_TOL
+
+
+@pytest.mark.parametrize("name", ["opt_pink3d_rk45.json", "opt_rk12a.json", "opt_rk23a.json", "opt_ctrl_elementary.json"])
+def test_option_adaptive_vs_reference(backend, golden, name):
+    """RK12Adaptive / RK23Adaptive, the `elementary` step-size controller and PinkNoise3D under the adaptive integrator on the GPU:
+    lock-step replay of the reference's accepted step sizes (every step time <= 1e-9, final state <= 1e-7); free-running, the flight
+    stays near the reference's (the step sequences decorrelate at the first rounding difference)."""
+    g = golden(name)
+    m = buildFrom(g["definition"], optionOverrides(g))
+    r = g["runs"][0]
+    o = gpuRun(backend, m, 1, {}, traceLane=0, traceRows=len(r["times"]) + 5, dtReplay=r["dts"])
+    assert o["status"][0] == L.ST_OK and o["counters"][0, 0] == r["steps"]
+    assert np.abs(o["trace"][:, 0] - np.array(r["times"])).max() < 1e-9
+    assert stateErr(o["finals"][0], r["final"]) < 1e-7
+    free = gpuRun(backend, m, 1, {})
+    assert free["status"][0] == L.ST_OK and abs(int(free["counters"][0, 0]) - r["steps"]) <= 0.15 * r["steps"]
+    assert relErr(free["finals"][0, 0:3], r["final"][1:4]) < 1e-3 and relErr(free["finals"][0, 3:6], r["final"][4:7]) < 1e-3

@@ -360,3 +360,63 @@ def test_reference_flight_regression_cases(name):
     o = oracle.run(blob, 1, {})
     assert o["status"][0] == L.ST_OK
     assert max(regressionErrors(o["finals"][0][:6], expected)) < 0.05
+
+
+# ---- one short flight per option the backend accepts (tests/golden/make_golden.py `options`) ----
+OPTION_FIXED = ["opt_atm_tabulated.json", "opt_wind_profile.json", "opt_pink1d.json", "opt_pink3d.json", "opt_euler.json", "opt_rk2mid.json",
+                "opt_rk2heun.json", "opt_rk4_38.json", "opt_constgain_pid.json"]
+OPTION_ADAPTIVE = ["opt_pink3d_rk45.json", "opt_rk12a.json", "opt_rk23a.json", "opt_ctrl_elementary.json"]
+
+
+def optionOverrides(g):
+    """The fixture's overrides with table paths re-pointed at this checkout (they were absolute on the generating host)."""
+    from conftest import REPO
+    out = dict(g["overrides"])
+    for k, v in out.items():
+        if k.endswith("filePath"):
+            out[k] = os.path.join(REPO, "mapleaf_b200", "data", "Environment", os.path.basename(v))
+    return out
+
+
+@pytest.mark.parametrize("name", OPTION_FIXED)
+def test_option_fixed_step(golden, name):
+    """TabulatedAtmosphere (ENV/AtmosphereModelling.py:79-96), CustomWindProfile (ENV/MeanWindModelling.py:165-196), PinkNoise1D / 3D with
+    fixed seeds (ENV/TurbulenceModelling.py:100-131: 3D reuses generator 2 for z), Euler / RK2Midpoint / RK2Heun / RK4_3/8
+    (Motion/Integration.py:144-236), ConstantGainPIDRocket (GNC/MomentControllers.py:58-83): fixed-step flights, same step count,
+    states along the flight and at the end <= 1e-12 from the reference."""
+    g = golden(name)
+    m = buildFrom(g["definition"], optionOverrides(g))
+    r = g["runs"][0]
+    o = oracle.run(m.blob, 1, {}, traceLane=0, traceMaxRows=4000)
+    assert o["status"][0] == L.ST_OK and o["counters"][0, 0] == r["steps"]
+    assert o["finals"][0, 13] == r["final"][0]
+    assert stateErr(o["finals"][0], r["final"]) < 1e-12
+    assert relErr(o["results"][0, 3:7], r["results"][3:7]) < 1e-12
+    for idx, row in zip(r["traceIdx"], r["trace"]):
+        assert o["trace"][idx, 0] == row[0]
+        assert stateErr(np.concatenate([o["trace"][idx, 1:14], [0]]), row) < 1e-12
+
+
+@pytest.mark.parametrize("name", OPTION_ADAPTIVE)
+def test_option_adaptive(golden, name):
+    """RK12Adaptive / RK23Adaptive (Integration.py:238-330; RK23 is first-same-as-last), the `elementary` step-size controller
+    (:359-382, safety factor), PinkNoise3D under the adaptive integrator. Lock-step replay of the reference's accepted step sizes
+    reproduces every step time and the final state; free-running, the accepted-step count stays within a few steps."""
+    g = golden(name)
+    m = buildFrom(g["definition"], optionOverrides(g))
+    r = g["runs"][0]
+    rep = oracle.run(m.blob, 1, {}, traceLane=0, traceMaxRows=len(r["times"]) + 5, dtReplay=r["dts"])
+    assert rep["counters"][0, 0] == r["steps"]
+    assert np.abs(rep["trace"][:, 0] - np.array(r["times"])).max() < 1e-9
+    assert stateErr(rep["finals"][0], r["final"]) < 1e-9
+    free = oracle.run(m.blob, 1, {})
+    assert free["status"][0] == L.ST_OK
+    assert abs(int(free["counters"][0, 0]) - r["steps"]) <= max(5, r["steps"] // 100)
+    assert relErr(free["finals"][0, 0:3], r["final"][1:4]) < 1e-4
+
+
+def test_constant_step_controller_is_rejected():
+    """`controller Constant` with an adaptive method cannot be flown by the reference (integratorFactory leaves safetyFactor unbound,
+    Integration.py:74-93): the backend refuses it when the model is built instead of flying something the reference never could."""
+    with pytest.raises(ValueError):
+        buildFrom("MonteCarloAdaptive.mapleaf", {"SimControl.TimeStepAdaptation.controller": "Constant"})

@@ -1,0 +1,27 @@
+"""Writes the environment tables used by the option-coverage fixtures (inputs made for this repository, reference file formats):
+   data/Environment/atmosphereTable.txt ... TabulatedAtmosphere (ENV/AtmosphereModelling.py:79-96): h [m ASL], T [K], P [Pa], rho [kg/m3], mu [1e-5 Pa s]
+   data/Environment/windProfile.txt ....... CustomWindProfile / InterpolatedWind (ENV/MeanWindModelling.py:165-196): AGL altitude, wind x y z [m/s]"""
+import math, os
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+out = os.path.join(REPO, "mapleaf_b200", "data", "Environment")
+os.makedirs(out, exist_ok=True)
+# a smooth, slightly non-standard atmosphere (warm day, 1.5 % denser): isothermal above 11.5 km
+rows = []
+for h in [-500, 0, 250, 500, 900, 1400, 2000, 2750, 3500, 4500, 6000, 7500, 9000, 11500, 14000, 18000, 24000, 32000]:
+    T = 293.65 - 0.0064 * min(h, 11500)
+    P = 101900.0 * (T / 293.65) ** 5.34 if h <= 11500 else 101900.0 * ((293.65 - 0.0064 * 11500) / 293.65) ** 5.34 * math.exp(-(h - 11500) / 6440.0)
+    rho = 1.015 * P / (287.05 * T)
+    mu = 1.458e-6 * T ** 1.5 / (T + 110.4) * 1e5
+    rows.append((h, T, P, rho, mu))
+with open(os.path.join(out, "atmosphereTable.txt"), "w") as f:
+    f.write("h\tT\tP\trho\tmu\n")
+    for r in rows:
+        f.write("%d\t%.3f\t%.1f\t%.5f\t%.4f\n" % r)
+# a veering, strengthening wind with a low-level jet and a small updraft band
+with open(os.path.join(out, "windProfile.txt"), "w") as f:
+    f.write("AGLAltitude(m) WindX(m/s) WindY(m/s) WindZ(m/s)\n")
+    for h in [0, 50, 150, 300, 600, 1000, 1600, 2500, 4000, 6000, 9000]:
+        speed = 2.5 + 9.0 * (1 - math.exp(-h / 900.0)) + 3.0 * math.exp(-((h - 450) / 200.0) ** 2)
+        ang = math.radians(15 + 40 * (1 - math.exp(-h / 1500.0)))
+        f.write("%d %.3f %.3f %.3f\n" % (h, speed * math.cos(ang), speed * math.sin(ang), 0.4 * math.exp(-((h - 800) / 400.0) ** 2)))
+print("wrote", os.listdir(out))

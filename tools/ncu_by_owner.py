@@ -4,7 +4,7 @@ ends up in `operator+`). Usage: ncu_by_owner.py src.csv nvdisasm_gi.txt kernelSu
 import bisect, collections, csv, os, re, sys
 rows = list(csv.reader(open(sys.argv[1]))); hdr = rows[1]; ix = {h: i for i, h in enumerate(hdr)}; d = rows[2:]
 kern, src = sys.argv[3], sys.argv[4]
-MAJOR = {"integrateStep", "stateDerivative", "appliedForce", "finSetForce", "noseConeForce", "bodyTubeForce", "transitionForce", "airProperties",
+MAJOR = {"flightLoop", "flightLanes", "chuteLanes", "finishLane", "integrateStep", "stateDerivative", "appliedForce", "finSetForce", "noseConeForce", "bodyTubeForce", "transitionForce", "airProperties",
          "aeroSetup", "rocketInertia", "rocketTimeStep", "triggerEvents", "laneInit", "pinkValue", "turbulenceAt", "atmosphere", "integrateLanes",
          "endDetector", "finStripTransonic", "finStripSubsonic", "cylinderSkinFriction", "forceFromCdCN", "meanWindAt", "gravityForceGlobal",
          "mtTwist", "mtInitByArray", "pinkInit", "runControlSystem", "ndInterpolate", "recoveryForce"}
@@ -44,12 +44,13 @@ def val(r, k):
 for o, r in zip(owners[:n], d[:n]):
     a = agg[o]; ex = val(r, "Instructions Executed")
     a["smp"] += val(r, "# Samples"); a["ex"] += ex; a["lsb"] += val(r, "stall_long_sb"); a["bar"] += val(r, "stall_barrier")
+    a["thr"] += val(r, "Thread Instructions Executed"); a["wait"] += val(r, "stall_wait")
     s = r[ix["Source"]].split(); op = s[1] if s[0].startswith("@") else s[0]
     if op.startswith("LDL"): a["ldl"] += ex
     if op.startswith("STL"): a["stl"] += ex
 T = sum(a["smp"] for a in agg.values()); X = sum(a["ex"] for a in agg.values()); LS = sum(a["lsb"] for a in agg.values())
 print("sass rows %d, disassembled %d" % (len(d), len(owners)))
-print("%-24s %7s %7s %14s %9s %7s %7s" % ("enclosing function", "smp%", "exec%", "long_sb share", "barrier%", "ldl%", "stl%"))
+print("%-24s %7s %7s %14s %9s %7s %7s %9s %7s" % ("enclosing function", "smp%", "exec%", "long_sb share", "barrier%", "ldl%", "stl%", "thr/inst", "wait%"))
 for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["smp"])[:26]:
-    print("%-24s %6.1f%% %6.1f%% %13.1f%% %8.1f%% %6.1f%% %6.1f%%" % (k, 100 * a["smp"] / T, 100 * a["ex"] / X, 100 * a["lsb"] / LS, 100 * a["bar"] / max(a["smp"], 1),
-                                                               100 * a["ldl"] / max(a["ex"], 1), 100 * a["stl"] / max(a["ex"], 1)))
+    print("%-24s %6.1f%% %6.1f%% %13.1f%% %8.1f%% %6.1f%% %6.1f%% %9.1f %6.1f%%" % (k, 100 * a["smp"] / T, 100 * a["ex"] / X, 100 * a["lsb"] / LS, 100 * a["bar"] / max(a["smp"], 1),
+                                                               100 * a["ldl"] / max(a["ex"], 1), 100 * a["stl"] / max(a["ex"], 1), a["thr"] / max(a["ex"], 1), 100 * a["wait"] / max(a["smp"], 1)))
