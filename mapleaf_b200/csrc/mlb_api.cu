@@ -65,6 +65,7 @@ struct LaneRec {
 #define REC_END 1
 #define REC_HAVE_FINAL 2
 #define REC_PRE_DONE 4              /* left the free-flight kernel after the first half of Rocket.timeStep (see rocketTimeStep) */
+#define REC_RETRY 8                 /* the last attempt was rejected: `dt` is the size it used (see integrateStep) */
 
 struct RunArgs {
     const double* blob; int blobLen; int blobPad; int nSlots;
@@ -79,6 +80,7 @@ struct RunArgs {
     int* qNext; int* qNextCount;          /* stragglers of this generation (free flight) */
     int* qChute; int* qChuteCount;        /* lanes whose first parachute has opened */
     int bailPermille;                     /* a free-flight CTA retires when fewer than this share of its initial lanes are still flying; 0: never */
+    int ctaSlots;                         /* free-flight CTAs resident at a time (SMs x CTAs per SM): the queue is spread evenly over whole waves of them */
 };
 
 /* One row of a lane's flight log (RocketFlight.times / rigidBodyStates, IO/rocketFlight.py:12-25). The log keeps every `stride`-th
@@ -157,9 +159,17 @@ MLB_DEV void finishLane(const RunArgs& a, long long lane, const Lane& L, V3 prev
    flow (out-of-range and finished threads stay and keep the barriers company). PH 1: under parachute, every thread on its own. */
 template <int PH, bool CONVOY>
 MLB_DEV void flightLoop(const RunArgs& a, const double* B) {
-    const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long count = a.qIn ? (long long)*a.qInCount : a.in.nLanes;
-    if ((long long)blockIdx.x * blockDim.x >= count) return;          /* CTA-uniform: nothing queued for this CTA */
+    /* Lanes per CTA. The convoy kernel spreads the queue evenly over whole waves of CTAs (a.ctaSlots CTAs run at a time): 10^5 lanes are
+       143 CTAs of 704 lanes, one on every SM, rather than 98 full ones; 10^6 lanes 7 equal waves rather than 6.6. A wave's duration follows
+       its warps per CTA closely (see mlb_run), so this is worth what the empty SMs were. Warps past `per` exit before the first barrier. */
+    int per = blockDim.x;
+    if (CONVOY && a.ctaSlots > 0) {
+        const long long full = (long long)a.ctaSlots * blockDim.x, waves = (count + full - 1) / full;
+        if (waves > 0) per = (int)min((long long)blockDim.x, (((count + a.ctaSlots * waves - 1) / (a.ctaSlots * waves)) + 31) & ~31LL);
+    }
+    if ((long long)blockIdx.x * per >= count || (int)threadIdx.x >= per) return;          /* nothing queued for this CTA / warp */
+    const long long slot = (long long)blockIdx.x * per + threadIdx.x;
     const bool inRange = slot < count;
     const long long lane = inRange ? (a.qIn ? (long long)a.qIn[slot] : slot) : 0;
     /* RK stage derivatives: per-thread local memory, indexed dynamically by the tableau loops */
@@ -172,12 +182,12 @@ MLB_DEV void flightLoop(const RunArgs& a, const double* B) {
     V3 prevPos = v3(0, 0, 0), lastPos = v3(0, 0, 0);
     long long rows = 0, traceStride = 1;
     int st = ST_OK;
-    bool end = true, haveFinal = false, skipPre = false, left = false;
+    bool end = true, haveFinal = false, skipPre = false, left = false, retry = false;
     if (inRange) {
         L = rec->L;
         dt = rec->dt; finalDt = rec->finalDt; apogee = rec->apogee; maxSpeed = rec->maxSpeed; maxH = rec->maxH;
         prevPos = rec->prevPos; lastPos = rec->lastPos; rows = rec->rows; traceStride = rec->traceStride; st = rec->st;
-        end = (rec->flags & REC_END) != 0; haveFinal = (rec->flags & REC_HAVE_FINAL) != 0; skipPre = (rec->flags & REC_PRE_DONE) != 0;
+        end = (rec->flags & REC_END) != 0; haveFinal = (rec->flags & REC_HAVE_FINAL) != 0; skipPre = (rec->flags & REC_PRE_DONE) != 0; retry = (rec->flags & REC_RETRY) != 0;
         if (L.haveCache) for (int k = 0; k < (PH == 1 ? 6 : 12); k++) kLocal[k] = rec->k0[k];
         L.G = a.blob;
     } else L.forceRK4 = false;          /* threads past the end of the queue only keep the barriers company: the one lane field that path reads */
@@ -187,20 +197,22 @@ MLB_DEV void flightLoop(const RunArgs& a, const double* B) {
 
     int bailBelow = 0;
     if (CONVOY && a.bailPermille > 0) {
-        const long long inCta = min((long long)blockDim.x, count - (long long)blockIdx.x * blockDim.x);
+        const long long inCta = min((long long)per, count - (long long)blockIdx.x * per);
         bailBelow = (int)((inCta * a.bailPermille + 999) / 1000);
     }
     for (;;) {
         const bool run = !end && !left;
         if (CONVOY) { const int flying = __syncthreads_count(run); if (flying == 0 || flying < bailBelow) break; }
         else if (!run) break;
-        if (run && !skipPre) {
+        if (run && !skipPre && !retry) {
             if (haveFinal) dt = finalDt;
             if (a.dtReplay && L.nSteps < a.nReplay) dt = a.dtReplay[L.nSteps];
         }
-        StepResult r = rocketTimeStep<PH, CONVOY>(B, a.blob, L, ks, dt, run, skipPre, left);
+        StepResult r = rocketTimeStep<PH, CONVOY>(B, a.blob, L, ks, dt, run, skipPre || retry, retry, left);
         skipPre = false;
-        if (run && !left) {
+        if (run && !left && r.rejected) { retry = true; dt = r.dt; }
+        else if (run && !left) {
+            retry = false;
             dt = r.dt * r.factor;
             prevPos = lastPos; lastPos = L.s.pos;
             if (L.s.pos.z > apogee) apogee = L.s.pos.z;
@@ -221,14 +233,14 @@ MLB_DEV void flightLoop(const RunArgs& a, const double* B) {
         rec->L = L;
         rec->dt = dt; rec->finalDt = finalDt; rec->apogee = apogee; rec->maxSpeed = maxSpeed; rec->maxH = maxH;
         rec->prevPos = prevPos; rec->lastPos = lastPos; rec->rows = rows; rec->traceStride = traceStride; rec->st = st;
-        rec->flags = (haveFinal ? REC_HAVE_FINAL : 0) | (left ? REC_PRE_DONE : 0);
+        rec->flags = (haveFinal ? REC_HAVE_FINAL : 0) | (left ? REC_PRE_DONE : 0) | (retry ? REC_RETRY : 0);
         if (L.haveCache) for (int k = 0; k < (PH == 1 ? 6 : 12); k++) rec->k0[k] = kLocal[k];
     }
     if (CONVOY) {
         /* one atomic per CTA and queue: warp ballots, then the warp totals through shared memory */
         __shared__ int warpBase[2][32];
         __shared__ int ctaBase[2];
-        const int w = threadIdx.x >> 5, ln = threadIdx.x & 31, nWarps = (blockDim.x + 31) >> 5;
+        const int w = threadIdx.x >> 5, ln = threadIdx.x & 31, nWarps = (per + 31) >> 5;
         const unsigned mNext = __ballot_sync(0xffffffffu, toNext), mChute = __ballot_sync(0xffffffffu, toChute);
         if (ln == 0) { warpBase[0][w] = __popc(mNext); warpBase[1][w] = __popc(mChute); }
         __syncthreads();
@@ -361,7 +373,7 @@ struct mlb_handle {
     bool ran = false;
     long long launches = 0;
     int nSlots = 0; size_t smemBytes = 0;
-    int nSM = 148; int forceBlock = 0; int lastBlock = 0; int bailPermille = 500; int generations = MLB_GENERATIONS;
+    int nSM = 148; int forceBlock = 0; int lastBlock = 0; int lastGenerations = 0; int bailPermille = 500; int generations = MLB_GENERATIONS; bool evenSplit = true;
     size_t sharedLen = 0;
 };
 
@@ -421,6 +433,7 @@ extern "C" int mlb_create(const void* model_blob, size_t n, int device, mlb_hand
     if (h->smemBytes > 226 * 1024) { delete h; return fail(MLB_ERR_UNSUPPORTED, "mlb_create: the shared part of the model block exceeds shared memory"); }
     { const char* e = getenv("MLB_BLOCK_SIZE"); h->forceBlock = e ? atoi(e) : 0; }
     { const char* e = getenv("MLB_BAIL_PERMILLE"); if (e) h->bailPermille = atoi(e); }
+    { const char* e = getenv("MLB_EVEN_SPLIT"); if (e) h->evenSplit = atoi(e) != 0; }
     { const char* e = getenv("MLB_NUM_GENERATIONS"); if (e) { int g = atoi(e); if (g >= 1 && g <= MLB_GENERATIONS) h->generations = g; } }
     int rc = createOnDevice(h, b, len);
     if (rc != MLB_OK) { mlb_destroy(h); return rc; }       /* g_err keeps the message of the failed call */
@@ -511,15 +524,27 @@ extern "C" int mlb_run(mlb_handle* h, void* stream) {
     a.dtReplay = h->d_replay; a.nReplay = h->nReplay;
     a.recs = h->d_recs;
     a.qIn = nullptr; a.qInCount = nullptr; a.qNext = nullptr; a.qNextCount = nullptr; a.qChute = h->d_queue[2]; a.qChuteCount = h->d_queueCount + MLB_GENERATIONS; a.bailPermille = 0;
-    /* CTA shape of the free-flight kernel: the largest convoy that still gives every SM a CTA (1024 lanes per SM at 64 registers,
-       512 at 128, 2 x 128 at 255). MLB_BLOCK_SIZE overrides, for tuning. */
-    int block = 128;
-    if (h->nLanes >= 512LL * h->nSM) block = 512;
-    if (h->nLanes >= 1024LL * h->nSM) block = 1024;
+    /* CTA shape of the free-flight kernel: the one with the fewest (waves of CTAs) x (duration of a wave of that shape relative to a
+       1024-lane wave). A wave's duration grows a little slower than its lane count (0.45 / 0.55 / 1 for 2 x 128 / 512 / 1024 lanes per SM,
+       profiles/r2c_shape_sweep.txt; the ratios are a property of the convoy, the same within a few per cent for every workload
+       measured), so large batches want the largest convoy, a batch that leaves SMs empty in one shape may fill them in a smaller
+       one, and a batch just over one wave is better off in a larger shape than in two waves of a smaller one. MLB_BLOCK_SIZE overrides. */
+    int block = 128; double bestCost = 1e300;
+    {
+        static const int shapeBlock[3] = { 128, 512, 1024 }, shapeCtas[3] = { 2, 1, 1 };
+        static const double shapeWave[3] = { 0.45, 0.55, 1.0 };
+        for (int k = 0; k < 3; k++) {
+            const long long ctas = (h->nLanes + shapeBlock[k] - 1) / shapeBlock[k], slots = (long long)h->nSM * shapeCtas[k];
+            const double cost = (double)((ctas + slots - 1) / slots) * shapeWave[k];
+            if (cost < bestCost) { bestCost = cost; block = shapeBlock[k]; }
+        }
+    }
 #define MLB_ALLOW_SHAPE(N, M) if (h->forceBlock == N) block = N;
     MLB_FLIGHT_SHAPES(MLB_ALLOW_SHAPE)
     h->lastBlock = block;
-    const unsigned grid = (unsigned)((h->nLanes + block - 1) / block);
+    const int ctaSlots = h->nSM * (block == 128 ? 2 : 1);
+    const unsigned grid = (unsigned)((h->nLanes + block - 1) / block) + (h->evenSplit ? ctaSlots + 1 : 0);      /* even split: at most this many CTAs */
+    a.ctaSlots = h->evenSplit ? ctaSlots : 0;
     h->launches = 0;
     CU(cudaEventRecord(h->ev0, s));
     CU(cudaMemsetAsync(h->d_queueCount, 0, (MLB_GENERATIONS + 2) * sizeof(int), s));
@@ -529,12 +554,15 @@ extern "C" int mlb_run(mlb_handle* h, void* stream) {
     /* Free flight, MLB_GENERATIONS launches over ping-pong straggler queues. Every launch is sized for the whole batch (CTAs past the end
        of their queue exit at once), so the sequence needs no host round trip. */
     CU(cudaEventRecord(h->evFlight0, s));
-    const int G = h->generations;
+    /* a batch that fits one wave gains nothing from re-packing (no CTA is waiting for the SM): one generation runs it to the end */
+    const bool singleWave = (h->nLanes + block - 1) / block <= (long long)ctaSlots;
+    const int G = singleWave ? 1 : h->generations;
+    h->lastGenerations = G;
     for (int g = 0; g < G; g++) {
         a.qIn = g == 0 ? nullptr : h->d_queue[(g - 1) & 1];
         a.qInCount = g == 0 ? nullptr : h->d_queueCount + (g - 1);
         a.qNext = h->d_queue[g & 1]; a.qNextCount = h->d_queueCount + g;
-        a.bailPermille = (g == G - 1) ? 0 : h->bailPermille;
+        a.bailPermille = (g == G - 1 || singleWave) ? 0 : h->bailPermille;
 #define MLB_LAUNCH_SHAPE(N, M) if (block == N) flightLanes<N, M><<<grid, N, h->smemBytes, s>>>(a);
         MLB_FLIGHT_SHAPES(MLB_LAUNCH_SHAPE)
         h->launches++;
@@ -542,7 +570,7 @@ extern "C" int mlb_run(mlb_handle* h, void* stream) {
     }
     CU(cudaEventRecord(h->evFlight1, s));
     /* Under parachute: everything the free-flight launches queued */
-    a.qIn = h->d_queue[2]; a.qInCount = h->d_queueCount + MLB_GENERATIONS; a.qNext = nullptr; a.qNextCount = nullptr; a.qChute = nullptr; a.qChuteCount = nullptr; a.bailPermille = 0;
+    a.qIn = h->d_queue[2]; a.qInCount = h->d_queueCount + MLB_GENERATIONS; a.qNext = nullptr; a.qNextCount = nullptr; a.qChute = nullptr; a.qChuteCount = nullptr; a.bailPermille = 0; a.ctaSlots = 0;
     chuteLanes<<<(unsigned)((h->nLanes + MLB_CHUTE_BLOCK - 1) / MLB_CHUTE_BLOCK), MLB_CHUTE_BLOCK, h->smemBytes, s>>>(a);
     h->launches++;
     CU(cudaGetLastError());
@@ -601,7 +629,7 @@ extern "C" int mlb_counters(mlb_handle* h, mlb_counters_t* out) {
     CU(cudaEventElapsedTime(&msFlight, h->evFlight0, h->evFlight1));
     CU(cudaEventElapsedTime(&msChute, h->evFlight1, h->ev1));
     out->last_run_ms = ms; out->dominant_kernel_ms = msFlight; out->kernel_launches = h->launches;
-    out->chute_kernel_ms = msChute; out->flight_block = h->lastBlock; out->flight_generations = h->generations;
+    out->chute_kernel_ms = msChute; out->flight_block = h->lastBlock; out->flight_generations = h->lastGenerations;
     return MLB_OK;
 }
 extern "C" int mlb_device_results(mlb_handle* h, void** results, void** status) {

@@ -63,7 +63,7 @@ MLB_DEV Deriv derivAdd(const Deriv& a, const Deriv& b, bool dof3) {             
     return r;
 }
 
-struct StepResult { State newValue; double dt, factor, err; };
+struct StepResult { State newValue; double dt, factor, err; bool rejected; };
 
 MLB_DEV double stepPID(const double* B, Lane& L, double currentError, double dt) {          /* GNC/PID.py:27-51, maxIntegral = 1 */
     double derivative = (currentError - L.pidLastError) / dt;
@@ -86,13 +86,16 @@ MLB_DEV bool pyIsClose(double a, double b) {                                    
    lanes that have nothing to do in a stage / attempt / step stay in the loops with `active` false. The under-chute
    kernel (CONVOY false) fits the instruction cache and runs without barriers: every predicate is then the thread's own. */
 template <bool CONVOY> MLB_DEV void convoySync() { if (CONVOY) __syncthreads(); }
-template <bool CONVOY> MLB_DEV bool convoyAny(bool pred) { return CONVOY ? (__syncthreads_or(pred) != 0) : pred; }
 
-/* One Runge-Kutta step of either family. The stage loop has ONE call site of the (large) state-derivative code, shared
-   by the first stage, the classical and the adaptive stage composition and the adaptive retry loop, so the force model is
-   instantiated once in the kernel. `active` false: the lane only keeps the CTA's barriers company. */
+/* One Runge-Kutta attempt of either family. The stage loop has ONE call site of the (large) state-derivative code, shared
+   by the first stage and by the classical and the adaptive stage composition, so the force model is instantiated once in the
+   kernel. `active` false: the lane only keeps the CTA's barriers company.
+   The reference's adaptive integrator retries a step in place with a third of the step size until the error estimate passes
+   (Integration.py:331-347). Here a rejected attempt returns (`rejected`, with the step size it used) and the lane re-attempts in
+   the time loop's next iteration with `retry` set: same arithmetic, same attempt sequence, but the re-attempt rides along with the
+   other lanes' next step instead of holding the whole convoy for a pass in which only the rejected lanes work. */
 template <int PH, bool CONVOY>
-MLB_DEV StepResult integrateStep(const double* B, Lane& L, const KStore& ks, State& y, double t, double dt, bool active) {
+MLB_DEV StepResult integrateStep(const double* B, Lane& L, const KStore& ks, State& y, double t, double dt, bool active, bool retry) {
     /* A fixed-rate control system swaps an adaptive integrator for RK4 while it is in charge (ControlSystems.py:126-135); the
        parachute switch restores the original one (rocket.py:700-726). So the method is a per-lane choice between two tableaus;
        the stage loop below runs to the CTA-uniform maximum row count and lanes with fewer rows sit out the extra stages. */
@@ -106,16 +109,16 @@ MLB_DEV StepResult integrateStep(const double* B, Lane& L, const KStore& ks, Sta
     const int nRows = L.forceRK4 ? 3 : nRows0;
     const int nResultRows = L.forceRK4 ? 1 : (int)B[H_TAB_NRESULT_ROWS];
     const double target = B[H_AD_TARGET], minDt = B[H_AD_MINDT];
-    StepResult r; r.factor = 1.0; r.err = 0.0; r.dt = dt;
+    StepResult r; r.factor = 1.0; r.err = 0.0; r.dt = dt; r.rejected = false;
     double err = 10000000;
-    if (adaptive) dt *= 3;                                                                  /* Integration.py:335: first attempt = requested dt */
+    constexpr bool dof3 = (PH == 1);
     bool attempting = active;
-    for (;;) {
-        constexpr bool dof3 = (PH == 1);
-        if (attempting && adaptive) {
-            if (err != 10000000) L.nRejects++;
-            dt = fmax(minDt, dt / 3);
-        }
+    if (attempting && adaptive) {
+        /* Integration.py:335-340: the first attempt uses max(minDt, (3 dt) / 3), every re-attempt a third of the previous attempt's size */
+        if (retry) { L.nRejects++; dt = fmax(minDt, dt / 3); }
+        else dt = fmax(minDt, (dt * 3) / 3);
+    }
+    {
         for (int i = -1; i < nRowsLoop; i++) {
             /* slot 0 may already hold the last stage of the previous accepted step (first-same-as-last) */
             const bool evalNow = attempting && i < nRows && !(i < 0 && adaptive && L.haveCache);
@@ -169,10 +172,10 @@ MLB_DEV StepResult integrateStep(const double* B, Lane& L, const KStore& ks, Sta
                 }
             }
         }
-        if (!convoyAny<CONVOY>(attempting)) break;
     }
     r.dt = dt;
     if (!active || !adaptive) return r;
+    if (attempting) { r.rejected = true; return r; }
     /* accepted adaptive step: FSAL cache, step-size controller (:349-389) */
     if (method == INT_RK45A || method == INT_RK23A) {
         ks.put(0, ks.get(nRows, PH == 1), PH == 1);          /* becomes k_0 of the next step (attempts never overwrite slot 0) */
@@ -374,7 +377,7 @@ MLB_DEV void railMotionConstraint(const double* B, Lane& L) {                   
    loop) can deploy the first parachute, which turns the lane into a 3-DoF body: a lane of the free-flight kernel then leaves
    (`left`) with the first half done and its step size already clamped, and the under-chute kernel resumes it with `skipPre`. */
 template <int PH, bool CONVOY>
-MLB_DEV StepResult rocketTimeStep(const double* B, const double* G, Lane& L, const KStore& ks, double& dt, bool active, bool skipPre, bool& left) {
+MLB_DEV StepResult rocketTimeStep(const double* B, const double* G, Lane& L, const KStore& ks, double& dt, bool active, bool skipPre, bool retry, bool& left) {
     if (active && !skipPre) {
         railMotionConstraint(B, L);
         double est; bool det;
@@ -386,8 +389,8 @@ MLB_DEV StepResult rocketTimeStep(const double* B, const double* G, Lane& L, con
         if (PH == 0) runControlSystem(B, G, L);             /* `not self.isUnderChute` (rocket.py:646-656) */
         if (L.dof3 != (PH == 1)) { left = true; active = false; }
     }
-    StepResult r = integrateStep<PH, CONVOY>(B, L, ks, L.s, L.time, dt, active);
-    if (active) {
+    StepResult r = integrateStep<PH, CONVOY>(B, L, ks, L.s, L.time, dt, active, retry);
+    if (active && !r.rejected) {
         if (PH == 1) L.nSteps3++;
         L.time += r.dt;
         if (L.qAliased) { L.targetQ = L.s.q; L.qAliased = false; }

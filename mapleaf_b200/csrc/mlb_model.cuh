@@ -789,31 +789,53 @@ MLB_COMP_FINS ForceMoment finSetForce(const double* B, const Lane& L, Aero& a, c
         const V3 vOuter = airVelRelativeToFin + ust * rOuter;
         const bool uniform = MLB_FIN_UNIFORM && (vOuter.x == airVelRelativeToFin.x) && (vOuter.y == airVelRelativeToFin.y) && (vOuter.z == airVelRelativeToFin.z)
                              && (C[FS_SLICE_R] <= rOuter);
-        /* Almost the same holds while the spin term is merely tiny next to the air speed (roll rates that grow out of rounding noise on a
-           rocket without fin cant, 1e-13 of the air speed in the bench workload): the slice angle is then its value on the axis plus a
-           term linear in the slice radius, alpha(r) = asin(b0) + r (db/dr) / sqrt(1 - b0^2) with b(r) = n.(A + U r) / |A + U r|. The
-           neglected second-order term is below (|U| r / |A|)^2 <= 1e-18 rad, under the last bit of the arcsine the reference takes per
-           slice. This is the GPU path's one departure from the reference's operation sequence in the force model; it replaces nine of
-           ten arcsine / square-root / reciprocal chains per fin, and because warps mix rolling-noise lanes with exactly non-rolling
-           ones, those chains used to run for every warp at a third of its lanes (profiles/r2a). Fin cant, real roll and stalled or
-           near-perpendicular flow take the per-slice path below. */
+        /* Almost the same holds while the spin term is merely small next to the air speed (roll that grows out of rounding noise on a
+           rocket without fin cant: 1e-13 of the air speed in the bench workload; the residual roll of a canard-controlled ascent: up to
+           4e-6): with eps = |U| r / |A| <= 1e-5 the slice angle alpha(r) = asin(n.(A + U r) / |A + U r|) is expanded about the axis,
+           1 / |A + U r| through the binomial series of (1 + x)^(-1/2) to x^3 (x = (2 A.U r + U.U r^2) / A.A, |x| <= 2.1e-5, next term
+           5e-20) and the arcsine to second order in b(r) - b(0) (next term 2e-16 rad). That is at the rounding level of the arcsine /
+           square-root / reciprocal chain the reference runs per slice, which this replaces for nine of ten slices per fin; it is the
+           GPU path's one departure from the reference's operation sequence in the force model (the oracle keeps the per-slice chain).
+           Because warps mix noise-level rollers with exactly non-rolling lanes, the per-slice chain used to run for every warp at a
+           third of its lanes (profiles/r2a). A warp takes this path only when all its lanes can (warp vote), so the two paths are never
+           both executed; fin cant, real roll and stalled or near-perpendicular flow take the per-slice path below. */
         bool linear = false;
         if (MLB_FIN_LINEAR) {                               /* exactly non-rolling lanes too: one code path for the whole warp */
             const double m2 = dot(airVelRelativeToFin, airVelRelativeToFin), u2 = dot(ust, ust);
-            if (m2 > 0.04 && u2 * (rOuter * rOuter) < 1e-18 * m2 && C[FS_SLICE_R] >= 0 && C[FS_SLICE_R] <= rOuter) {
-                const double m0 = sqrt(m2), rm = rcpNormal(m0);
-                double b0 = dot(finNormal, airVelRelativeToFin) * rm;
-                const double c2 = 1 - b0 * b0;
-                if (c2 > 1e-4) {
-                    const double al0 = m_asin(b0);
-                    const double dbdr = (dot(finNormal, ust) - b0 * (dot(airVelRelativeToFin, ust) * rm)) * rm;
-                    const double dadr = dbdr / sqrt(c2);
+            double b0 = 0, c2 = 0, rm = 0;
+            bool ok = m2 > 0.04 && u2 * (rOuter * rOuter) < 1e-10 * m2 && C[FS_SLICE_R] >= 0 && C[FS_SLICE_R] <= rOuter;
+            if (ok) {
+                rm = rcpNormal(sqrt(m2));
+                b0 = dot(finNormal, airVelRelativeToFin) * rm;
+                c2 = 1 - b0 * b0;
+                ok = c2 > 1e-4;
+            }
+            const unsigned warp = __activemask();
+            linear = __all_sync(warp, ok);
+            if (linear) {
+                const double al0 = m_asin(b0);
+                const double rc = 1.0 / sqrt(c2);                          /* d asin / d b */
+                const double q = dot(finNormal, ust), au = dot(airVelRelativeToFin, ust);
+                if (__all_sync(warp, u2 * (rOuter * rOuter) < 1e-18 * m2)) {
+                    /* noise-level roll in every lane of the warp (eps <= 1e-9): the first-order term alone is exact to 1e-18 rad */
+                    const double dadr = (q - b0 * (au * rm)) * rm * rc;
                     for (int i = 0; i < nS; i++) {
                         double al = fma(dadr, C[FS_SLICE_R + i], al0);
                         if (fabs(al) > stall) al *= fabs(stall / al);
                         aoa[i] = al;
                     }
-                    linear = true;
+                } else {
+                    const double k2 = 0.5 * b0 * (rc * rc * rc);            /* half the second derivative */
+                    const double au2 = 2 * au, p0 = dot(finNormal, airVelRelativeToFin), rm2 = rm * rm;
+                    for (int i = 0; i < nS; i++) {
+                        const double r = C[FS_SLICE_R + i];
+                        const double e = -(r * fma(u2, r, au2)) * rm2;     /* 1 - |A + U r|^2 / |A|^2 */
+                        const double poly = fma(e, fma(e, fma(e, 0.3125, 0.375), 0.5), 1.0);
+                        const double d = fma(fma(q, r, p0) * rm, poly, -b0);   /* b(r) - b(0) */
+                        double al = fma(d, fma(d, k2, rc), al0);
+                        if (fabs(al) > stall) al *= fabs(stall / al);
+                        aoa[i] = al;
+                    }
                 }
             }
         }

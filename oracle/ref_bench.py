@@ -39,12 +39,11 @@ def _initReference(defFile, overrides):
 
 
 def _runReference(job):
-    """job = (wind xyz, (pinkSeed1, pinkSeed2)). One trajectory through the reference's own Simulation.run()."""
-    wind, seeds = job
+    """job = {definition key: value} of one sample (sampled wind, pink-noise seeds, motor factors). One trajectory through the reference's
+    own Simulation.run()."""
     sd = _state["sd"]
-    sd.setValue("Environment.ConstantMeanWind.velocity", "({} {} {})".format(*wind))
-    sd.setValue("Environment.PinkNoiseModel.randomSeed1", str(int(seeds[0])))
-    sd.setValue("Environment.PinkNoiseModel.randomSeed2", str(int(seeds[1])))
+    for k, v in job.items():
+        sd.setValue(k, v)
     t0 = time.perf_counter()
     sim = _state["Simulation"](simDefinition=sd, silent=True)
     flights, _ = sim.run()
@@ -65,16 +64,15 @@ def _initPort(defFile, overrides):
 
 
 def _runPort(job):
-    """job = (winds [3, n], seeds [3, n])."""
+    """job = {LANE_* id: [components, n] array}."""
     import numpy as np
-    from mapleaf_b200 import L
     from oracle import oracle
-    w, s = job
-    w = np.asarray(w, dtype=float)
+    arrays = {k: np.asarray(a, dtype=float) for k, a in job.items()}
+    n = next(iter(arrays.values())).shape[1]
     t0 = time.perf_counter()
-    o = oracle.run(_state["model"].blob, w.shape[1], {L.LANE_WIND: w, L.LANE_PINK_SEED: np.asarray(s, dtype=float)})
+    o = oracle.run(_state["model"].blob, n, arrays)
     dt = time.perf_counter() - t0
-    return int(o["counters"][:, 0].sum()), w.shape[1], dt
+    return int(o["counters"][:, 0].sum()), n, dt
 
 
 class CpuArm:

@@ -221,21 +221,32 @@ def test_bench_flop_constants_are_the_oracle_op_counts():
     lanes of the bench workload; the op-counting build must also reproduce the plain oracle bit for bit."""
     import bench
     from oracle import oracle
-    sd = SimDefinition(bench.DEFINITION, silent=True, disableDistributionSampling=True)
-    m = buildModel(sd)
+    cfg = bench.CONFIGS[1]
+    m = bench.buildConfigModel(cfg)
     wind, seeds = np.array([[3.0, -1.0], [1.5, 4.0], [0.2, -0.3]]), np.array([[11.0, 5.0], [7.0, 123456.0], [0.0, 0.0]])
     arrays = {L.LANE_WIND: wind, L.LANE_PINK_SEED: seeds}
     out, ops = oracle.runCounted(m.blob, 2, arrays)
     plain = oracle.run(m.blob, 2, arrays)
     assert (out["finals"] == plain["finals"]).all() and (out["counters"] == plain["counters"]).all()
     per = {k: v["flops"] / v["count"] for k, v in ops["buckets"].items()}
-    for key, const in (("eval_6dof", bench.FLOP_EVAL_6DOF), ("eval_6dof_transonic", bench.FLOP_EVAL_6DOF_TRANSONIC), ("eval_3dof", bench.FLOP_EVAL_3DOF),
-                       ("step_rest_6dof", bench.FLOP_STEP_ALGEBRA_6DOF), ("step_rest_3dof", bench.FLOP_STEP_ALGEBRA_3DOF)):
+    f = cfg["flops"]
+    for key, const in (("eval_6dof", f["eval6"]), ("eval_6dof_transonic", f["eval6t"]), ("eval_3dof", f["eval3"]),
+                       ("step_rest_6dof", f["step6"]), ("step_rest_3dof", f["step3"])):
         assert abs(per[key] - const) <= 0.01 * const, (key, per[key], const)
     c = dict(derivative_evals=int(out["counters"][:, 1].sum()), derivative_evals_3dof=ops["buckets"]["eval_3dof"]["count"],
              derivative_evals_transonic=ops["buckets"]["eval_6dof_transonic"]["count"], steps=int(out["counters"][:, 0].sum()),
              steps_3dof=ops["buckets"]["step_rest_3dof"]["count"], rejected_steps=int(out["counters"][:, 2].sum()))
-    assert abs(bench.algorithmicFlops(c) - ops["flops"]) <= 0.01 * ops["flops"]          # the bench formula reproduces the total
+    assert abs(sum(bench.algorithmicFlops(c, f)) - ops["flops"]) <= 0.01 * ops["flops"]          # the bench formula reproduces the total
+
+
+def test_bench_reference_arm_inputs_match_the_product_sampler():
+    """The reference arm draws its inputs with CPython's `random` alone (no product library on that arm); the product arm draws the same
+    samples with the C++ sampler."""
+    import bench
+    w1, s1 = bench.sampleInputs(5, 7)
+    w2, s2 = bench.sampleInputsPython(5, 7)
+    assert (w1 == w2).all() and (s1 == s2).all()
+    assert (bench.motorFactors(3, 5) == bench.motorFactors(3, 5, python=True)).all()
 
 
 def test_runner_flight_paths_output(monkeypatch, tmp_path, golden):

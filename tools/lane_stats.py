@@ -5,8 +5,7 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.ins
 import bench
 from mapleaf_b200 import L, SimDefinition, backend, buildModel
 lanes = int(sys.argv[1]) if len(sys.argv) > 1 else 151552
-sd = SimDefinition(bench.DEFINITION, silent=True, disableDistributionSampling=True)
-m = buildModel(sd)
+m = bench.buildConfigModel(bench.CONFIGS[1])
 wind, seeds = bench.sampleInputs(0, lanes)
 with backend.TrajectoryBatch(m.blob) as b:
     b.setLanes(lanes, {L.LANE_WIND: wind, L.LANE_PINK_SEED: seeds}); b.run(); c = b.laneCounters(); tot = b.counters()

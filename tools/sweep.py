@@ -11,14 +11,22 @@ sys.path.insert(0, REPO)
 def child(args):
     import bench
     from mapleaf_b200 import L, SimDefinition, backend, buildModel
-    sd = SimDefinition(os.path.join(REPO, "mapleaf_b200", "data", "Simulations", args.definition), silent=True, disableDistributionSampling=True)
-    for kv in args.set or []:
-        k, v = kv.split("=", 1); sd.setValue(k, v)
-    m = buildModel(sd)
-    wind, seeds = bench.sampleInputs(0, args.lanes)
-    lanes = {L.LANE_WIND: wind}
-    if int(m.blob[L.H_TURB]) in (L.TURB_PINK1D, L.TURB_PINK2D, L.TURB_PINK3D):
-        lanes[L.LANE_PINK_SEED] = seeds
+    if args.config >= 0:
+        cfg = dict(bench.CONFIGS[args.config])
+        if args.no_motor:
+            cfg["motor"] = False
+        m = bench.buildConfigModel(cfg)
+        lanes = bench.laneInputs(cfg, m, 0, args.lanes)
+        args.definition = "config%d%s" % (args.config, "-nomotor" if args.no_motor else "")
+    else:
+        sd = SimDefinition(os.path.join(REPO, "mapleaf_b200", "data", "Simulations", args.definition), silent=True, disableDistributionSampling=True)
+        for kv in args.set or []:
+            k, v = kv.split("=", 1); sd.setValue(k, v)
+        m = buildModel(sd)
+        wind, seeds = bench.sampleInputs(0, args.lanes)
+        lanes = {L.LANE_WIND: wind}
+        if int(m.blob[L.H_TURB]) in (L.TURB_PINK1D, L.TURB_PINK2D, L.TURB_PINK3D):
+            lanes[L.LANE_PINK_SEED] = seeds
     for block, bail, gens in itertools.product(args.blocks.split(","), args.bails.split(","), args.gens.split(",")):
         os.environ["MLB_BLOCK_SIZE"] = block; os.environ["MLB_BAIL_PERMILLE"] = bail; os.environ["MLB_NUM_GENERATIONS"] = gens
         with backend.TrajectoryBatch(m.blob) as b:
@@ -41,6 +49,8 @@ if __name__ == "__main__":
     ap.add_argument("--bails", default="500")
     ap.add_argument("--gens", default="6")
     ap.add_argument("--set", action="append")
+    ap.add_argument("--config", type=int, default=-1, help="a bench.py configuration (definition, overrides and sampled inputs) instead of --def")
+    ap.add_argument("--no-motor", action="store_true", help="with --config 3: leave the motor factors unsampled")
     ap.add_argument("--child", action="store_true")
     args = ap.parse_args()
     if args.child or not args.libs:

@@ -7,14 +7,7 @@ VDIR = os.path.join(REPO, "mapleaf_b200", "lib", "variants")
 # name -> extra nvcc flags; edit for the experiment at hand (switches: MLB_FLIGHT_SHAPES, MLB_COMP_NOINLINE, MLB_COLD_MASK, MLB_MATH_NOINLINE,
 # MLB_FIN_UNIFORM, MLB_FIN_LINEAR, MLB_CHUTE_BLOCK, MLB_CHUTE_CTAS, MLB_DERIV_NOINLINE)
 VARIANTS = {
-    "shapes": ["-DMLB_FLIGHT_SHAPES(X)=X(640,1) X(768,1) X(896,1) X(256,1) X(384,1)"],
-    "comp0": ["-DMLB_FLIGHT_SHAPES(X)=X(1024,1) X(512,1)", "-DMLB_COMP_NOINLINE=0"],
-    "comp8": ["-DMLB_FLIGHT_SHAPES(X)=X(1024,1) X(512,1)", "-DMLB_COMP_NOINLINE=8"],
-    "cold15": ["-DMLB_FLIGHT_SHAPES(X)=X(1024,1) X(512,1)", "-DMLB_COLD_MASK=15"],
-    "derivnoinline": ["-DMLB_FLIGHT_SHAPES(X)=X(1024,1) X(512,1)", "-DMLB_DERIV_NOINLINE=1"],
-    "chute256x2": ["-DMLB_FLIGHT_SHAPES(X)=X(1024,1)", "-DMLB_CHUTE_BLOCK=256", "-DMLB_CHUTE_CTAS=2"],
-    "chute128x8": ["-DMLB_FLIGHT_SHAPES(X)=X(1024,1)", "-DMLB_CHUTE_BLOCK=128", "-DMLB_CHUTE_CTAS=8"],
-    "chute128x2": ["-DMLB_FLIGHT_SHAPES(X)=X(1024,1)", "-DMLB_CHUTE_BLOCK=128", "-DMLB_CHUTE_CTAS=2"],
+    "nolinear": ["-DMLB_FLIGHT_SHAPES(X)=X(1024,1) X(512,1)", "-DMLB_FIN_LINEAR=0"],
 }
 
 
