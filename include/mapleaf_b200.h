@@ -75,6 +75,15 @@ int mlb_set_lanes(mlb_handle* h, int64_t nLanes, const double* const* perLaneArr
 /* Same, with the arrays already resident in this device's memory (no copy is made; the caller keeps them alive). */
 int mlb_set_lanes_device(mlb_handle* h, int64_t nLanes, const double* const* devLaneArrays, const int* arrayIds, int nArrays);
 
+/* Per-lane MODEL blocks, for Monte Carlo keys that change what the constructors precompute (masses, geometry, launch site, rail ...;
+   SimDefinition.resampleProbabilisticValues re-draws ANY key that has a `_stdDev` companion, IO/simDefinition.py:471-532, and the reference
+   then rebuilds the whole rocket): models = nLanes x strideDoubles doubles, row i = the first H_SHARED_LEN doubles (or more) of lane i's own
+   model block, built by the host from that sample's values. Every row must have the structure of the handle's block (same layout, stages,
+   components, integrator); wind, initial state, rail and end condition are then read from the lane's own header. Call after mlb_set_lanes
+   (which clears it); models = NULL switches back to the handle's block for every lane. Slower than the shared block (each constant is a
+   global load): it is the general path, the common keys (wind, initial state, motor factors) stay per-lane arrays. */
+int mlb_set_lane_models(mlb_handle* h, const double* models, int64_t strideDoubles);
+
 /* Integrates every lane to its end condition. `stream` is a cudaStream_t (NULL = default stream). Asynchronous with
    respect to the host; mlb_results / mlb_finals / mlb_counters / mlb_sync wait for completion. */
 int mlb_run(mlb_handle* h, void* stream);

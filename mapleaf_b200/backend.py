@@ -73,6 +73,7 @@ def lib():
     l.mlb_destroy.restype = None
     l.mlb_set_lanes.argtypes = [vp, i64, ctypes.POINTER(dp), ip, ctypes.c_int]
     l.mlb_set_lanes_device.argtypes = [vp, i64, ctypes.POINTER(vp), ip, ctypes.c_int]
+    l.mlb_set_lane_models.argtypes = [vp, dp, i64]
     l.mlb_run.argtypes = [vp, vp]
     l.mlb_sync.argtypes = [vp]
     l.mlb_results.argtypes = [vp, dp, ctypes.POINTER(ctypes.c_int32)]
@@ -98,7 +99,7 @@ def lib():
     return l
 
 
-EXPORTED_SYMBOLS = ["mlb_create", "mlb_destroy", "mlb_last_error", "mlb_version", "mlb_set_lanes", "mlb_set_lanes_device", "mlb_run", "mlb_sync",
+EXPORTED_SYMBOLS = ["mlb_create", "mlb_destroy", "mlb_last_error", "mlb_version", "mlb_set_lanes", "mlb_set_lanes_device", "mlb_set_lane_models", "mlb_run", "mlb_sync",
                     "mlb_results", "mlb_finals", "mlb_counters", "mlb_lane_counters", "mlb_device_results", "mlb_set_result_buffers", "mlb_moments", "mlb_set_flight_log", "mlb_get_flight_log", "mlb_set_trace",
                     "mlb_get_trace", "mlb_set_dt_replay", "mlb_force_eval", "mlb_host_gauss_stream", "mlb_host_randrange_stream", "mlb_host_gauss_from_state", "mlb_host_randrange_from_state", "mlb_fp64_peak"]
 
@@ -166,6 +167,16 @@ class TrajectoryBatch:
         _check(lib().mlb_set_lanes_device(self._h, nLanes, ptrs, ids.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), len(devicePointers)), "mlb_set_lanes_device")
         self.nLanes = nLanes
         self._keep = [keepAlive]
+
+    def setLaneModels(self, models):
+        """models: float64 [nLanes, >= H_SHARED_LEN]: each lane's own model block (see mlb_set_lane_models); None switches back."""
+        if models is None:
+            _check(lib().mlb_set_lane_models(self._h, None, 0), "mlb_set_lane_models")
+            return
+        m = np.ascontiguousarray(models, dtype=np.float64)
+        if m.ndim != 2 or m.shape[0] != self.nLanes:
+            raise ValueError("lane models must have shape (nLanes, words), got {}".format(m.shape))
+        _check(lib().mlb_set_lane_models(self._h, _dp(m), m.shape[1]), "mlb_set_lane_models")
 
     def run(self, stream: int = 0, sync: bool = False):
         _check(lib().mlb_run(self._h, ctypes.c_void_p(stream)), "mlb_run")

@@ -39,6 +39,7 @@ using namespace mlb;
 #ifndef MLB_FLIGHT_SHAPES
 #define MLB_FLIGHT_SHAPES(X) X(128, 2) X(512, 1) X(1024, 1)
 #endif
+#define MLB_PERLANE_BLOCK 512        /* CTA shape of the free-flight kernel that reads per-lane model blocks */
 #ifndef MLB_CHUTE_BLOCK
 #define MLB_CHUTE_BLOCK 128         /* under-chute kernel: CTA size and CTAs per SM (registers per lane = 65536 / (block x CTAs)) */
 #endif
@@ -75,6 +76,7 @@ struct RunArgs {
     double* trace; long long traceLane, traceCount, traceMaxRows, traceEvery; long long* traceRows;     /* flight log of lanes [traceLane, traceLane + traceCount) */
     const double* dtReplay; long long nReplay;
     LaneRec* recs;
+    const double* laneModels; long long laneModelStride;      /* per-lane model blocks (mlb_set_lane_models): lane i reads its constants from laneModels + i * stride */
     /* lane queues: entries are lane indices. qIn == nullptr: the identity over [0, nLanes) */
     const int* qIn; const int* qInCount;
     int* qNext; int* qNextCount;          /* stragglers of this generation (free flight) */
@@ -107,13 +109,25 @@ __device__ __noinline__ void traceRow(const RunArgs& a, double* base, const Lane
 MLB_DEV bool laneTraced(const RunArgs& a, long long lane) { return a.trace != nullptr && lane >= a.traceLane && lane < a.traceLane + a.traceCount; }
 
 /* Lane prologue: Simulation.__init__ .. the first endDetector call of Simulation.run (SingleSimulations.py:89-101). */
-__global__ void __launch_bounds__(MLB_BLOCK) initLanes(const RunArgs a) {
+/* The model block every thread of a CTA reads: staged in shared memory once per CTA. PERLANE kernels (Monte Carlo keys that change the
+   model itself: masses, geometry, launch site ...) skip this and read each lane's own block from global memory. */
+template <bool PERLANE>
+MLB_DEV const double* stageModel(const RunArgs& a) {
     extern __shared__ double smem[];
-    double* B = smem;
-    for (int i = threadIdx.x; i < a.blobLen; i += blockDim.x) B[i] = a.blob[i];
-    __syncthreads();
+    if constexpr (PERLANE) return nullptr;
+    else {
+        for (int i = threadIdx.x; i < a.blobLen; i += blockDim.x) smem[i] = a.blob[i];
+        __syncthreads();
+        return smem;
+    }
+}
+
+template <bool PERLANE>
+__global__ void __launch_bounds__(MLB_BLOCK) initLanes(const RunArgs a) {
+    const double* B = stageModel<PERLANE>(a);
     const long long lane = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (lane >= a.in.nLanes) return;
+    if (PERLANE) B = a.laneModels + lane * a.laneModelStride;
     LaneRec& R = a.recs[lane];
     Lane L;
     laneInit(B, L, a.in, lane, a.mt, true);
@@ -131,6 +145,7 @@ __global__ void __launch_bounds__(MLB_BLOCK) initLanes(const RunArgs a) {
     bool end, haveFinal; double finalDt;
     endDetector(B, L, R.dt, end, haveFinal, finalDt);
     R.finalDt = finalDt;
+    if (L.eventOverflow) { R.st = ST_UNSUPPORTED; end = true; }
     R.flags = (end ? REC_END : 0) | (haveFinal ? REC_HAVE_FINAL : 0);
     for (int k = 0; k < 12; k++) R.k0[k] = 0;
     R.L = L;
@@ -157,7 +172,7 @@ MLB_DEV void finishLane(const RunArgs& a, long long lane, const Lane& L, V3 prev
 
 /* The Simulation.run loop (SingleSimulations.py:102-139) of one flight phase. PH 0: free flight, convoy execution, CTA-uniform control
    flow (out-of-range and finished threads stay and keep the barriers company). PH 1: under parachute, every thread on its own. */
-template <int PH, bool CONVOY>
+template <int PH, bool CONVOY, bool PERLANE>
 MLB_DEV void flightLoop(const RunArgs& a, const double* B) {
     const long long count = a.qIn ? (long long)*a.qInCount : a.in.nLanes;
     /* Lanes per CTA. The convoy kernel spreads the queue evenly over whole waves of CTAs (a.ctaSlots CTAs run at a time): 10^5 lanes are
@@ -172,6 +187,7 @@ MLB_DEV void flightLoop(const RunArgs& a, const double* B) {
     const long long slot = (long long)blockIdx.x * per + threadIdx.x;
     const bool inRange = slot < count;
     const long long lane = inRange ? (a.qIn ? (long long)a.qIn[slot] : slot) : 0;
+    if (PERLANE) B = a.laneModels + lane * a.laneModelStride;
     /* RK stage derivatives: per-thread local memory, indexed dynamically by the tableau loops */
     double kLocal[MLB_K_SLOTS_MAX * (PH == 1 ? 6 : 12)];
     KStore ks; ks.base = kLocal; ks.slotStride = (PH == 1 ? 6 : 12);
@@ -220,6 +236,7 @@ MLB_DEV void flightLoop(const RunArgs& a, const double* B) {
             double hv = sqrt(L.s.vel.x * L.s.vel.x + L.s.vel.y * L.s.vel.y); if (hv > maxH) maxH = hv;
             if (!(L.s.pos.z == L.s.pos.z) || !(L.s.vel.x == L.s.vel.x)) { st = ST_NAN; end = true; }
             else if (L.nSteps >= maxSteps) { st = ST_STEP_LIMIT; end = true; }
+            else if (L.eventOverflow) { st = ST_UNSUPPORTED; end = true; }
             else endDetector(B, L, dt, end, haveFinal, finalDt);
             if (tracing) traceRow(a, traceBase, L, rows, traceStride, r.dt, r.err, end);
         }
@@ -257,21 +274,14 @@ MLB_DEV void flightLoop(const RunArgs& a, const double* B) {
     }
 }
 
-template <int BLOCK, int MIN_BLOCKS>
+template <int BLOCK, int MIN_BLOCKS, bool PERLANE>
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) flightLanes(const RunArgs a) {
-    extern __shared__ double smem[];
-    double* B = smem;
-    for (int i = threadIdx.x; i < a.blobLen; i += blockDim.x) B[i] = a.blob[i];
-    __syncthreads();
-    flightLoop<0, true>(a, B);
+    flightLoop<0, true, PERLANE>(a, stageModel<PERLANE>(a));
 }
 
+template <bool PERLANE>
 __global__ void __launch_bounds__(MLB_CHUTE_BLOCK, MLB_CHUTE_CTAS) chuteLanes(const RunArgs a) {
-    extern __shared__ double smem[];
-    double* B = smem;
-    for (int i = threadIdx.x; i < a.blobLen; i += blockDim.x) B[i] = a.blob[i];
-    __syncthreads();
-    flightLoop<1, false>(a, B);
+    flightLoop<1, false, PERLANE>(a, stageModel<PERLANE>(a));
 }
 
 
@@ -363,6 +373,7 @@ struct mlb_handle {
     double* d_resultsOwned = nullptr; int* d_statusOwned = nullptr;
     uint32_t* d_mt = nullptr;
     LaneRec* d_recs = nullptr;
+    double* d_laneModels = nullptr; size_t laneModelBytes = 0; long long laneModelStride = 0; bool haveLaneModels = false;
     int* d_queue[3] = { nullptr, nullptr, nullptr };      /* two straggler queues (ping-pong) and the under-chute queue */
     int* d_queueCount = nullptr;                          /* MLB_GENERATIONS + 1 counters */
     double* d_trace = nullptr; long long traceLane = -1, traceCount = 0, traceMaxRows = 0, traceEvery = 1; long long* d_traceRows = nullptr;
@@ -383,7 +394,8 @@ static void freeLanes(mlb_handle* h) {
     for (int i = 0; i < LANE_NUM_ARRAYS; i++) { cudaFree(h->d_laneOwned[i]); h->d_laneOwned[i] = nullptr; h->laneBytes[i] = 0; h->d_lane[i] = nullptr; }
     cudaFree(h->d_resultsOwned); cudaFree(h->d_statusOwned);
     h->d_resultsOwned = nullptr; h->d_statusOwned = nullptr; h->ownResults = true;
-    cudaFree(h->d_finals); cudaFree(h->d_counters); cudaFree(h->d_mt); cudaFree(h->d_recs);
+    cudaFree(h->d_finals); cudaFree(h->d_counters); cudaFree(h->d_mt); cudaFree(h->d_recs); cudaFree(h->d_laneModels);
+    h->d_laneModels = nullptr; h->laneModelBytes = 0; h->haveLaneModels = false;
     for (int i = 0; i < 3; i++) { cudaFree(h->d_queue[i]); h->d_queue[i] = nullptr; }
     h->d_results = h->d_finals = nullptr; h->d_status = nullptr; h->d_counters = nullptr; h->d_mt = nullptr; h->d_recs = nullptr;
     h->nLanes = 0; h->capLanes = 0; h->ran = false;
@@ -395,10 +407,10 @@ extern "C" const char* mlb_version(void) { return "mapleaf_b200 0.2 (sm_100a)"; 
 static int createOnDevice(mlb_handle* h, const double* b, size_t len) {
     CU(cudaMalloc(&h->d_blob, len * sizeof(double)));
     CU(cudaMemcpy(h->d_blob, b, len * sizeof(double), cudaMemcpyHostToDevice));
-#define MLB_SET_SMEM(N, M) CU((cudaFuncSetAttribute(flightLanes<N, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes)));
+#define MLB_SET_SMEM(N, M) CU((cudaFuncSetAttribute(flightLanes<N, M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes)));
     MLB_FLIGHT_SHAPES(MLB_SET_SMEM)
-    CU(cudaFuncSetAttribute(chuteLanes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
-    CU(cudaFuncSetAttribute(initLanes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
+    CU(cudaFuncSetAttribute(chuteLanes<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
+    CU(cudaFuncSetAttribute(initLanes<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
     CU(cudaFuncSetAttribute(forceEvalKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
     { cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, h->device)); h->nSM = prop.multiProcessorCount; }
     CU(cudaEventCreate(&h->ev0)); CU(cudaEventCreate(&h->ev1)); CU(cudaEventCreate(&h->evFlight0)); CU(cudaEventCreate(&h->evFlight1));
@@ -502,11 +514,34 @@ static int setLanes(mlb_handle* h, int64_t nLanes, const double* const* arrays, 
         h->d_lane[id] = h->d_laneOwned[id];
     }
     h->d_results = h->d_resultsOwned; h->d_status = h->d_statusOwned; h->ownResults = true;
+    h->haveLaneModels = false;
     h->nLanes = nLanes;
     return MLB_OK;
 }
 extern "C" int mlb_set_lanes(mlb_handle* h, int64_t nLanes, const double* const* arrays, const int* ids, int nArrays) { return setLanes(h, nLanes, arrays, ids, nArrays, false); }
 extern "C" int mlb_set_lanes_device(mlb_handle* h, int64_t nLanes, const double* const* arrays, const int* ids, int nArrays) { return setLanes(h, nLanes, arrays, ids, nArrays, true); }
+
+extern "C" int mlb_set_lane_models(mlb_handle* h, const double* models, int64_t strideDoubles) {
+    if (!h) return fail(MLB_ERR_ARG, "null handle");
+    if (h->nLanes <= 0) return fail(MLB_ERR_STATE, "mlb_set_lane_models: call mlb_set_lanes first");
+    if (!models) { h->haveLaneModels = false; return MLB_OK; }
+    if (strideDoubles < (int64_t)h->sharedLen) return fail(MLB_ERR_ARG, "mlb_set_lane_models: stride shorter than the shared part of the model block (H_SHARED_LEN)");
+    /* every lane's block must be a variant of the handle's: same layout, same length, same integrator and structure offsets */
+    static const int same[] = { H_MAGIC, H_VERSION, H_LEN, H_SHARED_LEN, H_NSTAGES, H_INTEGRATOR, H_TAB_NSTAGE_ROWS, H_TAB_NRESULT_ROWS, H_TABLEAU_OFF, H_CTRL_OFF, H_RECOVERY_OFF, H_STAGE_OFF, H_TURB };
+    for (int64_t i = 0; i < h->nLanes; i++)
+        for (int k : same)
+            if (models[i * strideDoubles + k] != h->blob[k]) return fail(MLB_ERR_ARG, "mlb_set_lane_models: lane " + std::to_string(i) + " has a different model structure than the handle's model block (header word " + std::to_string(k) + ")");
+    CU(cudaSetDevice(h->device));
+    const size_t bytes = (size_t)h->nLanes * strideDoubles * sizeof(double);
+    if (bytes > h->laneModelBytes) {
+        cudaFree(h->d_laneModels); h->d_laneModels = nullptr; h->laneModelBytes = 0;
+        CU(cudaMalloc(&h->d_laneModels, bytes));
+        h->laneModelBytes = bytes;
+    }
+    CU(cudaMemcpy(h->d_laneModels, models, bytes, cudaMemcpyHostToDevice));
+    h->laneModelStride = strideDoubles; h->haveLaneModels = true; h->ran = false;
+    return MLB_OK;
+}
 
 extern "C" int mlb_run(mlb_handle* h, void* stream) {
     if (!h) return fail(MLB_ERR_ARG, "null handle");
@@ -523,6 +558,8 @@ extern "C" int mlb_run(mlb_handle* h, void* stream) {
     if (a.trace) CU(cudaMemsetAsync(h->d_traceRows, 0, (size_t)h->traceCount * sizeof(long long), s));
     a.dtReplay = h->d_replay; a.nReplay = h->nReplay;
     a.recs = h->d_recs;
+    a.laneModels = h->haveLaneModels ? h->d_laneModels : nullptr; a.laneModelStride = h->laneModelStride;
+    const bool perLane = h->haveLaneModels;
     a.qIn = nullptr; a.qInCount = nullptr; a.qNext = nullptr; a.qNextCount = nullptr; a.qChute = h->d_queue[2]; a.qChuteCount = h->d_queueCount + MLB_GENERATIONS; a.bailPermille = 0;
     /* CTA shape of the free-flight kernel: the one with the fewest (waves of CTAs) x (duration of a wave of that shape relative to a
        1024-lane wave). A wave's duration grows a little slower than its lane count (0.45 / 0.55 / 1 for 2 x 128 / 512 / 1024 lanes per SM,
@@ -541,6 +578,7 @@ extern "C" int mlb_run(mlb_handle* h, void* stream) {
     }
 #define MLB_ALLOW_SHAPE(N, M) if (h->forceBlock == N) block = N;
     MLB_FLIGHT_SHAPES(MLB_ALLOW_SHAPE)
+    if (perLane) block = MLB_PERLANE_BLOCK;                    /* one shape: every constant is a global load there, fewer lanes per SM keep them cached */
     h->lastBlock = block;
     const int ctaSlots = h->nSM * (block == 128 ? 2 : 1);
     const unsigned grid = (unsigned)((h->nLanes + block - 1) / block) + (h->evenSplit ? ctaSlots + 1 : 0);      /* even split: at most this many CTAs */
@@ -548,7 +586,8 @@ extern "C" int mlb_run(mlb_handle* h, void* stream) {
     h->launches = 0;
     CU(cudaEventRecord(h->ev0, s));
     CU(cudaMemsetAsync(h->d_queueCount, 0, (MLB_GENERATIONS + 2) * sizeof(int), s));
-    initLanes<<<(unsigned)((h->nLanes + MLB_BLOCK - 1) / MLB_BLOCK), MLB_BLOCK, h->smemBytes, s>>>(a);
+    if (perLane) initLanes<true><<<(unsigned)((h->nLanes + MLB_BLOCK - 1) / MLB_BLOCK), MLB_BLOCK, 0, s>>>(a);
+    else initLanes<false><<<(unsigned)((h->nLanes + MLB_BLOCK - 1) / MLB_BLOCK), MLB_BLOCK, h->smemBytes, s>>>(a);
     h->launches++;
     CU(cudaGetLastError());
     /* Free flight, MLB_GENERATIONS launches over ping-pong straggler queues. Every launch is sized for the whole batch (CTAs past the end
@@ -563,15 +602,17 @@ extern "C" int mlb_run(mlb_handle* h, void* stream) {
         a.qInCount = g == 0 ? nullptr : h->d_queueCount + (g - 1);
         a.qNext = h->d_queue[g & 1]; a.qNextCount = h->d_queueCount + g;
         a.bailPermille = (g == G - 1 || singleWave) ? 0 : h->bailPermille;
-#define MLB_LAUNCH_SHAPE(N, M) if (block == N) flightLanes<N, M><<<grid, N, h->smemBytes, s>>>(a);
+#define MLB_LAUNCH_SHAPE(N, M) if (block == N && !perLane) flightLanes<N, M, false><<<grid, N, h->smemBytes, s>>>(a);
         MLB_FLIGHT_SHAPES(MLB_LAUNCH_SHAPE)
+        if (perLane) flightLanes<MLB_PERLANE_BLOCK, 1, true><<<grid, MLB_PERLANE_BLOCK, 0, s>>>(a);
         h->launches++;
         CU(cudaGetLastError());
     }
     CU(cudaEventRecord(h->evFlight1, s));
     /* Under parachute: everything the free-flight launches queued */
     a.qIn = h->d_queue[2]; a.qInCount = h->d_queueCount + MLB_GENERATIONS; a.qNext = nullptr; a.qNextCount = nullptr; a.qChute = nullptr; a.qChuteCount = nullptr; a.bailPermille = 0; a.ctaSlots = 0;
-    chuteLanes<<<(unsigned)((h->nLanes + MLB_CHUTE_BLOCK - 1) / MLB_CHUTE_BLOCK), MLB_CHUTE_BLOCK, h->smemBytes, s>>>(a);
+    if (perLane) chuteLanes<true><<<(unsigned)((h->nLanes + MLB_CHUTE_BLOCK - 1) / MLB_CHUTE_BLOCK), MLB_CHUTE_BLOCK, 0, s>>>(a);
+    else chuteLanes<false><<<(unsigned)((h->nLanes + MLB_CHUTE_BLOCK - 1) / MLB_CHUTE_BLOCK), MLB_CHUTE_BLOCK, h->smemBytes, s>>>(a);
     h->launches++;
     CU(cudaGetLastError());
     CU(cudaEventRecord(h->ev1, s));

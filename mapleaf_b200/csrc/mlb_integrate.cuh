@@ -201,7 +201,7 @@ MLB_DEV bool laneAdaptive(const double* B, const Lane& L) { return !L.forceRK4 &
  * Flight events
  * ------------------------------------------------------------------------------------------- */
 MLB_DEV void subscribeEvent(Lane& L, int type, double value, double delay, int cb) {
-    if (L.nEvents >= MLB_MAX_EVENTS) return;
+    if (L.nEvents >= MLB_MAX_EVENTS) { L.eventOverflow = true; return; }      /* never dropped silently: the time loop ends the lane */
     Event& e = L.events[L.nEvents++];
     e.type = type; e.value = value; e.delay = delay; e.callback = cb;
 }
@@ -439,7 +439,7 @@ MLB_DEV void laneInit(const double* B, Lane& L, const LaneInputs& in, long long 
     L.time = B[H_START_TIME];
     L.dof3 = false; L.underChute = false; L.haveLast = false; L.haveCache = false; L.resorted = false;
     L.lastVz = 0; L.lastTime = 0; L.pidLastError = 0; L.pidIntegral = 0;
-    L.nSteps = 0; L.nEvals = 0; L.nRejects = 0; L.nEvents = 0; L.nSteps3 = 0; L.nEvals3 = 0; L.nEvalsTransonic = 0;
+    L.nSteps = 0; L.nEvals = 0; L.nRejects = 0; L.nEvents = 0; L.eventOverflow = false; L.nSteps3 = 0; L.nEvals3 = 0; L.nEvalsTransonic = 0;
     L.turb = (int)B[H_TURB];
     for (int g = 0; g < 3; g++) { L.png[g].rng.mt = nullptr; L.png[g].rng.idx = 624; L.png[g].rng.hasNext = 0; L.png[g].rng.next = 0; L.png[g].last0 = 0; L.png[g].last1 = 0; L.png[g].nextSlot = 0; L.png[g].lastValTime = 0; }
     if (live && L.turb >= TURB_PINK1D && L.turb <= TURB_PINK3D) {

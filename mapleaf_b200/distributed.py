@@ -55,16 +55,27 @@ def combineMoments(parts: Sequence[Tuple[float, np.ndarray, np.ndarray]]):
 
 
 def gatherResults(localResults, localStatus, group=None):
-    """All-gather of equally sized per-rank result blocks ([n, 7] float64, [n] int32 torch tensors on the collective's
-    device). Returns ([world * n, 7], [world * n]) in sample order on every rank."""
+    """All-gather of per-rank result blocks ([n_r, 7] float64, [n_r] int32 torch tensors on the collective's device) in rank order.
+    Ranks may hold different numbers of samples (shardRange with nTotal % world != 0): the blocks are padded to the largest for the
+    collective (all_gather_into_tensor needs equal sizes) and trimmed afterwards. Returns ([sum n_r, 7], [sum n_r]) in sample order."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    res = torch.empty((world,) + tuple(localResults.shape), dtype=localResults.dtype, device=localResults.device)
-    st = torch.empty((world,) + tuple(localStatus.shape), dtype=localStatus.dtype, device=localStatus.device)
-    dist.all_gather_into_tensor(res.view(-1), localResults.contiguous().view(-1), group=group)
-    dist.all_gather_into_tensor(st.view(-1), localStatus.contiguous().view(-1), group=group)
-    return res.view(-1, localResults.shape[-1]), st.view(-1)
+    n = int(localResults.shape[0])
+    counts = torch.zeros(world, dtype=torch.int64, device=localResults.device)
+    dist.all_gather_into_tensor(counts, torch.tensor([n], dtype=torch.int64, device=localResults.device), group=group)
+    counts = [int(c) for c in counts.tolist()]
+    nMax, ncol = max(counts), localResults.shape[-1]
+    sendR = torch.zeros((nMax, ncol), dtype=localResults.dtype, device=localResults.device)
+    sendS = torch.full((nMax,), -1, dtype=localStatus.dtype, device=localStatus.device)
+    sendR[:n], sendS[:n] = localResults, localStatus
+    res = torch.empty((world, nMax, ncol), dtype=localResults.dtype, device=localResults.device)
+    st = torch.empty((world, nMax), dtype=localStatus.dtype, device=localStatus.device)
+    dist.all_gather_into_tensor(res.view(-1), sendR.view(-1), group=group)
+    dist.all_gather_into_tensor(st.view(-1), sendS.view(-1), group=group)
+    if all(c == nMax for c in counts):
+        return res.view(-1, ncol), st.view(-1)
+    return torch.cat([res[r, :c] for r, c in enumerate(counts)]), torch.cat([st[r, :c] for r, c in enumerate(counts)])
 
 
 def gatherMoments(count: float, mean: np.ndarray, M2: np.ndarray, device=None, group=None):

@@ -1146,8 +1146,14 @@ def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000) -> Model:
     H[L.H_RAIL_LEN] = railLength
     initPos, initVel, q0, w0 = initialStateGlobalFrame(rk, earth, H[L.H_ELEV], H[L.H_LAT], H[L.H_LON], railLength > 0)
     if railLength > 0:
-        d = hm.v_normalize(env.getVector("Rocket.initialDirection"))
-        qr = hm.q_from_axis_angle(hm.v_cross((0, 0, 1), d), hm.v_angle((0, 0, 1), d))
+        # the rail is aligned with the rocket's initial orientation: rotationAxis / rotationAngle when given, else initialDirection
+        # (environment.py:63-80)
+        railAxis = env.tryGetVector("Rocket.rotationAxis", defaultValue=None)
+        if railAxis is not None:
+            qr = hm.q_from_axis_angle(railAxis, math.radians(env.getFloat("Rocket.rotationAngle")))
+        else:
+            d = hm.v_normalize(env.getVector("Rocket.initialDirection"))
+            qr = hm.q_from_axis_angle(hm.v_cross((0, 0, 1), d), hm.v_angle((0, 0, 1), d))
         railPos = hm.v_add(env.getVector("Rocket.position"), (0, 0, H[L.H_ELEV]))
         if earth in ("Round", "WGS84"):
             railPos, _, qr, _ = hm.convertIntoGlobalFrame(earth, railPos, (0, 0, 0), qr, (0, 0, 0), H[L.H_LAT], H[L.H_LON])

@@ -12,8 +12,8 @@ and the text half of IO/Plotting.plotAndSummarize{Vector,Scalar}Result (:671-752
 Sampling is the reference's: one `random.Random` owned by the SimDefinition, re-drawn once per run in dictionary order
 (IO/simDefinition.py:471-532), pink-noise seeds from the global `random` module, two (1D: one, 3D: three) per run
 (ENV/TurbulenceModelling.py:191-195). The Monte Carlo log has the same lines in the same order.
-What differs: all runs are sampled first and then flown together, so sampled keys must be ones the kernels take per
-lane (wind, initial state, motor adjust factors); any other `_stdDev` key raises NotImplementedError naming it. There is no CPU fallback.
+What differs: all runs are sampled first and then flown together. Wind, initial state and motor adjust factors are per-lane input
+arrays of the kernels; any other `_stdDev` key gives every run its own model block (mlb_set_lane_models). There is no CPU fallback.
 """
 import os
 import random
@@ -159,22 +159,48 @@ def _motorKeys(model):
     return keys
 
 
+_RAIL_STATE_KEYS = {"Rocket.position", "Rocket.rotationAngle", "Rocket.rotationAxis", "Rocket.initialDirection"}
+LANE_MODELS = "models"      # key of the per-lane model blocks in the dictionary sampleRuns returns
+
+
 def _checkSampledKeys(simDefinition, model=None):
+    """(sampled keys in draw order, needLaneModels). Wind, initial state and motor adjust factors are per-lane input arrays of the kernels;
+    any other `_stdDev` key (the reference re-draws whatever has one, IO/simDefinition.py:471-532) changes what the constructors
+    precompute, so every run gets its own model block. So does a sampled launch position / direction when there is a launch rail: the rail's
+    origin and direction and the choice of the Altitude end condition follow the sample (ENV/environment.py:82-91, SingleSimulations.py:214-231)."""
     keys = simDefinition.probabilisticKeys()
     motorKeys = _motorKeys(model)
-    bad = [k for k in keys if k != _WIND_KEY and k not in _INIT_STATE_KEYS and k not in motorKeys]
-    if bad:
-        raise NotImplementedError("Monte Carlo sampling of {} is not implemented by the B200 backend: per-lane inputs are {}, {} and the motors' "
-                                  "impulseAdjustFactor / burnTimeAdjustFactor".format(", ".join(bad), _WIND_KEY, ", ".join(sorted(_INIT_STATE_KEYS))))
-    if any(k in _INIT_STATE_KEYS for k in keys) and float(simDefinition.getValue("Environment.LaunchSite.railLength")) > 0 \
-            and "Rocket.initialDirection" in keys:
-        raise NotImplementedError("Sampling Rocket.initialDirection with a launch rail (the rail direction is part of the model block)")
-    return keys
+    other = [k for k in keys if k != _WIND_KEY and k not in _INIT_STATE_KEYS and k not in motorKeys]
+    onRail = float(simDefinition.getValue("Environment.LaunchSite.railLength")) > 0 and any(k in _RAIL_STATE_KEYS for k in keys)
+    return keys, bool(other) or onRail
+
+
+def _sampleRunsLaneModels(simDefinition, nRuns, mCLogger, model, nGen, hasSeed):
+    """One model block per run: resample, run the constructors' precomputation on the sampled definition (buildModel), keep the shared part.
+    ~0.1 s of host time per run for a Barrowman rocket (fin MAC integral, ogive area integral): the general path, not the fast one."""
+    shared = int(model.header("H_SHARED_LEN")) or model.blob.size
+    models = np.empty((nRuns, shared))
+    seeds = np.zeros((3, nRuns)) if nGen else None
+    for i in range(nRuns):
+        mCLogger.log("\nMonte Carlo Run #{}".format(i + 1))
+        simDefinition.resampleProbabilisticValues()
+        mi = buildModel(simDefinition)
+        if mi.blob.size != model.blob.size or int(mi.header("H_SHARED_LEN")) != int(model.header("H_SHARED_LEN")) \
+                or not np.array_equal(mi.blob[shared:], model.blob[shared:], equal_nan=True):
+            raise NotImplementedError("Monte Carlo sampling changed the structure of the model (component list, table sizes or interpolation tables) "
+                                      "in run {}: per-lane model blocks must share one layout".format(i + 1))
+        models[i] = mi.blob[:shared]
+        for g in range(nGen):
+            seeds[g, i] = mi.blob[L.H_PINK_SEED + g] if (hasSeed >> g) & 1 else random.randrange(1000000)
+    arrays = {LANE_MODELS: models}
+    if nGen:
+        arrays[L.LANE_PINK_SEED] = seeds
+    return arrays
 
 
 def sampleRuns(simDefinition, nRuns, mCLogger, model):
     """Draws every run's inputs in the reference's order (MonteCarlo.py:64-72) and returns the per-lane arrays."""
-    keys = _checkSampledKeys(simDefinition, model)
+    keys, needLaneModels = _checkSampledKeys(simDefinition, model)
     motorKeys = _motorKeys(model)
     sampleMotor = any(k in motorKeys for k in keys)
     sampleWind = _WIND_KEY in keys
@@ -182,6 +208,8 @@ def sampleRuns(simDefinition, nRuns, mCLogger, model):
     turb = int(model.header("H_TURB"))
     nGen = {L.TURB_PINK1D: 1, L.TURB_PINK2D: 2, L.TURB_PINK3D: 3}.get(turb, 0)
     hasSeed = int(model.header("H_PINK_HAS_SEED"))
+    if needLaneModels:
+        return _sampleRunsLaneModels(simDefinition, nRuns, mCLogger, model, nGen, hasSeed)
     if not sampleState and not simDefinition.disableDistributionSampling and nRuns >= _VECTORIZED_SAMPLING_FROM:
         return _sampleRunsVectorized(simDefinition, nRuns, mCLogger, model, keys, motorKeys, nGen, hasSeed)
     wind = np.empty((3, nRuns)) if sampleWind else None
@@ -285,6 +313,7 @@ def _runSimulations_B200(simDefinition, nRuns, outputLists, mCLogger, silent=Fal
         mCLogger.log("NOTE: MonteCarlo.output flightPaths: flight paths are kept for the first {} of {} runs".format(_FLIGHT_PATH_LIMIT, nRuns))
     model = buildModel(simDefinition)
     arrays = sampleRuns(simDefinition, nRuns, mCLogger, model)
+    laneModels = arrays.pop(LANE_MODELS, None)
 
     # contiguous sample ranges per GPU: gathered results are already in sample order
     nGPUs = max(1, min(int(nGPUs), nRuns))
@@ -294,6 +323,8 @@ def _runSimulations_B200(simDefinition, nRuns, outputLists, mCLogger, silent=Fal
         lo, hi = bounds[g], bounds[g + 1]
         b = backend.TrajectoryBatch(model.blob, device=device + g)
         b.setLanes(hi - lo, {k: np.ascontiguousarray(a[:, lo:hi]) for k, a in arrays.items()})
+        if laneModels is not None:
+            b.setLaneModels(laneModels[lo:hi])
         nLogged = max(0, min(hi, _FLIGHT_PATH_LIMIT) - lo) if wantPaths else 0
         if nLogged:
             b.setFlightLog(0, nLogged, 1, _FLIGHT_PATH_ROWS)

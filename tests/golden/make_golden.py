@@ -41,6 +41,8 @@ What is recorded, and which reference code produced it:
                             (ENV/AtmosphereModelling.py:79-96), CustomWindProfile / InterpolatedWind (ENV/MeanWindModelling.py:165-196),
                             PinkNoise1D / 3D with fixed seeds (ENV/TurbulenceModelling.py:100-131), Euler / RK2Midpoint / RK2Heun / RK4_3/8
                             (Motion/Integration.py:144-187,189-236), RK12Adaptive / RK23Adaptive (:238-330), the `elementary` step-size controller (:359-382), ConstantGainPIDRocket (GNC/MomentControllers.py:58-83)
+  perlane_*.json .......... Monte Carlo loops with `_stdDev` on keys that change the model itself (a mass and a fin span; the launch position and
+                            tilt with a launch rail): what mlb_set_lane_models / per-lane model blocks reproduce
   rng.json ................ random.Random / PinkNoiseGenerator known answers (test_SimDefinition.py:118-151,
                             test_TurbulenceModelling.py:37-60)
 """
@@ -101,7 +103,7 @@ def flightRecord(f, traceEvery=0, keepDts=False):
     return rec
 
 
-def monteCarlo(defFile, overrides, seed, nRuns, globalSeed=None, traceEvery=0, keepDts=False, motorKeys=()):
+def monteCarlo(defFile, overrides, seed, nRuns, globalSeed=None, traceEvery=0, keepDts=False, motorKeys=(), sampledKeys=()):
     """Same sampling order as Main.main -> runMonteCarloSimulation single-threaded (MonteCarlo.py:64-76)."""
     if globalSeed is not None:
         random.seed(globalSeed)          # the pink-noise seeds come from the *global* random module
@@ -125,6 +127,7 @@ def monteCarlo(defFile, overrides, seed, nRuns, globalSeed=None, traceEvery=0, k
         rec = flightRecord(f, traceEvery if i == 0 else 0, keepDts and i == 0)
         rec["wind"] = wind
         rec["motor"] = [float(sd.getValue(k)) for k in motorKeys]
+        rec["sampled"] = {k: sd.getValue(k) for k in sampledKeys}
         rec["pinkSeeds"] = seeds
         runs.append(rec)
         print("  run", i + 1, "steps", rec["steps"], "apogee", rec["results"][3], flush=True)
@@ -314,6 +317,16 @@ if __name__ == "__main__":
         mcK = "Rocket.ControlSystem.MomentController."
         dump("opt_constgain_pid.json", singleFlight(can, {mcK + "Type": "ConstantGainPIDRocket", mcK + "Pxy": "4", mcK + "Ixy": "0.5", mcK + "Dxy": "1.2",
                                                          mcK + "Pz": "0.5", mcK + "Iz": "0.1", mcK + "Dz": "0.2"}, traceEvery=50))
+    if "perlane" in which:
+        # `_stdDev` on keys that change what the constructors precompute: a mass (inertia, initial CG), a fin span (planform, MAC, slices, CP
+        # polynomial, interference factors) ...
+        keys = {"Rocket.Sustainer.GeneralMass.mass": "50", "Rocket.Sustainer.GeneralMass.mass_stdDev": "2.5",
+                "Rocket.Sustainer.TailFins.span": "0.1397", "Rocket.Sustainer.TailFins.span_stdDev": "0.006"}
+        dump("perlane_mass_span.json", monteCarlo(mc, keys, "2394781", 3, sampledKeys=("Rocket.Sustainer.GeneralMass.mass", "Rocket.Sustainer.TailFins.span")))
+        # ... and a sampled launch position with a launch rail (rail origin, direction and the end-condition choice follow the sample)
+        keys = {"Environment.LaunchSite.railLength": "6", "Rocket.position": "(0 0 15)", "Rocket.position_stdDev": "(3 3 1)", "Rocket.velocity": "(0 0 0)",
+                "Rocket.rotationAngle": "4", "Rocket.rotationAngle_stdDev": "1.5", "Rocket.rotationAxis": "(0 1 0)"}
+        dump("perlane_rail_position.json", monteCarlo(mc, keys, "2394781", 3, sampledKeys=("Rocket.position", "Rocket.rotationAngle")))
     if "rk45_pink" in which:
         dump("rk45_pink.json", monteCarlo(adaptive, {}, "2394781", 4, globalSeed=2394781, keepDts=True))
     if "ideal" in which:

@@ -655,3 +655,54 @@ def test_option_adaptive_vs_reference(backend, golden, name):
     free = gpuRun(backend, m, 1, {})
     assert free["status"][0] == L.ST_OK and abs(int(free["counters"][0, 0]) - r["steps"]) <= 0.15 * r["steps"]
     assert relErr(free["finals"][0, 0:3], r["final"][1:4]) < 1e-3 and relErr(free["finals"][0, 3:6], r["final"][4:7]) < 1e-3
+
+
+# ---- per-lane model blocks (mlb_set_lane_models): Monte Carlo keys that change the model itself ----
+@pytest.mark.parametrize("name", ["perlane_mass_span.json", "perlane_rail_position.json"])
+def test_per_lane_model_blocks_vs_reference(backend, golden, name):
+    """Three reference flights whose sampled keys change what the constructors precompute (a mass and a fin span; the launch position and
+    tilt under a launch rail, tests/golden/make_golden.py `perlane`) flown as ONE batch, each lane reading its own model block: same step
+    counts, results <= 1e-9 from the reference's."""
+    g = golden(name)
+    models = []
+    for r in g["runs"]:
+        ov = {**g["overrides"], **r["sampled"], "Environment.ConstantMeanWind.velocity": "({} {} {})".format(*r["wind"])}
+        models.append(buildFrom(g["definition"], ov))
+    shared = int(models[0].header("H_SHARED_LEN")) or models[0].blob.size
+    with backend.TrajectoryBatch(models[0].blob) as b:
+        b.setLanes(len(models), {})
+        b.setLaneModels(np.stack([m.blob[:shared] for m in models]))
+        b.run()
+        res, st = b.results()
+        counters = b.laneCounters()
+        fin = b.finals()
+        b.setLaneModels(None)                 # back to the handle's block for every lane
+        b.run()
+        res0, _ = b.results()
+    assert (st == L.ST_OK).all()
+    for i, r in enumerate(g["runs"]):
+        assert counters[i, 0] == r["steps"]
+        assert stateErr(fin[i], r["final"]) < FIXED_TOL
+        assert relErr(res[i, 3:7], r["results"][3:7]) < FIXED_TOL
+    assert np.array_equal(res0[0], res0[1]) and relErr(res0[0, 3:7], g["runs"][0]["results"][3:7]) < FIXED_TOL
+
+
+def test_per_lane_model_blocks_match_the_shared_block(backend, golden):
+    """Identical per-lane blocks must reproduce the shared-memory path bit for bit (adaptive, to the ground: both kernels and the hand-over),
+    and a block with another structure is refused."""
+    g = golden("rk45_pink.json")
+    m = buildFrom(g["definition"])
+    runs = g["runs"]
+    seeds = np.array([r["pinkSeeds"] + [0] for r in runs], dtype=float).T.copy()
+    arrays = {L.LANE_WIND: winds(runs), L.LANE_PINK_SEED: seeds}
+    with backend.TrajectoryBatch(m.blob) as b:
+        b.setLanes(len(runs), arrays)
+        b.run()
+        base = b.finals()
+        b.setLaneModels(np.tile(m.blob, (len(runs), 1)))
+        b.run()
+        assert np.array_equal(b.finals(), base)
+        bad = np.tile(m.blob, (len(runs), 1))
+        bad[1, L.H_NSTAGES] += 1
+        with pytest.raises(ValueError):
+            b.setLaneModels(bad)

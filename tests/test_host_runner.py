@@ -27,9 +27,20 @@ class OracleBatch:
     def setLanes(self, n, arrays=None):
         self.n, self.arrays = n, arrays or {}
 
+    def setLaneModels(self, models):
+        self.models = None if models is None else np.asarray(models, dtype=np.float64)
+
     def run(self, stream=0, sync=False):
         from oracle import oracle
-        self.out = oracle.run(self.blob, self.n, self.arrays)
+        if getattr(self, "models", None) is None:
+            self.out = oracle.run(self.blob, self.n, self.arrays)
+            return
+        # per-lane model blocks: one oracle flight per lane with its own block (shared part from the lane, tables from the handle's block)
+        outs = []
+        for i in range(self.n):
+            blob = np.concatenate([self.models[i], self.blob[self.models.shape[1]:]])
+            outs.append(oracle.run(blob, 1, {k: np.ascontiguousarray(a[:, i:i + 1]) for k, a in self.arrays.items()}))
+        self.out = {k: np.concatenate([o[k] for o in outs]) for k in ("results", "finals", "status", "counters")}
 
     def results(self):
         return self.out["results"], self.out["status"]
@@ -142,10 +153,21 @@ def test_runner_pink_noise_seeds_follow_the_global_stream(monkeypatch, tmp_path,
         assert list(arrays[L.LANE_PINK_SEED][:2, i]) == [float(s) for s in r["pinkSeeds"]]
 
 
-def test_runner_rejects_sampled_keys_it_cannot_vary_per_lane(tmp_path):
+def test_runner_routes_sampled_keys(tmp_path):
+    """Wind, initial state and motor factors are per-lane arrays; any other sampled key, and a sampled launch position / direction under
+    a launch rail (the rail origin and direction follow it, ENV/environment.py:57-91), gives every run its own model block."""
+    sd = montecarloDefinition(tmp_path, nRuns=2)
+    assert montecarlo._checkSampledKeys(sd, buildModel(sd)) == (["Environment.ConstantMeanWind.velocity"], False)
     sd = montecarloDefinition(tmp_path, nRuns=2, **{"Rocket.Sustainer.UpperBodyTube.mass_stdDev": "0.02"})
-    with pytest.raises(NotImplementedError, match="UpperBodyTube.mass"):
-        montecarlo._checkSampledKeys(sd, buildModel(sd))
+    keys, laneModels = montecarlo._checkSampledKeys(sd, buildModel(sd))
+    assert "Rocket.Sustainer.UpperBodyTube.mass" in keys and laneModels
+    sd = montecarloDefinition(tmp_path, nRuns=2, **{"Rocket.position_stdDev": "(1 1 0)"})
+    assert montecarlo._checkSampledKeys(sd, buildModel(sd))[1] is False
+    sd = montecarloDefinition(tmp_path, nRuns=2, **{"Rocket.position_stdDev": "(1 1 0)", "Environment.LaunchSite.railLength": "5"})
+    assert montecarlo._checkSampledKeys(sd, buildModel(sd))[1] is True
+    sd = montecarloDefinition(tmp_path, nRuns=2, **{"Rocket.rotationAngle": "3", "Rocket.rotationAngle_stdDev": "1", "Rocket.rotationAxis": "(0 1 0)",
+                                                    "Environment.LaunchSite.railLength": "5"})
+    assert montecarlo._checkSampledKeys(sd, buildModel(sd))[1] is True
 
 
 def test_runner_samples_motor_adjust_factors(monkeypatch, tmp_path, golden):
@@ -190,7 +212,7 @@ def _gatherWorker(rank, world, port, tmp):
     from mapleaf_b200 import L, SimDefinition, buildModel, distributed
     from oracle import oracle
     m = buildModel(SimDefinition(os.path.join(REPO, "mapleaf_b200", "data", "Simulations", "MonteCarlo.mapleaf"), silent=True, disableDistributionSampling=True))
-    nTotal = 8
+    nTotal = 7                                                            # not divisible by the world size: ranks hold 3 and 4 samples
     w = np.random.default_rng(11).normal(size=(3, nTotal)) * 5            # every rank derives the same full sample stream ...
     lo, hi = distributed.shardRange(nTotal, rank, world)                  # ... and flies its own contiguous range
     o = oracle.run(m.blob, hi - lo, {L.LANE_WIND: np.ascontiguousarray(w[:, lo:hi])})
@@ -202,18 +224,19 @@ def _gatherWorker(rank, world, port, tmp):
 
 
 def test_two_rank_gather_restores_sample_order(tmp_path):
-    """world_size 2 over gloo: contiguous shards, one all-gather of results + status, combined moments on every rank."""
+    """world_size 2 over gloo: contiguous shards of unequal size (7 samples), one all-gather of results + status padded to the larger
+    shard and trimmed, combined moments on every rank."""
     import torch.multiprocessing as mp
     from oracle import oracle
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     mp.spawn(_gatherWorker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     m = buildModel(SimDefinition(os.path.join(DATA, "MonteCarlo.mapleaf"), silent=True, disableDistributionSampling=True))
-    w = np.random.default_rng(11).normal(size=(3, 8)) * 5
-    full = oracle.run(m.blob, 8, {L.LANE_WIND: w})["results"]
+    w = np.random.default_rng(11).normal(size=(3, 7)) * 5
+    full = oracle.run(m.blob, 7, {L.LANE_WIND: w})["results"]
     for rank in range(2):
         assert np.array_equal(np.load(tmp_path / "res{}.npy".format(rank)), full)
         mom = np.load(tmp_path / "mom{}.npy".format(rank))
-        assert mom[0] == 8 and np.allclose(mom[1:8], full.mean(axis=0), rtol=1e-12) and np.allclose(mom[8:], full.std(axis=0, ddof=1), rtol=1e-10)
+        assert mom[0] == 7 and np.allclose(mom[1:8], full.mean(axis=0), rtol=1e-12) and np.allclose(mom[8:], full.std(axis=0, ddof=1), rtol=1e-10)
 
 
 def test_bench_flop_constants_are_the_oracle_op_counts():
@@ -293,3 +316,23 @@ def test_vectorized_sampling_is_the_per_run_loop(monkeypatch, tmp_path):
         assert np.array_equal(slow[0][k], fast[0][k])
     assert slow[1] == fast[1] and slow[2] == fast[2]
     assert slow[3] == fast[3] and slow[4] == fast[4] and slow[5:] == fast[5:]
+
+
+@pytest.mark.parametrize("name,keys", [("perlane_mass_span.json", ("Rocket.Sustainer.GeneralMass.mass", "Rocket.Sustainer.TailFins.span")),
+                                       ("perlane_rail_position.json", ("Rocket.position", "Rocket.rotationAngle"))])
+def test_runner_samples_any_key_through_per_lane_models(monkeypatch, tmp_path, golden, name, keys):
+    """`_stdDev` on keys that change what the constructors precompute (a mass and a fin span; the launch position and tilt under a launch
+    rail): the runner draws them in the reference's order (IO/simDefinition.py:471-532), builds one model block per run and flies them as
+    one batch; every run reproduces the reference's flight of the same sample (tests/golden/make_golden.py `perlane`)."""
+    g = golden(name)
+    monkeypatch.setattr(backend, "TrajectoryBatch", OracleBatch)
+    sd = montecarloDefinition(tmp_path, nRuns=3, **{"MonteCarlo.output": "landingLocations apogees"})
+    for k, v in g["overrides"].items():          # as the fixture's generator: added after the definition's construction draw
+        sd.setValue(k, v)
+    out = montecarlo.runMonteCarloSimulation(simDefinition=sd, silent=True)
+    assert (out.status == L.ST_OK).all()
+    for i, ref in enumerate(g["runs"]):
+        assert np.allclose(out.results[i, 3:7], ref["results"][3:7], rtol=1e-12, atol=1e-12), (i, out.results[i], ref["results"])
+    log = open(out.logPath).read()
+    for k in keys:
+        assert "parameter: " + k in log
