@@ -70,7 +70,7 @@ const char* mlb_version(void);
 
 /* Per-lane inputs. perLaneArrays[k] is a host array of [components(arrayIds[k])][nLanes] doubles, lane fastest
    (LANE_WIND: 3, LANE_INIT_STATE: 13, LANE_PINK_SEED: 3, LANE_MOTOR_ADJUST: 8 = impulseAdjustFactor and burnTimeAdjustFactor of the
-   motor of stages 0-3, Propulsion.py:38-40,109-128). Arrays not given use the model block's value for every lane. */
+   motor of stages 0-3, Propulsion.py:38-40,109-128; LANE_START: 2 = start time and first step size). Arrays not given use the model block's value for every lane. */
 int mlb_set_lanes(mlb_handle* h, int64_t nLanes, const double* const* perLaneArrays, const int* arrayIds, int nArrays);
 /* Same, with the arrays already resident in this device's memory (no copy is made; the caller keeps them alive). */
 int mlb_set_lanes_device(mlb_handle* h, int64_t nLanes, const double* const* devLaneArrays, const int* arrayIds, int nArrays);
@@ -97,6 +97,11 @@ int mlb_counters(mlb_handle* h, mlb_counters_t* out);
 /* per lane (nLanes x 6): steps, derivative evaluations, rejected attempts, 3-DoF steps, 3-DoF evaluations,
    transonic 6-DoF evaluations */
 int mlb_lane_counters(mlb_handle* h, int64_t* out);
+/* Stage separations of every lane: nLanes x (MLB_MAX_STAGES - 1) x SEP_W doubles (mlb_layout.h SEP_*): the whole rocket's state, the time
+   and the step size at each separation, i.e. what a dropped stage's own flight starts from (Rocket._stageSeparation ->
+   SingleSimulations.createNewDetachedStage, rocket.py:461-474, SingleSimulations.py:280-299). The caller flies the dropped stages as a second
+   batch: a handle built from the dropped stage's model block, LANE_INIT_STATE = the separation state, LANE_START = (time, step size). */
+int mlb_stage_separations(mlb_handle* h, double* out);
 /* Device addresses of the result block (nLanes x 7 doubles) and status (nLanes int32): the send buffers of the
    multi-GPU gather. Valid until the next mlb_set_lanes* or mlb_destroy. */
 int mlb_device_results(mlb_handle* h, void** results, void** status);

@@ -447,7 +447,14 @@
 #define LANE_INIT_STATE 1    /* 13: pos, vel, quat, body-frame angular velocity         */
 #define LANE_PINK_SEED 2     /* 3: integer seeds of the pink-noise generators           */
 #define LANE_MOTOR_ADJUST 3  /* 8: impulseAdjustFactor, burnTimeAdjustFactor of the motor of stage 0, 1, 2, 3 (definition order)   */
-#define LANE_NUM_ARRAYS 4
+#define LANE_START 4         /* 2: start time and first step size (dropped stages start at their separation, SingleSimulations.py:280-299) */
+#define LANE_NUM_ARRAYS 5
+/* One row per stage separation of a lane (mlb_stage_separations): the state the dropped stage starts from */
+#define SEP_STATE 0          /* 13: pos, vel, quat, body-frame angular velocity of the whole rocket at the separation                 */
+#define SEP_TIME 13
+#define SEP_DT 14            /* the step size the time loop was using (SimulationRunners' dts[0] at that moment)                        */
+#define SEP_VALID 15         /* 1 when the separation happened                                                                          */
+#define SEP_W 16
 #define MLB_MAX_STAGES 4
 
 /* ---- per-lane outputs -------------------------------------------------------------------- */

@@ -80,6 +80,7 @@ def lib():
     l.mlb_finals.argtypes = [vp, dp]
     l.mlb_counters.argtypes = [vp, ctypes.POINTER(Counters)]
     l.mlb_lane_counters.argtypes = [vp, ctypes.POINTER(ctypes.c_int64)]
+    l.mlb_stage_separations.argtypes = [vp, dp]
     l.mlb_device_results.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp)]
     l.mlb_set_result_buffers.argtypes = [vp, vp, vp]
     l.mlb_moments.argtypes = [vp, dp]
@@ -100,7 +101,7 @@ def lib():
 
 
 EXPORTED_SYMBOLS = ["mlb_create", "mlb_destroy", "mlb_last_error", "mlb_version", "mlb_set_lanes", "mlb_set_lanes_device", "mlb_set_lane_models", "mlb_run", "mlb_sync",
-                    "mlb_results", "mlb_finals", "mlb_counters", "mlb_lane_counters", "mlb_device_results", "mlb_set_result_buffers", "mlb_moments", "mlb_set_flight_log", "mlb_get_flight_log", "mlb_set_trace",
+                    "mlb_results", "mlb_finals", "mlb_counters", "mlb_lane_counters", "mlb_stage_separations", "mlb_device_results", "mlb_set_result_buffers", "mlb_moments", "mlb_set_flight_log", "mlb_get_flight_log", "mlb_set_trace",
                     "mlb_get_trace", "mlb_set_dt_replay", "mlb_force_eval", "mlb_host_gauss_stream", "mlb_host_randrange_stream", "mlb_host_gauss_from_state", "mlb_host_randrange_from_state", "mlb_fp64_peak"]
 
 
@@ -116,7 +117,7 @@ def _check(rc, what):
         raise ValueError("{}: {}".format(what, msg))
 
 
-_LANE_COMPONENTS = {L.LANE_WIND: 3, L.LANE_INIT_STATE: 13, L.LANE_PINK_SEED: 3, L.LANE_MOTOR_ADJUST: 2 * L.MLB_MAX_STAGES}
+_LANE_COMPONENTS = {L.LANE_WIND: 3, L.LANE_INIT_STATE: 13, L.LANE_PINK_SEED: 3, L.LANE_MOTOR_ADJUST: 2 * L.MLB_MAX_STAGES, L.LANE_START: 2}
 
 
 class TrajectoryBatch:
@@ -205,6 +206,12 @@ class TrajectoryBatch:
     def laneCounters(self):
         out = np.empty((self.nLanes, 6), dtype=np.int64)
         _check(lib().mlb_lane_counters(self._h, out.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))), "mlb_lane_counters")
+        return out
+
+    def stageSeparations(self):
+        """[nLanes, MLB_MAX_STAGES - 1, SEP_W]: state, time and step size of the rocket at each stage separation (SEP_VALID = 1 where one happened)."""
+        out = np.empty((self.nLanes, L.MLB_MAX_STAGES - 1, L.SEP_W))
+        _check(lib().mlb_stage_separations(self._h, _dp(out)), "mlb_stage_separations")
         return out
 
     def deviceResults(self):

@@ -73,6 +73,7 @@ struct RunArgs {
     LaneInputs in;
     double* results; double* finals; int* status; long long* counters;
     uint32_t* mt;
+    double* separations;                  /* [lane][MLB_MAX_STAGES - 1][SEP_W] */
     double* trace; long long traceLane, traceCount, traceMaxRows, traceEvery; long long* traceRows;     /* flight log of lanes [traceLane, traceLane + traceCount) */
     const double* dtReplay; long long nReplay;
     LaneRec* recs;
@@ -132,7 +133,8 @@ __global__ void __launch_bounds__(MLB_BLOCK) initLanes(const RunArgs a) {
     Lane L;
     laneInit(B, L, a.in, lane, a.mt, true);
     L.G = a.blob;
-    R.dt = B[H_DT0]; R.finalDt = 0;
+    R.dt = a.in.start ? a.in.start[a.in.nLanes + lane] : B[H_DT0]; R.finalDt = 0;
+    for (int k = 0; k < (MLB_MAX_STAGES - 1) * SEP_W; k++) a.separations[(size_t)lane * (MLB_MAX_STAGES - 1) * SEP_W + k] = 0;
     R.apogee = -10000000; R.maxSpeed = 0; R.maxH = 0;
     R.prevPos = L.s.pos; R.lastPos = L.s.pos;
     R.st = ST_OK;
@@ -205,7 +207,7 @@ MLB_DEV void flightLoop(const RunArgs& a, const double* B) {
         prevPos = rec->prevPos; lastPos = rec->lastPos; rows = rec->rows; traceStride = rec->traceStride; st = rec->st;
         end = (rec->flags & REC_END) != 0; haveFinal = (rec->flags & REC_HAVE_FINAL) != 0; skipPre = (rec->flags & REC_PRE_DONE) != 0; retry = (rec->flags & REC_RETRY) != 0;
         if (L.haveCache) for (int k = 0; k < (PH == 1 ? 6 : 12); k++) kLocal[k] = rec->k0[k];
-        L.G = a.blob;
+        L.G = a.blob; L.sepOut = a.separations + (size_t)lane * (MLB_MAX_STAGES - 1) * SEP_W;
     } else L.forceRK4 = false;          /* threads past the end of the queue only keep the barriers company: the one lane field that path reads */
     const bool tracing = inRange && laneTraced(a, lane);
     double* const traceBase = tracing ? a.trace + (size_t)(lane - a.traceLane) * a.traceMaxRows * TRACE_W : nullptr;
@@ -294,7 +296,7 @@ __global__ void __launch_bounds__(MLB_BLOCK) forceEvalKernel(const double* blob,
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Lane L;
-    LaneInputs in; in.wind = nullptr; in.initState = nullptr; in.pinkSeed = nullptr; in.motorAdjust = nullptr; in.nLanes = 1;
+    LaneInputs in; in.wind = nullptr; in.initState = nullptr; in.pinkSeed = nullptr; in.motorAdjust = nullptr; in.start = nullptr; in.nLanes = 1;
     laneInit(B, L, in, 0, mt ? mt + (size_t)i * 3 * 624 : nullptr, mt != nullptr);      /* each state gets its own generator block */
     L.G = blob;
     if (winds) { L.wind = v3(winds[3 * i], winds[3 * i + 1], winds[3 * i + 2]); laneFinConstants(B, L); }
@@ -365,13 +367,14 @@ struct mlb_handle {
     double* d_blob = nullptr;
     long long nLanes = 0;
     long long capLanes = 0;             /* lanes the per-lane device buffers below are sized for (kept across mlb_set_lanes calls) */
-    double* d_lane[LANE_NUM_ARRAYS] = { nullptr, nullptr, nullptr, nullptr };
-    size_t laneBytes[LANE_NUM_ARRAYS] = { 0, 0, 0, 0 };        /* capacity of the library-owned copies */
-    double* d_laneOwned[LANE_NUM_ARRAYS] = { nullptr, nullptr, nullptr, nullptr };
+    double* d_lane[LANE_NUM_ARRAYS] = {};
+    size_t laneBytes[LANE_NUM_ARRAYS] = {};        /* capacity of the library-owned copies */
+    double* d_laneOwned[LANE_NUM_ARRAYS] = {};
     bool ownResults = true;
     double* d_results = nullptr; double* d_finals = nullptr; int* d_status = nullptr; long long* d_counters = nullptr;
     double* d_resultsOwned = nullptr; int* d_statusOwned = nullptr;
     uint32_t* d_mt = nullptr;
+    double* d_separations = nullptr;
     LaneRec* d_recs = nullptr;
     double* d_laneModels = nullptr; size_t laneModelBytes = 0; long long laneModelStride = 0; bool haveLaneModels = false;
     int* d_queue[3] = { nullptr, nullptr, nullptr };      /* two straggler queues (ping-pong) and the under-chute queue */
@@ -388,13 +391,13 @@ struct mlb_handle {
     size_t sharedLen = 0;
 };
 
-static int laneArrayComponents(int id) { return id == LANE_WIND ? 3 : (id == LANE_INIT_STATE ? 13 : (id == LANE_PINK_SEED ? 3 : (id == LANE_MOTOR_ADJUST ? 2 * MLB_MAX_STAGES : -1))); }
+static int laneArrayComponents(int id) { return id == LANE_WIND ? 3 : (id == LANE_INIT_STATE ? 13 : (id == LANE_PINK_SEED ? 3 : (id == LANE_MOTOR_ADJUST ? 2 * MLB_MAX_STAGES : (id == LANE_START ? 2 : -1)))); }
 
 static void freeLanes(mlb_handle* h) {
     for (int i = 0; i < LANE_NUM_ARRAYS; i++) { cudaFree(h->d_laneOwned[i]); h->d_laneOwned[i] = nullptr; h->laneBytes[i] = 0; h->d_lane[i] = nullptr; }
     cudaFree(h->d_resultsOwned); cudaFree(h->d_statusOwned);
     h->d_resultsOwned = nullptr; h->d_statusOwned = nullptr; h->ownResults = true;
-    cudaFree(h->d_finals); cudaFree(h->d_counters); cudaFree(h->d_mt); cudaFree(h->d_recs); cudaFree(h->d_laneModels);
+    cudaFree(h->d_finals); cudaFree(h->d_counters); cudaFree(h->d_mt); cudaFree(h->d_recs); cudaFree(h->d_laneModels); cudaFree(h->d_separations); h->d_separations = nullptr;
     h->d_laneModels = nullptr; h->laneModelBytes = 0; h->haveLaneModels = false;
     for (int i = 0; i < 3; i++) { cudaFree(h->d_queue[i]); h->d_queue[i] = nullptr; }
     h->d_results = h->d_finals = nullptr; h->d_status = nullptr; h->d_counters = nullptr; h->d_mt = nullptr; h->d_recs = nullptr;
@@ -469,7 +472,8 @@ extern "C" void mlb_destroy(mlb_handle* h) {
    fresh sample block of the same size every pass re-uses them (at 10^6 lanes the generator states alone are 7.5 GB). */
 static int reserveLanes(mlb_handle* h, long long nLanes) {
     if (nLanes <= h->capLanes) return MLB_OK;
-    cudaFree(h->d_resultsOwned); cudaFree(h->d_statusOwned); cudaFree(h->d_finals); cudaFree(h->d_counters); cudaFree(h->d_mt); cudaFree(h->d_recs);
+    cudaFree(h->d_resultsOwned); cudaFree(h->d_statusOwned); cudaFree(h->d_finals); cudaFree(h->d_counters); cudaFree(h->d_mt); cudaFree(h->d_recs); cudaFree(h->d_separations);
+    h->d_separations = nullptr;
     for (int i = 0; i < 3; i++) { cudaFree(h->d_queue[i]); h->d_queue[i] = nullptr; }
     h->d_resultsOwned = nullptr; h->d_statusOwned = nullptr; h->d_finals = nullptr; h->d_counters = nullptr; h->d_mt = nullptr; h->d_recs = nullptr;
     h->capLanes = 0;
@@ -479,6 +483,7 @@ static int reserveLanes(mlb_handle* h, long long nLanes) {
     CU(cudaMalloc(&h->d_statusOwned, (size_t)nLanes * sizeof(int)));
     CU(cudaMalloc(&h->d_counters, (size_t)nLanes * MLB_NCOUNTERS * sizeof(long long)));
     CU(cudaMalloc(&h->d_recs, (size_t)nLanes * sizeof(LaneRec)));
+    CU(cudaMalloc(&h->d_separations, (size_t)nLanes * (MLB_MAX_STAGES - 1) * SEP_W * sizeof(double)));
     for (int i = 0; i < 3; i++) CU(cudaMalloc(&h->d_queue[i], (size_t)nLanes * sizeof(int)));
     int turb = (int)h->blob[H_TURB];
     if (turb >= TURB_PINK1D && turb <= TURB_PINK3D) CU(cudaMalloc(&h->d_mt, (size_t)nLanes * 3 * 624 * sizeof(uint32_t)));
@@ -551,8 +556,8 @@ extern "C" int mlb_run(mlb_handle* h, void* stream) {
     h->stream = s;
     RunArgs a;
     a.blob = h->d_blob; a.blobLen = (int)h->sharedLen; a.blobPad = (int)((h->sharedLen + 1) & ~(size_t)1); a.nSlots = h->nSlots;
-    a.in.wind = h->d_lane[LANE_WIND]; a.in.initState = h->d_lane[LANE_INIT_STATE]; a.in.pinkSeed = h->d_lane[LANE_PINK_SEED]; a.in.motorAdjust = h->d_lane[LANE_MOTOR_ADJUST]; a.in.nLanes = h->nLanes;
-    a.results = h->d_results; a.finals = h->d_finals; a.status = h->d_status; a.counters = h->d_counters; a.mt = h->d_mt;
+    a.in.wind = h->d_lane[LANE_WIND]; a.in.initState = h->d_lane[LANE_INIT_STATE]; a.in.pinkSeed = h->d_lane[LANE_PINK_SEED]; a.in.motorAdjust = h->d_lane[LANE_MOTOR_ADJUST]; a.in.start = h->d_lane[LANE_START]; a.in.nLanes = h->nLanes;
+    a.results = h->d_results; a.finals = h->d_finals; a.status = h->d_status; a.counters = h->d_counters; a.mt = h->d_mt; a.separations = h->d_separations;
     a.trace = (h->traceLane >= 0 && h->traceLane < h->nLanes) ? h->d_trace : nullptr;
     a.traceLane = h->traceLane; a.traceCount = h->traceCount; a.traceMaxRows = h->traceMaxRows; a.traceEvery = h->traceEvery; a.traceRows = h->d_traceRows;
     if (a.trace) CU(cudaMemsetAsync(h->d_traceRows, 0, (size_t)h->traceCount * sizeof(long long), s));
@@ -643,6 +648,12 @@ extern "C" int mlb_finals(mlb_handle* h, double* finals) {
     int rc = needRun(h, "mlb_finals"); if (rc) return rc;
     if (!finals) return fail(MLB_ERR_ARG, "mlb_finals: null buffer");
     CU(cudaMemcpy(finals, h->d_finals, (size_t)h->nLanes * FIN_SIZE * sizeof(double), cudaMemcpyDeviceToHost));
+    return MLB_OK;
+}
+extern "C" int mlb_stage_separations(mlb_handle* h, double* out) {
+    int rc = needRun(h, "mlb_stage_separations"); if (rc) return rc;
+    if (!out) return fail(MLB_ERR_ARG, "mlb_stage_separations: null buffer");
+    CU(cudaMemcpy(out, h->d_separations, (size_t)h->nLanes * (MLB_MAX_STAGES - 1) * SEP_W * sizeof(double), cudaMemcpyDeviceToHost));
     return MLB_OK;
 }
 extern "C" int mlb_lane_counters(mlb_handle* h, int64_t* out) {

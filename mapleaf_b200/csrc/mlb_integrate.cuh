@@ -222,6 +222,14 @@ MLB_DEV void deployNextRecoveryStage(const double* B, Lane& L) {                
 }
 MLB_DEV void stageSeparation(const double* B, Lane& L) {                                    /* Rocket._stageSeparation, rocket.py:461-479 */
     if (L.nStages <= 1) return;
+    if (L.sepOut) {
+        /* SingleSimulations.createNewDetachedStage (:280-299): the dropped stage starts from a copy of the whole rocket's state and time,
+           with the step size the time loop holds at this moment */
+        double* o = L.sepOut + (size_t)((int)B[H_NSTAGES] - L.nStages) * SEP_W;
+        o[0] = L.s.pos.x; o[1] = L.s.pos.y; o[2] = L.s.pos.z; o[3] = L.s.vel.x; o[4] = L.s.vel.y; o[5] = L.s.vel.z;
+        o[6] = L.s.q.w; o[7] = L.s.q.x; o[8] = L.s.q.y; o[9] = L.s.q.z; o[10] = L.s.w.x; o[11] = L.s.w.y; o[12] = L.s.w.z;
+        o[SEP_TIME] = L.time; o[SEP_DT] = L.dtEntry; o[SEP_VALID] = 1.0;
+    }
     L.nStages -= 1;                /* the bottom stage leaves; boat-tail ownership and fineness ratio follow the stage count */
     L.resorted = true;
     L.inertiaCached = false;       /* fewer stages, and the next motor is about to ignite */
@@ -379,6 +387,7 @@ MLB_DEV void railMotionConstraint(const double* B, Lane& L) {                   
 template <int PH, bool CONVOY>
 MLB_DEV StepResult rocketTimeStep(const double* B, const double* G, Lane& L, const KStore& ks, double& dt, bool active, bool skipPre, bool retry, bool& left) {
     if (active && !skipPre) {
+        L.dtEntry = dt;
         railMotionConstraint(B, L);
         double est; bool det;
         triggerEvents(B, L, est, det);
@@ -414,7 +423,7 @@ MLB_DEV void endDetector(const double* B, const Lane& L, double dt, bool& end, b
 }
 
 /* Per-lane inputs, SoA over lanes ([component][lane], lane fastest) */
-struct LaneInputs { const double* wind; const double* initState; const double* pinkSeed; const double* motorAdjust; long long nLanes; };
+struct LaneInputs { const double* wind; const double* initState; const double* pinkSeed; const double* motorAdjust; const double* start; long long nLanes; };
 
 /* fin-set constants that depend on the lane's sampled environment at t = 0 */
 MLB_DEV void laneFinConstants(const double* B, Lane& L) {
@@ -436,7 +445,8 @@ MLB_DEV void laneInit(const double* B, Lane& L, const LaneInputs& in, long long 
     for (int i = 0; i < 13; i++) st[i] = in.initState ? in.initState[i * in.nLanes + lane] : B[H_INIT_STATE + i];
     L.s.pos = v3(st[0], st[1], st[2]); L.s.vel = v3(st[3], st[4], st[5]);
     L.s.q = q4(st[6], st[7], st[8], st[9]); L.s.w = v3(st[10], st[11], st[12]);
-    L.time = B[H_START_TIME];
+    L.time = in.start ? in.start[lane] : B[H_START_TIME];
+    L.dtEntry = 0; L.sepOut = nullptr;
     L.dof3 = false; L.underChute = false; L.haveLast = false; L.haveCache = false; L.resorted = false;
     L.lastVz = 0; L.lastTime = 0; L.pidLastError = 0; L.pidIntegral = 0;
     L.nSteps = 0; L.nEvals = 0; L.nRejects = 0; L.nEvents = 0; L.eventOverflow = false; L.nSteps3 = 0; L.nEvals3 = 0; L.nEvalsTransonic = 0;

@@ -74,6 +74,8 @@ struct Lane {
     double actLastDefl[CS_MAX_ACT], actLastTime[CS_MAX_ACT], actTarget[CS_MAX_ACT];
     bool resorted;                              /* a stage has been dropped: inertia lists are in top-to-bottom order (rocket.py:476-479) */
     int recoveryStage, nStages, nEvents, turb;
+    double dtEntry;                             /* step size handed to Rocket.timeStep for the current step, before the event clamp */
+    double* sepOut;                             /* this lane's stage-separation rows (SEP_W doubles each), or nullptr */
     bool eventOverflow;                         /* an event subscription did not fit MLB_MAX_EVENTS: the lane ends with ST_UNSUPPORTED */
     double lastVz, lastTime;                    /* event detector memory (simEventDetector.py:120-132) */
     double pidLastError, pidIntegral;           /* step-size PID (GNC/PID.py:27-51) */

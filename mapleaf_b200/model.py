@@ -994,7 +994,13 @@ def _flattenTableau(rows, nResult):
     return flat
 
 
-def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000) -> Model:
+def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000, droppedStage: int = None, droppedFromAltitude: float = None) -> Model:
+    """Everything the reference's constructors precompute, flattened into one model block.
+    droppedStage = n builds the rocket the reference creates for the n-th dropped stage (`Simulation.createRocket(stage=n)`,
+    SingleSimulations.py:161-176,280-299; Rocket.__init__ with stageToInitialize, rocket.py:296-321,339-361): that stage alone, its motor burnt
+    out, no staging triggers, no control system, the end condition of SimControl.StageDropPaths; droppedFromAltitude is the altitude of the
+    separation (the Altitude end condition looks at it to decide between ascending and descending, SingleSimulations.py:240-247). The lanes
+    of such a model start from the separation states (LANE_INIT_STATE, LANE_START)."""
     sd = simDefinition
     env = SubDictReader("Environment", sd)
     rk = SubDictReader("Rocket", sd)
@@ -1173,6 +1179,8 @@ def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000) -> Model:
     idealControl = rk.tryGetString("ControlSystem.MomentController.Type") == "IdealMomentController"
     hasActuatedSystem = rk.tryGetString("ControlSystem.controlledSystem") is not None and not idealControl
     hasControl = hasActuatedSystem or idealControl
+    if droppedStage is not None:
+        hasActuatedSystem = idealControl = hasControl = False          # rocket.py:215: only a complete rocket gets the control system
     maxDiameter = 0
     for sdict in stageDicts:
         for cdict in sd.getImmediateSubDicts(sdict):
@@ -1181,6 +1189,14 @@ def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000) -> Model:
     H[L.H_MAXDIAM] = maxDiameter
     H[L.H_AREF] = math.pi * maxDiameter ** 2 / 4
     H[L.H_RAREF] = (1 / H[L.H_AREF]) if H[L.H_AREF] != 0 else float("inf")
+
+    if droppedStage is not None:
+        # rocket.py:296-321: the n-th smallest stageNumber; the reference area above stays that of the fully assembled rocket (:100-108)
+        numbers = [float(sd.getValue(d + ".stageNumber")) for d in stageDicts]
+        if len(set(numbers)) != len(numbers):
+            raise ValueError("For multi-stage rockets, each stage must have a unique stage number. Set the Rocket.StageName.stageNumber value for each stage. 0 for first stage, 1 for second, etc...")
+        wanted = sorted(numbers)[droppedStage]
+        stageDicts = [d for d, n in zip(stageDicts, numbers) if n == wanted]
 
     # ---- stages and components (stage.py:13-70; sort rules: stage.py:47-59, RocketComponents.py:131-143) ----
     stages = []
@@ -1261,6 +1277,12 @@ def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000) -> Model:
         raise NotImplementedError("more than 4 stages")
     if sum(1 for st in stages for c in st["comps"] if c["cls"] == "RecoverySystem") > 1:
         raise NotImplementedError("more than one RecoverySystem in a rocket (the reference keeps only the last one created as Rocket.recoverySystem)")
+    if droppedStage is not None:
+        for st in stages:
+            st["sepType"] = "None"                    # rocket.py:357-361: a dropped stage has no staging events, its motor is burnt out
+            if st["motor"] is None:
+                raise AttributeError("'NoneType' object has no attribute 'updateIgnitionTime'")
+    ignition0 = (lambda st: -1000000000) if droppedStage is not None else (lambda st: 0.0 if st is stages[-1] else 1000000000)
     for st in stages[:-1]:
         if st["motor"] is None:
             raise AttributeError("'NoneType' object has no attribute 'updateIgnitionTime'")      # the reference's failure mode (rocket.py:356)
@@ -1359,7 +1381,7 @@ def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000) -> Model:
         S[L.S_FIXED_MASS] = st["fixed"].mass
         S[L.S_MOTOR] = -1
         S[L.S_BURN_DURATION] = -1
-        S[L.S_IGNITION0] = 0.0 if si == len(stages) - 1 else 1000000000
+        S[L.S_IGNITION0] = ignition0(st)
         for ci, c in enumerate(st["comps"]):
             off = append(_derivedConstants(c["rec"], H[L.H_AREF]))
             S[L.S_COMP_OFF + ci] = off
@@ -1400,7 +1422,7 @@ def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000) -> Model:
         items = [st["fixed"]]
         for c in st["variable"]:
             if c["cls"] == "Motor":
-                items.append(motorInertia(c["motor"], max(0, t - (0.0 if st is stages[-1] else 1000000000))))
+                items.append(motorInertia(c["motor"], max(0, t - ignition0(st))))
             else:
                 items.append(tabulatedInertia(c["tabInertia"], t))
         comb = Inertia.combine(items)
@@ -1421,12 +1443,18 @@ def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000) -> Model:
     H[L.H_INIT_STATE:L.H_INIT_STATE + 13] = list(posCG) + list(initVel) + list(q0n) + list(w0)
 
     # ---- end condition (SingleSimulations.py:205-248) ----
-    endCondition = sd.getValue("SimControl.EndCondition")
-    endValue = float(sd.getValue("SimControl.EndConditionValue"))
+    if droppedStage is None:
+        endCondition = sd.getValue("SimControl.EndCondition")
+        endValue = float(sd.getValue("SimControl.EndConditionValue"))
+        startZ = posCG[2]
+    else:
+        endCondition = sd.getValue("SimControl.StageDropPaths.endCondition")
+        endValue = float(sd.getValue("SimControl.StageDropPaths.endConditionValue"))
+        startZ = posCG[2] if droppedFromAltitude is None else droppedFromAltitude
     H[L.H_END_VALUE] = endValue
     if endCondition == "Apogee":
         H[L.H_END_TYPE] = L.END_APOGEE
-    elif endCondition == "Altitude" and posCG[2] < endValue:
+    elif endCondition == "Altitude" and startZ < endValue:
         H[L.H_END_TYPE] = L.END_ALT_ASCENDING
     elif endCondition == "Altitude":
         H[L.H_END_TYPE] = L.END_ALT_DESCENDING

@@ -26,7 +26,7 @@ from . import hostmath as hm
 from .model import L, buildModel, initialStateGlobalFrame
 from .simdef import SimDefinition, SubDictReader, formatVector, parseVector
 
-__all__ = ["runMonteCarloSimulation", "MonteCarloLogger", "Vector", "MonteCarloResults", "laneInitialState"]
+__all__ = ["runMonteCarloSimulation", "MonteCarloLogger", "Vector", "MonteCarloResults", "laneInitialState", "flyDroppedStages"]
 
 # sampled keys the kernels accept per lane (everything else would change the model block itself)
 _WIND_KEY = "Environment.ConstantMeanWind.velocity"
@@ -91,6 +91,7 @@ class MonteCarloResults:
     def __init__(self, results, status, counters, logPath, outputLists):
         self.results, self.status, self.counters, self.logPath = results, status, counters, logPath
         self.landingLocations, self.apogees, self.maxSpeeds, self.flightTimes, self.maxHorizontalVels, self.flights = outputLists
+        self.droppedStages = []      # SimControl.StageDropPaths.compute: one dict per dropped stage (flyDroppedStages)
 
 
 _FLIGHT_PATH_LIMIT = 2000      # runs whose paths are kept (256 KB of device memory each while the batch runs)
@@ -333,10 +334,14 @@ def _runSimulations_B200(simDefinition, nRuns, outputLists, mCLogger, silent=Fal
     results = np.empty((nRuns, L.RES_SIZE))
     status = np.empty(nRuns, dtype=np.int32)
     counters = []
+    wantDrops = int(model.header("H_NSTAGES")) > 1 and str(simDefinition.getValue("SimControl.StageDropPaths.compute")).lower() == "true" and laneModels is None
+    separations = np.zeros((nRuns, L.MLB_MAX_STAGES - 1, L.SEP_W)) if wantDrops else None
     for g, b in enumerate(batches):
         r, s = b.results()
         results[bounds[g]:bounds[g + 1]], status[bounds[g]:bounds[g + 1]] = r, s
         counters.append(b.counters())
+        if wantDrops:
+            separations[bounds[g]:bounds[g + 1]] = b.stageSeparations()
         if wantPaths and bounds[g] < _FLIGHT_PATH_LIMIT:
             flights.extend(FlightPath.fromLog(rows) for rows in b.flightLog())
         b.close()
@@ -352,7 +357,59 @@ def _runSimulations_B200(simDefinition, nRuns, outputLists, mCLogger, silent=Fal
     maxSpeeds.extend(results[:, L.RES_MAX_SPEED].tolist())
     flightTimes.extend(results[:, L.RES_FLIGHT_TIME].tolist())
     maxHorizontalVels.extend(results[:, L.RES_MAX_HVEL].tolist())
-    return results, status, counters
+    droppedStages = flyDroppedStages(simDefinition, model, arrays, separations, device=device) if wantDrops else []
+    for k, d in enumerate(droppedStages):
+        mCLogger.log("Dropped stage {}: {} of {} runs separated; flown from the separation to SimControl.StageDropPaths.endCondition".format(k + 1, d["lanes"].size, nRuns))
+    return results, status, counters, droppedStages
+
+
+def flyDroppedStages(simDefinition, model, arrays, separations, device=0, batchClass=None):
+    """The dropped stages' own flights (SimControl.StageDropPaths.compute; SingleSimulations.py:91-145,280-299): for every separation the
+    reference creates a new rocket made of the dropped stage alone (burnt-out motor, its own recovery system if it has one), gives it the
+    whole rocket's state and time at the separation and flies it to SimControl.StageDropPaths.endCondition. Here every dropped stage of
+    every run is one lane of a second batch: model block of the dropped stage, LANE_INIT_STATE / LANE_START from the separation rows the
+    main batch recorded (mlb_stage_separations), the run's own sampled wind.
+    Returns one dict per dropped stage (first dropped first): lanes (indices of the runs in which it separated), results, status, finals."""
+    from . import backend
+    batchClass = batchClass or backend.TrajectoryBatch
+    if int(model.header("H_TURB")) in (L.TURB_PINK1D, L.TURB_PINK2D, L.TURB_PINK3D):
+        raise NotImplementedError("StageDropPaths with a pink-noise turbulence model: the reference flies the dropped stage through the generator "
+                                  "state the main flight left behind, backwards in time (ENV/TurbulenceModelling.py:197-247)")
+    out = []
+    nStages = int(model.header("H_NSTAGES"))
+    for k in range(nStages - 1):
+        rows = separations[:, k]
+        lanes = np.nonzero(rows[:, L.SEP_VALID] == 1)[0]
+        if lanes.size == 0:
+            out.append(dict(lanes=lanes, results=np.empty((0, L.RES_SIZE)), status=np.empty(0, dtype=np.int32), finals=np.empty((0, L.FIN_SIZE))))
+            continue
+        z = rows[lanes, L.SEP_STATE + 2]
+        endValue = float(simDefinition.getValue("SimControl.StageDropPaths.endConditionValue"))
+        if simDefinition.getValue("SimControl.StageDropPaths.endCondition") == "Altitude" and (z < endValue).any() and (z >= endValue).any():
+            raise NotImplementedError("StageDropPaths.endCondition Altitude with separations both below and above the end altitude")
+        dropModel = buildModel(simDefinition, droppedStage=k, droppedFromAltitude=float(z[0]))
+        laneArrays = {L.LANE_INIT_STATE: np.ascontiguousarray(rows[lanes, L.SEP_STATE:L.SEP_STATE + 13].T),
+                      L.LANE_START: np.ascontiguousarray(rows[lanes][:, [L.SEP_TIME, L.SEP_DT]].T)}
+        if L.LANE_WIND in arrays:
+            laneArrays[L.LANE_WIND] = np.ascontiguousarray(arrays[L.LANE_WIND][:, lanes])
+        if L.LANE_MOTOR_ADJUST in arrays:
+            # the dropped stage is stage 0 of its own model: its motor's factors move to rows 0 / 1 (the k-th dropped stage is the
+            # bottom stage of what is left of the rocket: stage nStages - 1 - k of the full model)
+            full = arrays[L.LANE_MOTOR_ADJUST][:, lanes]
+            adj = np.ones_like(full)
+            si = nStages - 1 - k
+            adj[0:2] = full[2 * si:2 * si + 2]
+            laneArrays[L.LANE_MOTOR_ADJUST] = np.ascontiguousarray(adj)
+        b = batchClass(dropModel.blob, device=device)
+        try:
+            b.setLanes(int(lanes.size), laneArrays)
+            b.run()
+            res, st = b.results()
+            fin = b.finals()
+        finally:
+            b.close()
+        out.append(dict(lanes=lanes, results=res, status=st, finals=fin))
+    return out
 
 
 def _mean(x):
@@ -421,6 +478,8 @@ def runMonteCarloSimulation(simDefinitionFilePath=None, simDefinition=None, sile
     and ignored; `nGPUs` spreads contiguous sample ranges over that many GPUs of this box. Returns MonteCarloResults."""
     simDefinition = loadSimDefinition(simDefinitionFilePath, simDefinition, silent)
     nRuns, mCLogger, outputLists = _prepSim(simDefinition, echo=not silent)
-    results, status, counters = _runSimulations_B200(simDefinition, nRuns, outputLists, mCLogger, silent, nGPUs=nGPUs or 1, device=device)
+    results, status, counters, droppedStages = _runSimulations_B200(simDefinition, nRuns, outputLists, mCLogger, silent, nGPUs=nGPUs or 1, device=device)
     logPath = _showResults(simDefinition, outputLists, mCLogger)
-    return MonteCarloResults(results, status, counters, logPath, outputLists)
+    out = MonteCarloResults(results, status, counters, logPath, outputLists)
+    out.droppedStages = droppedStages
+    return out

@@ -70,8 +70,9 @@ def _p(a, t=ctypes.c_double):
     return a.ctypes.data_as(ctypes.POINTER(t)) if a is not None else None
 
 
-def run(blob, nLanes, laneArrays=None, traceLane=-1, traceMaxRows=0, dtReplay=None):
-    """laneArrays: dict {arrayId: ndarray [ncomp, nLanes]}. Returns dict of results."""
+def run(blob, nLanes, laneArrays=None, traceLane=-1, traceMaxRows=0, dtReplay=None, separations=False):
+    """laneArrays: dict {arrayId: ndarray [ncomp, nLanes]}. Returns dict of results. separations: also return the stage-separation rows
+    [nLanes, 3, 16] (state, time, step size at each separation: what a dropped stage's flight starts from)."""
     blob = np.ascontiguousarray(blob, dtype=np.float64)
     laneArrays = laneArrays or {}
     ids = np.array(list(laneArrays.keys()), dtype=np.int32)
@@ -86,13 +87,19 @@ def run(blob, nLanes, laneArrays=None, traceLane=-1, traceMaxRows=0, dtReplay=No
     trace = np.zeros((max(1, traceMaxRows), TRACE_W))
     rows = ctypes.c_int64(0)
     replay = np.ascontiguousarray(dtReplay, dtype=np.float64) if dtReplay is not None else None
+    sep = np.zeros((nLanes, 3, 16)) if separations else None
+    lib().oracle_set_separation_buffer(_p(sep))
     rc = lib().oracle_run(_p(blob), ctypes.c_int64(nLanes), ptrs, _p(ids, ctypes.c_int), ctypes.c_int(len(arrs)),
                           _p(results), _p(finals), _p(status, ctypes.c_int32), _p(counters, ctypes.c_int64),
                           _p(trace) if traceMaxRows > 0 else None, ctypes.c_int64(traceLane), ctypes.c_int64(traceMaxRows),
                           ctypes.byref(rows), _p(replay), ctypes.c_int64(0 if replay is None else replay.size))
+    lib().oracle_set_separation_buffer(None)
     if rc != 0:
         raise ValueError("oracle_run failed: bad model block")
-    return dict(results=results, finals=finals, status=status, counters=counters, trace=trace[:rows.value])
+    out = dict(results=results, finals=finals, status=status, counters=counters, trace=trace[:rows.value])
+    if separations:
+        out["separations"] = sep
+    return out
 
 
 def forceEval(blob, state13, time=0.0, wind=None):

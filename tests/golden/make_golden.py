@@ -43,6 +43,8 @@ What is recorded, and which reference code produced it:
                             (Motion/Integration.py:144-187,189-236), RK12Adaptive / RK23Adaptive (:238-330), the `elementary` step-size controller (:359-382), ConstantGainPIDRocket (GNC/MomentControllers.py:58-83)
   perlane_*.json .......... Monte Carlo loops with `_stdDev` on keys that change the model itself (a mass and a fin span; the launch position and
                             tilt with a launch rail): what mlb_set_lane_models / per-lane model blocks reproduce
+  droppaths_*.json ........ TwoStage.mapleaf with SimControl.StageDropPaths.compute: the booster's own flight from the separation to the ground
+                            (SingleSimulations.py:91-145,280-299), fixed step and adaptive
   rng.json ................ random.Random / PinkNoiseGenerator known answers (test_SimDefinition.py:118-151,
                             test_TurbulenceModelling.py:37-60)
 """
@@ -235,6 +237,30 @@ def singleFlight(defFile, overrides, traceEvery=25, keepDts=False):
     return dict(definition=os.path.basename(defFile), overrides=overrides, runs=[rec])
 
 
+def stageDropFlight(defFile, overrides):
+    """Main flight + dropped-stage flights of one un-sampled definition (SingleSimulations.py:91-145,280-299)."""
+    sd = SimDefinition(defFile, silent=True, disableDistributionSampling=True)
+    for k, v in {**QUIET, **overrides}.items():
+        sd.setValue(k, v)
+    sim = Simulation(simDefinition=sd, silent=True)
+    flights, _ = sim.run()
+    sys.stdout = sys.__stdout__
+    main = flightRecord(flights[0], 50)
+    drops = []
+    for f in flights[1:]:
+        # a dropped stage's flight object starts as a copy of the main flight up to the separation (createNewDetachedStage)
+        k = 0
+        while k < min(len(f.times), len(flights[0].times)) and f.times[k] == flights[0].times[k] and \
+                [*f.rigidBodyStates[k].position] == [*flights[0].rigidBodyStates[k].position]:
+            k += 1
+        rec = flightRecord(f)
+        rec.update(separationIndex=k - 1, separationTime=f.times[k - 1], separationState=stateRow(f.times[k - 1], f.rigidBodyStates[k - 1]),
+                   stepsAfterSeparation=len(f.times) - k, firstStatesAfter=[stateRow(f.times[i], f.rigidBodyStates[i]) for i in range(k, min(k + 3, len(f.times)))])
+        drops.append(rec)
+        print("  dropped stage: separation at t =", rec["separationTime"], "steps after", rec["stepsAfterSeparation"], "final", rec["final"][:4], flush=True)
+    return dict(definition=os.path.basename(defFile), overrides=overrides, runs=[main], drops=drops)
+
+
 def dump(name, obj):
     with open(os.path.join(HERE, name), "w") as f:
         json.dump(obj, f)
@@ -327,6 +353,11 @@ if __name__ == "__main__":
         keys = {"Environment.LaunchSite.railLength": "6", "Rocket.position": "(0 0 15)", "Rocket.position_stdDev": "(3 3 1)", "Rocket.velocity": "(0 0 0)",
                 "Rocket.rotationAngle": "4", "Rocket.rotationAngle_stdDev": "1.5", "Rocket.rotationAxis": "(0 1 0)"}
         dump("perlane_rail_position.json", monteCarlo(mc, keys, "2394781", 3, sampledKeys=("Rocket.position", "Rocket.rotationAngle")))
+    if "droppaths" in which:
+        two = os.path.join(MY_DATA, "TwoStage.mapleaf")
+        drop = {"SimControl.StageDropPaths.compute": "true", "SimControl.StageDropPaths.endCondition": "Altitude", "SimControl.StageDropPaths.endConditionValue": "0"}
+        dump("droppaths_rk4.json", stageDropFlight(two, drop))
+        dump("droppaths_rk45.json", stageDropFlight(two, {**drop, "SimControl.timeDiscretization": "RK45Adaptive", "SimControl.EndCondition": "Altitude"}))
     if "rk45_pink" in which:
         dump("rk45_pink.json", monteCarlo(adaptive, {}, "2394781", 4, globalSeed=2394781, keepDts=True))
     if "ideal" in which:

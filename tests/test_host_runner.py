@@ -33,7 +33,7 @@ class OracleBatch:
     def run(self, stream=0, sync=False):
         from oracle import oracle
         if getattr(self, "models", None) is None:
-            self.out = oracle.run(self.blob, self.n, self.arrays)
+            self.out = oracle.run(self.blob, self.n, self.arrays, separations=True)
             return
         # per-lane model blocks: one oracle flight per lane with its own block (shared part from the lane, tables from the handle's block)
         outs = []
@@ -44,6 +44,12 @@ class OracleBatch:
 
     def results(self):
         return self.out["results"], self.out["status"]
+
+    def finals(self):
+        return self.out["finals"]
+
+    def stageSeparations(self):
+        return self.out["separations"]
 
     def setFlightLog(self, firstLane, nLanes, every=1, maxRowsPerLane=2048):
         self.logged = (firstLane, nLanes, maxRowsPerLane)
@@ -336,3 +342,32 @@ def test_runner_samples_any_key_through_per_lane_models(monkeypatch, tmp_path, g
     log = open(out.logPath).read()
     for k in keys:
         assert "parameter: " + k in log
+
+
+@pytest.mark.parametrize("name", ["droppaths_rk4.json", "droppaths_rk45.json"])
+def test_runner_flies_dropped_stages(monkeypatch, tmp_path, golden, name):
+    """SimControl.StageDropPaths.compute (SingleSimulations.py:91-145,280-299): the booster of TwoStage.mapleaf flown on from the separation
+    as a lane of a second batch (model block of the dropped stage alone, burnt-out motor, separation state / time / step size from the main
+    batch). Fixed step: same number of steps after the separation and the same final state as the reference's dropped-stage flight."""
+    g = golden(name)
+    monkeypatch.setattr(backend, "TrajectoryBatch", OracleBatch)
+    sd = SimDefinition(os.path.join(DATA, g["definition"]), silent=True, disableDistributionSampling=True)
+    for k, v in {**g["overrides"], "MonteCarlo.numberRuns": "2", "MonteCarlo.output": "landingLocations"}.items():
+        sd.setValue(k, v)
+    sd.fileName = str(tmp_path / "TwoStage.mapleaf")
+    out = montecarlo.runMonteCarloSimulation(simDefinition=sd, silent=True)
+    assert len(out.droppedStages) == 1
+    d, ref = out.droppedStages[0], g["drops"][0]
+    assert list(d["lanes"]) == [0, 1] and (d["status"] == L.ST_OK).all()
+    fixed = name.endswith("rk4.json")
+    for lane in range(2):            # nothing is sampled in this definition: both runs are the reference's flight
+        if fixed:
+            assert abs(d["finals"][lane, 13] - ref["final"][0]) < 1e-9
+            assert np.linalg.norm(d["finals"][lane, 0:3] - np.array(ref["final"][1:4])) <= 1e-11 * np.linalg.norm(ref["final"][1:4])
+        else:
+            # free-running adaptive: the main flight's step sequence decorrelates from the reference's near the separation (a step that just
+            # clears or just misses the event clamp), so the dropped stage starts 6e-7 s apart; where it comes down is what is compared
+            assert abs(d["finals"][lane, 13] - ref["final"][0]) < 0.5
+            assert np.linalg.norm(d["results"][lane, 0:2] - np.array(ref["results"][0:2])) <= 1e-3 * np.linalg.norm(ref["results"][0:2])
+    assert np.allclose(out.results[0, 3:7], g["runs"][0]["results"][3:7], rtol=1e-12 if fixed else 3e-3)
+    assert "Dropped stage 1: 2 of 2 runs separated" in open(out.logPath).read()

@@ -420,3 +420,37 @@ def test_constant_step_controller_is_rejected():
     Integration.py:74-93): the backend refuses it when the model is built instead of flying something the reference never could."""
     with pytest.raises(ValueError):
         buildFrom("MonteCarloAdaptive.mapleaf", {"SimControl.TimeStepAdaptation.controller": "Constant"})
+
+
+@pytest.mark.parametrize("name", ["droppaths_rk4.json", "droppaths_rk45.json"])
+def test_dropped_stage_flight(golden, name):
+    """SingleSimulations.createNewDetachedStage (:280-299) + Rocket.__init__(stageToInitialize) (rocket.py:296-321,339-361): the booster of
+    TwoStage.mapleaf as its own rocket (burnt-out motor, no staging, StageDropPaths end condition), started from the reference's separation
+    state, time and step size: same number of steps to the ground, first states <= 1e-12, final state 1e-12 (fixed step) / within the
+    adaptive band. The main flight records the separation row the dropped stage starts from."""
+    g = golden(name)
+    d = g["drops"][0]
+    m = buildFrom(g["definition"], g["overrides"])
+    main = oracle.run(m.blob, 1, {}, separations=True)
+    row = main["separations"][0, 0]
+    assert row[L.SEP_VALID] == 1 and abs(row[L.SEP_TIME] - d["separationTime"]) < 1e-6
+    if name.endswith("rk4.json"):
+        assert row[L.SEP_TIME] == d["separationTime"] and row[L.SEP_DT] == 0.02
+        assert stateErr(np.concatenate([row[:13], [0]]), d["separationState"]) < 1e-12
+    sd = SimDefinition(os.path.join(DATA, g["definition"]), silent=True, disableDistributionSampling=True)
+    for k, v in g["overrides"].items():
+        sd.setValue(k, v)
+    sep = np.array(d["separationState"])
+    dt0 = d["firstStatesAfter"][0][0] - d["separationTime"]
+    md = buildModel(sd, droppedStage=0, droppedFromAltitude=sep[3])
+    assert int(md.header("H_NSTAGES")) == 1 and md.header("H_CTRL_OFF") == 0
+    arrays = {L.LANE_INIT_STATE: sep[1:14].reshape(13, 1).copy(), L.LANE_START: np.array([[d["separationTime"]], [dt0]])}
+    o = oracle.run(md.blob, 1, arrays, traceLane=0, traceMaxRows=8)
+    assert o["status"][0] == L.ST_OK and o["counters"][0, 0] == d["stepsAfterSeparation"]
+    for i, row in enumerate(d["firstStatesAfter"]):
+        assert abs(o["trace"][1 + i, 0] - row[0]) < 1e-12
+        assert stateErr(np.concatenate([o["trace"][1 + i, 1:14], [0]]), row) < 1e-12
+    if name.endswith("rk4.json"):
+        assert stateErr(o["finals"][0], d["final"]) < 1e-11
+    else:
+        assert relErr(o["results"][0, 0:2], d["results"][0:2]) < 1e-4
