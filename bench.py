@@ -247,6 +247,9 @@ def runB200(args):
     mine, mineStatus = gathered[rank], gatheredStatus[rank]
     batch.setLanesDevice(n, {k: t.data_ptr() for k, t in devArrays.items()}, keepAlive=devArrays)
     batch.setResultBuffers(mine.data_ptr(), mineStatus.data_ptr(), keepAlive=(gathered, gatheredStatus))
+    if args.log_every > 0:
+        # north_star's log companion: every lane keeps every log_every-th accepted state (16 doubles = 128 B per kept step) in HBM
+        batch.setFlightLog(0, n, args.log_every, args.log_rows)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
 
     def onePass():
@@ -271,6 +274,7 @@ def runB200(args):
         barrier()
     totalMs = e0.elapsed_time(e1)
     c = batch.counters()                      # counters of the last pass (every pass integrates the same lanes)
+    logRows = int(batch.flightLogRowCounts().sum()) if args.log_every > 0 else 0
     launches = args.steps * (c["kernel_launches"] + (2 if world > 1 else 0))     # this library's kernels: prologue, free-flight generations, under-chute (+ the two moment kernels)
     if world > 1:
         t = torch.tensor([totalMs], dtype=torch.float64, device=dev)
@@ -353,6 +357,20 @@ def runB200(args):
         "clocks": clocks.summary(),
         "roofline": roofline,
     }
+    if args.log_every > 0:
+        hbmPeak, hbmSource = 6541.1, "MEASURED_PEAKS.json hbm_gbs of this pool's B200 (driver-written) not found: the pool's recorded 6541.1 GB/s"
+        try:
+            with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
+                hbmPeak, hbmSource = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy bandwidth)"
+        except Exception:
+            pass
+        logBytes = logRows * 16 * 8
+        gbs = logBytes / (c["last_run_ms"] * 1e-3) / 1e9
+        line["log_roofline"] = {"bound": "hbm", "achieved": gbs, "peak": hbmPeak, "unit": "GB/s", "frac": gbs / hbmPeak, "bytes_written": logBytes,
+                                "rows_kept": logRows, "every": args.log_every, "rows_per_lane_max": args.log_rows, "peak_source": hbmSource,
+                                "note": "flight log of EVERY lane: 128 B per kept step written by the lane itself (one 128-byte row = four full 32-byte sectors); a lane whose "
+                                        "buffer fills drops every other row in place and doubles its stride. The log rides on FP64-bound kernels: its write rate is what "
+                                        "the trajectory rate allows, far below what HBM could take"}
     if world == 1 and not args.skip_cpu:
         line["cpu_baseline"] = cpuBaseline(cfg, min(os.cpu_count() or 1, 16), 3, warmup=1)      # one untimed pass: worker start-up, first-call parsing
     print(json.dumps(line), flush=True)
@@ -430,6 +448,8 @@ def main():
     ap.add_argument("--total-lanes", type=int, default=0, help="with --scaling strong (default 10^7, BASELINE configs[4])")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs: leave out the cpu_baseline leg")
+    ap.add_argument("--log-every", type=int, default=0, help="keep every n-th accepted state of EVERY lane in the device flight log (0: no log) and report its HBM write rate")
+    ap.add_argument("--log-rows", type=int, default=256, help="log rows per lane (128 B each)")
     args = ap.parse_args()
     if args.impl == "reference":
         runReference(args)

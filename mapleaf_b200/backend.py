@@ -243,6 +243,13 @@ class TrajectoryBatch:
         _check(lib().mlb_get_flight_log(self._h, _dp(rows), counts.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))), "mlb_get_flight_log")
         return [rows[i, :counts[i]].copy() for i in range(n)]
 
+    def flightLogRowCounts(self):
+        """Rows kept per logged lane (without copying the rows)."""
+        n, _ = self._flightLog
+        counts = np.zeros(n, dtype=np.int64)
+        _check(lib().mlb_get_flight_log(self._h, None, counts.ctypes.data_as(ctypes.POINTER(ctypes.c_int64))), "mlb_get_flight_log")
+        return counts
+
     def setTrace(self, lane: int, maxRows: int):
         _check(lib().mlb_set_trace(self._h, lane, maxRows), "mlb_set_trace")
         self._traceMax = maxRows

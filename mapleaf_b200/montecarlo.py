@@ -92,8 +92,11 @@ class MonteCarloResults:
         self.results, self.status, self.counters, self.logPath = results, status, counters, logPath
         self.landingLocations, self.apogees, self.maxSpeeds, self.flightTimes, self.maxHorizontalVels, self.flights = outputLists
         self.droppedStages = []      # SimControl.StageDropPaths.compute: one dict per dropped stage (flyDroppedStages)
+        self.timeStepLogPaths = []   # SimControl.loggingLevel >= 1: the `<stage>_timeStepLog.csv` files written
 
 
+_TIME_STEP_LOG_LIMIT = 100     # runs whose per-step logs are written with SimControl.loggingLevel >= 1 (the reference writes every run's)
+_TIME_STEP_LOG_ROWS = 65536    # per-step rows kept per logged run (8 MB of device memory each); longer flights are decimated, with a note
 _FLIGHT_PATH_LIMIT = 2000      # runs whose paths are kept (256 KB of device memory each while the batch runs)
 _FLIGHT_PATH_ROWS = 2048       # strided states kept per flight on the device: 1024-2048 of them, whatever the flight's length
 _FLIGHT_PATH_FRAMES = 900      # MonteCarlo.py:60-62: Plotting._keepNTimeSteps(flight, 900)
@@ -313,6 +316,11 @@ def _runSimulations_B200(simDefinition, nRuns, outputLists, mCLogger, silent=Fal
     if wantPaths and nRuns > _FLIGHT_PATH_LIMIT:
         mCLogger.log("NOTE: MonteCarlo.output flightPaths: flight paths are kept for the first {} of {} runs".format(_FLIGHT_PATH_LIMIT, nRuns))
     model = buildModel(simDefinition)
+    # SimControl.loggingLevel >= 1: the reference writes `<definition>_RunN/<top stage>_timeStepLog.csv` for every run
+    # (SingleSimulations.py:351-392, rocket.py:729-738); here for the first _TIME_STEP_LOG_LIMIT runs, from the lanes' per-step flight log
+    wantStepLogs = int(simDefinition.getValue("SimControl.loggingLevel")) >= 1 and bool(simDefinition.fileName)
+    if wantStepLogs and nRuns > _TIME_STEP_LOG_LIMIT:
+        mCLogger.log("NOTE: SimControl.loggingLevel: time-step logs are written for the first {} of {} runs".format(_TIME_STEP_LOG_LIMIT, nRuns))
     arrays = sampleRuns(simDefinition, nRuns, mCLogger, model)
     laneModels = arrays.pop(LANE_MODELS, None)
 
@@ -327,13 +335,17 @@ def _runSimulations_B200(simDefinition, nRuns, outputLists, mCLogger, silent=Fal
         if laneModels is not None:
             b.setLaneModels(laneModels[lo:hi])
         nLogged = max(0, min(hi, _FLIGHT_PATH_LIMIT) - lo) if wantPaths else 0
-        if nLogged:
+        nStepLogged = max(0, min(hi, _TIME_STEP_LOG_LIMIT) - lo) if wantStepLogs else 0
+        if nStepLogged:           # every accepted step (the path frames below are interpolated from the same rows)
+            b.setFlightLog(0, max(nLogged, nStepLogged), 1, _TIME_STEP_LOG_ROWS)
+        elif nLogged:
             b.setFlightLog(0, nLogged, 1, _FLIGHT_PATH_ROWS)
         b.run()                                   # asynchronous: all GPUs integrate concurrently
         batches.append(b)
     results = np.empty((nRuns, L.RES_SIZE))
     status = np.empty(nRuns, dtype=np.int32)
     counters = []
+    stepLogPaths = []
     wantDrops = int(model.header("H_NSTAGES")) > 1 and str(simDefinition.getValue("SimControl.StageDropPaths.compute")).lower() == "true" and laneModels is None
     separations = np.zeros((nRuns, L.MLB_MAX_STAGES - 1, L.SEP_W)) if wantDrops else None
     for g, b in enumerate(batches):
@@ -342,8 +354,20 @@ def _runSimulations_B200(simDefinition, nRuns, outputLists, mCLogger, silent=Fal
         counters.append(b.counters())
         if wantDrops:
             separations[bounds[g]:bounds[g + 1]] = b.stageSeparations()
+        logged = b.flightLog() if ((wantPaths and bounds[g] < _FLIGHT_PATH_LIMIT) or (wantStepLogs and bounds[g] < _TIME_STEP_LOG_LIMIT)) else []
         if wantPaths and bounds[g] < _FLIGHT_PATH_LIMIT:
-            flights.extend(FlightPath.fromLog(rows) for rows in b.flightLog())
+            flights.extend(FlightPath.fromLog(rows) for rows in logged[:max(0, min(bounds[g + 1], _FLIGHT_PATH_LIMIT) - bounds[g])])
+        if wantStepLogs and bounds[g] < _TIME_STEP_LOG_LIMIT:
+            from .flightlog import writeTimeStepLog
+            base = simDefinition.fileName[:simDefinition.fileName.rfind(".")] + "_Run"
+            laneSteps = b.laneCounters() if hasattr(b, "laneCounters") else None
+            for i, rows in enumerate(logged[:max(0, min(bounds[g + 1], _TIME_STEP_LOG_LIMIT) - bounds[g])]):
+                folder = _nextNumberedName(base)
+                os.mkdir(folder)
+                if laneSteps is not None and len(rows) - 1 != int(laneSteps[i, 0]):
+                    mCLogger.log("NOTE: run {}: flight longer than {} steps, time-step log decimated".format(bounds[g] + i + 1, _TIME_STEP_LOG_ROWS))
+                path = writeTimeStepLog(os.path.join(folder, "{}_timeStepLog.csv".format(model.meta["stages"][0]["name"])), rows, model)
+                stepLogPaths.append(path)
         b.close()
 
     failed = np.nonzero(status != L.ST_OK)[0]
@@ -360,7 +384,15 @@ def _runSimulations_B200(simDefinition, nRuns, outputLists, mCLogger, silent=Fal
     droppedStages = flyDroppedStages(simDefinition, model, arrays, separations, device=device) if wantDrops else []
     for k, d in enumerate(droppedStages):
         mCLogger.log("Dropped stage {}: {} of {} runs separated; flown from the separation to SimControl.StageDropPaths.endCondition".format(k + 1, d["lanes"].size, nRuns))
-    return results, status, counters, droppedStages
+    return results, status, counters, droppedStages, stepLogPaths
+
+
+def _nextNumberedName(base):
+    """Logging.findNextAvailableNumberedFileName (IO/Logging.py): base + the first integer >= 1 that is not taken."""
+    n = 1
+    while os.path.exists(base + str(n)):
+        n += 1
+    return base + str(n)
 
 
 def flyDroppedStages(simDefinition, model, arrays, separations, device=0, batchClass=None):
@@ -478,8 +510,9 @@ def runMonteCarloSimulation(simDefinitionFilePath=None, simDefinition=None, sile
     and ignored; `nGPUs` spreads contiguous sample ranges over that many GPUs of this box. Returns MonteCarloResults."""
     simDefinition = loadSimDefinition(simDefinitionFilePath, simDefinition, silent)
     nRuns, mCLogger, outputLists = _prepSim(simDefinition, echo=not silent)
-    results, status, counters, droppedStages = _runSimulations_B200(simDefinition, nRuns, outputLists, mCLogger, silent, nGPUs=nGPUs or 1, device=device)
+    results, status, counters, droppedStages, stepLogPaths = _runSimulations_B200(simDefinition, nRuns, outputLists, mCLogger, silent, nGPUs=nGPUs or 1, device=device)
     logPath = _showResults(simDefinition, outputLists, mCLogger)
     out = MonteCarloResults(results, status, counters, logPath, outputLists)
     out.droppedStages = droppedStages
+    out.timeStepLogPaths = stepLogPaths
     return out

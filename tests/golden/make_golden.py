@@ -45,6 +45,7 @@ What is recorded, and which reference code produced it:
                             tilt with a launch rail): what mlb_set_lane_models / per-lane model blocks reproduce
   droppaths_*.json ........ TwoStage.mapleaf with SimControl.StageDropPaths.compute: the booster's own flight from the separation to the ground
                             (SingleSimulations.py:91-145,280-299), fixed step and adaptive
+  timesteplog_*.json ...... the reference's own `<stage>_timeStepLog.csv` (SimControl.loggingLevel 1) of two short flights, as text
   rng.json ................ random.Random / PinkNoiseGenerator known answers (test_SimDefinition.py:118-151,
                             test_TurbulenceModelling.py:37-60)
 """
@@ -261,6 +262,27 @@ def stageDropFlight(defFile, overrides):
     return dict(definition=os.path.basename(defFile), overrides=overrides, runs=[main], drops=drops)
 
 
+def timeStepLogText(defFile, overrides):
+    """The reference's own `<stage>_timeStepLog.csv` (SimControl.loggingLevel 1: rocket.py:155-170,615-644,729-738, IO/CythonLog.pyx:163-213) of
+    one un-sampled flight, as text."""
+    import shutil, tempfile
+    tmp = tempfile.mkdtemp()
+    sd = SimDefinition(defFile, silent=True, disableDistributionSampling=True)
+    for k, v in {**QUIET, **overrides, "SimControl.loggingLevel": "1"}.items():
+        sd.setValue(k, v)
+    sd.fileName = os.path.join(tmp, os.path.basename(defFile))
+    sim = Simulation(simDefinition=sd, silent=True)
+    flights, logPaths = sim.run()
+    sys.stdout = sys.__stdout__
+    path = [p for p in logPaths if p.endswith("_timeStepLog.csv")][0]
+    with open(path) as f:
+        text = f.read()
+    shutil.rmtree(tmp)
+    print("  time-step log:", os.path.basename(path), len(text.splitlines()), "lines", flush=True)
+    return dict(definition=os.path.basename(defFile), overrides=overrides, fileName=os.path.basename(path), csv=text,
+                runs=[flightRecord(flights[0])])
+
+
 def dump(name, obj):
     with open(os.path.join(HERE, name), "w") as f:
         json.dump(obj, f)
@@ -358,6 +380,14 @@ if __name__ == "__main__":
         drop = {"SimControl.StageDropPaths.compute": "true", "SimControl.StageDropPaths.endCondition": "Altitude", "SimControl.StageDropPaths.endConditionValue": "0"}
         dump("droppaths_rk4.json", stageDropFlight(two, drop))
         dump("droppaths_rk45.json", stageDropFlight(two, {**drop, "SimControl.timeDiscretization": "RK45Adaptive", "SimControl.EndCondition": "Altitude"}))
+    if "timesteplog" in which:
+        # 1.2 s of RK4 flight with the drogue opened at 0.5 s (6-DoF rows, then 3-DoF rows), and 2 s of the adaptive flight (error column)
+        early = {"Rocket.Sustainer.RecoverySystem.stage1Trigger": "Time", "Rocket.Sustainer.RecoverySystem.stage1TriggerValue": "0.5",
+                 "Rocket.Sustainer.RecoverySystem.stage1DelayTime": "0", "SimControl.EndCondition": "Time", "SimControl.EndConditionValue": "1.2",
+                 "SimControl.timeStep": "0.02", "Environment.ConstantMeanWind.velocity": "(4 -2.5 0.3)"}
+        dump("timesteplog_rk4.json", timeStepLogText(mc, early))
+        dump("timesteplog_rk45.json", timeStepLogText(adaptive, {"Environment.TurbulenceModel": "None", "SimControl.EndCondition": "Time", "SimControl.EndConditionValue": "2",
+                                                                 "Environment.ConstantMeanWind.velocity": "(4 -2.5 0.3)"}))
     if "rk45_pink" in which:
         dump("rk45_pink.json", monteCarlo(adaptive, {}, "2394781", 4, globalSeed=2394781, keepDts=True))
     if "ideal" in which:

@@ -371,3 +371,18 @@ def test_runner_flies_dropped_stages(monkeypatch, tmp_path, golden, name):
             assert np.linalg.norm(d["results"][lane, 0:2] - np.array(ref["results"][0:2])) <= 1e-3 * np.linalg.norm(ref["results"][0:2])
     assert np.allclose(out.results[0, 3:7], g["runs"][0]["results"][3:7], rtol=1e-12 if fixed else 3e-3)
     assert "Dropped stage 1: 2 of 2 runs separated" in open(out.logPath).read()
+
+
+def test_runner_writes_time_step_logs(monkeypatch, tmp_path, golden):
+    """SimControl.loggingLevel 1 in a Monte Carlo run: every run gets `<definition>_RunN/<top stage>_timeStepLog.csv` like the reference's
+    runs do (SingleSimulations.py:351-392); an un-sampled definition reproduces the reference's file byte for byte."""
+    g = golden("timesteplog_rk4.json")
+    monkeypatch.setattr(backend, "TrajectoryBatch", OracleBatch)
+    sd = SimDefinition(os.path.join(DATA, g["definition"]), silent=True, disableDistributionSampling=True)
+    for k, v in {**g["overrides"], "MonteCarlo.numberRuns": "2", "MonteCarlo.output": "apogees", "SimControl.loggingLevel": "1"}.items():
+        sd.setValue(k, v)
+    sd.fileName = str(tmp_path / "MonteCarlo.mapleaf")
+    out = montecarlo.runMonteCarloSimulation(simDefinition=sd, silent=True)
+    assert [os.path.relpath(p, tmp_path) for p in out.timeStepLogPaths] == ["MonteCarlo_Run1/Sustainer_timeStepLog.csv", "MonteCarlo_Run2/Sustainer_timeStepLog.csv"]
+    for p in out.timeStepLogPaths:
+        assert open(p).read() == g["csv"]

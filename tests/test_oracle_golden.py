@@ -454,3 +454,16 @@ def test_dropped_stage_flight(golden, name):
         assert stateErr(o["finals"][0], d["final"]) < 1e-11
     else:
         assert relErr(o["results"][0, 0:2], d["results"][0:2]) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["timesteplog_rk4.json", "timesteplog_rk45.json"])
+def test_time_step_log_csv_is_the_reference_file(golden, name, tmp_path):
+    """SimControl.loggingLevel 1: `<stage>_timeStepLog.csv` written from a lane's per-step flight-log rows is byte for byte the file the
+    reference writes for the same flight (rocket.py:155-170,615-644,729-738; IO/CythonLog.pyx:163-213): column order, the three quaternion
+    columns, TimeStep(s), the error estimate shifted to the row the step starts from, fill values under the parachute."""
+    from mapleaf_b200 import flightlog
+    g = golden(name)
+    m = buildFrom(g["definition"], g["overrides"])
+    o = oracle.run(m.blob, 1, {}, traceLane=0, traceMaxRows=2000)
+    path = flightlog.writeTimeStepLog(str(tmp_path / g["fileName"]), o["trace"], m)
+    assert open(path).read() == g["csv"]
