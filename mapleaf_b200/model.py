@@ -994,7 +994,7 @@ def _flattenTableau(rows, nResult):
     return flat
 
 
-def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000, droppedStage: int = None, droppedFromAltitude: float = None) -> Model:
+def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000, droppedStage: int = None, droppedFromAltitude: float = None, groundWind=None) -> Model:
     """Everything the reference's constructors precompute, flattened into one model block.
     droppedStage = n builds the rocket the reference creates for the n-th dropped stage (`Simulation.createRocket(stage=n)`,
     SingleSimulations.py:161-176,280-299; Rocket.__init__ with stageToInitialize, rocket.py:296-321,339-361): that stage alone, its motor burnt
@@ -1093,14 +1093,27 @@ def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000, droppedStag
         raise ValueError("Atmospheric model: {} not implemented, try using 'USStandardAtmosphere'".format(atm))
 
     wind = env.getString("MeanWindModel")
+    # ground wind drawn from wind roses (MeanWindModelling.py:41-93): a host-side draw per constructed Environment. A Monte Carlo run passes
+    # the winds it drew per lane (groundWind / LANE_WIND); building a model on its own draws one here, as constructing the Environment would
+    sampledGroundWind = None
+    if wind == "SampledGroundWindData" or (wind == "Hellman" and env.getString("Hellman.groundWindModel") == "SampledGroundWindData"):
+        if groundWind is not None:
+            sampledGroundWind = list(groundWind)
+        else:
+            from .windsampling import samplerFromDefinition
+            sampledGroundWind = samplerFromDefinition(env).sample()
     if wind == "Constant":
         H[L.H_WIND] = L.WIND_CONSTANT
         H[L.H_WIND_V:L.H_WIND_V + 3] = env.getVector("ConstantMeanWind.velocity")
+    elif wind == "SampledGroundWindData":
+        H[L.H_WIND] = L.WIND_CONSTANT                      # "Wind is not a function of altitude" (:74-78)
+        H[L.H_WIND_V:L.H_WIND_V + 3] = sampledGroundWind
     elif wind == "Hellman":
-        if env.getString("Hellman.groundWindModel") != "Constant":
-            raise NotImplementedError("Hellman.groundWindModel other than 'Constant' (wind-rose sampling is host-side, SURVEY §8f)")
+        groundModel = env.getString("Hellman.groundWindModel")
+        if groundModel not in ("Constant", "SampledGroundWindData"):
+            raise UnboundLocalError("cannot access local variable 'meanGroundWind' where it is not associated with a value")      # the reference's failure (:80-93)
         H[L.H_WIND] = L.WIND_HELLMAN
-        H[L.H_WIND_V:L.H_WIND_V + 3] = env.getVector("ConstantMeanWind.velocity")
+        H[L.H_WIND_V:L.H_WIND_V + 3] = env.getVector("ConstantMeanWind.velocity") if groundModel == "Constant" else sampledGroundWind
         H[L.H_HELLMAN_ALPHA] = env.getFloat("Hellman.alphaCoeff")
         H[L.H_HELLMAN_LIMIT] = env.getFloat("Hellman.altitudeLimit")
     elif wind == "CustomWindProfile":

@@ -179,7 +179,7 @@ def _checkSampledKeys(simDefinition, model=None):
     return keys, bool(other) or onRail
 
 
-def _sampleRunsLaneModels(simDefinition, nRuns, mCLogger, model, nGen, hasSeed):
+def _sampleRunsLaneModels(simDefinition, nRuns, mCLogger, model, nGen, hasSeed, windSampler=None):
     """One model block per run: resample, run the constructors' precomputation on the sampled definition (buildModel), keep the shared part.
     ~0.1 s of host time per run for a Barrowman rocket (fin MAC integral, ogive area integral): the general path, not the fast one."""
     shared = int(model.header("H_SHARED_LEN")) or model.blob.size
@@ -188,7 +188,7 @@ def _sampleRunsLaneModels(simDefinition, nRuns, mCLogger, model, nGen, hasSeed):
     for i in range(nRuns):
         mCLogger.log("\nMonte Carlo Run #{}".format(i + 1))
         simDefinition.resampleProbabilisticValues()
-        mi = buildModel(simDefinition)
+        mi = buildModel(simDefinition, groundWind=windSampler.sample() if windSampler is not None else None)
         if mi.blob.size != model.blob.size or int(mi.header("H_SHARED_LEN")) != int(model.header("H_SHARED_LEN")) \
                 or not np.array_equal(mi.blob[shared:], model.blob[shared:], equal_nan=True):
             raise NotImplementedError("Monte Carlo sampling changed the structure of the model (component list, table sizes or interpolation tables) "
@@ -202,8 +202,10 @@ def _sampleRunsLaneModels(simDefinition, nRuns, mCLogger, model, nGen, hasSeed):
     return arrays
 
 
-def sampleRuns(simDefinition, nRuns, mCLogger, model):
-    """Draws every run's inputs in the reference's order (MonteCarlo.py:64-72) and returns the per-lane arrays."""
+def sampleRuns(simDefinition, nRuns, mCLogger, model, windSampler=None):
+    """Draws every run's inputs in the reference's order (MonteCarlo.py:64-72) and returns the per-lane arrays. windSampler: the ground
+    wind of every run comes from wind roses (two draws of the global generator per run, made when the run's Environment is constructed:
+    after the run's resample, before its pink-noise seeds, ENV/environment.py:47-48)."""
     keys, needLaneModels = _checkSampledKeys(simDefinition, model)
     motorKeys = _motorKeys(model)
     sampleMotor = any(k in motorKeys for k in keys)
@@ -213,8 +215,10 @@ def sampleRuns(simDefinition, nRuns, mCLogger, model):
     nGen = {L.TURB_PINK1D: 1, L.TURB_PINK2D: 2, L.TURB_PINK3D: 3}.get(turb, 0)
     hasSeed = int(model.header("H_PINK_HAS_SEED"))
     if needLaneModels:
-        return _sampleRunsLaneModels(simDefinition, nRuns, mCLogger, model, nGen, hasSeed)
-    if not sampleState and not simDefinition.disableDistributionSampling and nRuns >= _VECTORIZED_SAMPLING_FROM:
+        return _sampleRunsLaneModels(simDefinition, nRuns, mCLogger, model, nGen, hasSeed, windSampler)
+    if windSampler is not None:
+        sampleWind = True
+    if windSampler is None and not sampleState and not simDefinition.disableDistributionSampling and nRuns >= _VECTORIZED_SAMPLING_FROM:
         return _sampleRunsVectorized(simDefinition, nRuns, mCLogger, model, keys, motorKeys, nGen, hasSeed)
     wind = np.empty((3, nRuns)) if sampleWind else None
     state = np.empty((13, nRuns)) if sampleState else None
@@ -223,7 +227,9 @@ def sampleRuns(simDefinition, nRuns, mCLogger, model):
     for i in range(nRuns):
         mCLogger.log("\nMonte Carlo Run #{}".format(i + 1))
         simDefinition.resampleProbabilisticValues()
-        if sampleWind:
+        if windSampler is not None:
+            wind[:, i] = windSampler.sample()
+        elif sampleWind:
             wind[:, i] = parseVector(simDefinition.getValue(_WIND_KEY))
         if sampleState:
             state[:, i] = laneInitialState(simDefinition, model)
@@ -315,13 +321,15 @@ def _runSimulations_B200(simDefinition, nRuns, outputLists, mCLogger, silent=Fal
     wantPaths = "flightPaths" in resultsToOutput
     if wantPaths and nRuns > _FLIGHT_PATH_LIMIT:
         mCLogger.log("NOTE: MonteCarlo.output flightPaths: flight paths are kept for the first {} of {} runs".format(_FLIGHT_PATH_LIMIT, nRuns))
-    model = buildModel(simDefinition)
+    from .windsampling import samplerFromDefinition
+    windSampler = samplerFromDefinition(SubDictReader("Environment", simDefinition))
+    model = buildModel(simDefinition, groundWind=(0.0, 0.0, 0.0) if windSampler is not None else None)      # no draw from the global generator here
     # SimControl.loggingLevel >= 1: the reference writes `<definition>_RunN/<top stage>_timeStepLog.csv` for every run
     # (SingleSimulations.py:351-392, rocket.py:729-738); here for the first _TIME_STEP_LOG_LIMIT runs, from the lanes' per-step flight log
     wantStepLogs = int(simDefinition.getValue("SimControl.loggingLevel")) >= 1 and bool(simDefinition.fileName)
     if wantStepLogs and nRuns > _TIME_STEP_LOG_LIMIT:
         mCLogger.log("NOTE: SimControl.loggingLevel: time-step logs are written for the first {} of {} runs".format(_TIME_STEP_LOG_LIMIT, nRuns))
-    arrays = sampleRuns(simDefinition, nRuns, mCLogger, model)
+    arrays = sampleRuns(simDefinition, nRuns, mCLogger, model, windSampler)
     laneModels = arrays.pop(LANE_MODELS, None)
 
     # contiguous sample ranges per GPU: gathered results are already in sample order

@@ -46,6 +46,7 @@ What is recorded, and which reference code produced it:
   droppaths_*.json ........ TwoStage.mapleaf with SimControl.StageDropPaths.compute: the booster's own flight from the separation to the ground
                             (SingleSimulations.py:91-145,280-299), fixed step and adaptive
   timesteplog_*.json ...... the reference's own `<stage>_timeStepLog.csv` (SimControl.loggingLevel 1) of two short flights, as text
+  windrose.json ........... ground winds drawn by the reference's WindRoseDataSampler (seeded global random)
   rng.json ................ random.Random / PinkNoiseGenerator known answers (test_SimDefinition.py:118-151,
                             test_TurbulenceModelling.py:37-60)
 """
@@ -85,6 +86,7 @@ def runOne(sd):
     sim = Simulation(simDefinition=sd, silent=True)
     flights, _ = sim.run()
     sys.stdout = sys.__stdout__
+    runOne.lastSimulation = sim
     return flights[0]
 
 
@@ -131,6 +133,7 @@ def monteCarlo(defFile, overrides, seed, nRuns, globalSeed=None, traceEvery=0, k
         rec["wind"] = wind
         rec["motor"] = [float(sd.getValue(k)) for k in motorKeys]
         rec["sampled"] = {k: sd.getValue(k) for k in sampledKeys}
+        rec["groundWind"] = [*runOne.lastSimulation.environment.meanWindModel.getMeanWind(10.0)]      # at the 10 m reference height of the Hellman law
         rec["pinkSeeds"] = seeds
         runs.append(rec)
         print("  run", i + 1, "steps", rec["steps"], "apogee", rec["results"][3], flush=True)
@@ -388,6 +391,27 @@ if __name__ == "__main__":
         dump("timesteplog_rk4.json", timeStepLogText(mc, early))
         dump("timesteplog_rk45.json", timeStepLogText(adaptive, {"Environment.TurbulenceModel": "None", "SimControl.EndCondition": "Time", "SimControl.EndConditionValue": "2",
                                                                  "Environment.ConstantMeanWind.velocity": "(4 -2.5 0.3)"}))
+    if "windrose" in which:
+        # WindRoseDataSampler (ENV/MeanWindModelling.py:198-329) on this repository's synthetic tables (the reference reads them from its
+        # own Examples/Wind folder, so they are copied into the built copy under baseline/_ref for the run) and, separately, on two of the
+        # reference's own tables: seeded global random, ten ground winds each
+        import shutil
+        from MAPLEAF.ENV.MeanWindModelling import WindRoseDataSampler
+        mine = os.path.join(REPO, "mapleaf_b200", "data", "Wind")
+        for f in os.listdir(mine):
+            shutil.copy(os.path.join(mine, f), os.path.join(REF_DIR, "MAPLEAF", "Examples", "Wind", f))
+        out = {}
+        for label, locs, weights in (("synthetic", ["TestFieldA", "TestFieldB"], [0.35, 0.65]), ("synthetic_single", ["TestFieldB"], [1.0]),
+                                     ("reference_tables", ["Suffield", "MedecineHat"], [0.4, 0.6])):
+            random.seed(20240611)
+            smp = WindRoseDataSampler(silent=True)
+            out[label] = dict(locations=locs, weights=weights, month="Apr", seed=20240611,
+                              winds=[[*smp.sampleWindRoses(locs, weights, "Apr")] for _ in range(10)])
+        dump("windrose.json", out)
+        rose = {"Environment.SampledGroundWindData.locationsToSample": "TestFieldA 0.35 TestFieldB 0.65", "Environment.SampledGroundWindData.launchMonth": "Apr"}
+        dump("windrose_mc.json", monteCarlo(mc, {**rose, "Environment.MeanWindModel": "SampledGroundWindData"}, "2394781", 3, globalSeed=777))
+        dump("windrose_hellman_mc.json", monteCarlo(adaptive, {**rose, "Environment.Hellman.groundWindModel": "SampledGroundWindData", "SimControl.EndCondition": "Apogee"},
+                                                    "2394781", 2, globalSeed=778, keepDts=True))
     if "rk45_pink" in which:
         dump("rk45_pink.json", monteCarlo(adaptive, {}, "2394781", 4, globalSeed=2394781, keepDts=True))
     if "ideal" in which:

@@ -1,6 +1,7 @@
 """Writes the environment tables used by the option-coverage fixtures (inputs made for this repository, reference file formats):
    data/Environment/atmosphereTable.txt ... TabulatedAtmosphere (ENV/AtmosphereModelling.py:79-96): h [m ASL], T [K], P [Pa], rho [kg/m3], mu [1e-5 Pa s]
-   data/Environment/windProfile.txt ....... CustomWindProfile / InterpolatedWind (ENV/MeanWindModelling.py:165-196): AGL altitude, wind x y z [m/s]"""
+   data/Environment/windProfile.txt ....... CustomWindProfile / InterpolatedWind (ENV/MeanWindModelling.py:165-196): AGL altitude, wind x y z [m/s]
+   data/Wind/WindroseApr<TestField>.txt ... two synthetic wind roses for SampledGroundWindData (ENV/MeanWindModelling.py:198-329)"""
 import math, os
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 out = os.path.join(REPO, "mapleaf_b200", "data", "Environment")
@@ -24,4 +25,28 @@ with open(os.path.join(out, "windProfile.txt"), "w") as f:
         speed = 2.5 + 9.0 * (1 - math.exp(-h / 900.0)) + 3.0 * math.exp(-((h - 450) / 200.0) ** 2)
         ang = math.radians(15 + 40 * (1 - math.exp(-h / 1500.0)))
         f.write("%d %.3f %.3f %.3f\n" % (h, speed * math.cos(ang), speed * math.sin(ang), 0.4 * math.exp(-((h - 800) / 400.0) ** 2)))
-print("wrote", os.listdir(out))
+
+
+def rose(name, month, peakDir, spread, calm, scale):
+    """A synthetic wind-rose table in the Iowa Environmental Mesonet layout the reference parses (ENV/MeanWindModelling.py:228-260): 36
+    direction rows, calm (first row only) + six speed classes in percent frequency, one preferred direction."""
+    wdir = os.path.join(REPO, "mapleaf_b200", "data", "Wind")
+    os.makedirs(wdir, exist_ok=True)
+    lines = ["# Windrose Data Table (Percent Frequency) for %s (synthetic table written for mapleaf_b200's tests, Iowa Environmental Mesonet layout)" % name,
+             "# Wind Speed Units: miles per hour", "# First value in table is CALM",
+             "Direction,     Calm, 2.0  4.9, 5.0  6.9, 7.0  9.9,10.0 14.9,15.0 19.9,    20.0+"]
+    bins = [(0, 10)] + [(10 * (i - 1), 10 * (i + 1)) for i in range(1, 36)]
+    for k, (a, b) in enumerate(bins):
+        mid = (a + b) / 2
+        d = min(abs(mid - peakDir), 360 - abs(mid - peakDir))
+        w = math.exp(-(d / spread) ** 2) + 0.15
+        vals = [w * scale * f for f in (0.55, 0.45, 0.62, 0.9, 0.5, 0.22)]
+        first = "%9.2f" % calm if k == 0 else "         "
+        lines.append("%03d-%03d  ,%s,%s" % (a, b, first, ",".join("%9.3f" % v for v in vals)))
+    with open(os.path.join(wdir, "Windrose%s%s.txt" % (month, name)), "w") as f:
+        f.write("\n".join(lines) + "\n")
+
+
+rose("TestFieldA", "Apr", 240, 60, 2.1, 0.55)
+rose("TestFieldB", "Apr", 300, 35, 0.8, 0.6)
+print("wrote", os.listdir(out), os.listdir(os.path.join(REPO, "mapleaf_b200", "data", "Wind")))
