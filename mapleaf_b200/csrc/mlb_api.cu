@@ -191,8 +191,8 @@ MLB_DEV void flightLoop(const RunArgs& a, const double* B) {
     const long long lane = inRange ? (a.qIn ? (long long)a.qIn[slot] : slot) : 0;
     if (PERLANE) B = a.laneModels + lane * a.laneModelStride;
     /* RK stage derivatives: per-thread local memory, indexed dynamically by the tableau loops */
-    double kLocal[MLB_K_SLOTS_MAX * (PH == 1 ? 6 : 12)];
-    KStore ks; ks.base = kLocal; ks.slotStride = (PH == 1 ? 6 : 12);
+    double kLocal[MLB_K_SLOTS_MAX * (PH == 1 ? 6 : MLB_K_SLOT_6DOF)];
+    KStore ks; ks.base = kLocal; ks.slotStride = (PH == 1 ? 6 : MLB_K_SLOT_6DOF);
 
     LaneRec* const rec = a.recs + lane;
     Lane L;
@@ -206,7 +206,12 @@ MLB_DEV void flightLoop(const RunArgs& a, const double* B) {
         dt = rec->dt; finalDt = rec->finalDt; apogee = rec->apogee; maxSpeed = rec->maxSpeed; maxH = rec->maxH;
         prevPos = rec->prevPos; lastPos = rec->lastPos; rows = rec->rows; traceStride = rec->traceStride; st = rec->st;
         end = (rec->flags & REC_END) != 0; haveFinal = (rec->flags & REC_HAVE_FINAL) != 0; skipPre = (rec->flags & REC_PRE_DONE) != 0; retry = (rec->flags & REC_RETRY) != 0;
-        if (L.haveCache) for (int k = 0; k < (PH == 1 ? 6 : 12); k++) kLocal[k] = rec->k0[k];
+        if (L.haveCache) {
+            Deriv k0;
+            k0.vel = v3(rec->k0[0], rec->k0[1], rec->k0[2]); k0.acc = v3(rec->k0[3], rec->k0[4], rec->k0[5]);
+            k0.angvel = v3(rec->k0[6], rec->k0[7], rec->k0[8]); k0.angacc = v3(rec->k0[9], rec->k0[10], rec->k0[11]);
+            ks.put(0, k0, PH == 1);
+        }
         L.G = a.blob; L.sepOut = a.separations + (size_t)lane * (MLB_MAX_STAGES - 1) * SEP_W;
     } else L.forceRK4 = false;          /* threads past the end of the queue only keep the barriers company: the one lane field that path reads */
     const bool tracing = inRange && laneTraced(a, lane);

@@ -26,8 +26,19 @@
 
 namespace mlb {
 
+/* Tuning switch, off: keep the unit rotation axis and the magnitude of every slot's angular velocity next to the slot, so that a term of
+   the adaptive stage composition costs one sincos instead of two normalisations and three square roots, and normalise the composed
+   quaternion once per stage. Measured (profiles/r2h_rotation_cache_sweep.txt): 9 % fewer executed instructions and 2 % SLOWER at 10^6 lanes
+   (364 vs 371 M steps/s): four more doubles per slot in local memory cost more than the shorter instruction stream saves. The free-flight
+   kernel is bound by the latency of its local-memory working set, not by its instruction count. */
+#ifndef MLB_ROTATION_CACHE
+#define MLB_ROTATION_CACHE 0
+#endif
+/* Slot layout: 12 doubles of the derivative (6 in the 3-DoF kernel, which never touches the rotational half), then, in the free-flight
+   kernel, 4 more: the unit rotation axis and the magnitude of the slot's angular velocity (see stageIncrement). */
+#define MLB_K_SLOT_6DOF (MLB_ROTATION_CACHE ? 16 : 12)
 struct KStore {
-    double* base; int slotStride;          /* 12 doubles per slot; 6 in the 3-DoF kernel, which never touches the rotational half */
+    double* base; int slotStride;
     MLB_DEV void put(int slot, const Deriv& d, bool dof3) const {
         double* p = base + slot * slotStride;
         p[0] = d.vel.x; p[1] = d.vel.y; p[2] = d.vel.z;
@@ -35,6 +46,11 @@ struct KStore {
         if (dof3) return;
         p[6] = d.angvel.x; p[7] = d.angvel.y; p[8] = d.angvel.z;
         p[9] = d.angacc.x; p[10] = d.angacc.y; p[11] = d.angacc.z;
+#if MLB_ROTATION_CACHE
+        const double m = len(d.angvel);
+        const V3 u = normalize(d.angvel);
+        p[12] = u.x; p[13] = u.y; p[14] = u.z; p[15] = m;
+#endif
     }
     MLB_DEV Deriv get(int slot, bool dof3) const {
         const double* p = base + slot * slotStride;
@@ -46,6 +62,28 @@ struct KStore {
         d.angacc = v3(p[9], p[10], p[11]);
         return d;
     }
+    MLB_DEV void copy(int to, int from) const {
+        double* a = base + to * slotStride; const double* b = base + from * slotStride;
+        for (int k = 0; k < slotStride; k++) a[k] = b[k];
+    }
+#if MLB_ROTATION_CACHE
+    /* derivTimes(k_slot, c) of the 6-DoF body (RigidBodyStates.py:173-188): the increment's rotation is the quaternion of the rotation
+       vector angvel * c, i.e. angle |angvel| |c| about angvel / |angvel| (CythonAngularVelocity.pyx:78-86, CythonQuaternion.pyx:50-60). The
+       reference recomputes axis and magnitude (two normalisations, three square roots) for every (slot, coefficient) pair of the adaptive
+       stage composition, 27 times per RK45 attempt; both depend on the slot alone, so they are taken once when the slot is written and a
+       term costs one sincos. Same quaternion up to the rounding of |v c| against |v| |c|. */
+    MLB_DEV State increment(int slot, double c) const {
+        const double* p = base + slot * slotStride;
+        State r;
+        r.pos = v3(p[0], p[1], p[2]) * c;
+        r.vel = v3(p[3], p[4], p[5]) * c;
+        r.w = v3(p[9], p[10], p[11]) * c;
+        double sn, cs;
+        m_sincos((p[15] * c) / 2, &sn, &cs);
+        r.q = q4(cs, sn * p[12], sn * p[13], sn * p[14]);
+        return r;
+    }
+#endif
 };
 
 MLB_DEV Deriv derivScaled(const Deriv& d, double s, bool dof3) {                            /* RigidBodyStates.py:190-202 (already 1/invScalar) */
@@ -133,9 +171,25 @@ MLB_DEV StepResult integrateStep(const double* B, Lane& L, const KStore& ks, Sta
                         for (int a = 2; a < i + 2; a++) evalK = derivAdd(evalK, derivScaled(ks.get(a - 1, dof3), 1 / (1 / (row[a] * dt)), dof3), dof3);
                         evalY = stateAdd(y, derivTimes(evalK, 1.0, dof3), dof3);
                     } else {                                                                /* :420-432 */
-                        State evalK = derivTimes(ks.get(0, dof3), row[1], dof3);
-                        for (int a = 2; a < i + 2; a++) evalK = stateAdd(evalK, derivTimes(ks.get(a - 1, dof3), row[a], dof3), dof3);
-                        evalY = stateAdd(y, stateScale(evalK, dt, dof3), dof3);
+#if MLB_ROTATION_CACHE
+                        if (!dof3) {
+                            /* the same sum of increments, composed as unit quaternions and normalised once at the end instead of before
+                               and after every product (the products of unit quaternions stay unit to rounding) */
+                            State evalK = ks.increment(0, row[1]);
+                            for (int a = 2; a < i + 2; a++) {
+                                const State term = ks.increment(a - 1, row[a]);
+                                evalK.pos = evalK.pos + term.pos; evalK.vel = evalK.vel + term.vel; evalK.w = evalK.w + term.w;
+                                evalK.q = term.q * evalK.q;
+                            }
+                            qNormalize(evalK.q);
+                            evalY = stateAdd(y, stateScale(evalK, dt, dof3), dof3);
+                        } else
+#endif
+                        {
+                            State evalK = derivTimes(ks.get(0, dof3), row[1], dof3);
+                            for (int a = 2; a < i + 2; a++) evalK = stateAdd(evalK, derivTimes(ks.get(a - 1, dof3), row[a], dof3), dof3);
+                            evalY = stateAdd(y, stateScale(evalK, dt, dof3), dof3);
+                        }
                     }
                 }
             }
@@ -178,7 +232,7 @@ MLB_DEV StepResult integrateStep(const double* B, Lane& L, const KStore& ks, Sta
     if (attempting) { r.rejected = true; return r; }
     /* accepted adaptive step: FSAL cache, step-size controller (:349-389) */
     if (method == INT_RK45A || method == INT_RK23A) {
-        ks.put(0, ks.get(nRows, PH == 1), PH == 1);          /* becomes k_0 of the next step (attempts never overwrite slot 0) */
+        ks.copy(0, nRows);                                   /* becomes k_0 of the next step (attempts never overwrite slot 0) */
         L.haveCache = true;
     }
     const double maxDt = B[H_AD_MAXDT];

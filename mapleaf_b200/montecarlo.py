@@ -202,10 +202,19 @@ def _sampleRunsLaneModels(simDefinition, nRuns, mCLogger, model, nGen, hasSeed, 
     return arrays
 
 
-def sampleRuns(simDefinition, nRuns, mCLogger, model, windSampler=None):
+def sampleRuns(simDefinition, nRuns, mCLogger, model, windSampler=None, parallelSeeding=False):
     """Draws every run's inputs in the reference's order (MonteCarlo.py:64-72) and returns the per-lane arrays. windSampler: the ground
     wind of every run comes from wind roses (two draws of the global generator per run, made when the run's Environment is constructed:
-    after the run's resample, before its pink-noise seeds, ENV/environment.py:47-48)."""
+    after the run's resample, before its pink-noise seeds, ENV/environment.py:47-48).
+    parallelSeeding: the seeding of the reference's ray branch (nCores > 1, MonteCarlo.py:110-136): a master generator seeded with
+    MonteCarlo.randomSeed hands every run its own seed, master.randrange(10^7), and the run's `_stdDev` keys are drawn from
+    random.Random(that seed) - a different, equally repeatable stream than the single-threaded one."""
+    if parallelSeeding:
+        try:
+            masterSeed = simDefinition.getValue("MonteCarlo.randomSeed")
+        except KeyError:
+            masterSeed = random.randrange(10000000)
+        master = random.Random(masterSeed)
     keys, needLaneModels = _checkSampledKeys(simDefinition, model)
     motorKeys = _motorKeys(model)
     sampleMotor = any(k in motorKeys for k in keys)
@@ -215,10 +224,12 @@ def sampleRuns(simDefinition, nRuns, mCLogger, model, windSampler=None):
     nGen = {L.TURB_PINK1D: 1, L.TURB_PINK2D: 2, L.TURB_PINK3D: 3}.get(turb, 0)
     hasSeed = int(model.header("H_PINK_HAS_SEED"))
     if needLaneModels:
+        if parallelSeeding:
+            raise NotImplementedError("nCores > 1 seeding together with Monte Carlo keys that need per-lane model blocks")
         return _sampleRunsLaneModels(simDefinition, nRuns, mCLogger, model, nGen, hasSeed, windSampler)
     if windSampler is not None:
         sampleWind = True
-    if windSampler is None and not sampleState and not simDefinition.disableDistributionSampling and nRuns >= _VECTORIZED_SAMPLING_FROM:
+    if windSampler is None and not parallelSeeding and not sampleState and not simDefinition.disableDistributionSampling and nRuns >= _VECTORIZED_SAMPLING_FROM:
         return _sampleRunsVectorized(simDefinition, nRuns, mCLogger, model, keys, motorKeys, nGen, hasSeed)
     wind = np.empty((3, nRuns)) if sampleWind else None
     state = np.empty((13, nRuns)) if sampleState else None
@@ -226,6 +237,8 @@ def sampleRuns(simDefinition, nRuns, mCLogger, model, windSampler=None):
     motor = np.ones((2 * L.MLB_MAX_STAGES, nRuns)) if sampleMotor else None
     for i in range(nRuns):
         mCLogger.log("\nMonte Carlo Run #{}".format(i + 1))
+        if parallelSeeding:
+            simDefinition.rng = random.Random(master.randrange(10000000))      # randrange(1e7) of the reference, an int since Python 3.12
         simDefinition.resampleProbabilisticValues()
         if windSampler is not None:
             wind[:, i] = windSampler.sample()
@@ -313,7 +326,7 @@ def _sampleRunsVectorized(simDefinition, nRuns, mCLogger, model, keys, motorKeys
     return arrays
 
 
-def _runSimulations_B200(simDefinition, nRuns, outputLists, mCLogger, silent=False, nGPUs=1, device=0):
+def _runSimulations_B200(simDefinition, nRuns, outputLists, mCLogger, silent=False, nGPUs=1, device=0, parallelSeeding=False):
     """Same fill contract as _runSimulations_SingleThreaded: outputLists filled in sample order."""
     from . import backend
     landingLocations, apogees, maxSpeeds, flightTimes, maxHorizontalVels, flights = outputLists
@@ -329,7 +342,7 @@ def _runSimulations_B200(simDefinition, nRuns, outputLists, mCLogger, silent=Fal
     wantStepLogs = int(simDefinition.getValue("SimControl.loggingLevel")) >= 1 and bool(simDefinition.fileName)
     if wantStepLogs and nRuns > _TIME_STEP_LOG_LIMIT:
         mCLogger.log("NOTE: SimControl.loggingLevel: time-step logs are written for the first {} of {} runs".format(_TIME_STEP_LOG_LIMIT, nRuns))
-    arrays = sampleRuns(simDefinition, nRuns, mCLogger, model, windSampler)
+    arrays = sampleRuns(simDefinition, nRuns, mCLogger, model, windSampler, parallelSeeding=parallelSeeding)
     laneModels = arrays.pop(LANE_MODELS, None)
 
     # contiguous sample ranges per GPU: gathered results are already in sample order
@@ -514,11 +527,16 @@ def _showResults(simDefinition, outputLists, mCLogger):
 
 
 def runMonteCarloSimulation(simDefinitionFilePath=None, simDefinition=None, silent=False, nCores=1, nGPUs: Optional[int] = None, device: int = 0):
-    """Drop-in for MAPLEAF.SimulationRunners.runMonteCarloSimulation. `nCores` (the reference's ray fan-out) is accepted
-    and ignored; `nGPUs` spreads contiguous sample ranges over that many GPUs of this box. Returns MonteCarloResults."""
+    """Drop-in for MAPLEAF.SimulationRunners.runMonteCarloSimulation. `nGPUs` spreads contiguous sample ranges over that many GPUs of
+    this box. `nCores` > 1 selects the SEEDING of the reference's ray branch (every run draws from its own generator, seeded by a
+    master generator: MonteCarlo.py:110-136), so that a definition run with `--parallel` keeps drawing the samples it drew there; the
+    work itself is not fanned out over processes. Two things of that branch are not reproducible even in the reference and are not
+    imitated: its results arrive in completion order (here: sample order), and its pink-noise seeds come from each worker process's own,
+    OS-seeded global generator (here: this process's global generator, as in the single-threaded branch). Returns MonteCarloResults."""
     simDefinition = loadSimDefinition(simDefinitionFilePath, simDefinition, silent)
     nRuns, mCLogger, outputLists = _prepSim(simDefinition, echo=not silent)
-    results, status, counters, droppedStages, stepLogPaths = _runSimulations_B200(simDefinition, nRuns, outputLists, mCLogger, silent, nGPUs=nGPUs or 1, device=device)
+    results, status, counters, droppedStages, stepLogPaths = _runSimulations_B200(simDefinition, nRuns, outputLists, mCLogger, silent, nGPUs=nGPUs or 1, device=device,
+                                                                                  parallelSeeding=int(nCores or 1) > 1)
     logPath = _showResults(simDefinition, outputLists, mCLogger)
     out = MonteCarloResults(results, status, counters, logPath, outputLists)
     out.droppedStages = droppedStages

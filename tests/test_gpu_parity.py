@@ -754,3 +754,31 @@ def test_dropped_stage_flight_vs_reference(backend, golden, name):
     else:
         assert abs(int(o["counters"][0, 0]) - d["stepsAfterSeparation"]) <= 0.1 * d["stepsAfterSeparation"]
         assert relErr(o["results"][0, 0:2], d["results"][0:2]) < 1e-3
+
+
+# ---- ensemble statistics of the other BASELINE configurations (the ones bench.py --config 2 / 3 fly) ----
+@pytest.mark.parametrize("config,n,cols", [(2, 96, (3, 4, 5)), (3, 128, (3, 4, 6))])
+def test_ensemble_statistics_of_bench_configs_vs_oracle(backend, config, n, cols):
+    """The canard-controlled rocket (fixed-step while the controller is in charge: lane by lane <= 1e-9) and the NASA two-stage rocket with
+    sampled motor factors (adaptive, separation and ignition at a different time in every lane): the batch's apogee / maximum speed /
+    flight time (or maximum horizontal speed) agree with the CPU oracle lane by lane for the fixed-step case and in mean and standard
+    deviation for the adaptive one. Inputs are the bench's own (bench.laneInputs)."""
+    import bench
+    from oracle import oracle
+    cfg = bench.CONFIGS[config]
+    m = bench.buildConfigModel(cfg)
+    arrays = bench.laneInputs(cfg, m, 0, n)
+    gp = gpuRun(backend, m, n, arrays)
+    cp = oracle.run(m.blob, n, arrays)
+    assert (gp["status"] == L.ST_OK).all() and (cp["status"] == L.ST_OK).all()
+    if config == 2:
+        assert np.array_equal(gp["counters"][:, 0], cp["counters"][:, 0])
+        for i in range(n):
+            assert stateErr(gp["finals"][i], np.concatenate([[0], cp["finals"][i, :13]])) < FIXED_TOL
+    else:
+        assert abs(int(gp["counters"][:, 0].sum()) - int(cp["counters"][:, 0].sum())) <= 0.02 * cp["counters"][:, 0].sum()
+    for col in cols:
+        a, b = gp["results"][:, col], cp["results"][:, col]
+        sd = max(b.std(ddof=1), 1e-9 * abs(b.mean()))
+        assert abs(a.mean() - b.mean()) <= 5e-3 * sd + 1e-9 * abs(b.mean()), (col, a.mean(), b.mean(), sd)
+        assert abs(a.std(ddof=1) - b.std(ddof=1)) <= 2e-2 * sd + 1e-9 * abs(b.mean()), (col, a.std(ddof=1), b.std(ddof=1))

@@ -437,3 +437,23 @@ def test_runner_samples_ground_winds_from_wind_roses(monkeypatch, tmp_path, gold
             assert abs(out.results[i, L.RES_APOGEE] - ref["results"][3]) < 2.0 and abs(out.results[i, L.RES_MAX_SPEED] - ref["results"][4]) < 0.2
         else:
             assert np.allclose(out.results[i, 3:7], ref["results"][3:7], rtol=1e-10)
+
+
+def test_runner_parallel_branch_seeding(monkeypatch, tmp_path):
+    """nCores > 1: the seeding of the reference's ray branch (MonteCarlo.py:110-136): master = Random(MonteCarlo.randomSeed); run i draws
+    its `_stdDev` keys from Random(master.randrange(10^7)). The expected winds are drawn here with CPython's random, as that branch does."""
+    monkeypatch.setattr(backend, "TrajectoryBatch", OracleBatch)
+    sd = montecarloDefinition(tmp_path, nRuns=3, **{"MonteCarlo.output": "apogees", "SimControl.EndCondition": "Time", "SimControl.EndConditionValue": "0.5"})
+    captured = {}
+    realSample = montecarlo.sampleRuns
+
+    def spy(*a, **k):
+        captured["arrays"] = realSample(*a, **k)
+        return captured["arrays"]
+    monkeypatch.setattr(montecarlo, "sampleRuns", spy)
+    montecarlo.runMonteCarloSimulation(simDefinition=sd, silent=True, nCores=4)
+    master = random.Random("2394781")
+    for i in range(3):
+        r = random.Random(master.randrange(10000000))
+        expected = [r.gauss(2, 5), r.gauss(0, 5), r.gauss(0, 5)]
+        assert list(captured["arrays"][L.LANE_WIND][:, i]) == expected
