@@ -289,32 +289,34 @@ def runB200(args):
     value = stepsAll / (msPerStep * 1e-3)
 
     # ---- end to end through the public call sequence with host buffers ----
-    pinned = {k: torch.from_numpy(a).pin_memory() for k, a in arrays.items()}
-    hostArrays = {k: t.numpy() for k, t in pinned.items()}
     batch.close()
     del gathered, gatheredStatus, flush
     torch.cuda.empty_cache()
-    e2eBatch = backend.TrajectoryBatch(model.blob, device=local)
-
-    def e2ePass():
-        e2eBatch.setLanes(n, hostArrays)                     # H2D of the step's inputs
-        e2eBatch.run()
-        return e2eBatch.results()                             # D2H of the step's results
-    e2ePass()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        res, st = e2ePass()
-    torch.cuda.synchronize()
-    e2eS = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2eS], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2eS = float(t.item())
-    e2eValue = stepsAll / (e2eS / args.steps)
     h2d = sum(a.nbytes for a in arrays.values())
     d2h = n * (L.RES_SIZE * 8 + 4)
-    e2eBatch.close()
+    e2eValue = e2eS = None
+    if not args.skip_e2e:
+        pinned = {k: torch.from_numpy(a).pin_memory() for k, a in arrays.items()}
+        hostArrays = {k: t.numpy() for k, t in pinned.items()}
+        e2eBatch = backend.TrajectoryBatch(model.blob, device=local)
+
+        def e2ePass():
+            e2eBatch.setLanes(n, hostArrays)                     # H2D of the step's inputs
+            e2eBatch.run()
+            return e2eBatch.results()                             # D2H of the step's results
+        e2ePass()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            res, st = e2ePass()
+        torch.cuda.synchronize()
+        e2eS = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([e2eS], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2eS = float(t.item())
+        e2eValue = stepsAll / (e2eS / args.steps)
+        e2eBatch.close()
 
     if rank != 0:
         if world > 1:
@@ -349,10 +351,12 @@ def runB200(args):
                    "lanes_total": n * world, "accepted_steps_per_pass": stepsAll, "derivative_evals_per_pass": evalsAll,
                    "rejected_steps_per_pass": rejAll, "lanes_ok": okAll,
                    "rank0_steps_3dof": c["steps_3dof"], "rank0_evals_3dof": c["derivative_evals_3dof"], "rank0_evals_transonic": c["derivative_evals_transonic"],
+                   "host_sampling_s": tSample,
                    "sampling": "random.Random('%s') winds, Random(%s).randrange seeds%s (C++ bit-exact sampler, %.2f s host)" % (SEED, SEED, ", motor factors" if cfg.get("motor") else "", tSample),
                    "l2": "256 MiB device buffer zeroed between passes (L2 flush)", "parallelism": "lanes sharded contiguously over %d GPU(s); NCCL all-gather of the 7 result columns + moments" % world},
         "sims_per_sec": n * world / (msPerStep * 1e-3),
-        "e2e": {"value": e2eValue, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "sims_per_sec": n * world / (e2eS / args.steps)},
+        "e2e": ({"value": e2eValue, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "sims_per_sec": n * world / (e2eS / args.steps)}
+                if e2eValue is not None else None),
         "gpu_launches": launches,
         "clocks": clocks.summary(),
         "roofline": roofline,
@@ -448,6 +452,7 @@ def main():
     ap.add_argument("--total-lanes", type=int, default=0, help="with --scaling strong (default 10^7, BASELINE configs[4])")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs: leave out the cpu_baseline leg")
+    ap.add_argument("--skip-e2e", action="store_true", help="record runs of the large configurations: leave out the end-to-end leg (e2e: null)")
     ap.add_argument("--log-every", type=int, default=0, help="keep every n-th accepted state of EVERY lane in the device flight log (0: no log) and report its HBM write rate")
     ap.add_argument("--log-rows", type=int, default=256, help="log rows per lane (128 B each)")
     args = ap.parse_args()

@@ -415,7 +415,10 @@ extern "C" const char* mlb_version(void) { return "mapleaf_b200 0.2 (sm_100a)"; 
 static int createOnDevice(mlb_handle* h, const double* b, size_t len) {
     CU(cudaMalloc(&h->d_blob, len * sizeof(double)));
     CU(cudaMemcpy(h->d_blob, b, len * sizeof(double), cudaMemcpyHostToDevice));
-#define MLB_SET_SMEM(N, M) CU((cudaFuncSetAttribute(flightLanes<N, M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes)));
+    /* the kernels' working set is per-thread local memory: leave to L1 everything the staged model block does not need */
+    const int carveout = getenv("MLB_SMEM_CARVEOUT") ? atoi(getenv("MLB_SMEM_CARVEOUT")) : (int)((h->smemBytes + 1024) * 100 / (228 * 1024)) + 1;
+#define MLB_SET_SMEM(N, M) CU((cudaFuncSetAttribute(flightLanes<N, M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes))); \
+    if (carveout >= 0) CU((cudaFuncSetAttribute(flightLanes<N, M, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout)));
     MLB_FLIGHT_SHAPES(MLB_SET_SMEM)
     CU(cudaFuncSetAttribute(chuteLanes<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
     CU(cudaFuncSetAttribute(initLanes<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));

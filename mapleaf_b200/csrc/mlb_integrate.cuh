@@ -26,13 +26,12 @@
 
 namespace mlb {
 
-/* Tuning switch, off: keep the unit rotation axis and the magnitude of every slot's angular velocity next to the slot, so that a term of
-   the adaptive stage composition costs one sincos instead of two normalisations and three square roots, and normalise the composed
-   quaternion once per stage. Measured (profiles/r2h_rotation_cache_sweep.txt): 9 % fewer executed instructions and 2 % SLOWER at 10^6 lanes
-   (364 vs 371 M steps/s): four more doubles per slot in local memory cost more than the shorter instruction stream saves. The free-flight
-   kernel is bound by the latency of its local-memory working set, not by its instruction count. */
+/* Keep the unit rotation axis and the magnitude of every slot's angular velocity next to the slot, so that a term of the adaptive stage
+   composition costs one sincos instead of two normalisations and three square roots, and normalise the composed quaternion once per
+   stage. Measured in one run on one box (profiles/r2j_rotation_cache_ab.txt; runs on different boxes of the pool differ by +-3 %, more than
+   this effect): 9 % fewer executed instructions, +2.4 % steps/s at 10^6 lanes. */
 #ifndef MLB_ROTATION_CACHE
-#define MLB_ROTATION_CACHE 0
+#define MLB_ROTATION_CACHE 1
 #endif
 /* Slot layout: 12 doubles of the derivative (6 in the 3-DoF kernel, which never touches the rotational half), then, in the free-flight
    kernel, 4 more: the unit rotation axis and the magnitude of the slot's angular velocity (see stageIncrement). */
