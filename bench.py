@@ -186,18 +186,20 @@ def algorithmicFlops(c, f):
 
 def measuredKernelMetrics(configId):
     """Per-lane DRAM traffic and executed FP64 instructions of the free-flight kernel from the committed ncu metrics pass of this
-    code and workload (profiles/*_full_occupancy_metrics.csv, newest first): (dict per lane, source file) or (None, None)."""
+    code and workload (profiles/*_full_occupancy_metrics_lanes<N>.csv: one launch over N lanes, newest first; files of another
+    configuration carry `config<C>` in their name): (dict per lane, source file) or (None, None)."""
+    import re
     pdir = os.path.join(REPO, "profiles")
     want = "config%d" % configId
-    for name in sorted((f for f in os.listdir(pdir) if f.endswith("_full_occupancy_metrics.csv") and (want in f or (configId == 1 and "config" not in f))), reverse=True):
-        vals, lanes = {}, None
+    names = [f for f in os.listdir(pdir) if re.search(r"_full_occupancy_metrics_lanes\d+\.csv$", f) and (want in f or (configId == 1 and "config" not in f))]
+    for name in sorted(names, reverse=True):
+        lanes = int(re.search(r"_lanes(\d+)\.csv$", name).group(1))
+        vals = {}
         with open(os.path.join(pdir, name)) as fh:
             for row in csv.reader(l for l in fh if l.startswith('"')):
                 if len(row) >= 15 and row[0] != "ID" and "flightLanes" in row[4]:
                     vals[row[12]] = float(row[14].replace(",", ""))
-                    bs, gs = row[7].strip("()").split(",")[0], row[8].strip("()").split(",")[0]
-                    lanes = int(bs) * int(gs)
-        if lanes and "dram__bytes_read.sum" in vals:
+        if "dram__bytes_read.sum" in vals:
             out = {"dram_bytes": (vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"]) / lanes}
             for k, short in (("smsp__sass_thread_inst_executed_op_dfma_pred_on.sum", "dfma"), ("smsp__sass_thread_inst_executed_op_dadd_pred_on.sum", "dadd"),
                              ("smsp__sass_thread_inst_executed_op_dmul_pred_on.sum", "dmul")):

@@ -7,8 +7,7 @@ VDIR = os.path.join(REPO, "mapleaf_b200", "lib", "variants")
 # name -> extra nvcc flags; edit for the experiment at hand (switches: MLB_FLIGHT_SHAPES, MLB_COMP_NOINLINE, MLB_COLD_MASK, MLB_MATH_NOINLINE,
 # MLB_FIN_UNIFORM, MLB_FIN_LINEAR, MLB_CHUTE_BLOCK, MLB_CHUTE_CTAS, MLB_DERIV_NOINLINE)
 VARIANTS = {
-    "rotcache": ["-DMLB_FLIGHT_SHAPES(X)=X(1024,1) X(512,1)", "-DMLB_ROTATION_CACHE=1"],
-    "base": ["-DMLB_FLIGHT_SHAPES(X)=X(1024,1) X(512,1)"],
+    "shapes": ["-DMLB_FLIGHT_SHAPES(X)=X(1024,1) X(896,1) X(768,1) X(640,1) X(512,1)"],
 }
 
 
@@ -23,9 +22,11 @@ def build(names=None):
         hdr = os.path.join(VDIR, name + ".h")
         with open(hdr, "w") as f:
             for fl in flags:
+                if fl.startswith("NVCC:"):
+                    continue
                 k, v = fl[2:].split("=", 1)
                 f.write("#define %s %s\n" % (k, v))
-        cmd = ["nvcc"] + backend.NVCC_FLAGS + ["-include", hdr, "-Xptxas", "-v", "-o", out, os.path.join(backend.CSRC_DIR, "mlb_api.cu")]
+        cmd = ["nvcc"] + backend.NVCC_FLAGS + [fl[5:] for fl in flags if fl.startswith("NVCC:")] + ["-include", hdr, "-Xptxas", "-v", "-o", out, os.path.join(backend.CSRC_DIR, "mlb_api.cu")]
         procs.append((name, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for name, p in procs:
         txt = p.communicate()[0]
