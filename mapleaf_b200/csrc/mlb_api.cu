@@ -615,8 +615,10 @@ extern "C" int mlb_run(mlb_handle* h, void* stream) {
         a.qInCount = g == 0 ? nullptr : h->d_queueCount + (g - 1);
         a.qNext = h->d_queue[g & 1]; a.qNextCount = h->d_queueCount + g;
         a.bailPermille = (g == G - 1 || singleWave) ? 0 : h->bailPermille;
-#define MLB_LAUNCH_SHAPE(N, M) if (block == N && !perLane) flightLanes<N, M, false><<<grid, N, h->smemBytes, s>>>(a);
+        bool launched = perLane;
+#define MLB_LAUNCH_SHAPE(N, M) if (block == N && !perLane) { flightLanes<N, M, false><<<grid, N, h->smemBytes, s>>>(a); launched = true; }
         MLB_FLIGHT_SHAPES(MLB_LAUNCH_SHAPE)
+        if (!launched) return fail(MLB_ERR_STATE, "mlb_run: this build has no free-flight kernel of " + std::to_string(block) + " threads (tuning build with a reduced MLB_FLIGHT_SHAPES list)");
         if (perLane) flightLanes<MLB_PERLANE_BLOCK, 1, true><<<grid, MLB_PERLANE_BLOCK, 0, s>>>(a);
         h->launches++;
         CU(cudaGetLastError());

@@ -7,7 +7,8 @@ VDIR = os.path.join(REPO, "mapleaf_b200", "lib", "variants")
 # name -> extra nvcc flags; edit for the experiment at hand (switches: MLB_FLIGHT_SHAPES, MLB_COMP_NOINLINE, MLB_COLD_MASK, MLB_MATH_NOINLINE,
 # MLB_FIN_UNIFORM, MLB_FIN_LINEAR, MLB_CHUTE_BLOCK, MLB_CHUTE_CTAS, MLB_DERIV_NOINLINE)
 VARIANTS = {
-    "shapes": ["-DMLB_FLIGHT_SHAPES(X)=X(1024,1) X(896,1) X(768,1) X(640,1) X(512,1)"],
+    "base": ["-DMLB_FLIGHT_SHAPES(X)=X(1024,1) X(512,1)"],
+    "explog": ["-DMLB_FLIGHT_SHAPES(X)=X(1024,1) X(512,1)", "-DMLB_POW_EXPLOG=1"],
 }
 
 
