@@ -994,7 +994,8 @@ def _flattenTableau(rows, nResult):
     return flat
 
 
-def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000, droppedStage: int = None, droppedFromAltitude: float = None, groundWind=None) -> Model:
+def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000, droppedStage: int = None, droppedFromAltitude: float = None, groundWind=None,
+               windProfile=None, windProfileRows: int = None) -> Model:
     """Everything the reference's constructors precompute, flattened into one model block.
     droppedStage = n builds the rocket the reference creates for the n-th dropped stage (`Simulation.createRocket(stage=n)`,
     SingleSimulations.py:161-176,280-299; Rocket.__init__ with stageToInitialize, rocket.py:296-321,339-361): that stage alone, its motor burnt
@@ -1118,6 +1119,20 @@ def buildModel(simDefinition: SimDefinition, maxSteps: int = 400000, droppedStag
         H[L.H_HELLMAN_LIMIT] = env.getFloat("Hellman.altitudeLimit")
     elif wind == "CustomWindProfile":
         prof = np.loadtxt(env.getString("CustomWindProfile.filePath"), skiprows=1)
+        H[L.H_WIND] = L.WIND_INTERPOLATED
+        H[L.H_WIND_TAB_N] = prof.shape[0]
+        H[L.H_WIND_TAB_OFF] = append(prof.T.reshape(-1))
+    elif wind == "SampledRadioSondeData":
+        # one measured profile per constructed Environment (MeanWindModelling.py:96-118): given by the Monte Carlo runner, else drawn here.
+        # windProfileRows pads the table with copies of its last row (linInterp returns the last row beyond it, Interpolation.py:22-25), so
+        # that the per-lane model blocks of a run share one layout whatever the sounding's length
+        if windProfile is None:
+            from .windsampling import samplerFromDefinition
+            windProfile = samplerFromDefinition(env).sample()
+        alt, vec = np.asarray(windProfile[0], dtype=np.float64), np.asarray(windProfile[1], dtype=np.float64).reshape(-1, 3)
+        prof = np.column_stack([alt, vec])
+        if windProfileRows is not None and windProfileRows > prof.shape[0]:
+            prof = np.vstack([prof] + [prof[-1:]] * (windProfileRows - prof.shape[0]))
         H[L.H_WIND] = L.WIND_INTERPOLATED
         H[L.H_WIND_TAB_N] = prof.shape[0]
         H[L.H_WIND_TAB_OFF] = append(prof.T.reshape(-1))

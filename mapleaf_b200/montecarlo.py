@@ -188,7 +188,10 @@ def _sampleRunsLaneModels(simDefinition, nRuns, mCLogger, model, nGen, hasSeed, 
     for i in range(nRuns):
         mCLogger.log("\nMonte Carlo Run #{}".format(i + 1))
         simDefinition.resampleProbabilisticValues()
-        mi = buildModel(simDefinition, groundWind=windSampler.sample() if windSampler is not None else None)
+        if windSampler is not None and windSampler.kind == "profile":
+            mi = buildModel(simDefinition, windProfile=windSampler.sample(), windProfileRows=windSampler.maxRows)
+        else:
+            mi = buildModel(simDefinition, groundWind=windSampler.sample() if windSampler is not None else None)
         if mi.blob.size != model.blob.size or int(mi.header("H_SHARED_LEN")) != int(model.header("H_SHARED_LEN")) \
                 or not np.array_equal(mi.blob[shared:], model.blob[shared:], equal_nan=True):
             raise NotImplementedError("Monte Carlo sampling changed the structure of the model (component list, table sizes or interpolation tables) "
@@ -223,6 +226,8 @@ def sampleRuns(simDefinition, nRuns, mCLogger, model, windSampler=None, parallel
     turb = int(model.header("H_TURB"))
     nGen = {L.TURB_PINK1D: 1, L.TURB_PINK2D: 2, L.TURB_PINK3D: 3}.get(turb, 0)
     hasSeed = int(model.header("H_PINK_HAS_SEED"))
+    if windSampler is not None and windSampler.kind == "profile":
+        needLaneModels = True              # a wind table per run
     if needLaneModels:
         if parallelSeeding:
             raise NotImplementedError("nCores > 1 seeding together with Monte Carlo keys that need per-lane model blocks")
@@ -336,7 +341,11 @@ def _runSimulations_B200(simDefinition, nRuns, outputLists, mCLogger, silent=Fal
         mCLogger.log("NOTE: MonteCarlo.output flightPaths: flight paths are kept for the first {} of {} runs".format(_FLIGHT_PATH_LIMIT, nRuns))
     from .windsampling import samplerFromDefinition
     windSampler = samplerFromDefinition(SubDictReader("Environment", simDefinition))
-    model = buildModel(simDefinition, groundWind=(0.0, 0.0, 0.0) if windSampler is not None else None)      # no draw from the global generator here
+    # the template model is built without a draw from the global generator: placeholders stand in for the sampled wind
+    if windSampler is not None and windSampler.kind == "profile":
+        model = buildModel(simDefinition, windProfile=(np.arange(windSampler.maxRows, dtype=float), np.zeros((windSampler.maxRows, 3))))
+    else:
+        model = buildModel(simDefinition, groundWind=(0.0, 0.0, 0.0) if windSampler is not None else None)
     # SimControl.loggingLevel >= 1: the reference writes `<definition>_RunN/<top stage>_timeStepLog.csv` for every run
     # (SingleSimulations.py:351-392, rocket.py:729-738); here for the first _TIME_STEP_LOG_LIMIT runs, from the lanes' per-step flight log
     wantStepLogs = int(simDefinition.getValue("SimControl.loggingLevel")) >= 1 and bool(simDefinition.fileName)

@@ -19,7 +19,7 @@ from typing import List, Sequence
 
 import numpy as np
 
-__all__ = ["WindRoseSampler", "windRosePath", "samplerFromDefinition"]
+__all__ = ["WindRoseSampler", "RadioSondeSampler", "windRosePath", "samplerFromDefinition"]
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 _MPH = 0.44704
@@ -65,6 +65,7 @@ def _readWindRose(path: str) -> np.ndarray:
 
 class WindRoseSampler:
     """WindRoseDataSampler.sampleWindRoses (MeanWindModelling.py:213-226) for a fixed set of locations, weights and month."""
+    kind = "ground"
 
     def __init__(self, locations: Sequence[str], weights: Sequence[float], month: str):
         from scipy.stats import rv_histogram
@@ -103,10 +104,89 @@ class WindRoseSampler:
         return [(-1 * x) * windSpeed, (-1 * y) * windSpeed, (-1 * 0) * windSpeed]
 
 
-def samplerFromDefinition(envReader) -> "WindRoseSampler":
-    """The sampler an Environment of this definition would use (meanWindModelFactory, MeanWindModelling.py:43-53), or None when the
-    definition's ground wind is not sampled from wind roses."""
+def _windDataPath(name: str) -> str:
+    cands = [os.path.join(_PKG_DIR, "data", "Wind", name)]
+    if os.environ.get("MAPLEAF_WIND_DATA"):
+        cands.append(os.path.join(os.environ["MAPLEAF_WIND_DATA"], name))
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("MAPLEAF")
+        if spec is not None and spec.submodule_search_locations:
+            cands.append(os.path.join(list(spec.submodule_search_locations)[0], "Examples", "Wind", name))
+    except Exception:
+        pass
+    cands += [os.path.join("MAPLEAF", "Examples", "Wind", name), name]
+    for c in cands:
+        if os.path.exists(c):
+            return c
+    raise FileNotFoundError("wind data file {} not found (looked in {})".format(name, ", ".join(cands)))
+
+
+_MONTHS = ["noZerothMonth", "Jan", "Feb", "Mar", "Apr", "May", "Jun", "Jul", "Aug", "Sep", "Oct", "Nov", "Dec"]
+
+
+class RadioSondeSampler:
+    """RadioSondeDataSampler.getRadioSondeWindProfile (MeanWindModelling.py:331-485): one measured wind profile per constructed Environment.
+    Every draw RE-SEEDS the global generator with `SampledRadioSondeData.randomSeed` (None: from the operating system) before choosing a
+    location (random.choices) and one of its soundings of the launch month (random.randint) - so with a seed every run flies the same
+    profile and the run's later global draws (pink-noise seeds) repeat too, and without one nothing is repeatable; both as in the reference.
+    Files: `RadioSonde<Location>_filtered.txt` (reduced IGRA-2: `#station yyyy mm dd hh ...` headers, rows of altitude m ASL, heading deg,
+    speed m/s x 10)."""
+    kind = "profile"
+
+    def __init__(self, locations: Sequence[str], weights: Sequence[float], aslAltitudes: Sequence[float], month, randomSeed=None):
+        self.locations, self.weights, self.aslAltitudes = list(locations), list(weights), list(aslAltitudes)
+        self.month = None if month in (None, "Yearly") else month
+        self.randomSeed = randomSeed
+        self._files = {}
+        for loc in self.locations:
+            with open(_windDataPath("RadioSonde{}_filtered.txt".format(loc))) as f:
+                self._files[loc] = f.readlines()
+        # the longest sounding of any candidate file: per-lane wind tables are padded to this many rows
+        self.maxRows = 1
+        for data in self._files.values():
+            n = 0
+            for line in data + ["#"]:
+                if line[0] == "#":
+                    self.maxRows, n = max(self.maxRows, n), 0
+                else:
+                    n += 1
+
+    def sample(self, rng=random):
+        """(altitudes [n] in m AGL ascending, winds [n, 3] in m/s) of one sounding."""
+        rng.seed(self.randomSeed)
+        loc = rng.choices(self.locations, self.weights, k=1)[0]
+        asl = self.aslAltitudes[self.locations.index(loc)]
+        data = self._files[loc]
+        monthNumber = _MONTHS.index(self.month) if self.month is not None else None
+        starts = [i for i, line in enumerate(data) if line[0] == "#" and (monthNumber is None or int(line.split()[2]) == monthNumber)]
+        first = starts[rng.randint(0, len(starts) - 1)] + 1
+        rows = []
+        i = first
+        while i < len(data) and data[i][0] != "#":
+            rows.append([float(x) for x in data[i].split()])
+            i += 1
+        a = np.array(rows)
+        a[:, 2] = a[:, 2] / 10
+        a = a[a[:, 0].argsort()]
+        altitudes = a[:, 0] - asl
+        winds = np.empty((a.shape[0], 3))
+        for k in range(a.shape[0]):
+            y, x = math.cos(math.radians(a[k, 1] + 0)), math.sin(math.radians(a[k, 1] + 0))
+            winds[k] = ((-1 * x) * a[k, 2], (-1 * y) * a[k, 2], (-1 * 0) * a[k, 2])
+        return altitudes, winds
+
+
+def samplerFromDefinition(envReader):
+    """The sampler an Environment of this definition would use (meanWindModelFactory, MeanWindModelling.py:43-53,96-118): a WindRoseSampler
+    (kind "ground": sample() is a ground-wind vector), a RadioSondeSampler (kind "profile": sample() is an (altitudes, winds) profile), or
+    None when the mean wind is not drawn per Environment."""
     model = envReader.getString("MeanWindModel")
+    if model == "SampledRadioSondeData":
+        words = envReader.getString("SampledRadioSondeData.locationsToSample").split()
+        asl = [float(x) for x in envReader.getString("SampledRadioSondeData.locationASLAltitudes").split()]
+        return RadioSondeSampler(words[0::2], [float(w) for w in words[1::2]], asl, envReader.getString("SampledRadioSondeData.launchMonth"),
+                                 envReader.tryGetString("SampledRadioSondeData.randomSeed"))
     if not (model == "SampledGroundWindData" or (model == "Hellman" and envReader.getString("Hellman.groundWindModel") == "SampledGroundWindData")):
         return None
     words = envReader.getString("SampledGroundWindData.locationsToSample").split()

@@ -47,6 +47,7 @@ What is recorded, and which reference code produced it:
                             (SingleSimulations.py:91-145,280-299), fixed step and adaptive
   timesteplog_*.json ...... the reference's own `<stage>_timeStepLog.csv` (SimControl.loggingLevel 1) of two short flights, as text
   windrose.json ........... ground winds drawn by the reference's WindRoseDataSampler (seeded global random)
+  radiosonde_mc.json ...... wind profiles picked by the reference's RadioSondeDataSampler and a Monte Carlo loop flown on one
   rng.json ................ random.Random / PinkNoiseGenerator known answers (test_SimDefinition.py:118-151,
                             test_TurbulenceModelling.py:37-60)
 """
@@ -412,6 +413,26 @@ if __name__ == "__main__":
         dump("windrose_mc.json", monteCarlo(mc, {**rose, "Environment.MeanWindModel": "SampledGroundWindData"}, "2394781", 3, globalSeed=777))
         dump("windrose_hellman_mc.json", monteCarlo(adaptive, {**rose, "Environment.Hellman.groundWindModel": "SampledGroundWindData", "SimControl.EndCondition": "Apogee"},
                                                     "2394781", 2, globalSeed=778, keepDts=True))
+    if "radiosonde" in which:
+        # RadioSondeDataSampler (ENV/MeanWindModelling.py:331-485) on this repository's synthetic archives (copied into the built reference's
+        # Examples/Wind for the run): the profiles it picks for a few seeds, and a 2-run Monte Carlo loop flown on a sampled profile
+        import shutil
+        from MAPLEAF.ENV.MeanWindModelling import RadioSondeDataSampler
+        mine = os.path.join(REPO, "mapleaf_b200", "data", "Wind")
+        for f in os.listdir(mine):
+            shutil.copy(os.path.join(mine, f), os.path.join(REF_DIR, "MAPLEAF", "Examples", "Wind", f))
+        locs, weights, asl = ["TestFieldA", "TestFieldB"], [0.48, 0.52], [710.0, 638.0]
+        picks = []
+        for seed, month in (("11", "Apr"), ("12", "Apr"), ("13", "Jul"), ("14", "Yearly"), ("15", "Yearly")):
+            alt, vec = RadioSondeDataSampler(silent=True).getRadioSondeWindProfile(locs, weights, asl, month, seed)
+            picks.append(dict(seed=seed, month=month, altitudes=[float(x) for x in alt], winds=[[float(c) for c in v] for v in vec]))
+        sonde = {"Environment.MeanWindModel": "SampledRadioSondeData", "Environment.SampledRadioSondeData.locationsToSample": "TestFieldA 0.48 TestFieldB 0.52",
+                 "Environment.SampledRadioSondeData.locationASLAltitudes": "710 638", "Environment.SampledRadioSondeData.launchMonth": "Apr",
+                 "Environment.SampledRadioSondeData.randomSeed": "12"}
+        out = monteCarlo(mc, sonde, "2394781", 2)
+        out["picks"] = picks
+        out["sampler"] = dict(locations=locs, weights=weights, aslAltitudes=asl)
+        dump("radiosonde_mc.json", out)
     if "rk45_pink" in which:
         dump("rk45_pink.json", monteCarlo(adaptive, {}, "2394781", 4, globalSeed=2394781, keepDts=True))
     if "ideal" in which:

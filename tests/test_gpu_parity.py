@@ -782,3 +782,26 @@ def test_ensemble_statistics_of_bench_configs_vs_oracle(backend, config, n, cols
         sd = max(b.std(ddof=1), 1e-9 * abs(b.mean()))
         assert abs(a.mean() - b.mean()) <= 5e-3 * sd + 1e-9 * abs(b.mean()), (col, a.mean(), b.mean(), sd)
         assert abs(a.std(ddof=1) - b.std(ddof=1)) <= 2e-2 * sd + 1e-9 * abs(b.mean()), (col, a.std(ddof=1), b.std(ddof=1))
+
+
+def test_radio_sonde_profiles_as_per_lane_models_vs_reference(backend, golden):
+    """SampledRadioSondeData on the GPU: each lane's own wind table (padded to the longest sounding) in its model block, interpolated by
+    the per-lane kernels; the reference's Monte Carlo flights on the sampled profile (tests/golden/make_golden.py `radiosonde`)."""
+    from mapleaf_b200 import SubDictReader
+    from mapleaf_b200.windsampling import samplerFromDefinition
+    g = golden("radiosonde_mc.json")
+    sd = SimDefinition(os.path.join(DATA, g["definition"]), silent=True, disableDistributionSampling=True)
+    for k, v in g["overrides"].items():
+        sd.setValue(k, v)
+    sampler = samplerFromDefinition(SubDictReader("Environment", sd))
+    models = [buildModel(sd, windProfile=sampler.sample(), windProfileRows=sampler.maxRows) for _ in g["runs"]]
+    shared = int(models[0].header("H_SHARED_LEN")) or models[0].blob.size
+    with backend.TrajectoryBatch(models[0].blob) as b:
+        b.setLanes(len(models), {})
+        b.setLaneModels(np.stack([m.blob[:shared] for m in models]))
+        b.run()
+        res, st = b.results()
+        counters = b.laneCounters()
+    assert (st == L.ST_OK).all()
+    for i, r in enumerate(g["runs"]):
+        assert counters[i, 0] == r["steps"] and relErr(res[i, 3:7], r["results"][3:7]) < FIXED_TOL

@@ -457,3 +457,25 @@ def test_runner_parallel_branch_seeding(monkeypatch, tmp_path):
         r = random.Random(master.randrange(10000000))
         expected = [r.gauss(2, 5), r.gauss(0, 5), r.gauss(0, 5)]
         assert list(captured["arrays"][L.LANE_WIND][:, i]) == expected
+
+
+def test_radio_sonde_sampler_and_runner_match_the_reference(monkeypatch, tmp_path, golden):
+    """MeanWindModel SampledRadioSondeData (ENV/MeanWindModelling.py:96-118,331-485): the sampler re-seeds the global generator, picks a
+    location and one of its soundings of the month and turns it into an altitude / wind-vector profile; every run flies its own profile
+    as a per-lane model block whose wind table is padded to the longest sounding of the archives. Same profiles as the reference picked
+    for the same seeds, and the reference's Monte Carlo flights on the sampled profile."""
+    from mapleaf_b200.windsampling import RadioSondeSampler
+    g = golden("radiosonde_mc.json")
+    sm = g["sampler"]
+    for pick in g["picks"]:
+        s = RadioSondeSampler(sm["locations"], sm["weights"], sm["aslAltitudes"], pick["month"], pick["seed"])
+        alt, vec = s.sample()
+        assert list(alt) == pick["altitudes"] and np.allclose(vec, np.array(pick["winds"]), rtol=1e-15, atol=0)
+        assert s.maxRows >= len(alt)
+    monkeypatch.setattr(backend, "TrajectoryBatch", OracleBatch)
+    sd = montecarloDefinition(tmp_path, nRuns=2, **{"MonteCarlo.output": "apogees"})
+    for k, v in g["overrides"].items():
+        sd.setValue(k, v)
+    out = montecarlo.runMonteCarloSimulation(simDefinition=sd, silent=True)
+    for i, ref in enumerate(g["runs"]):
+        assert np.allclose(out.results[i, 3:7], ref["results"][3:7], rtol=1e-12), (out.results[i], ref["results"])

@@ -1,7 +1,8 @@
 """Writes the environment tables used by the option-coverage fixtures (inputs made for this repository, reference file formats):
    data/Environment/atmosphereTable.txt ... TabulatedAtmosphere (ENV/AtmosphereModelling.py:79-96): h [m ASL], T [K], P [Pa], rho [kg/m3], mu [1e-5 Pa s]
    data/Environment/windProfile.txt ....... CustomWindProfile / InterpolatedWind (ENV/MeanWindModelling.py:165-196): AGL altitude, wind x y z [m/s]
-   data/Wind/WindroseApr<TestField>.txt ... two synthetic wind roses for SampledGroundWindData (ENV/MeanWindModelling.py:198-329)"""
+   data/Wind/WindroseApr<TestField>.txt ... two synthetic wind roses for SampledGroundWindData (ENV/MeanWindModelling.py:198-329)
+   data/Wind/RadioSonde<TestField>_filtered.txt  two synthetic radio-sonde archives for SampledRadioSondeData (:331-485)"""
 import math, os
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 out = os.path.join(REPO, "mapleaf_b200", "data", "Environment")
@@ -47,6 +48,28 @@ def rose(name, month, peakDir, spread, calm, scale):
         f.write("\n".join(lines) + "\n")
 
 
+
+
+def radioSonde(name, elevation, nSoundings=9):
+    """A synthetic radio-sonde archive in the reduced IGRA-2 layout the reference reads (ENV/MeanWindModelling.py:386-485): soundings headed
+    by `#<station> yyyy mm dd hh ...`, rows of altitude (m ASL), wind heading (deg), wind speed (m/s x 10); different lengths on purpose."""
+    wdir = os.path.join(REPO, "mapleaf_b200", "data", "Wind")
+    lines = []
+    for k in range(nSoundings):
+        month = 4 if k % 3 else 7
+        lines.append("#SYN%08d 2019 %02d %02d %02d 2315   83 synthetic synthetic  510000 -1120000" % (k, month, 3 + 2 * k, 12 * (k % 2)))
+        nLevels = 9 + (k * 5) % 7
+        for j in range(nLevels):
+            alt = elevation + 30 + 900 * j + 37 * ((k * 7 + j * 3) % 11)
+            heading = (200 + 12 * j + 25 * k) % 360
+            speed = 40 + 28 * j + 13 * ((k + j) % 5)
+            lines.append("%5d   %3d   %3d" % (alt, heading, speed))
+    with open(os.path.join(wdir, "RadioSonde%s_filtered.txt" % name), "w") as f:
+        f.write("\n".join(lines) + "\n")
+
+
+radioSonde("TestFieldA", 710)
+radioSonde("TestFieldB", 638, nSoundings=7)
 rose("TestFieldA", "Apr", 240, 60, 2.1, 0.55)
 rose("TestFieldB", "Apr", 300, 35, 0.8, 0.6)
 print("wrote", os.listdir(out), os.listdir(os.path.join(REPO, "mapleaf_b200", "data", "Wind")))
