@@ -40,14 +40,18 @@ using namespace mlb;
 #define MLB_FLIGHT_SHAPES(X) X(128, 2) X(512, 1) X(1024, 1)
 #endif
 #define MLB_PERLANE_BLOCK 512        /* CTA shape of the free-flight kernel that reads per-lane model blocks */
+/* under-chute kernel: CTA size and CTAs per SM (registers per lane = 65536 / (block x CTAs)). Same-box sweep (profiles/r2o): 256 x 2 at 128
+   registers is 3 % faster than 128 x 4; 96 or 80 registers per lane (128 x 5 / 6) cost 25-30 %. */
 #ifndef MLB_CHUTE_BLOCK
-#define MLB_CHUTE_BLOCK 128         /* under-chute kernel: CTA size and CTAs per SM (registers per lane = 65536 / (block x CTAs)) */
+#define MLB_CHUTE_BLOCK 256
 #endif
 #ifndef MLB_CHUTE_CTAS
-#define MLB_CHUTE_CTAS 4
+#define MLB_CHUTE_CTAS 2
 #endif
+/* launches of the free-flight kernel per run; the last one runs its lanes to the end. A CTA hands its stragglers on when fewer than
+   bailPermille of its lanes are still flying: 750 / 12 generations is 1.3 % faster than 500 / 6 at 10^6 lanes (profiles/r2o) */
 #ifndef MLB_GENERATIONS
-#define MLB_GENERATIONS 6           /* launches of the free-flight kernel per run; the last one runs its lanes to the end */
+#define MLB_GENERATIONS 12
 #endif
 #define TRACE_W 16
 #define MLB_NCOUNTERS 6
@@ -392,7 +396,7 @@ struct mlb_handle {
     bool ran = false;
     long long launches = 0;
     int nSlots = 0; size_t smemBytes = 0;
-    int nSM = 148; int forceBlock = 0; int lastBlock = 0; int lastGenerations = 0; int bailPermille = 500; int generations = MLB_GENERATIONS; bool evenSplit = true;
+    int nSM = 148; int forceBlock = 0; int lastBlock = 0; int lastGenerations = 0; int bailPermille = 750; int generations = MLB_GENERATIONS; bool evenSplit = true;
     size_t sharedLen = 0;
 };
 
