@@ -28,13 +28,17 @@ def child(args):
         if int(m.blob[L.H_TURB]) in (L.TURB_PINK1D, L.TURB_PINK2D, L.TURB_PINK3D):
             lanes[L.LANE_PINK_SEED] = seeds
     for block, bail, gens in itertools.product(args.blocks.split(","), args.bails.split(","), args.gens.split(",")):
-        os.environ["MLB_BLOCK_SIZE"] = block; os.environ["MLB_BAIL_PERMILLE"] = bail; os.environ["MLB_NUM_GENERATIONS"] = gens
+        for key, val in (("MLB_BLOCK_SIZE", block), ("MLB_BAIL_PERMILLE", bail), ("MLB_NUM_GENERATIONS", gens)):
+            if val in ("", "default"):
+                os.environ.pop(key, None)          # the library's own default
+            else:
+                os.environ[key] = val
         with backend.TrajectoryBatch(m.blob) as b:
             b.setLanes(args.lanes, lanes)
             b.run(); b.sync()
             b.run(); b.sync()
             c = b.counters()
-        print(json.dumps({"lib": os.path.basename(os.environ.get("MLB_LIB", "default")), "def": args.definition, "lanes": args.lanes, "block": c["flight_block"], "bail": int(bail),
+        print(json.dumps({"lib": os.path.basename(os.environ.get("MLB_LIB", "default")), "def": args.definition, "lanes": args.lanes, "block": c["flight_block"], "bail": bail or "default",
                           "gens": c["flight_generations"], "ms": round(c["last_run_ms"], 2), "flight_ms": round(c["dominant_kernel_ms"], 2), "chute_ms": round(c["chute_kernel_ms"], 2),
                           "Msteps_per_s": round(c["steps"] / c["last_run_ms"] / 1e3, 2), "steps": c["steps"], "ok": c["lanes_ok"], "steps_3dof": c["steps_3dof"],
                           "evals": c["derivative_evals"], "rejects": c["rejected_steps"]}), flush=True)
@@ -45,9 +49,9 @@ if __name__ == "__main__":
     ap.add_argument("--lanes", type=int, default=151552)
     ap.add_argument("--def", dest="definition", default="MonteCarloAdaptive.mapleaf")
     ap.add_argument("--libs", default="")
-    ap.add_argument("--blocks", default="0")
-    ap.add_argument("--bails", default="500")
-    ap.add_argument("--gens", default="6")
+    ap.add_argument("--blocks", default="", help="comma list of CTA shapes (MLB_BLOCK_SIZE); empty: the library's choice")
+    ap.add_argument("--bails", default="", help="comma list of hand-over thresholds in permille (MLB_BAIL_PERMILLE); empty: the library's default")
+    ap.add_argument("--gens", default="", help="comma list of generation counts (MLB_NUM_GENERATIONS); empty: the library's default")
     ap.add_argument("--set", action="append")
     ap.add_argument("--config", type=int, default=-1, help="a bench.py configuration (definition, overrides and sampled inputs) instead of --def")
     ap.add_argument("--no-motor", action="store_true", help="with --config 3: leave the motor factors unsampled")
