@@ -5,3 +5,4 @@ mapleaf_b200 — B200-native batched Monte Carlo 6-DOF trajectory integration be
 from .simdef import SimDefinition, SubDictReader, defaultConfigValues  # noqa: F401
 from .model import buildModel, L  # noqa: F401
 from .montecarlo import runMonteCarloSimulation  # noqa: F401,E402
+from .convergence import ConvergenceSimRunner  # noqa: F401,E402

@@ -48,6 +48,8 @@ What is recorded, and which reference code produced it:
   timesteplog_*.json ...... the reference's own `<stage>_timeStepLog.csv` (SimControl.loggingLevel 1) of two short flights, as text
   windrose.json ........... ground winds drawn by the reference's WindRoseDataSampler (seeded global random)
   radiosonde_mc.json ...... wind profiles picked by the reference's RadioSondeDataSampler and a Monte Carlo loop flown on one
+  convergence.json ........ ConvergenceSimRunner.convergeSimEndPosition: final positions at successively halved time steps / target errors and
+                            the convergence checks computed from them
   rng.json ................ random.Random / PinkNoiseGenerator known answers (test_SimDefinition.py:118-151,
                             test_TurbulenceModelling.py:37-60)
 """
@@ -433,6 +435,34 @@ if __name__ == "__main__":
         out["picks"] = picks
         out["sampler"] = dict(locations=locs, weights=weights, aslAltitudes=asl)
         dump("radiosonde_mc.json", out)
+    if "convergence" in which:
+        # ConvergenceSimRunner.convergeSimEndPosition (SimulationRunners/Convergence.py:15-149): the same flight at time steps (or target errors)
+        # divided by the refinement ratio each time, Richardson-style convergence check of the final position (IO/gridConvergenceFunctions.py)
+        import contextlib, io
+        from MAPLEAF.SimulationRunners.Convergence import ConvergenceSimRunner
+        from MAPLEAF.IO.gridConvergenceFunctions import checkConvergence
+        out = {}
+        for label, defFile, ov, limit in (("rk4", mc, {"SimControl.EndCondition": "Time", "SimControl.EndConditionValue": "3", "SimControl.timeStep": "0.04",
+                                                       "Environment.ConstantMeanWind.velocity": "(4 -2.5 0.3)"}, 4),
+                                          ("rk45", adaptive, {"SimControl.EndCondition": "Time", "SimControl.EndConditionValue": "3", "Environment.TurbulenceModel": "None",
+                                                              "SimControl.TimeStepAdaptation.targetError": "0.01", "Environment.ConstantMeanWind.velocity": "(4 -2.5 0.3)"}, 3),
+                                          ("rk4_apogee", mc, {"SimControl.timeStep": "0.04", "Environment.ConstantMeanWind.velocity": "(4 -2.5 0.3)"}, 3)):
+            sd = SimDefinition(defFile, silent=True, disableDistributionSampling=True)
+            for k, v in {**QUIET, **ov}.items():
+                sd.setValue(k, v)
+            runner = ConvergenceSimRunner(simDefinition=sd, silent=True)
+            buf = io.StringIO()
+            with contextlib.redirect_stdout(buf):
+                steps, positions, _ = runner.convergeSimEndPosition(refinementRatio=2, simLimit=limit, plot=False, showPlot=False)
+            sys.stdout = sys.__stdout__
+            pos = [[*p] for p in positions]
+            checks = [checkConvergence(positions[i], positions[i + 1], positions[i + 2], 2) for i in range(len(positions) - 2)]
+            out[label] = dict(definition=os.path.basename(defFile), overrides=ov, simLimit=limit, steps=[float(x) for x in steps], positions=pos,
+                              checks=[[[float(x) for x in part] for part in c] for c in checks],
+                              endCondition=[sd.getValue("SimControl.EndCondition"), sd.getValue("SimControl.EndConditionValue")],
+                              lines=[l for l in buf.getvalue().splitlines() if l.startswith(("Simulation ", "Final Position", "X-Direction", "Y-Direction", "Z-Direction", "Setting EndCondition"))])
+            print(" ", label, steps, pos[-1], flush=True)
+        dump("convergence.json", out)
     if "rk45_pink" in which:
         dump("rk45_pink.json", monteCarlo(adaptive, {}, "2394781", 4, globalSeed=2394781, keepDts=True))
     if "ideal" in which:

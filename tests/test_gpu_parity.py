@@ -805,3 +805,18 @@ def test_radio_sonde_profiles_as_per_lane_models_vs_reference(backend, golden):
     assert (st == L.ST_OK).all()
     for i, r in enumerate(g["runs"]):
         assert counters[i, 0] == r["steps"] and relErr(res[i, 3:7], r["results"][3:7]) < FIXED_TOL
+
+
+@pytest.mark.parametrize("label", ["rk4", "rk45"])
+def test_convergence_study_on_the_gpu_vs_reference(backend, golden, label):
+    """ConvergenceSimRunner.convergeSimEndPosition with every refinement level as a lane of one batch: per-lane first step size (LANE_START)
+    for RK4, per-lane model blocks (target error) for RK45Adaptive; final positions against the reference's sequential runs."""
+    from mapleaf_b200 import ConvergenceSimRunner
+    g = golden("convergence.json")[label]
+    sd = SimDefinition(os.path.join(DATA, g["definition"]), silent=True, disableDistributionSampling=True)
+    for k, v in g["overrides"].items():
+        sd.setValue(k, v)
+    steps, positions, times = ConvergenceSimRunner(simDefinition=sd, silent=True).convergeSimEndPosition(refinementRatio=2, simLimit=g["simLimit"], plot=False)
+    assert steps == g["steps"] and all(t > 0 for t in times)
+    for mine, ref in zip(positions, g["positions"]):
+        assert relErr(list(mine), ref) < (FIXED_TOL if label == "rk4" else 1e-5)

@@ -48,6 +48,10 @@ class OracleBatch:
     def finals(self):
         return self.out["finals"]
 
+    def laneCounters(self):
+        c = self.out["counters"]
+        return np.concatenate([c, np.zeros((c.shape[0], 3), dtype=c.dtype)], axis=1)
+
     def stageSeparations(self):
         return self.out["separations"]
 
@@ -61,10 +65,16 @@ class OracleBatch:
 
     def counters(self):
         c = self.out["counters"]
-        return dict(lanes=self.n, steps=int(c[:, 0].sum()), derivative_evals=int(c[:, 1].sum()), rejected_steps=int(c[:, 2].sum()))
+        return dict(lanes=self.n, steps=int(c[:, 0].sum()), derivative_evals=int(c[:, 1].sum()), rejected_steps=int(c[:, 2].sum()), last_run_ms=1000.0)
 
     def close(self):
         pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
 
 
 def montecarloDefinition(tmp_path, nRuns=3, **overrides):
@@ -479,3 +489,42 @@ def test_radio_sonde_sampler_and_runner_match_the_reference(monkeypatch, tmp_pat
     out = montecarlo.runMonteCarloSimulation(simDefinition=sd, silent=True)
     for i, ref in enumerate(g["runs"]):
         assert np.allclose(out.results[i, 3:7], ref["results"][3:7], rtol=1e-12), (out.results[i], ref["results"])
+
+
+@pytest.mark.parametrize("label", ["rk4", "rk45", "rk4_apogee"])
+def test_convergence_runner_matches_the_reference(monkeypatch, golden, label, capsys):
+    """ConvergenceSimRunner.convergeSimEndPosition (SimulationRunners/Convergence.py:15-149, IO/gridConvergenceFunctions.py): the refinement
+    levels fly as lanes of one batch (per-lane first step size for fixed-step methods, per-lane model blocks for the adaptive target
+    error); the final positions, the convergence checks and the printed lines are the reference's. `rk4_apogee`: a definition that does
+    not end on Time is flown once to find its end time first (:300-317)."""
+    from mapleaf_b200 import ConvergenceSimRunner
+    from mapleaf_b200.convergence import checkConvergence
+    g = golden("convergence.json")[label]
+    monkeypatch.setattr(backend, "TrajectoryBatch", OracleBatch)
+    sd = SimDefinition(os.path.join(DATA, g["definition"]), silent=True, disableDistributionSampling=True)
+    for k, v in g["overrides"].items():
+        sd.setValue(k, v)
+    runner = ConvergenceSimRunner(simDefinition=sd, silent=False)
+    steps, positions, times = runner.convergeSimEndPosition(refinementRatio=2, simLimit=g["simLimit"], plot=False, showPlot=False)
+    assert steps == g["steps"] and len(times) == g["simLimit"]
+    tol = 1e-12 if label != "rk45" else 1e-6
+    for mine, ref in zip(positions, g["positions"]):
+        assert np.allclose(list(mine), ref, rtol=tol, atol=tol)
+    assert [sd.getValue("SimControl.EndCondition"), float(sd.getValue("SimControl.EndConditionValue"))] == [g["endCondition"][0], float(g["endCondition"][1])]
+    for i, ref in enumerate(g["checks"]):
+        mine = checkConvergence(g["positions"][i], g["positions"][i + 1], g["positions"][i + 2], 2)
+        assert np.allclose(np.array(mine), np.array(ref), rtol=1e-12, atol=0)
+    if label != "rk45":
+        # the lines the reference prints (Convergence.py:100-131), rebuilt from its recorded numbers with its format strings (the fixture
+        # itself caught only the first one: the reference's run() re-routes sys.stdout)
+        printed = [l for l in capsys.readouterr().out.splitlines() if l.startswith(("Simulation ", "Final Position", "X-Direction", "Y-Direction", "Z-Direction"))]
+        expected = []
+        for i, (dt, pos) in enumerate(zip(g["steps"], g["positions"])):
+            expected.append("Simulation {}, Time step: {}".format(i + 1, dt))
+            expected.append("Final Position: {:1.3f} {:1.3f} {:1.3f}".format(*pos))
+            if i >= 2:
+                orders, _, _, asym, rich, unc = g["checks"][i - 2]
+                for d, name in enumerate("XYZ"):
+                    expected.append("{}-Direction: Order: {:>4.3f}, Asymptotic Check: {:>6.3f}, RichardsonExtrap: {:>7.3f}, Estimated Uncertainty: {:>6.3f}".format(
+                        name, orders[d], asym[d], rich[d], unc[d]))
+        assert printed == expected and (not g["lines"] or g["lines"][0] in printed)
