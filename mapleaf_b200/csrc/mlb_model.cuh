@@ -673,9 +673,18 @@ MLB_DEV double finCPX(const double* C, double Mach) {                           
     return polyval * C[FS_MAC_LEN] + C[FS_XMAC_LE];
 }
 
+#ifndef MLB_SLICE_UNROLL
+#define MLB_SLICE_UNROLL 0
+#endif
+#if MLB_SLICE_UNROLL
+#define MLB_SLICE_LOOP _Pragma("unroll 1")
+#else
+#define MLB_SLICE_LOOP
+#endif
 /* Strip sums over the span slices with the slice angles of attack already known (CythonFinFunctions.pyx:52-116) */
 MLB_DEV void finStripSubsonic(const double* C, const double* aoa, int n, double spanwiseCP, double CnAlpha, double& force, double& moment) {
     double f = 0, m = 0;
+    MLB_SLICE_LOOP
     for (int i = 0; i < n; i++) {
         double sliceForce = CnAlpha * aoa[i] * C[FS_SLICE_A + i];
         f += sliceForce;
@@ -686,6 +695,7 @@ MLB_DEV void finStripSubsonic(const double* C, const double* aoa, int n, double 
 MLB_DEV void finStripSupersonic(const double* C, const double* aoa, int n, double spanwiseCP, const Busemann& k, double& force, double& moment) {
     double f = 0, m = 0;
     double outerRadius = C[FS_SLICE_R + n - 1];
+    MLB_SLICE_LOOP
     for (int i = 0; i < n; i++) {
         double machCone = (outerRadius - C[FS_SLICE_R + i]) * k.negZPerRadius + C[FS_TIP_POS];
         double al = aoa[i];
@@ -708,6 +718,7 @@ MLB_DEV void finStripTransonic(const double* C, const double* aoa, int n, double
     const double cnA1 = C[FS_TRANS_CNA], cnA2 = C[FS_TRANS_CNA + 1];
     const double* K = C + FS_TRANS_K; const double* W = C + FS_TRANS_W;
     double f0 = 0, m0 = 0, f1 = 0, m1 = 0, f2 = 0, m2 = 0, f3 = 0, m3 = 0;
+    MLB_SLICE_LOOP
     for (int i = 0; i < n; i++) {
         const double al = aoa[i], area = C[FS_SLICE_A + i], arm = spanwiseCP - C[FS_SLICE_R + i], al2 = al * al;
         double sf = cnA1 * al * area; f0 += sf; m0 += sf * arm;
@@ -736,6 +747,7 @@ MLB_DEV double actuatorDeflection(const double* B, const Lane& L, int i, double 
 #ifndef MLB_FIN_LINEAR
 #define MLB_FIN_LINEAR 1
 #endif
+
 MLB_COMP_FINS ForceMoment finSetForce(const double* B, const Lane& L, Aero& a, const double* C, V3 CG, double thickK) {   /* Fins.py:263-358,463-551 */
     const double Mach = a.Mach, Aref = a.Aref, q = dynamicPressure(a);
     /* drag build-up common to all fins of the set (Fins.py:289-358) */
@@ -822,6 +834,7 @@ MLB_COMP_FINS ForceMoment finSetForce(const double* B, const Lane& L, Aero& a, c
                 if (__all_sync(warp, u2 * (rOuter * rOuter) < 1e-18 * m2)) {
                     /* noise-level roll in every lane of the warp (eps <= 1e-9): the first-order term alone is exact to 1e-18 rad */
                     const double dadr = (q - b0 * (au * rm)) * rm * rc;
+                    MLB_SLICE_LOOP
                     for (int i = 0; i < nS; i++) {
                         double al = fma(dadr, C[FS_SLICE_R + i], al0);
                         if (fabs(al) > stall) al *= fabs(stall / al);
@@ -830,6 +843,7 @@ MLB_COMP_FINS ForceMoment finSetForce(const double* B, const Lane& L, Aero& a, c
                 } else {
                     const double k2 = 0.5 * b0 * (rc * rc * rc);            /* half the second derivative */
                     const double au2 = 2 * au, p0 = dot(finNormal, airVelRelativeToFin), rm2 = rm * rm;
+                    MLB_SLICE_LOOP
                     for (int i = 0; i < nS; i++) {
                         const double r = C[FS_SLICE_R + i];
                         const double e = -(r * fma(u2, r, au2)) * rm2;     /* 1 - |A + U r|^2 / |A|^2 */

@@ -7,12 +7,8 @@ VDIR = os.path.join(REPO, "mapleaf_b200", "lib", "variants")
 # name -> extra nvcc flags; edit for the experiment at hand (switches: MLB_FLIGHT_SHAPES, MLB_COMP_NOINLINE, MLB_COLD_MASK, MLB_MATH_NOINLINE,
 # MLB_FIN_UNIFORM, MLB_FIN_LINEAR, MLB_CHUTE_BLOCK, MLB_CHUTE_CTAS, MLB_DERIV_NOINLINE)
 VARIANTS = {
-    "gens12": ["-DMLB_FLIGHT_SHAPES(X)=X(1024,1)", "-DMLB_GENERATIONS=12"],
-    "chute128x3": ["-DMLB_FLIGHT_SHAPES(X)=X(1024,1)", "-DMLB_CHUTE_BLOCK=128", "-DMLB_CHUTE_CTAS=3"],
-    "chute128x5": ["-DMLB_FLIGHT_SHAPES(X)=X(1024,1)", "-DMLB_CHUTE_BLOCK=128", "-DMLB_CHUTE_CTAS=5"],
-    "chute128x6": ["-DMLB_FLIGHT_SHAPES(X)=X(1024,1)", "-DMLB_CHUTE_BLOCK=128", "-DMLB_CHUTE_CTAS=6"],
-    "chute64x8": ["-DMLB_FLIGHT_SHAPES(X)=X(1024,1)", "-DMLB_CHUTE_BLOCK=64", "-DMLB_CHUTE_CTAS=8"],
-    "chute256x2": ["-DMLB_FLIGHT_SHAPES(X)=X(1024,1)", "-DMLB_CHUTE_BLOCK=256", "-DMLB_CHUTE_CTAS=2"],
+    "base": ["-DMLB_FLIGHT_SHAPES(X)=X(1024,1)"],
+    "unroll1": ["-DMLB_FLIGHT_SHAPES(X)=X(1024,1)", "-DMLB_SLICE_UNROLL=1"],
 }
 
 
