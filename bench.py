@@ -184,14 +184,15 @@ def algorithmicFlops(c, f):
     return (f["eval6"] * (e6 - et) + f["eval6t"] * et + f["step6"] * attempts6, f["eval3"] * e3 + f["step3"] * attempts3)
 
 
-def measuredKernelMetrics(configId):
+def measuredKernelMetrics(configId, specialised=False):
     """Per-lane DRAM traffic and executed FP64 instructions of the free-flight kernel from the committed ncu metrics pass of this
     code and workload (profiles/*_full_occupancy_metrics_lanes<N>.csv: one launch over N lanes, newest first; files of another
     configuration carry `config<C>` in their name): (dict per lane, source file) or (None, None)."""
     import re
     pdir = os.path.join(REPO, "profiles")
     want = "config%d" % configId
-    names = [f for f in os.listdir(pdir) if re.search(r"_full_occupancy_metrics_lanes\d+\.csv$", f) and (want in f or (configId == 1 and "config" not in f))]
+    names = [f for f in os.listdir(pdir) if re.search(r"_full_occupancy_metrics_lanes\d+\.csv$", f) and (want in f or (configId == 1 and "config" not in f))
+             and (("_spec_" in f) == bool(specialised))]         # passes of the model-specialised build carry `_spec_` in their name
     for name in sorted(names, reverse=True):
         lanes = int(re.search(r"_lanes(\d+)\.csv$", name).group(1))
         vals = {}
@@ -241,7 +242,19 @@ def runB200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    batch = backend.TrajectoryBatch(model.blob, device=local)
+    # model-specialised library (default): compiled for this model block, normally ahead of time by __graft_entry__.build(); a missing one is
+    # compiled here by rank 0, before any timed region
+    specInfo = None
+    if not args.generic:
+        cached = os.path.exists(backend.specializedLibraryPath(model.blob))
+        tBuild = time.perf_counter()
+        if rank == 0:
+            backend.buildSpecializedLibrary(model.blob)
+        if world > 1:
+            dist.barrier()
+        specInfo = {"library": "mapleaf_b200/lib/spec/" + os.path.basename(backend.specializedLibraryPath(model.blob)),
+                    "compiled": "ahead of time (cached by content hash)" if cached else "in this run, %.1f s of nvcc before the timed region" % (time.perf_counter() - tBuild)}
+    batch = backend.TrajectoryBatch(model.blob, device=local, specialize=not args.generic)
     devArrays = {k: torch.from_numpy(a).to(dev) for k, a in arrays.items()}
     # the kernels write their results straight into the all-gather send buffer
     gathered = torch.empty((world, n, L.RES_SIZE), dtype=torch.float64, device=dev)
@@ -300,7 +313,7 @@ def runB200(args):
     if not args.skip_e2e:
         pinned = {k: torch.from_numpy(a).pin_memory() for k, a in arrays.items()}
         hostArrays = {k: t.numpy() for k, t in pinned.items()}
-        e2eBatch = backend.TrajectoryBatch(model.blob, device=local)
+        e2eBatch = backend.TrajectoryBatch(model.blob, device=local, specialize=not args.generic)
 
         def e2ePass():
             e2eBatch.setLanes(n, hostArrays)                     # H2D of the step's inputs
@@ -330,7 +343,7 @@ def runB200(args):
     flightMs, chuteMs = c["dominant_kernel_ms"], c["chute_kernel_ms"]
     achieved = flops6 / (flightMs * 1e-3) / 1e12
     hbmBytes = n * (sum(a.shape[0] for a in arrays.values()) * 8 + L.RES_SIZE * 8 + L.FIN_SIZE * 8 + 4 + 6 * 8)
-    perLane, source = measuredKernelMetrics(args.config)
+    perLane, source = measuredKernelMetrics(args.config, specialised=not args.generic)
     roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": perLane["dram_bytes"] * n if perLane else None,
                 "traffic_source": (source + " (ncu dram__bytes_read.sum + dram__bytes_write.sum of one full-occupancy launch of this code and workload, per lane x lanes)") if perLane else None,
@@ -350,6 +363,8 @@ def runB200(args):
         "ms_per_step": msPerStep, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": cfg["workload"], "config_id": args.config, "definition": "mapleaf_b200/data/Simulations/" + cfg["definition"],
                    "overrides": cfg["overrides"], "lanes_per_gpu": n,
+                   "library": ("model-specialised build: the model block compiled into the kernels as constants (backend.specializedLibrary); " + json.dumps(specInfo))
+                              if specInfo else "generic build (interprets the model block from shared memory)",
                    "lanes_total": n * world, "accepted_steps_per_pass": stepsAll, "derivative_evals_per_pass": evalsAll,
                    "rejected_steps_per_pass": rejAll, "lanes_ok": okAll,
                    "rank0_steps_3dof": c["steps_3dof"], "rank0_evals_3dof": c["derivative_evals_3dof"], "rank0_evals_transonic": c["derivative_evals_transonic"],
@@ -453,6 +468,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="strong: --total-lanes split over the GPUs")
     ap.add_argument("--total-lanes", type=int, default=0, help="with --scaling strong (default 10^7, BASELINE configs[4])")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--generic", action="store_true", help="fly on the generic library (interprets the model block) instead of the one compiled for this model block")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs: leave out the cpu_baseline leg")
     ap.add_argument("--skip-e2e", action="store_true", help="record runs of the large configurations: leave out the end-to-end leg (e2e: null)")
     ap.add_argument("--log-every", type=int, default=0, help="keep every n-th accepted state of EVERY lane in the device flight log (0: no log) and report its HBM write rate")

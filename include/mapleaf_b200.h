@@ -67,6 +67,13 @@ int mlb_create(const void* model_blob, size_t n, int device, mlb_handle** out);
 void mlb_destroy(mlb_handle* h);
 const char* mlb_last_error(void);
 const char* mlb_version(void);
+/* 1 when this build of the library is MODEL-SPECIALISED: compiled with one model block baked into the kernels as constants
+   (mapleaf_b200.backend.specializedLibrary: the host writes the block as a header and compiles csrc/mlb_api.cu with -DMLB_SPEC). The
+   reference rebuilds its Python object graph per sample (Rocket/rocket.py:34-219); the generic library interprets one flattened block for
+   all samples; a specialised one has the block's structure (stages, component list, tableau, environment models) resolved at compile time.
+   Same ABI, same results up to the rounding of folded constants; mlb_create refuses any other model block and mlb_set_lane_models is
+   unsupported (MLB_ERR_UNSUPPORTED). 0 for the generic library. */
+int mlb_is_specialized(void);
 
 /* Per-lane inputs. perLaneArrays[k] is a host array of [components(arrayIds[k])][nLanes] doubles, lane fastest
    (LANE_WIND: 3, LANE_INIT_STATE: 13, LANE_PINK_SEED: 3, LANE_MOTOR_ADJUST: 8 = impulseAdjustFactor and burnTimeAdjustFactor of the

@@ -120,11 +120,15 @@ template <bool PERLANE>
 MLB_DEV const double* stageModel(const RunArgs& a) {
     extern __shared__ double smem[];
     if constexpr (PERLANE) return nullptr;
+#ifdef MLB_SPEC
+    else return kSpecBlob;          /* model-specialised build (tools/spec_header.py): constant-index reads fold into the code */
+#else
     else {
         for (int i = threadIdx.x; i < a.blobLen; i += blockDim.x) smem[i] = a.blob[i];
         __syncthreads();
         return smem;
     }
+#endif
 }
 
 template <bool PERLANE>
@@ -414,7 +418,13 @@ static void freeLanes(mlb_handle* h) {
 }
 
 extern "C" const char* mlb_last_error(void) { return g_err.c_str(); }
+#ifdef MLB_SPEC
+extern "C" const char* mlb_version(void) { return "mapleaf_b200 0.2 (sm_100a, model-specialised)"; }
+extern "C" int mlb_is_specialized(void) { return 1; }
+#else
 extern "C" const char* mlb_version(void) { return "mapleaf_b200 0.2 (sm_100a)"; }
+extern "C" int mlb_is_specialized(void) { return 0; }
+#endif
 
 static int createOnDevice(mlb_handle* h, const double* b, size_t len) {
     CU(cudaMalloc(&h->d_blob, len * sizeof(double)));
@@ -441,6 +451,16 @@ extern "C" int mlb_create(const void* model_blob, size_t n, int device, mlb_hand
     size_t len = n / sizeof(double);
     if ((int)b[H_MAGIC] != MLB_MAGIC || (int)b[H_VERSION] != MLB_VERSION) return fail(MLB_ERR_ARG, "mlb_create: not a model block (magic / version mismatch)");
     if ((size_t)b[H_LEN] != len) return fail(MLB_ERR_ARG, "mlb_create: model block length field does not match the buffer");
+#ifdef MLB_SPEC
+    /* model-specialised build: the kernels carry ONE model block as constants and serve no other */
+    {
+        const size_t shared = (size_t)b[H_SHARED_LEN] > 0 && (size_t)b[H_SHARED_LEN] <= len ? (size_t)b[H_SHARED_LEN] : len;
+        if (shared != (size_t)MLB_SPEC_LEN) return fail(MLB_ERR_ARG, "mlb_create: this library is specialised for another model block (length)");
+        for (size_t i = 0; i < shared; i++)
+            if (memcmp(&b[i], &kSpecBlobHost[i], sizeof(double)) != 0 && !(b[i] != b[i] && kSpecBlobHost[i] != kSpecBlobHost[i]))
+                return fail(MLB_ERR_ARG, "mlb_create: this library is specialised for another model block (word " + std::to_string(i) + " differs)");
+    }
+#endif
     int nStages = (int)b[H_NSTAGES];
     if (nStages < 1 || nStages > MLB_MAX_STAGES) return fail(MLB_ERR_UNSUPPORTED, "mlb_create: stage count out of range");
     int count = 0;
@@ -542,6 +562,9 @@ extern "C" int mlb_set_lane_models(mlb_handle* h, const double* models, int64_t 
     if (!h) return fail(MLB_ERR_ARG, "null handle");
     if (h->nLanes <= 0) return fail(MLB_ERR_STATE, "mlb_set_lane_models: call mlb_set_lanes first");
     if (!models) { h->haveLaneModels = false; return MLB_OK; }
+#ifdef MLB_SPEC
+    return fail(MLB_ERR_UNSUPPORTED, "mlb_set_lane_models: a model-specialised library flies one model block; per-lane model blocks need the generic library");
+#endif
     if (strideDoubles < (int64_t)h->sharedLen) return fail(MLB_ERR_ARG, "mlb_set_lane_models: stride shorter than the shared part of the model block (H_SHARED_LEN)");
     /* every lane's block must be a variant of the handle's: same layout, same length, same integrator and structure offsets */
     static const int same[] = { H_MAGIC, H_VERSION, H_LEN, H_SHARED_LEN, H_NSTAGES, H_INTEGRATOR, H_TAB_NSTAGE_ROWS, H_TAB_NRESULT_ROWS, H_TABLEAU_OFF, H_CTRL_OFF, H_RECOVERY_OFF, H_STAGE_OFF, H_TURB };
@@ -597,14 +620,20 @@ extern "C" int mlb_run(mlb_handle* h, void* stream) {
     MLB_FLIGHT_SHAPES(MLB_ALLOW_SHAPE)
     if (perLane) block = MLB_PERLANE_BLOCK;                    /* one shape: every constant is a global load there, fewer lanes per SM keep them cached */
     h->lastBlock = block;
-    const int ctaSlots = h->nSM * (block == 128 ? 2 : 1);
+    int ctasPerSM = 1;
+#define MLB_SHAPE_CTAS(N, M) if (block == N) ctasPerSM = M;
+    MLB_FLIGHT_SHAPES(MLB_SHAPE_CTAS)
+    const int ctaSlots = h->nSM * ctasPerSM;
     const unsigned grid = (unsigned)((h->nLanes + block - 1) / block) + (h->evenSplit ? ctaSlots + 1 : 0);      /* even split: at most this many CTAs */
     a.ctaSlots = h->evenSplit ? ctaSlots : 0;
     h->launches = 0;
     CU(cudaEventRecord(h->ev0, s));
     CU(cudaMemsetAsync(h->d_queueCount, 0, (MLB_GENERATIONS + 2) * sizeof(int), s));
+#ifndef MLB_SPEC
     if (perLane) initLanes<true><<<(unsigned)((h->nLanes + MLB_BLOCK - 1) / MLB_BLOCK), MLB_BLOCK, 0, s>>>(a);
-    else initLanes<false><<<(unsigned)((h->nLanes + MLB_BLOCK - 1) / MLB_BLOCK), MLB_BLOCK, h->smemBytes, s>>>(a);
+    else
+#endif
+    initLanes<false><<<(unsigned)((h->nLanes + MLB_BLOCK - 1) / MLB_BLOCK), MLB_BLOCK, h->smemBytes, s>>>(a);
     h->launches++;
     CU(cudaGetLastError());
     /* Free flight, MLB_GENERATIONS launches over ping-pong straggler queues. Every launch is sized for the whole batch (CTAs past the end
@@ -623,15 +652,20 @@ extern "C" int mlb_run(mlb_handle* h, void* stream) {
 #define MLB_LAUNCH_SHAPE(N, M) if (block == N && !perLane) { flightLanes<N, M, false><<<grid, N, h->smemBytes, s>>>(a); launched = true; }
         MLB_FLIGHT_SHAPES(MLB_LAUNCH_SHAPE)
         if (!launched) return fail(MLB_ERR_STATE, "mlb_run: this build has no free-flight kernel of " + std::to_string(block) + " threads (tuning build with a reduced MLB_FLIGHT_SHAPES list)");
+#ifndef MLB_SPEC
         if (perLane) flightLanes<MLB_PERLANE_BLOCK, 1, true><<<grid, MLB_PERLANE_BLOCK, 0, s>>>(a);
+#endif
         h->launches++;
         CU(cudaGetLastError());
     }
     CU(cudaEventRecord(h->evFlight1, s));
     /* Under parachute: everything the free-flight launches queued */
     a.qIn = h->d_queue[2]; a.qInCount = h->d_queueCount + MLB_GENERATIONS; a.qNext = nullptr; a.qNextCount = nullptr; a.qChute = nullptr; a.qChuteCount = nullptr; a.bailPermille = 0; a.ctaSlots = 0;
+#ifndef MLB_SPEC
     if (perLane) chuteLanes<true><<<(unsigned)((h->nLanes + MLB_CHUTE_BLOCK - 1) / MLB_CHUTE_BLOCK), MLB_CHUTE_BLOCK, 0, s>>>(a);
-    else chuteLanes<false><<<(unsigned)((h->nLanes + MLB_CHUTE_BLOCK - 1) / MLB_CHUTE_BLOCK), MLB_CHUTE_BLOCK, h->smemBytes, s>>>(a);
+    else
+#endif
+    chuteLanes<false><<<(unsigned)((h->nLanes + MLB_CHUTE_BLOCK - 1) / MLB_CHUTE_BLOCK), MLB_CHUTE_BLOCK, h->smemBytes, s>>>(a);
     h->launches++;
     CU(cudaGetLastError());
     CU(cudaEventRecord(h->ev1, s));

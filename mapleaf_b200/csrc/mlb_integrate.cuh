@@ -122,7 +122,10 @@ MLB_DEV bool pyIsClose(double a, double b) {                                    
    derivative evaluation, so one warp's fetch serves the others. All control flow around the barriers is CTA-uniform:
    lanes that have nothing to do in a stage / attempt / step stay in the loops with `active` false. The under-chute
    kernel (CONVOY false) fits the instruction cache and runs without barriers: every predicate is then the thread's own. */
-template <bool CONVOY> MLB_DEV void convoySync() { if (CONVOY) __syncthreads(); }
+#ifndef MLB_EVAL_BARRIER
+#define MLB_EVAL_BARRIER 1
+#endif
+template <bool CONVOY> MLB_DEV void convoySync() { if (CONVOY && MLB_EVAL_BARRIER) __syncthreads(); }
 
 /* One Runge-Kutta attempt of either family. The stage loop has ONE call site of the (large) state-derivative code, shared
    by the first stage and by the classical and the adaptive stage composition, so the force model is instantiated once in the
@@ -140,11 +143,12 @@ MLB_DEV StepResult integrateStep(const double* B, Lane& L, const KStore& ks, Sta
     const bool rk4Lanes = B[H_CTRL_OFF] != 0 && B[(int)B[H_CTRL_OFF] + CS_FORCE_RK4] != 0;
     const int nRows0 = (method0 == INT_EULER) ? 0 : (int)B[H_TAB_NSTAGE_ROWS];
     const int nRowsLoop = rk4Lanes ? max(nRows0, 3) : nRows0;
-    const int method = L.forceRK4 ? INT_RK4 : method0;
+    const bool forced = rk4Lanes && L.forceRK4;             /* without such a control system the choice is the model block's alone */
+    const int method = forced ? INT_RK4 : method0;
     const bool adaptive = method >= INT_RK12A;
-    const double* tab = B + (L.forceRK4 ? (int)B[(int)B[H_CTRL_OFF] + CS_TABLEAU2_OFF] : (int)B[H_TABLEAU_OFF]);
-    const int nRows = L.forceRK4 ? 3 : nRows0;
-    const int nResultRows = L.forceRK4 ? 1 : (int)B[H_TAB_NRESULT_ROWS];
+    const double* tab = B + (forced ? (int)B[(int)B[H_CTRL_OFF] + CS_TABLEAU2_OFF] : (int)B[H_TABLEAU_OFF]);
+    const int nRows = forced ? 3 : nRows0;
+    const int nResultRows = forced ? 1 : (int)B[H_TAB_NRESULT_ROWS];
     const double target = B[H_AD_TARGET], minDt = B[H_AD_MINDT];
     StepResult r; r.factor = 1.0; r.err = 0.0; r.dt = dt; r.rejected = false;
     double err = 10000000;
@@ -248,7 +252,10 @@ MLB_DEV StepResult integrateStep(const double* B, Lane& L, const KStore& ks, Sta
 }
 
 MLB_DEV bool isAdaptive(const double* B) { return (int)B[H_INTEGRATOR] >= INT_RK12A; }
-MLB_DEV bool laneAdaptive(const double* B, const Lane& L) { return !L.forceRK4 && isAdaptive(B); }
+MLB_DEV bool laneAdaptive(const double* B, const Lane& L) {
+    const bool rk4Lanes = B[H_CTRL_OFF] != 0 && B[(int)B[H_CTRL_OFF] + CS_FORCE_RK4] != 0;
+    return !(rk4Lanes && L.forceRK4) && isAdaptive(B);
+}
 
 /* ---------------------------------------------------------------------------------------------
  * Flight events
@@ -293,7 +300,7 @@ MLB_DEV void stageSeparation(const double* B, Lane& L) {                        
     double burnTime = S0[S_BURN_DURATION];
     if ((int)S0[S_MOTOR] >= 0) {
         const double* C = B + (int)S0[S_COMP_OFF + (int)S0[S_MOTOR]]; const int n = (int)C[MT_NROWS];
-        burnTime = L.motorAdj ? C[MT_TABLE + MT_COL_RAW_TIME * n + n - 1] * L.motorBurn[0] : C[MT_TABLE + n - 1];
+        burnTime = motorAdjOf(L) ? C[MT_TABLE + MT_COL_RAW_TIME * n + n - 1] * L.motorBurn[0] : C[MT_TABLE + n - 1];
     }
     L.engineShutOff[0] = L.time + burnTime;
 }
@@ -329,8 +336,8 @@ MLB_DEV void triggerEvents(const double* B, Lane& L, double& estTimeToNext, bool
                 if (vz < 0) timeTo = (ev.value - alt) / vz;
                 break;
             case EV_MOTOR_BURNOUT:
-                occurred = (L.time >= L.engineShutOff[L.nStages - 1]);
-                timeTo = L.engineShutOff[L.nStages - 1] - L.time; timeDet = true;
+                occurred = (L.time >= L.engineShutOff[stagesOf(B, L) - 1]);
+                timeTo = L.engineShutOff[stagesOf(B, L) - 1] - L.time; timeDet = true;
                 break;
             case EV_TIME_REACHED:
                 occurred = (L.time >= ev.value);
@@ -365,7 +372,7 @@ MLB_DEV double aeroKeyOf(const State& s, const Air& e, int key) {               
    stabiliser target, orientation error as a rotation vector, (scheduled) PID gains, vector PID, deflection table, actuators.
    G is the model block in global memory (interpolation tables). */
 MLB_COLD_CONTROL void runControlSystem(const double* B, const double* G, Lane& L) {
-    if (!L.hasControl || L.underChute) return;
+    if (B[H_CTRL_OFF] == 0 || L.underChute) return;        /* L.hasControl */
     const double* CS = B + (int)B[H_CTRL_OFF];
     const double currentTime = L.time;
     Air env = airProperties(B, L, L.s.pos, currentTime, false);
@@ -421,7 +428,7 @@ MLB_COLD_CONTROL void runControlSystem(const double* B, const double* G, Lane& L
 }
 
 MLB_DEV void railMotionConstraint(const double* B, Lane& L) {                                /* launchRail.py:58-81, environment.py:195-207 */
-    if (!L.onRail) return;
+    if (!(B[H_RAIL_LEN] > 0) || !L.onRail) return;
     Q4 rot = qAxisAngle(v3(0, 0, 1), B[H_EARTH_ROT] * L.time);
     V3 currPosition = qRotate(rot, ld3(B + H_RAIL_POS));
     V3 currDirection = qRotate(rot, ld3(B + H_RAIL_DIR));

@@ -95,6 +95,16 @@ struct Lane {
     long long nSteps3, nEvals3, nEvalsTransonic;    /* of which: under-chute (3-DoF) steps / evaluations, 6-DoF evaluations at 0.8 < Mach < 1.4 */
 };
 
+/* Stages still attached. A single-stage model never separates (stageSeparation returns at once), so the count is the model block's: in a
+   model-specialised build (MLB_SPEC) the stage and component loops below then have constant trip counts and unroll into straight-line code. */
+MLB_DEV int stagesOf(const double* B, const Lane& L) { return (B[H_NSTAGES] == 1) ? 1 : L.nStages; }
+MLB_DEV bool motorAdjOf(const Lane& L) { return L.motorAdj; }
+#ifdef MLB_SPEC
+#define MLB_MODEL_LOOP _Pragma("unroll")
+#else
+#define MLB_MODEL_LOOP _Pragma("unroll 1")
+#endif
+
 MLB_DEV ForceMoment fm(V3 f, V3 loc, V3 m) { ForceMoment r; r.force = f; r.location = loc; r.moment = m; return r; }
 MLB_DEV ForceMoment fmZero() { return fm(v3(0, 0, 0), v3(0, 0, 0), v3(0, 0, 0)); }
 MLB_DEV ForceMoment fmAt(ForceMoment a, V3 newLoc) {                                        /* forceMomentSystem.py:40-51 */
@@ -216,7 +226,7 @@ MLB_DEV V3 meanWindAt(const double* B, const Lane& L, double agl) {
 }
 
 MLB_DEV V3 turbulenceAt(const double* B, Lane& L, double altitude, V3 meanWind, double time) {
-    int model = L.turb;
+    int model = (int)B[H_TURB];                             /* L.turb */
     if (model == TURB_NONE) return v3(0, 0, 0);
     if (model == TURB_SINE_GUST) {                                                          /* TurbulenceModelling.py:133-166 */
         double start = B[H_GUST_START], blend = B[H_GUST_BLEND], mag = B[H_GUST_MAG];
@@ -390,7 +400,7 @@ MLB_DEV Inertia stageInertia(const double* B, const Lane& L, int si, double time
         const double* C = B + (int)S[S_COMP_OFF + (int)S[(L.resorted ? S_VAR2_IDX : S_VAR_IDX) + k]];
         if ((int)C[C_TYPE] == CT_MOTOR) {
             double tIgn = fmax(0.0, time - L.ignitionTime[si]);
-            list[n++] = L.motorAdj ? motorInertiaAdjusted(C, tIgn, L.motorBurn[si], L.motorOxW0[si], L.motorFuelW0[si]) : motorInertia(C, tIgn);
+            list[n++] = motorAdjOf(L) ? motorInertiaAdjusted(C, tIgn, L.motorBurn[si], L.motorOxW0[si], L.motorFuelW0[si]) : motorInertia(C, tIgn);
         }
         else list[n++] = tabulatedInertia(C, time);
     }
@@ -404,7 +414,8 @@ MLB_COLD_INERTIA Inertia rocketInertia(const double* B, const Lane& L, double ti
     Inertia list[MLB_MAX_STAGES + 1]; int n = 0;
     list[n].MOI = v3(0, 0, 0); list[n].CG = v3(0, 0, 0); list[n].mass = 0; n++;            /* rocket-level fixed-mass component (empty) */
     double m = 0;
-    for (int si = 0; si < L.nStages; si++) { list[n] = stageInertia(B, L, si, time); m += list[n].mass; n++; }
+    const int nStages = stagesOf(B, L);
+    for (int si = 0; si < nStages; si++) { list[n] = stageInertia(B, L, si, time); m += list[n].mass; n++; }
     *massSum = m;                                                                           /* CompositeObject.getMass: plain sum over stages */
     return combineInertias(list, n);
 }
@@ -413,7 +424,8 @@ MLB_COLD_INERTIA Inertia rocketInertia(const double* B, const Lane& L, double ti
    row for timeSinceIgnition >= times[-1] (Propulsion.py:171-204 through linInterp's end clamp, Interpolation.py:22-25), a TabulatedInertia
    its last row for time >= its last time. The tests are the clamps' own comparisons, so the frozen value is bit-identical. */
 MLB_DEV bool rocketInertiaFrozen(const double* B, const Lane& L, double time) {
-    for (int si = 0; si < L.nStages; si++) {
+    const int nStages = stagesOf(B, L);
+    for (int si = 0; si < nStages; si++) {
         const double* S = B + (int)B[H_STAGE_OFF + si];
         if ((int)S[S_OVR_FLAGS] == (OVR_CG | OVR_MASS | OVR_MOI)) continue;
         const int nVar = (int)S[S_NVAR];
@@ -421,7 +433,7 @@ MLB_DEV bool rocketInertiaFrozen(const double* B, const Lane& L, double time) {
             const double* C = B + (int)S[S_COMP_OFF + (int)S[S_VAR_IDX + k]];
             if ((int)C[C_TYPE] == CT_MOTOR) {
                 const int n = (int)C[MT_NROWS]; const double* T = C + MT_TABLE;
-                const double tEnd = L.motorAdj ? T[MT_COL_RAW_TIME * n + n - 1] * L.motorBurn[si] : T[n - 1];
+                const double tEnd = motorAdjOf(L) ? T[MT_COL_RAW_TIME * n + n - 1] * L.motorBurn[si] : T[n - 1];
                 if (!(fmax(0.0, time - L.ignitionTime[si]) >= tEnd)) return false;
             } else {
                 const int n = (int)C[TI_NROWS];
@@ -461,9 +473,10 @@ MLB_DEV void aeroSetup(const double* B, const Lane& L, Aero& a, const State& s, 
     else a.normalDir = normalize(v3(a.lfav.x, a.lfav.y, 0));
     a.qValid = false; a.q = 0;
     a.unitRe = a.airSpeed * e.density / e.viscosity;                                        /* :22-27 */
-    a.finenessRatio = B[H_FINENESS + L.nStages - 1];
+    const int nStages = stagesOf(B, L);
+    a.finenessRatio = B[H_FINENESS + nStages - 1];
     a.fullyTurb = B[H_FULLY_TURB] != 0;
-    a.Aref = B[H_AREF]; a.rAref = B[H_RAREF]; a.finenessF = B[H_FINENESS_F + L.nStages - 1];
+    a.Aref = B[H_AREF]; a.rAref = B[H_RAREF]; a.finenessF = B[H_FINENESS_F + nStages - 1];
     a.sinAOA = m_sin(a.totalAOA);
     a.axialFactor = dragToAxialFactor(a.totalAOA);
     a.baseDrag = baseDragCoefficient(a.Mach);
@@ -775,7 +788,7 @@ MLB_COMP_FINS ForceMoment finSetForce(const double* B, const Lane& L, Aero& a, c
     const double stall = C[FS_STALL];
     const double* Ainv = B + (int)B[H_FIN_CUBIC_OFF];
     const int regime = (Mach <= 0.8) ? 0 : (Mach < 1.4 ? 1 : 2);
-    const bool actuated = (C[FS_ACTUATED] != 0) && L.hasControl;
+    const bool actuated = (C[FS_ACTUATED] != 0) && B[H_CTRL_OFF] != 0;      /* L.hasControl */
     double cnA = 0; Busemann kM;
     if (regime == 0) cnA = finCnAlphaSubsonic(C, Mach);
     else if (regime == 2) kM = busemann(Mach);
@@ -1018,7 +1031,7 @@ MLB_DEV ForceMoment jetDampingForce(const double* B, const Lane& L, const Aero& 
 MLB_DEV double motorThrust(const Lane& L, const double* C, int si, double time) {           /* Propulsion.py:138-151 */
     double t = fmax(0.0, time - L.ignitionTime[si]);
     int n = (int)C[MT_NROWS]; const double* T = C + MT_TABLE;
-    if (L.motorAdj) {                                       /* thrust * impulseAdjustFactor / burnTimeAdjustFactor over time * burnTimeAdjustFactor */
+    if (motorAdjOf(L)) {                                    /* thrust * impulseAdjustFactor / burnTimeAdjustFactor over time * burnTimeAdjustFactor */
         const double* rawT = T + MT_COL_RAW_TIME * n; const double* rawF = T + MT_COL_RAW_THRUST * n;
         const double imp = L.motorImp[si], burn = L.motorBurn[si];
         if (t < 0 || t > rawT[n - 1] * burn) return 0;
@@ -1060,7 +1073,7 @@ MLB_DEV double finThicknessK(const double* B, Lane& L, const double* C) {
  * Rocket._getAppliedForce + RigidBody.getRigidBodyStateDerivative
  * ------------------------------------------------------------------------------------------- */
 MLB_DEV ForceMoment launchRailForce(const double* B, const Lane& L, const State& s, double time, ForceMoment unadjusted) {   /* launchRail.py:37-56 */
-    if (!L.onRail) return unadjusted;
+    if (!(B[H_RAIL_LEN] > 0) || !L.onRail) return unadjusted;
     V3 railDir = ld3(B + H_RAIL_DIR);
     Q4 rot = qAxisAngle(v3(0, 0, 1), B[H_EARTH_ROT] * time);
     V3 currPos = qRotate(rot, ld3(B + H_RAIL_POS));
@@ -1095,11 +1108,12 @@ MLB_DEV ForceMoment appliedForce(const double* B, Lane& L, double time, State& s
         if (probe) { probe->Mach = a.Mach; probe->density = e.density; probe->wind = e.wind; }
         ForceMoment rocketTotal = fm(v3(0, 0, 0), inertia.CG, v3(0, 0, 0));
         int finIdx = 0;
-        for (int si = 0; si < L.nStages; si++) {
+        const int nStages = stagesOf(B, L);
+        for (int si = 0; si < nStages; si++) {
             const double* S = B + (int)B[H_STAGE_OFF + si];
             const int nc = (int)S[S_NCOMP];
             ForceMoment stageTotal = fm(v3(0, 0, 0), inertia.CG, v3(0, 0, 0));
-#pragma unroll 1
+            MLB_MODEL_LOOP
             for (int ci = 0; ci < nc; ci++) {
                 const double* C = B + (int)S[S_COMP_OFF + ci];
                 ForceMoment f;
@@ -1120,7 +1134,7 @@ MLB_DEV ForceMoment appliedForce(const double* B, Lane& L, double time, State& s
                 stageTotal = fmAdd(stageTotal, f);
             }
             /* the automatic zero-length boat tail belongs to whichever stage is currently the bottom one (rocket.py:489-519) */
-            if (si == L.nStages - 1 && S[S_AUTO_BT_OFF] != 0) stageTotal = fmAdd(stageTotal, transitionForce(L, a, B + (int)S[S_AUTO_BT_OFF], si, true));
+            if (si == nStages - 1 && S[S_AUTO_BT_OFF] != 0) stageTotal = fmAdd(stageTotal, transitionForce(L, a, B + (int)S[S_AUTO_BT_OFF], si, true));
             rocketTotal = fmAdd(rocketTotal, stageTotal);
         }
         comp = rocketTotal;
