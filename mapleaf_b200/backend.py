@@ -117,7 +117,7 @@ def _bind(path):
 # steps/s (gpurun_out r2t sweep, profiles/r2t_*). Cost: one nvcc run per distinct model block (~1 min), cached by content hash.
 # ---------------------------------------------------------------------------------------------------------------------
 SPEC_DIR = os.path.join(_PKG_DIR, "lib", "spec")
-SPEC_FLAGS = ["-DMLB_COMP_NOINLINE=0"]       # with the block folded in, inlined component routines win (generic build: out of line)
+SPEC_FLAGS = ["-DMLB_COMP_NOINLINE=0", "-DMLB_COLD_MASK=0"]       # with the block folded in, inlined component / cold routines win (generic build: out of line)
 
 
 def _specLiteral(v):

@@ -226,6 +226,16 @@ MLB_DEV void flightLoop(const RunArgs& a, const double* B) {
     double* const traceBase = tracing ? a.trace + (size_t)(lane - a.traceLane) * a.traceMaxRows * TRACE_W : nullptr;
     const long long maxSteps = (long long)B[H_MAX_STEPS];
 
+    Convoy cv; cv.bar = 0; cv.phase = 0;
+#if MLB_SPLIT_BARRIER
+    if (CONVOY) {
+        /* one arrival per warp of the CTA's `per` threads; the first wait of the time loop answers the arrival made here */
+        __shared__ unsigned long long convoyBarrier;
+        convoyInit(cv, &convoyBarrier, (per + 31) >> 5);
+        __syncthreads();
+        convoyDone<CONVOY>(cv);
+    }
+#endif
     int bailBelow = 0;
     if (CONVOY && a.bailPermille > 0) {
         const long long inCta = min((long long)per, count - (long long)blockIdx.x * per);
@@ -239,7 +249,7 @@ MLB_DEV void flightLoop(const RunArgs& a, const double* B) {
             if (haveFinal) dt = finalDt;
             if (a.dtReplay && L.nSteps < a.nReplay) dt = a.dtReplay[L.nSteps];
         }
-        StepResult r = rocketTimeStep<PH, CONVOY>(B, a.blob, L, ks, dt, run, skipPre || retry, retry, left);
+        StepResult r = rocketTimeStep<PH, CONVOY>(B, a.blob, L, ks, cv, dt, run, skipPre || retry, retry, left);
         skipPre = false;
         if (run && !left && r.rejected) { retry = true; dt = r.dt; }
         else if (run && !left) {

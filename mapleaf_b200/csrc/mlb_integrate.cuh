@@ -125,7 +125,42 @@ MLB_DEV bool pyIsClose(double a, double b) {                                    
 #ifndef MLB_EVAL_BARRIER
 #define MLB_EVAL_BARRIER 1
 #endif
-template <bool CONVOY> MLB_DEV void convoySync() { if (CONVOY && MLB_EVAL_BARRIER) __syncthreads(); }
+/* MLB_SPLIT_BARRIER: the per-evaluation barrier as a split-phase mbarrier. A warp ARRIVES when it has finished a derivative evaluation and
+   WAITS just before the next one; the stage algebra in between (slot write, next stage's increments, error estimate) is slack in which the
+   CTA's slower warps catch up, instead of every warp standing at a hard barrier for the slowest one. Warps still enter every evaluation
+   together (that is what the instruction cache needs); the arithmetic is untouched. One arrival per warp (lane 0 after __syncwarp). */
+#ifndef MLB_SPLIT_BARRIER
+#define MLB_SPLIT_BARRIER 0
+#endif
+struct Convoy {
+    unsigned bar;       /* shared-memory address of the CTA's mbarrier */
+    unsigned phase;     /* parity of the phase the next wait is for */
+};
+MLB_DEV void convoyInit(Convoy& c, unsigned long long* barrier, int nWarps) {
+    c.bar = (unsigned)__cvta_generic_to_shared(barrier); c.phase = 0;
+    if (threadIdx.x == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(c.bar), "r"(nWarps) : "memory");
+}
+MLB_DEV void convoyArrive(const Convoy& c) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) { unsigned long long st; asm volatile("mbarrier.arrive.shared::cta.b64 %0, [%1];" : "=l"(st) : "r"(c.bar) : "memory"); (void)st; }
+}
+MLB_DEV void convoyWait(Convoy& c) {
+    asm volatile("{\n\t.reg .pred p;\n\tMLB_WAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra MLB_WAIT_%=;\n\t}" :: "r"(c.bar), "r"(c.phase) : "memory");
+    c.phase ^= 1u;
+}
+template <bool CONVOY> MLB_DEV void convoySync(Convoy& c) {
+    if (!CONVOY || !MLB_EVAL_BARRIER) return;
+#if MLB_SPLIT_BARRIER
+    convoyWait(c);
+#else
+    __syncthreads();
+#endif
+}
+template <bool CONVOY> MLB_DEV void convoyDone(const Convoy& c) {
+#if MLB_SPLIT_BARRIER
+    if (CONVOY && MLB_EVAL_BARRIER) convoyArrive(c);
+#endif
+}
 
 /* One Runge-Kutta attempt of either family. The stage loop has ONE call site of the (large) state-derivative code, shared
    by the first stage and by the classical and the adaptive stage composition, so the force model is instantiated once in the
@@ -135,7 +170,7 @@ template <bool CONVOY> MLB_DEV void convoySync() { if (CONVOY && MLB_EVAL_BARRIE
    the time loop's next iteration with `retry` set: same arithmetic, same attempt sequence, but the re-attempt rides along with the
    other lanes' next step instead of holding the whole convoy for a pass in which only the rejected lanes work. */
 template <int PH, bool CONVOY>
-MLB_DEV StepResult integrateStep(const double* B, Lane& L, const KStore& ks, State& y, double t, double dt, bool active, bool retry) {
+MLB_DEV StepResult integrateStep(const double* B, Lane& L, const KStore& ks, Convoy& cv, State& y, double t, double dt, bool active, bool retry) {
     /* A fixed-rate control system swaps an adaptive integrator for RK4 while it is in charge (ControlSystems.py:126-135); the
        parachute switch restores the original one (rocket.py:700-726). So the method is a per-lane choice between two tableaus;
        the stage loop below runs to the CTA-uniform maximum row count and lanes with fewer rows sit out the extra stages. */
@@ -196,8 +231,11 @@ MLB_DEV StepResult integrateStep(const double* B, Lane& L, const KStore& ks, Sta
                     }
                 }
             }
-            convoySync<CONVOY>();
-            if (evalNow) ks.put(i + 1, stateDerivative<PH>(B, L, evalTime, evalY), dof3);
+            convoySync<CONVOY>(cv);
+            Deriv kNew;
+            if (evalNow) kNew = stateDerivative<PH>(B, L, evalTime, evalY);
+            convoyDone<CONVOY>(cv);
+            if (evalNow) ks.put(i + 1, kNew, dof3);
         }
         if (attempting) {
             if (method == INT_EULER) {                                                      /* :192-195 */
@@ -445,7 +483,7 @@ MLB_DEV void railMotionConstraint(const double* B, Lane& L) {                   
    loop) can deploy the first parachute, which turns the lane into a 3-DoF body: a lane of the free-flight kernel then leaves
    (`left`) with the first half done and its step size already clamped, and the under-chute kernel resumes it with `skipPre`. */
 template <int PH, bool CONVOY>
-MLB_DEV StepResult rocketTimeStep(const double* B, const double* G, Lane& L, const KStore& ks, double& dt, bool active, bool skipPre, bool retry, bool& left) {
+MLB_DEV StepResult rocketTimeStep(const double* B, const double* G, Lane& L, const KStore& ks, Convoy& cv, double& dt, bool active, bool skipPre, bool retry, bool& left) {
     if (active && !skipPre) {
         L.dtEntry = dt;
         railMotionConstraint(B, L);
@@ -458,7 +496,7 @@ MLB_DEV StepResult rocketTimeStep(const double* B, const double* G, Lane& L, con
         if (PH == 0) runControlSystem(B, G, L);             /* `not self.isUnderChute` (rocket.py:646-656) */
         if (L.dof3 != (PH == 1)) { left = true; active = false; }
     }
-    StepResult r = integrateStep<PH, CONVOY>(B, L, ks, L.s, L.time, dt, active, retry);
+    StepResult r = integrateStep<PH, CONVOY>(B, L, ks, cv, L.s, L.time, dt, active, retry);
     if (active && !r.rejected) {
         if (PH == 1) L.nSteps3++;
         L.time += r.dt;

@@ -95,14 +95,17 @@ struct Lane {
     long long nSteps3, nEvals3, nEvalsTransonic;    /* of which: under-chute (3-DoF) steps / evaluations, 6-DoF evaluations at 0.8 < Mach < 1.4 */
 };
 
-/* Stages still attached. A single-stage model never separates (stageSeparation returns at once), so the count is the model block's: in a
-   model-specialised build (MLB_SPEC) the stage and component loops below then have constant trip counts and unroll into straight-line code. */
+/* Stage loops run over the model block's stage count and leave at the lane's own (stages drop from the bottom, the remaining ones are a
+   prefix): in a model-specialised build (MLB_SPEC) the trip counts are constants, so the stage and component loops unroll into the
+   rocket's own straight-line force model with every record offset and constant folded. */
 MLB_DEV int stagesOf(const double* B, const Lane& L) { return (B[H_NSTAGES] == 1) ? 1 : L.nStages; }
 MLB_DEV bool motorAdjOf(const Lane& L) { return L.motorAdj; }
 #ifdef MLB_SPEC
 #define MLB_MODEL_LOOP _Pragma("unroll")
+#define MLB_COMPONENT_LOOP _Pragma("unroll")
 #else
-#define MLB_MODEL_LOOP _Pragma("unroll 1")
+#define MLB_MODEL_LOOP
+#define MLB_COMPONENT_LOOP _Pragma("unroll 1")
 #endif
 
 MLB_DEV ForceMoment fm(V3 f, V3 loc, V3 m) { ForceMoment r; r.force = f; r.location = loc; r.moment = m; return r; }
@@ -341,6 +344,7 @@ MLB_DEV int bisectRightScaled(const double* X, int n, double x, double scale) {
 }
 MLB_DEV double motorWeightFromEnd(const double* rawT, const double* flow, int n, int k, double burn) {      /* weights[k], :119-128 */
     double sum = 0;
+#pragma unroll 1            /* a table-length loop: a specialised build knows n and would otherwise unroll it whole */
     for (int i = n - 1; i > k; i--) { double deltaT = rawT[i] * burn - rawT[i - 1] * burn; sum += deltaT * (flow[i - 1] + flow[i]) / 2; }
     return sum;
 }
@@ -396,6 +400,7 @@ MLB_DEV Inertia stageInertia(const double* B, const Lane& L, int si, double time
     list[0].MOI = ld3(S + (L.resorted ? S_FIXED2_MOI : S_FIXED_MOI)); list[0].CG = ld3(S + (L.resorted ? S_FIXED2_CG : S_FIXED_CG));
     list[0].mass = L.resorted ? S[S_FIXED2_MASS] : S[S_FIXED_MASS];
     const int nVar = (int)S[S_NVAR];
+    MLB_MODEL_LOOP
     for (int k = 0; k < nVar; k++) {                       /* variable-mass components, in the order the reference combines them */
         const double* C = B + (int)S[S_COMP_OFF + (int)S[(L.resorted ? S_VAR2_IDX : S_VAR_IDX) + k]];
         if ((int)C[C_TYPE] == CT_MOTOR) {
@@ -414,8 +419,9 @@ MLB_COLD_INERTIA Inertia rocketInertia(const double* B, const Lane& L, double ti
     Inertia list[MLB_MAX_STAGES + 1]; int n = 0;
     list[n].MOI = v3(0, 0, 0); list[n].CG = v3(0, 0, 0); list[n].mass = 0; n++;            /* rocket-level fixed-mass component (empty) */
     double m = 0;
-    const int nStages = stagesOf(B, L);
-    for (int si = 0; si < nStages; si++) { list[n] = stageInertia(B, L, si, time); m += list[n].mass; n++; }
+    const int nStages = stagesOf(B, L), maxStages = (int)B[H_NSTAGES];
+    MLB_MODEL_LOOP
+    for (int si = 0; si < maxStages; si++) { if (si >= nStages) break; list[n] = stageInertia(B, L, si, time); m += list[n].mass; n++; }
     *massSum = m;                                                                           /* CompositeObject.getMass: plain sum over stages */
     return combineInertias(list, n);
 }
@@ -424,8 +430,10 @@ MLB_COLD_INERTIA Inertia rocketInertia(const double* B, const Lane& L, double ti
    row for timeSinceIgnition >= times[-1] (Propulsion.py:171-204 through linInterp's end clamp, Interpolation.py:22-25), a TabulatedInertia
    its last row for time >= its last time. The tests are the clamps' own comparisons, so the frozen value is bit-identical. */
 MLB_DEV bool rocketInertiaFrozen(const double* B, const Lane& L, double time) {
-    const int nStages = stagesOf(B, L);
-    for (int si = 0; si < nStages; si++) {
+    const int nStages = stagesOf(B, L), maxStages = (int)B[H_NSTAGES];
+    MLB_MODEL_LOOP
+    for (int si = 0; si < maxStages; si++) {
+        if (si >= nStages) break;
         const double* S = B + (int)B[H_STAGE_OFF + si];
         if ((int)S[S_OVR_FLAGS] == (OVR_CG | OVR_MASS | OVR_MOI)) continue;
         const int nVar = (int)S[S_NVAR];
@@ -1108,12 +1116,14 @@ MLB_DEV ForceMoment appliedForce(const double* B, Lane& L, double time, State& s
         if (probe) { probe->Mach = a.Mach; probe->density = e.density; probe->wind = e.wind; }
         ForceMoment rocketTotal = fm(v3(0, 0, 0), inertia.CG, v3(0, 0, 0));
         int finIdx = 0;
-        const int nStages = stagesOf(B, L);
-        for (int si = 0; si < nStages; si++) {
+        const int nStages = stagesOf(B, L), maxStages = (int)B[H_NSTAGES];
+        MLB_MODEL_LOOP
+        for (int si = 0; si < maxStages; si++) {
+            if (si >= nStages) break;
             const double* S = B + (int)B[H_STAGE_OFF + si];
             const int nc = (int)S[S_NCOMP];
             ForceMoment stageTotal = fm(v3(0, 0, 0), inertia.CG, v3(0, 0, 0));
-            MLB_MODEL_LOOP
+            MLB_COMPONENT_LOOP
             for (int ci = 0; ci < nc; ci++) {
                 const double* C = B + (int)S[S_COMP_OFF + ci];
                 ForceMoment f;

@@ -75,9 +75,28 @@ MLB_HD_COLD static void mtTwist(uint32_t* mt) {
     for (; kk < 623; kk++) { y = (mt[kk] & 0x80000000U) | (mt[kk + 1] & 0x7fffffffU); mt[kk] = mt[kk + (397 - 624)] ^ (y >> 1) ^ ((y & 1U) ? 0x9908b0dfU : 0U); }
     y = (mt[623] & 0x80000000U) | (mt[0] & 0x7fffffffU); mt[623] = mt[396] ^ (y >> 1) ^ ((y & 1U) ? 0x9908b0dfU : 0U);
 }
+/* Device code regenerates the state ONE WORD PER DRAW, in place, instead of all 624 words when the block runs out: word i of the next
+   block is a function of mt[i], mt[i + 1] and mt[i + 397] (indices mod 624), and walking i upwards in place reads exactly the old / new
+   words the block twist reads (genrand_int32 is that same loop), so the stream is bit-identical. Why: a lane's block twist is ~9 k
+   instructions executed by ONE thread of its warp while the CTA's other warps wait at the convoy barrier (ncu: the twist ran at 1.03
+   threads per instruction, profiles/r3b). In this representation words at and above idx are still the previous block's; idx 624 and
+   idx 0 are the same position. Host code (the Monte Carlo samplers, which take over CPython generator states) keeps the block twist. */
+#ifndef MLB_MT_INCREMENTAL
+#define MLB_MT_INCREMENTAL 1
+#endif
 MLB_HD uint32_t mtGenrand(PyRandom& r) {
+#if defined(__CUDA_ARCH__) && MLB_MT_INCREMENTAL
+    uint32_t* mt = r.mt;
+    const int i = r.idx >= 624 ? 0 : r.idx;
+    const int i1 = (i == 623) ? 0 : i + 1, im = (i < 624 - 397) ? i + 397 : i + (397 - 624);
+    uint32_t y = (mt[i] & 0x80000000U) | (mt[i1] & 0x7fffffffU);
+    y = mt[im] ^ (y >> 1) ^ ((y & 1U) ? 0x9908b0dfU : 0U);
+    mt[i] = y;
+    r.idx = i + 1;
+#else
     if (r.idx >= 624) { mtTwist(r.mt); r.idx = 0; }
     uint32_t y = r.mt[r.idx++];
+#endif
     y ^= (y >> 11); y ^= (y << 7) & 0x9d2c5680U; y ^= (y << 15) & 0xefc60000U; y ^= (y >> 18);
     return y;
 }
@@ -106,10 +125,10 @@ struct PinkNoise {
 };
 
 MLB_HD double pinkNewSample(PinkNoise& g, double c0, double c1) {
-    double white = pyRandomGauss(g.rng, 0, 1);
     /* coefficient i multiplies the sample written (i+1) calls ago */
     double newest = g.nextSlot ? g.last0 : g.last1;
     double older = g.nextSlot ? g.last1 : g.last0;
+    double white = pyRandomGauss(g.rng, 0, 1);
     white -= c0 * newest;
     white -= c1 * older;
     if (g.nextSlot) g.last1 = white; else g.last0 = white;
