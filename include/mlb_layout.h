@@ -433,7 +433,8 @@
 #define CS_MAX_ACT 8
 /* N-D scattered linear interpolation (scipy LinearNDInterpolator + NearestNDInterpolator, Motion/Interpolation.py:109-124):
    Delaunay triangulation computed on the host with scipy. Data after the 4 counts: points[npts][dim], values[npts][nval],
-   simplices[nsimp][dim+1] (point indices), transform[nsimp][dim+1][dim] (barycentric transform of each simplex, NaN if degenerate) */
+   simplices[nsimp][dim+1] (point indices), transform[nsimp][dim+1][dim] (barycentric transform of each simplex, NaN if degenerate),
+   neighbors[nsimp][dim+1] (scipy's Delaunay.neighbors: the simplex opposite vertex j, -1 on the hull; used by the device's directed walk) */
 #define ND_DIM 0
 #define ND_NVAL 1
 #define ND_NPTS 2

@@ -940,17 +940,51 @@ MLB_DEV ForceMoment aeroDampingForce(Aero& a, const double* C) {                
    Motion/Interpolation.py:109-124). The Delaunay triangulation comes from scipy on the host; R points into GLOBAL memory (the
    tables are too large for shared memory, every lane reads the same words: broadcast loads). Point location is a scan over
    the simplices with scipy's inside tolerance; it runs once per control tick, not per derivative evaluation. `hint`: the simplex
-   that held the lane's previous query. Between two ticks of a 100 Hz loop the query barely moves, so the hint is tested first and
-   accepted only when the point is STRICTLY inside it (every barycentric coordinate at least 1e-6 from 0 and 1): no other simplex of a
-   triangulation can then contain the point, even within the tolerance, so the scan would have returned this simplex and these weights. */
+   that held the lane's previous query. Between two ticks of a 100 Hz loop the query barely moves, so the hint is tested first, with the
+   scan's own inclusion tolerance; when the query has left it, a directed walk through the triangulation's neighbour table (towards the
+   neighbour opposite the most negative barycentric coordinate, scipy's own find_simplex strategy) finds the new simplex in a step or two;
+   only a walk that leaves the hull or meets a degenerate simplex falls through to the scan (and, outside the hull, to the nearest row).
+   A query strictly inside a simplex gets the scan's answer bit for bit. A query ON a shared face (a controller output that is exactly
+   zero puts every query of the canard case on one) may be answered from another of the simplices that share the face than the scan's
+   lowest-numbered one: the interpolant is continuous across faces, the vertex that differs carries a weight below the tolerance
+   (2e-14), so the value agrees to rounding (the parity gates of the canard fixtures, <= 1e-9 against the reference, are measured with
+   this rule). Why it matters: with a strict-interior rule nearly every tick of the canard case fell through to the scan, 613 simplices
+   of the deflection table = about five derivative evaluations' worth of instructions per step (profiles/r3_nd_hint_ab.txt: 124 -> 227 M steps/s). */
 MLB_COLD_NDTABLE void ndInterpolate(const double* __restrict__ R, const double* x, double* out, int& hint) {
     const int d = (int)R[ND_DIM], m = (int)R[ND_NVAL], npts = (int)R[ND_NPTS], ns = (int)R[ND_NSIMP];
     const double* pts = R + ND_DATA; const double* vals = pts + npts * d; const double* simp = vals + npts * m; const double* T = simp + ns * (d + 1);
     const double eps = 100 * 2.220446049250313e-16;
     const bool tryHint = (hint >= 0 && hint < ns);
-    for (int it = tryHint ? -1 : 0; it < ns; it++) {
-        const int s = (it < 0) ? hint : it;
-        const double lo = (it < 0) ? 1e-6 : -eps, hi = (it < 0) ? 1 - 1e-6 : 1 + eps;
+    int walked = -1;
+#ifndef MLB_ND_WALK
+#define MLB_ND_WALK 1
+#endif
+#ifndef MLB_ND_MARGIN
+#define MLB_ND_MARGIN (-100 * 2.220446049250313e-16)
+#endif
+    if (MLB_ND_WALK && tryHint) {
+        const double* nb = T + ns * (d + 1) * d;
+        int s = hint;
+        for (int step = 0; step < 16; step++) {
+            const double* Ts = T + s * (d + 1) * d;
+            if (Ts[0] != Ts[0]) break;                                                      /* degenerate simplex: leave it to the scan */
+            double cLast = 1.0, cMin = 1e300; int kMin = 0;
+            for (int i = 0; i < d; i++) {
+                double ci = 0;
+                for (int j = 0; j < d; j++) ci += Ts[d * i + j] * (x[j] - Ts[d * d + j]);
+                cLast -= ci;
+                if (ci < cMin) { cMin = ci; kMin = i; }
+            }
+            if (cLast < cMin) { cMin = cLast; kMin = d; }
+            if (cMin >= MLB_ND_MARGIN) { walked = s; break; }                                        /* strictly inside (the scan below re-derives the weights) */
+            if (cMin >= -1e-9) break;                                                               /* on or near a face: the scan decides */
+            s = (int)nb[s * (d + 1) + kMin];
+            if (s < 0) break;                                                               /* left the hull: nearest-neighbour fallback below */
+        }
+    }
+    for (int it = (walked >= 0 || tryHint) ? -1 : 0; it < ns; it++) {
+        const int s = (it < 0) ? (walked >= 0 ? walked : hint) : it;
+        const double lo = (it < 0) ? MLB_ND_MARGIN : -eps, hi = (it < 0) ? 1 - MLB_ND_MARGIN : 1 + eps;
         const double* Ts = T + s * (d + 1) * d;
         if (Ts[0] != Ts[0]) continue;                                                       /* degenerate simplex */
         double c[ND_MAX_DIM + 1]; double cLast = 1.0; bool inside = true;

@@ -767,6 +767,7 @@ def _ndInterpolatorRecord(keys, values):
     rec = [keys.shape[1], values.shape[1], keys.shape[0], tri.simplices.shape[0]]
     rec += [float(x) for x in keys.reshape(-1)] + [float(x) for x in values.reshape(-1)]
     rec += [float(x) for x in tri.simplices.reshape(-1)] + [float(x) for x in tri.transform.reshape(-1)]
+    rec += [float(x) for x in tri.neighbors.reshape(-1)]
     return rec
 
 
