@@ -331,7 +331,7 @@ def _sampleRunsVectorized(simDefinition, nRuns, mCLogger, model, keys, motorKeys
     return arrays
 
 
-def _runSimulations_B200(simDefinition, nRuns, outputLists, mCLogger, silent=False, nGPUs=1, device=0, parallelSeeding=False):
+def _runSimulations_B200(simDefinition, nRuns, outputLists, mCLogger, silent=False, nGPUs=1, device=0, parallelSeeding=False, specialize="cached"):
     """Same fill contract as _runSimulations_SingleThreaded: outputLists filled in sample order."""
     from . import backend
     landingLocations, apogees, maxSpeeds, flightTimes, maxHorizontalVels, flights = outputLists
@@ -360,7 +360,8 @@ def _runSimulations_B200(simDefinition, nRuns, outputLists, mCLogger, silent=Fal
     batches = []
     for g in range(nGPUs):
         lo, hi = bounds[g], bounds[g + 1]
-        b = backend.TrajectoryBatch(model.blob, device=device + g)
+        # the library compiled for this very model block when there is one (or when asked for); per-lane model blocks need the generic one
+        b = backend.TrajectoryBatch(model.blob, device=device + g, specialize=False if laneModels is not None else specialize)
         b.setLanes(hi - lo, {k: np.ascontiguousarray(a[:, lo:hi]) for k, a in arrays.items()})
         if laneModels is not None:
             b.setLaneModels(laneModels[lo:hi])
@@ -535,17 +536,20 @@ def _showResults(simDefinition, outputLists, mCLogger):
     return logPath
 
 
-def runMonteCarloSimulation(simDefinitionFilePath=None, simDefinition=None, silent=False, nCores=1, nGPUs: Optional[int] = None, device: int = 0):
+def runMonteCarloSimulation(simDefinitionFilePath=None, simDefinition=None, silent=False, nCores=1, nGPUs: Optional[int] = None, device: int = 0, specialize="cached"):
     """Drop-in for MAPLEAF.SimulationRunners.runMonteCarloSimulation. `nGPUs` spreads contiguous sample ranges over that many GPUs of
     this box. `nCores` > 1 selects the SEEDING of the reference's ray branch (every run draws from its own generator, seeded by a
     master generator: MonteCarlo.py:110-136), so that a definition run with `--parallel` keeps drawing the samples it drew there; the
     work itself is not fanned out over processes. Two things of that branch are not reproducible even in the reference and are not
     imitated: its results arrive in completion order (here: sample order), and its pink-noise seeds come from each worker process's own,
-    OS-seeded global generator (here: this process's global generator, as in the single-threaded branch). Returns MonteCarloResults."""
+    OS-seeded global generator (here: this process's global generator, as in the single-threaded branch).
+    `specialize`: "cached" (default) flies on the library compiled for this definition's model block if one is cached
+    (backend.buildSpecializedLibrary, ~1 min of nvcc per distinct rocket), True compiles it on first use, False always uses the generic
+    library. Returns MonteCarloResults."""
     simDefinition = loadSimDefinition(simDefinitionFilePath, simDefinition, silent)
     nRuns, mCLogger, outputLists = _prepSim(simDefinition, echo=not silent)
     results, status, counters, droppedStages, stepLogPaths = _runSimulations_B200(simDefinition, nRuns, outputLists, mCLogger, silent, nGPUs=nGPUs or 1, device=device,
-                                                                                  parallelSeeding=int(nCores or 1) > 1)
+                                                                                  parallelSeeding=int(nCores or 1) > 1, specialize=specialize)
     logPath = _showResults(simDefinition, outputLists, mCLogger)
     out = MonteCarloResults(results, status, counters, logPath, outputLists)
     out.droppedStages = droppedStages

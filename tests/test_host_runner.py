@@ -21,7 +21,7 @@ from mapleaf_b200 import backend, distributed
 class OracleBatch:
     """Stands in for backend.TrajectoryBatch in host-logic tests: same methods, trajectories from the CPU oracle."""
 
-    def __init__(self, blob, device=0):
+    def __init__(self, blob, device=0, specialize=None):
         self.blob, self.device = np.asarray(blob, dtype=np.float64), device
 
     def setLanes(self, n, arrays=None):
