@@ -17,6 +17,8 @@ Inputs are synthetic in the sense of the contract (no data files): winds are dra
 (random.Random("2394781").gauss per component), pink-noise seeds like random.Random(2394781).randrange(10^6).
 
 What the JSON line reports:
+By default the batch flies on the library compiled for the configuration's model block (backend.specializedLibrary: compiled ahead of
+time by __graft_entry__.build(), or here before any timed region; `config.library` says which); `--generic` uses the generic library.
   value ......... accepted integrator steps of all lanes of all GPUs / device time, inputs resident in HBM
   e2e ........... same metric through the public call sequence with HOST buffers: mlb_set_lanes (H2D of the sampled
                   inputs from pinned memory) -> mlb_run -> mlb_results (D2H of the 7 result columns + status) each step
