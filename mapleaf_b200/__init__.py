@@ -6,3 +6,4 @@ from .simdef import SimDefinition, SubDictReader, defaultConfigValues  # noqa: F
 from .model import buildModel, L  # noqa: F401
 from .montecarlo import runMonteCarloSimulation  # noqa: F401,E402
 from .convergence import ConvergenceSimRunner  # noqa: F401,E402
+from .optimization import optimizationRunnerFactory  # noqa: F401,E402

@@ -292,6 +292,35 @@ class SimDefinition:
     def removeKey(self, key: str):
         return self.dict.pop(key, None)
 
+    def writeToFile(self, fileName: str, writeHeader=True) -> None:
+        """Writes the (possibly modified) definition in the .mapleaf format, keys sorted so that dictionaries stay together, tab-indented,
+        without comments: the layout of the reference's writer (IO/simDefinition.py:582-645), which its optimisers use for continuation files."""
+        from datetime import datetime
+        self.fileName = fileName
+        lines = []
+        if writeHeader:
+            lines += ["# MAPLEAF", "# File: {}".format(fileName), "# Autowritten on: " + str(datetime.now())]
+        open_ = []                                           # dictionaries currently open, outermost first
+        for key in sorted(self.dict):
+            *dicts, name = key.split(".")
+            if dicts != open_:
+                common = 0
+                while common < min(len(open_), len(dicts)) and open_[common] == dicts[common]:
+                    common += 1
+                for depth in range(len(open_), common, -1):
+                    lines.append("\t" * (depth - 1) + "}")
+                if common == len(dicts):
+                    lines.append("")                         # back in an enclosing dictionary: a spacing line before its next keys
+                for depth in range(common, len(dicts)):
+                    lines.append("")
+                    lines.append("\t" * depth + dicts[depth] + "{")
+                open_ = dicts
+            lines.append("\t" * len(open_) + name + "\t" + str(self.dict[key]))
+        for depth in range(len(open_), 0, -1):
+            lines.append("\t" * (depth - 1) + "}")
+        with open(fileName, "w") as f:
+            f.write("\n".join(lines) + "\n")
+
     def setIfAbsent(self, key: str, value) -> None:
         if key not in self.dict:
             self.setValue(key, value)
@@ -397,6 +426,21 @@ class SubDictReader:
             if len(result) != 0:
                 return result
         return self.simDefinition.getImmediateSubDicts(key)
+
+    def _relativeThenAbsolute(self, fn, key):
+        if key is None:
+            key = self.simDefDictPathToReadFrom
+        else:
+            result = fn(self.simDefDictPathToReadFrom + "." + key)
+            if len(result) != 0:
+                return result
+        return fn(key)
+
+    def getImmediateSubKeys(self, key=None) -> List[str]:
+        return self._relativeThenAbsolute(self.simDefinition.getImmediateSubKeys, key)
+
+    def getSubKeys(self, key=None) -> List[str]:
+        return self._relativeThenAbsolute(self.simDefinition.getSubKeys, key)
 
     def getDictName(self) -> str:
         return self.simDefDictPathToReadFrom[self.simDefDictPathToReadFrom.rfind(".") + 1:]

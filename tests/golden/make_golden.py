@@ -50,6 +50,8 @@ What is recorded, and which reference code produced it:
   radiosonde_mc.json ...... wind profiles picked by the reference's RadioSondeDataSampler and a Monte Carlo loop flown on one
   convergence.json ........ ConvergenceSimRunner.convergeSimEndPosition: final positions at successively halved time steps / target errors and
                             the convergence checks computed from them
+  optimization.json ....... ScipyMinimizeRunner (SimulationRunners/Optimization.py:507-614, Nelder-Mead, two independent and one dependent variable):
+                            every (trial point, cost) the reference evaluated, its optimum and the continuation definition it wrote
   rng.json ................ random.Random / PinkNoiseGenerator known answers (test_SimDefinition.py:118-151,
                             test_TurbulenceModelling.py:37-60)
 """
@@ -463,6 +465,41 @@ if __name__ == "__main__":
                               lines=[l for l in buf.getvalue().splitlines() if l.startswith(("Simulation ", "Final Position", "X-Direction", "Y-Direction", "Z-Direction", "Setting EndCondition"))])
             print(" ", label, steps, pos[-1], flush=True)
         dump("convergence.json", out)
+    if "optimization" in which:
+        # ScipyMinimizeRunner of the reference (SimulationRunners/Optimization.py:507-614) on the single-stage rocket: every cost evaluation it
+        # made (trial point, cost), the optimum it returned, and the continuation definition it wrote
+        import contextlib, io, tempfile
+        from MAPLEAF.SimulationRunners.Optimization import optimizationRunnerFactory
+        opt = {"Optimization.method": "scipy.optimize.minimize Nelder-Mead",
+               "Optimization.costFunction": "1/apogee if (apogee > 1) else max(1, -1*apogee)",
+               "Optimization.IndependentVariables.finSpan": "0.08 < Rocket.Sustainer.TailFins.span < 0.25",
+               "Optimization.IndependentVariables.noseAR": "2 < Rocket.Sustainer.Nosecone.aspectRatio < 8",
+               "Optimization.DependentVariables.Rocket.Sustainer.TailFins.tipChord": "!0.1 + 0.4*finSpan!",
+               "Optimization.ScipyMinimize.tolerance": "1e-6", "Optimization.ScipyMinimize.maxIterations": "8",
+               "Optimization.showConvergencePlot": "false", "Environment.ConstantMeanWind.velocity": "(4 -2.5 0.3)"}
+        sd = SimDefinition(mc, silent=True, disableDistributionSampling=True)
+        for k, v in {**QUIET, **opt}.items():
+            sd.setValue(k, v)
+        tmp = tempfile.mkdtemp()
+        # the continuation file is written next to the definition file
+        sd.fileName = os.path.join(tmp, "Optimization.mapleaf")
+        runner = optimizationRunnerFactory(simDefinition=sd, silent=True)
+        evaluations = []
+        inner = runner._evaluateCostFunction
+
+        def record(x):
+            c = inner(x)
+            evaluations.append(dict(x=[float(v) for v in x], cost=float(c)))
+            return c
+        runner._evaluateCostFunction = record
+        with contextlib.redirect_stdout(io.StringIO()):
+            cost, pos = runner.runOptimization()
+        sys.stdout = sys.__stdout__
+        cont = SimDefinition(os.path.join(tmp, "Optimization_continue.mapleaf"), silent=True, disableDistributionSampling=True)
+        dump("optimization.json", dict(definition="MonteCarlo.mapleaf", overrides=opt, 
+                                       evaluations=evaluations, bestCost=float(cost), bestPosition=[float(v) for v in pos],
+                                       continuation={k: cont.getValue(k) for k in cont.dict if k.startswith("Optimization.IndependentVariables.")}))
+        print("  optimisation:", len(evaluations), "evaluations, best", float(cost), [float(v) for v in pos], flush=True)
     if "rk45_pink" in which:
         dump("rk45_pink.json", monteCarlo(adaptive, {}, "2394781", 4, globalSeed=2394781, keepDts=True))
     if "ideal" in which:

@@ -820,3 +820,25 @@ def test_convergence_study_on_the_gpu_vs_reference(backend, golden, label):
     assert steps == g["steps"] and all(t > 0 for t in times)
     for mine, ref in zip(positions, g["positions"]):
         assert relErr(list(mine), ref) < (FIXED_TOL if label == "rk4" else 1e-5)
+
+
+def test_optimisation_runner_on_the_gpu_vs_reference(backend, golden, tmp_path):
+    """ScipyMinimizeRunner (SimulationRunners/Optimization.py:507-614) with every cost evaluation flown by the CUDA kernels: scipy asks for
+    the very points the reference's run asked for, costs agree to 1e-9, same optimum; then one particle-swarm iteration as ONE batch of
+    per-lane model blocks whose costs equal the single flights'."""
+    from mapleaf_b200.optimization import optimizationRunnerFactory
+    g = golden("optimization.json")
+    sd = SimDefinition(os.path.join(DATA, g["definition"]), silent=True, disableDistributionSampling=True)
+    for k, v in g["overrides"].items():
+        sd.setValue(k, v)
+    sd.fileName = str(tmp_path / "Optimization.mapleaf")
+    runner = optimizationRunnerFactory(simDefinition=sd, silent=True)
+    cost, pos = runner.runOptimization()
+    assert [e["x"] for e in g["evaluations"]] == runner.positionHistory
+    for mine, ref in zip(runner.costHistory, g["evaluations"]):
+        assert abs(mine - ref["cost"]) <= 1e-9 * abs(ref["cost"])
+    assert list(pos) == g["bestPosition"] and abs(cost - g["bestCost"]) <= 1e-9 * g["bestCost"]
+    points = [e["x"] for e in g["evaluations"][:6]]
+    batched = runner._computeCostFunctionValues(points)              # six trial rockets, six model blocks, one kernel run
+    for c, e in zip(batched, g["evaluations"]):
+        assert abs(c - e["cost"]) <= 1e-9 * abs(e["cost"])
