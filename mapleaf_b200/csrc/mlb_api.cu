@@ -24,6 +24,8 @@
 #include <string.h>
 #include <string>
 #include <vector>
+#include <map>
+#include <mutex>
 
 #include "../../include/mapleaf_b200.h"
 #include "mlb_integrate.cuh"
@@ -409,10 +411,41 @@ struct mlb_handle {
     cudaStream_t stream = nullptr;
     bool ran = false;
     long long launches = 0;
-    int nSlots = 0; size_t smemBytes = 0;
+    int nSlots = 0; size_t smemBytes = 0;       /* the staged model block (forceEvalKernel; the trajectory kernels of the generic build) */
+    size_t trajSmemBytes = 0;                   /* dynamic shared memory of the trajectory kernels: smemBytes, or 0 in a model-specialised build (no staging) */
     int nSM = 148; int forceBlock = 0; int lastBlock = 0; int lastGenerations = 0; int bailPermille = 750; int generations = MLB_GENERATIONS; bool evenSplit = true;
     size_t sharedLen = 0;
+    long long tuneLanes = 0; double tuneMs[2] = { -1, -1 };    /* free-flight time of this batch size in the 1024- and the 512-lane shape (shape tuning, mlb_run) */
+    int tuneRunBlock = 0;                                      /* shape of the last run if its time has not been read yet */
 };
+
+#ifdef MLB_SPEC
+/* Shape tuning of a model-specialised library. Once the model block is compiled in, 512 lanes x 128 registers and 1024 x 64 are within a
+   few per cent of each other and which one wins depends on the rocket (same-box sweep of the five bench workloads, profiles/r3l: 512 is
+   +4 % / +13 % / +5 % on the single-stage adaptive / fixed-step / NASA cases, 1024 is +15 % on the canard case, whose force model and
+   control loop are twice the code). Results do not depend on the shape (same arithmetic per lane), so a handle simply measures: the
+   first multi-wave run of a batch size flies in the 1024-lane shape, the second in the 512-lane one, later runs in the faster of the
+   two; the choice is kept per library (= per model block) and batch size for every handle of the process. */
+static std::mutex g_tuneMutex;
+static std::map<long long, int> g_tunedBlock;
+static int tunedShape(mlb_handle* h) {
+    std::lock_guard<std::mutex> lock(g_tuneMutex);
+    auto it = g_tunedBlock.find(h->nLanes);
+    if (it != g_tunedBlock.end()) return it->second;
+    if (h->tuneLanes != h->nLanes) { h->tuneLanes = h->nLanes; h->tuneMs[0] = h->tuneMs[1] = -1; h->tuneRunBlock = 0; }
+    else if (h->tuneRunBlock && cudaEventQuery(h->evFlight1) == cudaSuccess) {      /* the previous run of this batch size has finished: take its time */
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, h->evFlight0, h->evFlight1) == cudaSuccess) h->tuneMs[h->tuneRunBlock == 1024 ? 0 : 1] = ms;
+    }
+    h->tuneRunBlock = 0;
+    (void)cudaGetLastError();                               /* cudaEventQuery of a pending event reports cudaErrorNotReady: not an error */
+    if (h->tuneMs[0] < 0) return 1024;
+    if (h->tuneMs[1] < 0) return 512;
+    const int best = h->tuneMs[1] < h->tuneMs[0] ? 512 : 1024;
+    g_tunedBlock[h->nLanes] = best;
+    return best;
+}
+#endif
 
 static int laneArrayComponents(int id) { return id == LANE_WIND ? 3 : (id == LANE_INIT_STATE ? 13 : (id == LANE_PINK_SEED ? 3 : (id == LANE_MOTOR_ADJUST ? 2 * MLB_MAX_STAGES : (id == LANE_START ? 2 : -1)))); }
 
@@ -440,12 +473,12 @@ static int createOnDevice(mlb_handle* h, const double* b, size_t len) {
     CU(cudaMalloc(&h->d_blob, len * sizeof(double)));
     CU(cudaMemcpy(h->d_blob, b, len * sizeof(double), cudaMemcpyHostToDevice));
     /* the kernels' working set is per-thread local memory: leave to L1 everything the staged model block does not need */
-    const int carveout = getenv("MLB_SMEM_CARVEOUT") ? atoi(getenv("MLB_SMEM_CARVEOUT")) : (int)((h->smemBytes + 1024) * 100 / (228 * 1024)) + 1;
-#define MLB_SET_SMEM(N, M) CU((cudaFuncSetAttribute(flightLanes<N, M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes))); \
+    const int carveout = getenv("MLB_SMEM_CARVEOUT") ? atoi(getenv("MLB_SMEM_CARVEOUT")) : (int)((h->trajSmemBytes + 1024) * 100 / (228 * 1024)) + 1;
+#define MLB_SET_SMEM(N, M) CU((cudaFuncSetAttribute(flightLanes<N, M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->trajSmemBytes))); \
     if (carveout >= 0) CU((cudaFuncSetAttribute(flightLanes<N, M, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout)));
     MLB_FLIGHT_SHAPES(MLB_SET_SMEM)
-    CU(cudaFuncSetAttribute(chuteLanes<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
-    CU(cudaFuncSetAttribute(initLanes<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
+    CU(cudaFuncSetAttribute(chuteLanes<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->trajSmemBytes));
+    CU(cudaFuncSetAttribute(initLanes<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->trajSmemBytes));
     CU(cudaFuncSetAttribute(forceEvalKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smemBytes));
     { cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, h->device)); h->nSM = prop.multiProcessorCount; }
     CU(cudaEventCreate(&h->ev0)); CU(cudaEventCreate(&h->ev1)); CU(cudaEventCreate(&h->evFlight0)); CU(cudaEventCreate(&h->evFlight1));
@@ -488,6 +521,11 @@ extern "C" int mlb_create(const void* model_blob, size_t n, int device, mlb_hand
     size_t blobPad = (h->sharedLen + 1) & ~(size_t)1;
     h->smemBytes = blobPad * sizeof(double);
     if (h->smemBytes > 226 * 1024) { delete h; return fail(MLB_ERR_UNSUPPORTED, "mlb_create: the shared part of the model block exceeds shared memory"); }
+#ifdef MLB_SPEC
+    h->trajSmemBytes = 0;
+#else
+    h->trajSmemBytes = h->smemBytes;
+#endif
     { const char* e = getenv("MLB_BLOCK_SIZE"); h->forceBlock = e ? atoi(e) : 0; }
     { const char* e = getenv("MLB_BAIL_PERMILLE"); if (e) h->bailPermille = atoi(e); }
     { const char* e = getenv("MLB_EVEN_SPLIT"); if (e) h->evenSplit = atoi(e) != 0; }
@@ -626,6 +664,10 @@ extern "C" int mlb_run(mlb_handle* h, void* stream) {
             if (cost < bestCost) { bestCost = cost; block = shapeBlock[k]; }
         }
     }
+#ifdef MLB_SPEC
+    { const char* e = getenv("MLB_SHAPE_TUNING");
+      if (block == 1024 && !h->forceBlock && !perLane && h->nLanes >= 2LL * h->nSM * 1024 && !(e && atoi(e) == 0)) { block = tunedShape(h); h->tuneRunBlock = block; } }
+#endif
 #define MLB_ALLOW_SHAPE(N, M) if (h->forceBlock == N) block = N;
     MLB_FLIGHT_SHAPES(MLB_ALLOW_SHAPE)
     if (perLane) block = MLB_PERLANE_BLOCK;                    /* one shape: every constant is a global load there, fewer lanes per SM keep them cached */
@@ -643,7 +685,7 @@ extern "C" int mlb_run(mlb_handle* h, void* stream) {
     if (perLane) initLanes<true><<<(unsigned)((h->nLanes + MLB_BLOCK - 1) / MLB_BLOCK), MLB_BLOCK, 0, s>>>(a);
     else
 #endif
-    initLanes<false><<<(unsigned)((h->nLanes + MLB_BLOCK - 1) / MLB_BLOCK), MLB_BLOCK, h->smemBytes, s>>>(a);
+    initLanes<false><<<(unsigned)((h->nLanes + MLB_BLOCK - 1) / MLB_BLOCK), MLB_BLOCK, h->trajSmemBytes, s>>>(a);
     h->launches++;
     CU(cudaGetLastError());
     /* Free flight, MLB_GENERATIONS launches over ping-pong straggler queues. Every launch is sized for the whole batch (CTAs past the end
@@ -659,7 +701,7 @@ extern "C" int mlb_run(mlb_handle* h, void* stream) {
         a.qNext = h->d_queue[g & 1]; a.qNextCount = h->d_queueCount + g;
         a.bailPermille = (g == G - 1 || singleWave) ? 0 : h->bailPermille;
         bool launched = perLane;
-#define MLB_LAUNCH_SHAPE(N, M) if (block == N && !perLane) { flightLanes<N, M, false><<<grid, N, h->smemBytes, s>>>(a); launched = true; }
+#define MLB_LAUNCH_SHAPE(N, M) if (block == N && !perLane) { flightLanes<N, M, false><<<grid, N, h->trajSmemBytes, s>>>(a); launched = true; }
         MLB_FLIGHT_SHAPES(MLB_LAUNCH_SHAPE)
         if (!launched) return fail(MLB_ERR_STATE, "mlb_run: this build has no free-flight kernel of " + std::to_string(block) + " threads (tuning build with a reduced MLB_FLIGHT_SHAPES list)");
 #ifndef MLB_SPEC
@@ -675,7 +717,7 @@ extern "C" int mlb_run(mlb_handle* h, void* stream) {
     if (perLane) chuteLanes<true><<<(unsigned)((h->nLanes + MLB_CHUTE_BLOCK - 1) / MLB_CHUTE_BLOCK), MLB_CHUTE_BLOCK, 0, s>>>(a);
     else
 #endif
-    chuteLanes<false><<<(unsigned)((h->nLanes + MLB_CHUTE_BLOCK - 1) / MLB_CHUTE_BLOCK), MLB_CHUTE_BLOCK, h->smemBytes, s>>>(a);
+    chuteLanes<false><<<(unsigned)((h->nLanes + MLB_CHUTE_BLOCK - 1) / MLB_CHUTE_BLOCK), MLB_CHUTE_BLOCK, h->trajSmemBytes, s>>>(a);
     h->launches++;
     CU(cudaGetLastError());
     CU(cudaEventRecord(h->ev1, s));

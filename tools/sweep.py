@@ -9,6 +9,7 @@ sys.path.insert(0, REPO)
 
 
 def child(args):
+    os.environ.setdefault("MLB_SHAPE_TUNING", "0")         # sweeps time the shape they name, not the library's measured choice
     import bench
     from mapleaf_b200 import L, SimDefinition, backend, buildModel
     if args.config >= 0:
