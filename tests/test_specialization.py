@@ -101,3 +101,21 @@ def test_trajectory_batch_library_choice(monkeypatch):
     except RuntimeError:
         pass
     assert seen[:1] == ["generic"]
+
+
+def test_bench_reads_the_metrics_pass_of_the_library_and_shape_it_flew():
+    """roofline.traffic comes from the committed ncu pass of the SAME library (generic / specialised) and CTA shape; a pass over the
+    generations of one flight adds up its .sum metrics."""
+    import bench
+    generic, gsrc = bench.measuredKernelMetrics(1, specialised=False)
+    spec, ssrc = bench.measuredKernelMetrics(1, specialised=True, block=1024)
+    spec512, s512src = bench.measuredKernelMetrics(1, specialised=True, block=512)
+    assert "_spec_" not in gsrc and "_spec_" in ssrc and "_block" not in ssrc and "_block512_" in s512src
+    assert generic["dram_bytes"] > spec["dram_bytes"] > spec512["dram_bytes"] > 1e6
+    # the same flights execute the same FP64 work in both shapes
+    for k in ("dfma", "dadd", "dmul"):
+        assert abs(spec[k] - spec512[k]) <= 1e-3 * spec[k]
+    assert bench.measuredKernelMetrics(1, specialised=True, block=768) == (None, None)      # no pass of that shape: traffic stays null
+    for c in (0, 2, 3, 4):
+        per, src = bench.measuredKernelMetrics(c, specialised=True)
+        assert per is not None and "config%d" % c in src
