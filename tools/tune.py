@@ -6,9 +6,11 @@ sys.path.insert(0, REPO)
 VDIR = os.path.join(REPO, "mapleaf_b200", "lib", "variants")
 # name -> extra nvcc flags; edit for the experiment at hand (switches: MLB_FLIGHT_SHAPES, MLB_COMP_NOINLINE, MLB_COLD_MASK, MLB_MATH_NOINLINE,
 # MLB_FIN_UNIFORM, MLB_FIN_LINEAR, MLB_CHUTE_BLOCK, MLB_CHUTE_CTAS, MLB_DERIV_NOINLINE)
+# a model-specialised variant also needs the block header: `#include "<path>/libmapleaf_b200_<hash>.h"` (backend.writeSpecializationHeader) as
+# the LAST line of the generated header, e.g. "-DMLB_SPEC_HEADER=..." is not needed: add the flag "NVCC:-include", "NVCC:<header>" instead
 VARIANTS = {
     "base": ["-DMLB_FLIGHT_SHAPES(X)=X(1024,1)"],
-    "unroll1": ["-DMLB_FLIGHT_SHAPES(X)=X(1024,1)", "-DMLB_SLICE_UNROLL=1"],
+    "split_barrier": ["-DMLB_FLIGHT_SHAPES(X)=X(1024,1)", "-DMLB_SPLIT_BARRIER=1"],
 }
 
 
