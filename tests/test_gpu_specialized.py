@@ -138,3 +138,30 @@ def test_specialised_library_serves_one_model_block_only(backend):
         b.setLanes(4, {})
         with pytest.raises(ValueError, match="per-lane model blocks need the generic library"):
             b.setLaneModels(np.tile(m.blob[:int(m.blob[L.H_SHARED_LEN])], (4, 1)))
+
+
+def test_shape_tuning_measures_both_shapes_and_changes_no_result(backend):
+    """A specialised library times the 1024- and the 512-lane CTA shape on the first two multi-wave runs of a batch size and keeps the
+    faster (mlb_run, tunedShape). The shape changes where lanes run, not what they compute: every run returns the same results (the
+    10^6-lane adaptive sweeps of profiles/r3l count identical steps in both shapes; gated here at 1e-12)."""
+    m = T.buildFrom("MonteCarlo.mapleaf", {"SimControl.EndCondition": "Altitude", "SimControl.EndConditionValue": "0"})
+    n = 2 * 148 * 1024 + 17 * 32              # two waves of the chip and a bit: a batch size no other test uses
+    rng = np.random.default_rng(12)
+    w = rng.normal(size=(3, n)) * np.array([[5.0], [5.0], [0.5]]) + np.array([[2.0], [0.0], [0.0]])
+    shapes, outs = [], []
+    with backend.TrajectoryBatch(m.blob, specialize=True) as b:
+        b.setLanes(n, {L.LANE_WIND: w})
+        for _ in range(3):
+            b.run()
+            res, st = b.results()                      # synchronises: the next run can read this one's time
+            shapes.append(b.counters()["flight_block"])
+            outs.append((res.copy(), st.copy()))
+    assert shapes[0] == 1024 and shapes[1] == 512 and shapes[2] in (512, 1024)
+    assert (outs[0][1] == L.ST_OK).all()
+    for res, st in outs[1:]:
+        assert np.allclose(res, outs[0][0], rtol=1e-12, atol=1e-9) and np.array_equal(st, outs[0][1])
+    # a second handle of the same library and batch size starts with the settled shape
+    with backend.TrajectoryBatch(m.blob, specialize=True) as b:
+        b.setLanes(n, {L.LANE_WIND: w})
+        b.run()
+        assert b.counters()["flight_block"] == shapes[2]
