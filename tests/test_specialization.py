@@ -119,3 +119,23 @@ def test_bench_reads_the_metrics_pass_of_the_library_and_shape_it_flew():
     for c in (0, 2, 3, 4):
         per, src = bench.measuredKernelMetrics(c, specialised=True)
         assert per is not None and "config%d" % c in src
+
+
+def test_the_model_block_really_folds_into_the_kernel():
+    """Static check on the compiled code (cuobjdump, no GPU): the free-flight kernel of the library compiled for configs[1] is less than half
+    the generic kernel, carries no shared-memory staging loop's loads of the block, and keeps its launch bounds (64 registers at 1024 lanes)."""
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("CUDA binary utilities not installed")
+
+    def kernelSass(path):
+        txt = subprocess.run(["cuobjdump", "-sass", "-fun", "_Z11flightLanesILi1024ELi1ELb0EEv7RunArgs", path], capture_output=True, text=True).stdout
+        return [l for l in txt.splitlines() if re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+\S", l)]
+    m = _model()
+    generic = kernelSass(backend.buildLibrary())
+    spec = kernelSass(backend.buildSpecializedLibrary(m.blob))
+    assert len(generic) > 30000 and 5000 < len(spec) < 0.5 * len(generic), (len(generic), len(spec))
+    usage = subprocess.run(["cuobjdump", "-res-usage", backend.specializedLibraryPath(m.blob)], capture_output=True, text=True).stdout
+    row = usage[usage.index("_Z11flightLanesILi1024ELi1ELb0EEv7RunArgs"):].splitlines()[1]
+    assert "REG:64 " in row, row
