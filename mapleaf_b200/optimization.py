@@ -119,7 +119,7 @@ class OptimizingSimRunner:
         batchDefinition = SimDefinition(path, silent=True, disableDistributionSampling=True)
         self.simDefinitions = []
         self._print("Found the following cases:")
-        for case in sorted(batchDefinition.getImmediateSubDicts("")):
+        for case in sorted({k.split(".")[0] for k in batchDefinition.dict if "." in k}):          # every root-level dictionary is a case
             self._print(case)
             simDefPath = batchDefinition.getValue("{}.simDefinitionFile".format(case))
             if not os.path.isabs(simDefPath) and not os.path.exists(simDefPath):

@@ -114,3 +114,50 @@ def test_written_definition_reads_back_identically(tmp_path):
     assert back.dict == before
     text = open(path).read()
     assert text.startswith("# MAPLEAF\n# File: " + path) and "\nRocket{\n" in text and text.rstrip().endswith("}")
+
+
+def test_batch_of_cases_and_inner_optimisation(golden, tmp_path):
+    """Optimization.batchDefinition: the cost of a trial solution is the mean over the cases (Optimization.py:201-233,268-298), all cases of all
+    trial solutions in one batch. InnerOptimization: every outer trial first optimises the inner variables (:240-247,286-290)."""
+    g = golden("optimization.json")
+    deck = os.path.join(DATA, g["definition"])
+    batchFile = tmp_path / "cases.mapleaf"
+    batchFile.write_text("calm{\n    simDefinitionFile " + deck + "\n    ParameterOverrides{\n        Environment.ConstantMeanWind.velocity (0 0 0)\n    }\n}\n"
+                         "windy{\n    simDefinitionFile " + deck + "\n    ParameterOverrides{\n        Environment.ConstantMeanWind.velocity (9 -4 0.3)\n    }\n}\n")
+    base = {k: v for k, v in g["overrides"].items() if "noseAR" not in k}
+    single = {}
+    for name, wind in (("calm", "(0 0 0)"), ("windy", "(9 -4 0.3)")):
+        sd = SimDefinition(deck, silent=True, disableDistributionSampling=True)
+        for k, v in {**base, "Environment.ConstantMeanWind.velocity": wind}.items():
+            sd.setValue(k, v)
+        single[name] = optimizationRunnerFactory(simDefinition=sd, silent=True, batchClass=OracleBatch)._computeCostFunctionValues([[0.1], [0.2]])
+    sd = SimDefinition(deck, silent=True, disableDistributionSampling=True)
+    for k, v in {**base, "Optimization.batchDefinition": str(batchFile)}.items():
+        sd.setValue(k, v)
+    runner = optimizationRunnerFactory(simDefinition=sd, silent=True, batchClass=OracleBatch)
+    assert len(runner.simDefinitions) == 2
+    both = runner._computeCostFunctionValues([[0.1], [0.2]])
+    assert runner.nBatches == 1 and runner.nSimulations == 4                       # 2 trial solutions x 2 cases, one kernel run
+    for i in range(2):
+        assert abs(both[i] - (single["calm"][i] + single["windy"][i]) / 2) <= 1e-15
+    assert single["calm"][0] != single["windy"][0]
+
+    # nested: the outer variable is the fin span, the inner optimisation (Nelder-Mead, 2 iterations) picks the nose aspect ratio for each trial
+    sd = SimDefinition(deck, silent=True, disableDistributionSampling=True)
+    nested = {**base, "Optimization.InnerOptimization.method": "scipy.optimize.minimize Nelder-Mead",
+              "Optimization.InnerOptimization.costFunction": g["overrides"]["Optimization.costFunction"],
+              "Optimization.InnerOptimization.IndependentVariables.noseAR": g["overrides"]["Optimization.IndependentVariables.noseAR"],
+              "Optimization.InnerOptimization.ScipyMinimize.maxIterations": "2", "Optimization.InnerOptimization.showConvergencePlot": "false"}
+    for k, v in nested.items():
+        sd.setValue(k, v)
+    sd.fileName = str(tmp_path / "Nested.mapleaf")
+    outer = optimizationRunnerFactory(simDefinition=sd, silent=True, batchClass=OracleBatch)
+    assert outer.varNames == ["finSpan"] and outer._hasInnerOptimization()
+    cost = outer._computeCostFunctionValues([[0.165]])[0]
+    plain = single["calm"]          # (other wind; only used for the type) the nested cost is a flight's cost at the inner optimum:
+    inner = outer._createNestedOptimization(sd)
+    assert inner.varNames == ["noseAR"] and isinstance(inner, ScipyMinimizeRunner)
+    assert isinstance(cost, float) and isinstance(plain[0], float) and outer.nSimulations > 3       # inner evaluations are counted
+    # the inner optimum is at least as good as the inner start point (centre of its bounds, noseAR = 5) at the same fin span
+    ref = {tuple(e["x"]): e["cost"] for e in g["evaluations"]}
+    assert cost <= ref[(0.165, 5.0)] * (1 + 1e-11)
