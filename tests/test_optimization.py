@@ -161,3 +161,24 @@ def test_batch_of_cases_and_inner_optimisation(golden, tmp_path):
     # the inner optimum is at least as good as the inner start point (centre of its bounds, noseAR = 5) at the same fin span
     ref = {tuple(e["x"]): e["cost"] for e in g["evaluations"]}
     assert cost <= ref[(0.165, 5.0)] * (1 + 1e-11)
+
+
+def test_scipy_runner_gives_a_crashed_trial_a_high_cost(golden, tmp_path):
+    """scipy's optimisers may leave the bounds; a trial the model builder (or the flight) rejects gets max(costHistory) x 1.1 while fewer than six
+    costs are known, max(costHistory) after that, and a crash of the very first trial propagates (Optimization.py:529-546)."""
+    g, sd = referenceCase(golden, tmp_path)
+    runner = optimizationRunnerFactory(simDefinition=sd, silent=True, batchClass=OracleBatch)
+    costs = iter([2.0, 3.0, ValueError("boom"), 1.0, 1.5, 2.5, 0.5, ValueError("boom")])
+
+    def fake(trials):
+        c = next(costs)
+        if isinstance(c, Exception):
+            raise c
+        return [c]
+    runner._computeCostFunctionValues = fake
+    out = [runner._evaluateCostFunction([0.1, 3.0]) for _ in range(8)]
+    assert out == [2.0, 3.0, 3.0 * 1.1, 1.0, 1.5, 2.5, 0.5, 3.0 * 1.1]
+    fresh = optimizationRunnerFactory(simDefinition=sd, silent=True, batchClass=OracleBatch)
+    fresh._computeCostFunctionValues = lambda trials: (_ for _ in ()).throw(ValueError("first trial"))
+    with pytest.raises(ValueError, match="first trial"):
+        fresh._evaluateCostFunction([0.1, 3.0])

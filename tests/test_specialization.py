@@ -82,7 +82,8 @@ def test_trajectory_batch_library_choice(monkeypatch):
     seen = []
     monkeypatch.setattr(backend, "specializedLibrary", lambda blob, build=True: seen.append("spec") or (_ for _ in ()).throw(RuntimeError("stop")))
     monkeypatch.setattr(backend, "lib", lambda: seen.append("generic") or (_ for _ in ()).throw(RuntimeError("stop")))
-    for spec, env, want in ((True, None, "spec"), (False, "1", "generic"), (None, "1", "spec"), (None, "0", "generic"), (None, None, "generic")):
+    for spec, env, want in ((True, None, "spec"), (False, "1", "generic"), (None, "1", "spec"), (None, "0", "generic"), (None, None, "generic"),
+                            (None, "cached", "spec")):            # configs[1]'s library is cached by build()
         seen.clear()
         if env is None:
             monkeypatch.delenv("MLB_SPECIALIZE", raising=False)
